@@ -1,0 +1,159 @@
+/* ndt_b200.h — C ABI of libndt_b200.so, the B200-native NDT registration hot path.
+ *
+ * The reference (ToySLAM's vendored ndt_omp) has no FFI: its boundary is the public method set of
+ * the C++ class pclomp::NormalDistributionsTransform (ndt_omp/include/pclomp/ndt_omp.h:70-502).
+ * Each entry point below names the reference method(s) it replaces.  The header-only C++ shim
+ * include/pclomp_b200/ndt_b200.hpp forwards the reference's method names to these calls, so a
+ * caller such as ndt_omp/apps/align.cpp or lidar_subscriber/src/ndt_rosbag_mapping_node.cpp
+ * only changes its include and namespace.
+ *
+ * Conventions: plain C types only; every call returns an ndtb200_status (0 = ok); no exceptions
+ * cross the ABI; the caller owns all host buffers; the library owns all device memory and one
+ * CUDA stream per handle.  A handle is single-threaded (as one reference object is: it keeps
+ * mutable per-evaluation tables, ndt_omp.h:473-488); distinct handles are independent.
+ * Point buffers are arrays of structs whose first 12 bytes are x,y,z as fp32 and whose size is
+ * `stride_bytes` (16 for pcl::PointXYZ, 32 for PointXYZI / PointXYZRGB — the three instantiations
+ * in ndt_omp/src/pclomp/ndt_omp.cpp:4-6).  4x4 matrices are column-major fp32 (Eigen::Matrix4f).
+ *
+ * There is NO CPU fallback: every compute entry point fails with NDTB200_ERR_NO_DEVICE when no
+ * CUDA device is usable.
+ */
+#ifndef NDT_B200_H_
+#define NDT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ndtb200_handle ndtb200_handle;
+
+typedef enum ndtb200_status {
+  NDTB200_OK = 0,
+  NDTB200_ERR_NO_INPUT = 1,      /* no target / source set (voxel_grid_covariance_omp_impl.hpp:54-60) */
+  NDTB200_ERR_GRID_OVERFLOW = 2, /* int32 voxel index would overflow (…_impl.hpp:75-84): map left empty */
+  NDTB200_ERR_CUDA = 3,          /* a CUDA call failed; see ndtb200_last_error */
+  NDTB200_ERR_INVALID = 4,       /* bad argument */
+  NDTB200_ERR_NO_DEVICE = 5      /* no usable CUDA device (the library never falls back to the CPU) */
+} ndtb200_status;
+
+/* pclomp::NeighborSearchMethod (ndt_omp.h:52-57), same values. KDTREE is not implemented yet. */
+enum { NDTB200_KDTREE = 0, NDTB200_DIRECT26 = 1, NDTB200_DIRECT7 = 2, NDTB200_DIRECT1 = 3 };
+
+/* Setters of the reference object, as one struct.  Defaults = ndt_omp_impl.hpp:46-76 and
+ * voxel_grid_covariance_omp.h:208-211. */
+typedef struct ndtb200_params {
+  float resolution;         /* setResolution            (1.0)  */
+  double step_size;         /* setStepSize              (0.1)  */
+  double outlier_ratio;     /* setOutlierRatio          (0.55) */
+  double trans_eps;         /* setTransformationEpsilon (0.1)  */
+  int32_t max_iterations;   /* setMaximumIterations     (35)   */
+  int32_t search_method;    /* setNeighborhoodSearchMethod (DIRECT7) */
+  int32_t min_points_per_voxel; /* VoxelGridCovariance::setMinPointPerVoxel (6) */
+  double eig_ratio;         /* setCovEigValueInflationRatio (0.01) */
+} ndtb200_params;
+
+/* What the reference object exposes after align(). */
+typedef struct ndtb200_result {
+  float final_transformation[16]; /* getFinalTransformation(): pose of the LAST line-search trial */
+  float last_increment[16];       /* pcl::Registration::getLastIncrementalTransformation() */
+  int32_t converged;              /* hasConverged() */
+  int32_t iterations;             /* getFinalNumIteration() */
+  double trans_probability;       /* getTransformationProbability() */
+  double final_pose[6];           /* x,y,z,roll,pitch,yaw of the last evaluated trial (fp64) */
+  double final_score;             /* score of the last derivative evaluation */
+  int32_t n_evaluations;          /* computeDerivatives calls in this align() */
+  int32_t n_hessian_passes;       /* computeHessian calls in this align() */
+  int64_t n_hits;                 /* (point, voxel) pairs summed over all evaluations */
+} ndtb200_result;
+
+typedef struct ndtb200_map_info {
+  int32_t min_b[3], max_b[3], div_b[3]; /* VoxelGrid::min_b_/max_b_/div_b_ */
+  int64_t n_points;  /* target points handed in */
+  int64_t n_voxels;  /* occupied voxels (leaves_.size()) */
+  int64_t n_valid;   /* voxels a lookup can return (count >= min_points and spectrum/inverse ok) */
+  int64_t hash_capacity;
+} ndtb200_map_info;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int ndtb200_create(ndtb200_handle** out, int device);        /* NormalDistributionsTransform()        */
+int ndtb200_destroy(ndtb200_handle* h);                      /* ~NormalDistributionsTransform()       */
+int ndtb200_clone(const ndtb200_handle* src, ndtb200_handle** out); /* copy-construction
+                                                                (ndt_omp_mapping_node.cpp:151-169)   */
+const char* ndtb200_last_error(const ndtb200_handle* h);
+int ndtb200_device_count(void);
+
+/* ---- parameters ---------------------------------------------------------------------------- */
+int ndtb200_default_params(ndtb200_params* p);
+/* Stores the parameters.  Like setResolution (ndt_omp.h:132-142) a CHANGED resolution rebuilds the
+ * target map only if a source is already set; other fields never trigger work. */
+int ndtb200_set_params(ndtb200_handle* h, const ndtb200_params* p);
+int ndtb200_get_params(const ndtb200_handle* h, ndtb200_params* p);
+
+/* ---- inputs -------------------------------------------------------------------------------- */
+/* setInputTarget (ndt_omp.h:122-127): copies the cloud to the device and builds the voxel map now
+ * (VoxelGridCovariance::applyFilter, voxel_grid_covariance_omp_impl.hpp:48-370). */
+int ndtb200_set_target(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, int is_dense);
+/* setInputSource (pcl::Registration). */
+int ndtb200_set_source(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes);
+/* Same, for clouds already resident in device memory (16-byte float4 records, this device). */
+int ndtb200_set_target_device(ndtb200_handle* h, const void* d_points_xyzw, size_t n, int is_dense);
+int ndtb200_set_source_device(ndtb200_handle* h, const void* d_points_xyzw, size_t n);
+
+/* ---- registration -------------------------------------------------------------------------- */
+/* align(output[, guess]) (pcl::Registration::align -> computeTransformation, ndt_omp_impl.hpp:80-171).
+ * guess: column-major 4x4 or NULL (= identity).  out_points: NULL or a buffer of n_source records of
+ * out_stride_bytes each; x,y,z receive the source transformed by the final pose, the 4th float is 1. */
+int ndtb200_align(ndtb200_handle* h, const float* guess, void* out_points, size_t out_stride_bytes);
+/* The two halves of ndtb200_align for callers that keep everything on the device: enqueue the whole
+ * Newton / More-Thuente solve on the handle's stream without any host synchronisation ... */
+int ndtb200_align_async(ndtb200_handle* h, const float* guess);
+/* ... and wait for it + fetch the result block (one small D2H copy). */
+int ndtb200_sync(ndtb200_handle* h);
+int ndtb200_get_result(ndtb200_handle* h, ndtb200_result* out);
+/* getFitnessScore(max_range) (pcl::Registration): mean squared distance of T*source to its exact
+ * nearest raw target point. */
+int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out);
+/* calculateScore(cloud) (ndt_omp_impl.hpp:935-983). */
+int ndtb200_calculate_score(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, double* out);
+
+/* ---- parity / inspection (stage dumps; used by tests, not by callers) ------------------------ */
+int ndtb200_get_map_info(const ndtb200_handle* h, ndtb200_map_info* out);
+/* voxel key of every target point, input order (-1 = skipped non-finite point). */
+int ndtb200_dump_point_keys(ndtb200_handle* h, int32_t* keys);
+/* all occupied voxels in ascending key order: counts (-1 = rejected leaf), mean[3], cov[9], icov[9]
+ * (row-major fp64), inflated flag.  Any pointer may be NULL. */
+int ndtb200_dump_voxels(ndtb200_handle* h, int32_t* keys, int32_t* counts, double* mean, double* cov,
+                        double* icov, int32_t* inflated);
+/* One computeDerivatives(p) (ndt_omp_impl.hpp:179-285) at pose p.  T: matrix to transform the source
+ * with, or NULL (= built from p like computeStepLengthMT does).  out43 = score, gradient[6],
+ * hessian[36] row-major; n_hits may be NULL. */
+int ndtb200_eval_derivatives(ndtb200_handle* h, const double p[6], const float* T, int compute_hessian,
+                             double out43[43], int64_t* n_hits);
+/* One computeHessian (ndt_omp_impl.hpp:540-645) at pose p (fp64 path, fp64 angle tables). */
+int ndtb200_eval_hessian(ndtb200_handle* h, const double p[6], const float* T, double out36[36]);
+/* getNeighborhoodAtPoint{,7,1} (voxel_grid_covariance_omp_impl.hpp:373-442) for n query points:
+ * out_keys[n][26], -1 padded, in the reference's offset order. */
+int ndtb200_lookup(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, int search_method,
+                   int32_t* out_keys);
+
+/* The on-device Newton / More-Thuente trace of the last align: one entry per evaluation
+ * (kind 0 = derivatives+Hessian, 1 = derivatives only, 2 = Hessian only; pose; step length; score).
+ * n_out receives the number of evaluations; at most `cap` entries are written. */
+int ndtb200_get_trace(ndtb200_handle* h, int32_t* kinds, double* x6, double* a_t, double* score, int cap, int* n_out);
+
+/* ---- plumbing for benchmarks ----------------------------------------------------------------- */
+/* The handle's cudaStream_t (as void*), so a caller can record CUDA events on it. */
+void* ndtb200_stream(ndtb200_handle* h);
+/* Kernels launched by this handle since creation (or since the last reset). */
+int64_t ndtb200_launch_count(const ndtb200_handle* h);
+void ndtb200_reset_launch_count(ndtb200_handle* h);
+/* Milliseconds the last ndtb200_align_async solve kernel took (CUDA events on the handle stream). */
+int ndtb200_last_align_ms(ndtb200_handle* h, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDT_B200_H_ */

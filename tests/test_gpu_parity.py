@@ -1,0 +1,287 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): voxel keys / point-to-voxel assignment / per-voxel counts bit-exact;
+means, covariances, score, gradient, Hessian within 1e-5 relative (of the max-magnitude entry);
+final transform within 1e-4 m translation and 1e-4 rad rotation.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from util import golden, load_pair, pose_matrix, rel_err, synthetic_scene, transform_delta
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+TRANS_TOL = 1e-4
+ROT_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import toyslam_b200
+    return toyslam_b200
+
+
+def make_pair(nb, tgt, src, method=oracle.DIRECT7, res=1.0, **kw):
+    ref = oracle.NormalDistributionsTransform()
+    gpu = nb.NormalDistributionsTransform()
+    for o in (ref, gpu):
+        o.setResolution(res)
+        o.setNeighborhoodSearchMethod(method)
+        if "eps" in kw:
+            o.setTransformationEpsilon(kw["eps"])
+        if "max_iter" in kw:
+            o.setMaximumIterations(kw["max_iter"])
+        if "step" in kw:
+            o.setStepSize(kw["step"])
+    st_ref = ref.setInputTarget(tgt)
+    st_gpu = gpu.setInputTarget(tgt)
+    assert st_ref == st_gpu
+    ref.setInputSource(src)
+    gpu.setInputSource(src)
+    return ref, gpu
+
+
+def check_map(ref, gpu):
+    ri, gi = ref.map_info(), gpu.map_info()
+    for k in ("min_b", "max_b", "div_b"):
+        assert np.array_equal(ri[k], gi[k]), k
+    assert ri["n_voxels"] == gi["n_voxels"]
+    assert ri["n_valid"] == gi["n_valid"]
+    assert np.array_equal(ref.point_keys(), gpu.point_keys())  # bit-exact keys, input order
+    rl, gl = ref.dump_leaves(), gpu.dump_voxels()
+    assert np.array_equal(rl["keys"], gl["keys"])
+    assert np.array_equal(rl["counts"], gl["counts"])      # incl. -1 flags
+    assert np.array_equal(rl["inflated"], gl["inflated"])
+    valid = rl["counts"] >= 6
+    assert rel_err(gl["mean"], rl["mean"]) < REL
+    # covariances / inverse covariances per voxel, relative to that voxel's largest entry
+    for name in ("cov", "icov"):
+        a, b = gl[name][valid], rl[name][valid]
+        scale = np.abs(b).reshape(len(b), -1).max(axis=1)
+        err = np.abs(a - b).reshape(len(b), -1).max(axis=1) / scale
+        assert err.max() < REL, (name, err.max())
+
+
+@pytest.mark.parametrize("res", [1.0, 0.5, 2.0, 0.3])
+def test_map_build_bundled(nb, res):
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src, res=res)
+    check_map(ref, gpu)
+
+
+def test_map_build_c1_known_values(nb):
+    tgt, src = load_pair()
+    gpu = nb.NormalDistributionsTransform()
+    gpu.setInputTarget(tgt)
+    info = gpu.map_info()
+    assert list(info["min_b"]) == [-24, -75, -3] and list(info["max_b"]) == [19, 8, 10]
+    assert info["n_voxels"] == 1098 and info["n_valid"] == 599
+
+
+@pytest.mark.parametrize("offset", [(0, 0, 0), (2000.0, -1500.0, 50.0), (20000.0, -15000.0, 50.0)])
+def test_map_build_synthetic_offsets(nb, offset):
+    tgt, src = synthetic_scene(offset=offset, seed=3)
+    ref, gpu = make_pair(nb, tgt, src)
+    check_map(ref, gpu)
+
+
+def test_map_build_degenerate_voxels(nb):
+    rng = np.random.default_rng(5)
+    pts = []
+    for n, c in ((5, (0.5, 0.5, 0.5)), (6, (1.5, 0.5, 0.5)), (7, (2.5, 0.5, 0.5))):
+        pts.append(np.asarray(c) + rng.uniform(-0.3, 0.3, size=(n, 3)))
+    t = rng.uniform(-0.4, 0.4, size=(20, 1))
+    pts.append(np.array([4.5, 0.5, 0.5]) + t * np.array([1.0, 0.5, 0.2]))             # collinear
+    uv = rng.uniform(-0.4, 0.4, size=(30, 2))
+    pts.append(np.array([6.5, 0.5, 0.5]) + np.c_[uv, np.zeros(30)])                   # coplanar
+    pts.append(np.repeat(np.array([[8.5, 0.5, 0.5]]), 12, axis=0))                    # duplicated point
+    pts.append(np.array([[-3.0, -2.0, -1.0], [12.0, 3.0, 2.0]]))                      # bbox corners
+    tgt = np.concatenate(pts).astype(np.float32)
+    ref, gpu = make_pair(nb, tgt, tgt[:10])
+    check_map(ref, gpu)
+    assert gpu.dump_voxels()["inflated"].sum() >= 2
+
+
+def test_map_build_non_dense_and_faces(nb):
+    rng = np.random.default_rng(7)
+    tgt = rng.uniform(-8, 8, size=(20000, 3)).astype(np.float32)
+    tgt[::7] = np.round(tgt[::7])          # points exactly on voxel faces
+    tgt[5] = [np.nan, 0, 0]
+    tgt[100] = [0, np.inf, 0]
+    ref = oracle.NormalDistributionsTransform()
+    gpu = nb.NormalDistributionsTransform()
+    assert ref.setInputTarget(tgt, is_dense=False) == gpu.setInputTarget(tgt, is_dense=False) == 0
+    ref.setInputSource(tgt[:10]); gpu.setInputSource(tgt[:10])
+    check_map(ref, gpu)
+
+
+def test_grid_overflow_guard(nb):
+    tgt = np.array([[0, 0, 0], [3000, 3000, 3000], [1, 1, 1]], dtype=np.float32)
+    ref = oracle.NormalDistributionsTransform()
+    gpu = nb.NormalDistributionsTransform()
+    for o in (ref, gpu):
+        o.setResolution(0.5)
+    assert ref.setInputTarget(tgt) == oracle.BUILD_GRID_OVERFLOW
+    assert gpu.setInputTarget(tgt) == 2  # NDTB200_ERR_GRID_OVERFLOW
+    assert gpu.map_info()["n_voxels"] == 0
+
+
+@pytest.mark.parametrize("method", [oracle.DIRECT1, oracle.DIRECT7, oracle.DIRECT26])
+def test_lookup(nb, method):
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src, method=method)
+    rng = np.random.default_rng(11)
+    q = np.concatenate([src[:4000], rng.uniform(-40, 40, size=(2000, 3)).astype(np.float32),
+                        np.round(src[:500])]).astype(np.float32)
+    a, b = gpu.lookup(q, method), ref.lookup(q, method)
+    assert np.array_equal(a, b)   # same keys in the same (reference offset) order
+
+
+POSES = [np.zeros(6),
+         np.array([0.4, 0.1, -0.02, 0.005, -0.001, -0.01]),
+         np.array([0.1, -0.3, 0.05, 0.3, -0.25, 0.6]),        # large angles: exposes Q2 (+sy / -sy)
+         np.array([-0.2, 0.2, 0.0, 5e-5, -5e-5, 2e-5]),       # small-angle snap (|a| < 1e-4)
+         np.array([1.0, 0.5, 0.1, -0.05, 0.08, -1.2])]
+
+
+@pytest.mark.parametrize("method", [oracle.DIRECT1, oracle.DIRECT7, oracle.DIRECT26])
+@pytest.mark.parametrize("hess", [True, False])
+def test_derivatives(nb, method, hess):
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src, method=method)
+    for p in POSES:
+        a = gpu.eval_derivatives(p, compute_hessian=hess)
+        b = ref.eval_derivatives(p, compute_hessian=hess)
+        assert a["hits"] == b["hits"], (p, a["hits"], b["hits"])
+        assert abs(a["score"] - b["score"]) <= REL * abs(b["score"])
+        assert rel_err(a["gradient"], b["gradient"]) < REL
+        if hess:
+            assert rel_err(a["hessian"], b["hessian"]) < REL
+        else:
+            assert np.all(a["hessian"] == 0) and np.all(b["hessian"] == 0)
+
+
+@pytest.mark.parametrize("method", [oracle.DIRECT1, oracle.DIRECT7, oracle.DIRECT26])
+def test_hessian_only(nb, method):
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src, method=method)
+    for p in POSES:
+        assert rel_err(gpu.eval_hessian(p), ref.eval_hessian(p)) < REL
+
+
+def test_derivatives_far_from_origin(nb):
+    """fp64 voxel means: parity must hold at map-scale coordinates (SURVEY §7 hard part 2)."""
+    for off in ((2000.0, -1500.0, 50.0), (20000.0, -15000.0, 50.0)):
+        tgt, src = synthetic_scene(offset=off, seed=9)
+        ref, gpu = make_pair(nb, tgt, src)
+        p = np.array([off[0] + 0.2, off[1] - 0.1, off[2] + 0.02, 0.003, -0.002, 0.01])
+        a, b = gpu.eval_derivatives(p), ref.eval_derivatives(p)
+        assert a["hits"] == b["hits"] and b["hits"] > 1000
+        assert abs(a["score"] - b["score"]) <= REL * abs(b["score"])
+        assert rel_err(a["gradient"], b["gradient"]) < REL
+        assert rel_err(a["hessian"], b["hessian"]) < REL
+
+
+def check_align(ref, gpu, guess=None):
+    ref.align(guess)
+    out = gpu.align(guess)
+    rr, rg = ref.result(), gpu.result()
+    tr, tg = ref.trace(), gpu.trace()
+    assert rg["iterations"] == rr["iterations"]
+    assert rg["n_evaluations"] == rr["n_evaluations"]
+    assert rg["n_hessian_passes"] == rr["n_hessian_passes"]
+    assert rg["converged"] == rr["converged"]
+    assert np.array_equal(tg["kind"], tr["kind"])
+    assert np.abs(tg["a_t"] - tr["a_t"]).max() < 1e-6        # trial step-length sequence
+    assert np.abs(tg["x"] - tr["x"]).max() < 1e-6            # evaluated poses
+    dt, dr = transform_delta(rg["final"], rr["final"])
+    assert dt < TRANS_TOL and dr < ROT_TOL, (dt, dr)
+    assert abs(rg["trans_probability"] - rr["trans_probability"]) <= 1e-5 * abs(rr["trans_probability"])
+    return out, rr, rg
+
+
+@pytest.mark.parametrize("method,name", [(oracle.DIRECT7, "DIRECT7"), (oracle.DIRECT1, "DIRECT1")])
+def test_align_config1_golden_fitness(nb, method, name):
+    """Config 1: the reference's own published known answers (ndt_omp/README.md:26,31)."""
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src, method=method)
+    out, rr, rg = check_align(ref, gpu)
+    fit = gpu.getFitnessScore()
+    assert abs(fit - golden()["fitness"][name]) < 5e-7, fit           # 6 printed digits
+    assert abs(fit - ref.getFitnessScore()) <= 1e-6 * fit
+    # output cloud = source transformed by the final pose
+    exp = oracle.transform_points(rg["final"], src)
+    assert np.array_equal(out[:, :3], exp[:, :3])
+    # repeated align() on the same pair returns identical results (apps/align.cpp:25-27)
+    gpu.align()
+    assert np.array_equal(gpu.result()["final"], rg["final"])
+
+
+def test_align_direct26(nb):
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src, method=oracle.DIRECT26)
+    _, rr, rg = check_align(ref, gpu)
+    assert rr["n_hessian_passes"] >= 1   # exercises the Hessian-only pass inside the solver
+
+
+def test_align_line_search_fixture_b(nb):
+    """0.3 m downsample + mapping-node parameters: 10 extra More-Thuente trials."""
+    tgt, src = load_pair("pair_ds0p3.npz")
+    ref, gpu = make_pair(nb, tgt, src, eps=0.01, max_iter=64)
+    _, rr, rg = check_align(ref, gpu)
+    assert rr["n_evaluations"] > rr["iterations"] + 1
+
+
+@pytest.mark.parametrize("guess_p", [[0.3, 0.1, 0.0, 0.0, 0.0, 0.0],
+                                     [0.2, 0.05, -0.01, 0.01, -0.02, 0.03],
+                                     [0.2, 0.05, -0.01, -0.01, 0.02, -0.03]])   # negative roll: Q5
+def test_align_with_guess(nb, guess_p):
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src)
+    check_align(ref, gpu, guess=pose_matrix(guess_p))
+
+
+def test_align_scan_to_map_offset(nb):
+    off = (2000.0, -1500.0, 50.0)
+    tgt, src = synthetic_scene(offset=off, seed=21)
+    ref, gpu = make_pair(nb, tgt, src)
+    check_align(ref, gpu, guess=pose_matrix([off[0], off[1], off[2], 0, 0, 0]))
+
+
+def test_calculate_score(nb):
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src)
+    a, b = gpu.calculateScore(src), ref.calculateScore(src)
+    assert abs(a - b) <= 1e-9 * abs(b)
+
+
+def test_clone_is_independent(nb):
+    tgt, src = load_pair("pair_ds0p3.npz")
+    gpu = nb.NormalDistributionsTransform()
+    gpu.setInputTarget(tgt); gpu.setInputSource(src)
+    gpu.align()
+    r0 = gpu.result()
+    other = gpu.clone()
+    other.align()
+    assert np.array_equal(other.result()["final"], r0["final"])
+    other.setInputSource(src[:100])
+    gpu.align()
+    assert np.array_equal(gpu.result()["final"], r0["final"])
+
+
+def test_point_strides(nb):
+    """PointXYZI / PointXYZRGB are 32-byte records (ndt_omp.cpp:4-6): same answer as 16-byte PointXYZ."""
+    tgt, src = load_pair("pair_ds0p3.npz")
+    a = nb.NormalDistributionsTransform()
+    a.setInputTarget(tgt); a.setInputSource(src); a.align()
+    t32 = np.zeros((len(tgt), 8), dtype=np.float32); t32[:, :3] = tgt; t32[:, 4] = 7.0
+    s32 = np.zeros((len(src), 8), dtype=np.float32); s32[:, :3] = src
+    b = nb.NormalDistributionsTransform()
+    b.set_target_raw(t32.ctypes.data, len(tgt), 32)
+    b.set_source_raw(s32.ctypes.data, len(src), 32)
+    out = np.zeros((len(src), 8), dtype=np.float32)
+    b.align_raw(None, out.ctypes.data, 32)
+    assert np.array_equal(a.result()["final"], b.result()["final"])
+    assert np.all(out[:, 3] == 1.0) and np.all(out[:, 4:] == 0.0)

@@ -1,0 +1,49 @@
+"""In-tree build of libndt_b200.so (sm_100a only) with nvcc.  No JIT cache, no torch extension:
+the .so lands in toyslam_b200/lib/ and travels to the GPU box with the repo snapshot."""
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libndt_b200.so")
+SOURCES = ["capi.cu"]
+HEADERS = ["common.cuh", "map_build.cuh", "ndt_solve.cuh", "ndt_align.cuh", "ndt_aux.cuh",
+           os.path.join("..", "..", "include", "ndt_b200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library for sm_100a.  Cross-compiles without a GPU."""
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    env = dict(os.environ)
+    # the image exports CC/CXX=/opt/gcc/bin/* wrappers; nvcc wants the stock host compiler
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    subprocess.check_call(cmd, cwd=CSRC, env=env)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

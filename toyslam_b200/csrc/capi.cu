@@ -1,0 +1,926 @@
+// capi.cu — host side of libndt_b200.so: handle, device memory, kernel orchestration, C ABI.
+// See include/ndt_b200.h for the contract of every entry point and the reference method it replaces.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ndt_b200.h"
+#include "map_build.cuh"
+#include "ndt_align.cuh"
+#include "ndt_aux.cuh"
+
+using namespace ndtb200;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct ndtb200_handle {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  ndtb200_params prm{};
+  long long launches = 0;
+
+  // target cloud + map
+  DevBuf d_target;
+  size_t n_target = 0;
+  bool target_dense = true, has_target = false;
+  int map_status = NDTB200_ERR_NO_INPUT;
+  GridDesc grid{};
+  long long n_voxels = 0, n_valid = 0;
+  uint32_t hash_cap = 0;
+  int hash_shift = 0;
+  DevBuf d_grid, d_mm_partial, d_mm_finite, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_scan_tmp, d_scalar;
+  DevBuf d_voxel_key, d_voxel_start, d_moments, d_records, d_icov64, d_hash;
+
+  // source cloud
+  DevBuf d_source;
+  size_t n_source = 0;
+  bool has_source = false;
+
+  // align workspace
+  DevBuf d_partials, d_totals, d_sync, d_result, d_trace, d_out, d_tmp;
+  int coop_blocks[4] = {0, 0, 0, 0};  // max co-resident CTAs per search method
+  AlignResultDev* h_result = nullptr;  // pinned
+  bool result_valid = false;
+  float last_final_T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  static constexpr int kTraceCap = 1024;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                \
+      return NDTB200_ERR_CUDA;                                                                     \
+    }                                                                                              \
+  } while (0)
+
+#define LAUNCHED(h) ((h)->launches++)
+
+inline int grid_for(size_t n, int per_block, int cap) {
+  size_t b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > static_cast<size_t>(cap)) b = cap;
+  return static_cast<int>(b);
+}
+
+// ---- host copies of a strided host cloud into a packed float4 device buffer ------------------
+int upload_points(ndtb200_handle* h, DevBuf& dst, const void* points, size_t n, size_t stride) {
+  if (n == 0) return NDTB200_OK;
+  if (stride < 12) { h->err = "stride_bytes must be >= 12"; return NDTB200_ERR_INVALID; }
+  CK(dst.ensure(n * sizeof(float4)));
+  if (stride == 16) {
+    CK(cudaMemcpyAsync(dst.p, points, n * 16, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    size_t width = stride < 16 ? stride : 16;
+    if (width < 16) CK(cudaMemsetAsync(dst.p, 0, n * 16, h->stream));
+    CK(cudaMemcpy2DAsync(dst.p, 16, points, stride, width, n, cudaMemcpyHostToDevice, h->stream));
+  }
+  return NDTB200_OK;
+}
+
+// ---- exclusive scan (recursive 3-kernel) ------------------------------------------------------
+int exclusive_scan(ndtb200_handle* h, uint32_t* d_data, size_t n, uint32_t* d_tmp, uint32_t* d_total) {
+  // in-place exclusive scan of d_data[0..n); d_tmp must hold sum over levels of ceil(n / tile^k)
+  const int ntiles = static_cast<int>((n + kScanTile - 1) / kScanTile);
+  scan_tiles_kernel<<<ntiles, kBuildThreads, 0, h->stream>>>(d_data, d_data, n, d_tmp);
+  LAUNCHED(h);
+  if (ntiles == 1) {
+    if (d_total) CK(cudaMemcpyAsync(d_total, d_tmp, sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+    return NDTB200_OK;
+  }
+  int st = exclusive_scan(h, d_tmp, ntiles, d_tmp + ((ntiles + 63) & ~63), d_total);
+  if (st != NDTB200_OK) return st;
+  scan_add_kernel<<<ntiles, kBuildThreads, 0, h->stream>>>(d_data, n, d_tmp);
+  LAUNCHED(h);
+  return NDTB200_OK;
+}
+
+size_t scan_tmp_elems(size_t n) {
+  size_t total = 0;
+  while (true) {
+    size_t t = (n + kScanTile - 1) / kScanTile;
+    total += (t + 63) & ~size_t(63);
+    if (t <= 1) break;
+    n = t;
+  }
+  return total + 64;
+}
+
+void clear_map(ndtb200_handle* h) {
+  h->n_voxels = 0;
+  h->n_valid = 0;
+}
+
+int ensure_empty_hash(ndtb200_handle* h) {
+  h->hash_cap = 1024;
+  h->hash_shift = 32 - 10;
+  CK(h->d_hash.ensure(h->hash_cap * sizeof(HashSlot)));
+  CK(cudaMemsetAsync(h->d_hash.p, 0xFF, h->hash_cap * sizeof(HashSlot), h->stream));
+  CK(h->d_records.ensure(sizeof(VoxelRecord)));
+  CK(h->d_icov64.ensure(6 * sizeof(double)));
+  return NDTB200_OK;
+}
+
+// ---- VoxelGridCovariance::applyFilter on the device -------------------------------------------
+int build_map(ndtb200_handle* h) {
+  clear_map(h);
+  std::memset(&h->grid, 0, sizeof(GridDesc));
+  for (int a = 0; a < 3; ++a) h->grid.leaf[a] = h->prm.resolution;
+  const size_t n = h->n_target;
+  if (!h->has_target || n == 0) {
+    h->map_status = NDTB200_ERR_NO_INPUT;
+    int st = ensure_empty_hash(h);
+    return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
+  }
+  if (n > 0xFFFFFFF0ull) { h->err = "target cloud too large (>= 2^32 points)"; return NDTB200_ERR_INVALID; }
+  const float4* pts = h->d_target.as<float4>();
+  const int dense = h->target_dense ? 1 : 0;
+
+  // 1. bounding box + grid description
+  const int mm_blocks = grid_for(n, kBuildThreads * 4, h->num_sms * 8);
+  CK(h->d_mm_partial.ensure(mm_blocks * 6 * sizeof(float)));
+  CK(h->d_mm_finite.ensure(mm_blocks * sizeof(unsigned int)));
+  CK(h->d_grid.ensure(sizeof(GridDesc)));
+  minmax3d_kernel<<<mm_blocks, kBuildThreads, 0, h->stream>>>(pts, n, dense, h->d_mm_partial.as<float>(),
+                                                               h->d_mm_finite.as<unsigned int>());
+  LAUNCHED(h);
+  grid_setup_kernel<<<1, 32, 0, h->stream>>>(h->d_mm_partial.as<float>(), h->d_mm_finite.as<unsigned int>(),
+                                              mm_blocks, h->prm.resolution, h->d_grid.as<GridDesc>());
+  LAUNCHED(h);
+  CK(cudaMemcpyAsync(&h->grid, h->d_grid.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->grid.n_finite == 0) {
+    h->map_status = NDTB200_ERR_NO_INPUT;
+    int st = ensure_empty_hash(h);
+    return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
+  }
+  if (h->grid.overflow) {  // voxel_grid_covariance_omp_impl.hpp:79-84: warn, leave the map empty
+    h->map_status = NDTB200_ERR_GRID_OVERFLOW;
+    int st = ensure_empty_hash(h);
+    return st != NDTB200_OK ? st : NDTB200_ERR_GRID_OVERFLOW;
+  }
+
+  // 2. keys
+  unsigned long long key_space =
+      (unsigned long long)h->grid.div_b[0] * (unsigned long long)h->grid.div_b[1] * (unsigned long long)h->grid.div_b[2];
+  if (key_space > 0xFFFFFFFEull) key_space = 0xFFFFFFFEull;
+  const uint32_t sentinel = static_cast<uint32_t>(key_space);  // sorts after every real key
+  unsigned long long max_key = dense ? (key_space - 1) : key_space;
+  int bits = 1;
+  while (bits < 32 && (max_key >> bits) != 0) ++bits;
+  const int passes = (bits + 7) / 8;
+
+  CK(h->d_keys_a.ensure(n * sizeof(uint32_t)));
+  CK(h->d_keys_b.ensure(n * sizeof(uint32_t)));
+  CK(h->d_vals_a.ensure(n * sizeof(uint32_t)));
+  CK(h->d_vals_b.ensure(n * sizeof(uint32_t)));
+  const int key_blocks = grid_for(n, kBuildThreads * 4, h->num_sms * 16);
+  voxel_key_kernel<<<key_blocks, kBuildThreads, 0, h->stream>>>(pts, n, dense, h->d_grid.as<GridDesc>(), sentinel,
+                                                                 h->d_keys_a.as<uint32_t>(), nullptr);
+  LAUNCHED(h);
+
+  // 3. stable LSD radix sort of (key, point index)
+  const int ntiles = static_cast<int>((n + kSortTile - 1) / kSortTile);
+  const size_t hist_n = (size_t)256 * ntiles;
+  CK(h->d_hist.ensure(hist_n * sizeof(uint32_t)));
+  CK(h->d_scan_tmp.ensure(scan_tmp_elems(std::max(hist_n, n)) * sizeof(uint32_t)));
+  uint32_t *ka = h->d_keys_a.as<uint32_t>(), *kb = h->d_keys_b.as<uint32_t>();
+  uint32_t *va = h->d_vals_a.as<uint32_t>(), *vb = h->d_vals_b.as<uint32_t>();
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = pass * 8;
+    radix_count_kernel<<<ntiles, kBuildThreads, 0, h->stream>>>(ka, n, shift, h->d_hist.as<uint32_t>(), ntiles);
+    LAUNCHED(h);
+    int st = exclusive_scan(h, h->d_hist.as<uint32_t>(), hist_n, h->d_scan_tmp.as<uint32_t>(), nullptr);
+    if (st != NDTB200_OK) return st;
+    radix_scatter_kernel<<<ntiles, kBuildThreads, 0, h->stream>>>(ka, pass == 0 ? nullptr : va, n, shift,
+                                                                   h->d_hist.as<uint32_t>(), ntiles, kb, vb);
+    LAUNCHED(h);
+    std::swap(ka, kb);
+    std::swap(va, vb);
+  }
+  // sorted keys in ka, sorted point indices in va.  Keep them addressable through fixed members.
+  if (ka != h->d_keys_a.as<uint32_t>()) { std::swap(h->d_keys_a, h->d_keys_b); std::swap(h->d_vals_a, h->d_vals_b); }
+
+  // 4. occupied voxels = segment heads
+  const int stiles = static_cast<int>((n + kScanTile - 1) / kScanTile);
+  uint32_t* tile_counts = h->d_hist.as<uint32_t>();  // reuse (hist_n >= stiles)
+  head_count_kernel<<<stiles, kBuildThreads, 0, h->stream>>>(ka, n, sentinel, tile_counts);
+  LAUNCHED(h);
+  uint32_t* d_total = h->d_scalar.as<uint32_t>();
+  {
+    int st = exclusive_scan(h, tile_counts, stiles, h->d_scan_tmp.as<uint32_t>(), d_total);
+    if (st != NDTB200_OK) return st;
+  }
+  uint32_t n_vox = 0;
+  CK(cudaMemcpyAsync(&n_vox, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_voxels = n_vox;
+  CK(h->d_voxel_key.ensure((size_t)n_vox * sizeof(int32_t)));
+  CK(h->d_voxel_start.ensure((size_t)n_vox * sizeof(uint32_t)));
+  CK(h->d_moments.ensure((size_t)n_vox * 9 * sizeof(double)));
+  CK(h->d_records.ensure((size_t)n_vox * sizeof(VoxelRecord)));
+  CK(h->d_icov64.ensure((size_t)n_vox * 6 * sizeof(double)));
+  head_write_kernel<<<stiles, kBuildThreads, 0, h->stream>>>(ka, n, sentinel, tile_counts, h->d_voxel_key.as<int32_t>(),
+                                                              h->d_voxel_start.as<uint32_t>());
+  LAUNCHED(h);
+
+  // 5. moments + finalize
+  const uint32_t n_finite = static_cast<uint32_t>(h->grid.n_finite);
+  const double avg = static_cast<double>(n_finite) / std::max<uint32_t>(1u, n_vox);
+  if (avg >= 48.0) {
+    const int blocks = static_cast<int>(((size_t)n_vox * 32 + kBuildThreads - 1) / kBuildThreads);
+    voxel_moments_kernel<32><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
+                                                                      n_finite, h->d_moments.as<double>());
+  } else if (avg >= 10.0) {
+    const int blocks = static_cast<int>(((size_t)n_vox * 8 + kBuildThreads - 1) / kBuildThreads);
+    voxel_moments_kernel<8><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
+                                                                     n_finite, h->d_moments.as<double>());
+  } else {
+    const int blocks = static_cast<int>(((size_t)n_vox * 4 + kBuildThreads - 1) / kBuildThreads);
+    voxel_moments_kernel<4><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
+                                                                     n_finite, h->d_moments.as<double>());
+  }
+  LAUNCHED(h);
+  unsigned int* d_nvalid = h->d_scalar.as<unsigned int>() + 4;
+  CK(cudaMemsetAsync(d_nvalid, 0, sizeof(unsigned int), h->stream));
+  const int vblocks = static_cast<int>(((size_t)n_vox + kBuildThreads - 1) / kBuildThreads);
+  finalize_voxels_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(
+      h->d_moments.as<double>(), h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), n_vox, n_finite,
+      h->prm.min_points_per_voxel, h->prm.eig_ratio, h->d_records.as<VoxelRecord>(), h->d_icov64.as<double>(),
+      d_nvalid, nullptr, nullptr, nullptr);
+  LAUNCHED(h);
+  unsigned int n_valid = 0;
+  CK(cudaMemcpyAsync(&n_valid, d_nvalid, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_valid = n_valid;
+
+  // 6. hash over the valid voxels, load <= 0.25
+  uint32_t cap = 1024;
+  int log2cap = 10;
+  while (cap < 4ull * n_valid && log2cap < 31) { cap <<= 1; ++log2cap; }
+  h->hash_cap = cap;
+  h->hash_shift = 32 - log2cap;
+  CK(h->d_hash.ensure((size_t)cap * sizeof(HashSlot)));
+  CK(cudaMemsetAsync(h->d_hash.p, 0xFF, (size_t)cap * sizeof(HashSlot), h->stream));
+  hash_insert_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
+                                                               h->prm.min_points_per_voxel, h->d_hash.as<HashSlot>(),
+                                                               cap - 1, h->hash_shift);
+  LAUNCHED(h);
+  h->map_status = NDTB200_OK;
+  return NDTB200_OK;
+}
+
+MapView make_view(const ndtb200_handle* h) {
+  MapView m;
+  m.records = h->d_records.as<VoxelRecord>();
+  m.icov64 = h->d_icov64.as<double>();
+  m.hash = h->d_hash.as<HashSlot>();
+  m.hash_mask = h->hash_cap - 1;
+  m.hash_shift = h->hash_shift;
+  for (int a = 0; a < 3; ++a) {
+    m.min_b[a] = h->grid.min_b[a];
+    m.max_b[a] = h->grid.max_b[a];
+    m.mul[a] = h->grid.mul[a];
+    m.leaf[a] = h->grid.leaf[a];
+  }
+  if (h->n_voxels == 0) {  // empty map: every bounds test fails
+    for (int a = 0; a < 3; ++a) { m.min_b[a] = 1; m.max_b[a] = 0; m.mul[a] = 0; }
+  }
+  m.min_points = h->prm.min_points_per_voxel;
+  return m;
+}
+
+// ---- guess -> pose vector (host; tiny) ---------------------------------------------------------
+// Transform<float,3,Affine>::rotation() (polar factor via SVD) then eulerAngles(0,1,2) as Eigen 3.3
+// (ndt_omp_impl.hpp:103-111).
+void rotation_polar_host(const float* T /*row-major 3x4*/, float R[3][3]) {
+  double W[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) W[i][j] = T[i * 4 + j];
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int k = 0; k < 3; ++k) { alpha += W[k][p] * W[k][p]; beta += W[k][q] * W[k][q]; gamma += W[k][p] * W[k][q]; }
+        if (gamma == 0.0 || std::fabs(gamma) <= 1e-17 * std::sqrt(alpha * beta)) continue;
+        rotated = true;
+        double zeta = (beta - alpha) / (2.0 * gamma);
+        double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+        for (int k = 0; k < 3; ++k) {
+          double wp = W[k][p], wq = W[k][q];
+          W[k][p] = c * wp - s * wq; W[k][q] = s * wp + c * wq;
+          double vp = V[k][p], vq = V[k][q];
+          V[k][p] = c * vp - s * vq; V[k][q] = s * vp + c * vq;
+        }
+      }
+    if (!rotated) break;
+  }
+  double U[3][3];
+  for (int j = 0; j < 3; ++j) {
+    double nrm = std::sqrt(W[0][j] * W[0][j] + W[1][j] * W[1][j] + W[2][j] * W[2][j]);
+    for (int k = 0; k < 3; ++k) U[k][j] = (nrm > 0) ? W[k][j] / nrm : (k == j ? 1.0 : 0.0);
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += U[i][k] * V[j][k];
+      R[i][j] = static_cast<float>(s);
+    }
+}
+
+void euler_angles_012_host(const float R[3][3], float res[3]) {
+  const float pi = static_cast<float>(M_PI);
+  res[0] = std::atan2(R[1][2], R[2][2]);
+  const float c2 = std::sqrt(R[0][0] * R[0][0] + R[0][1] * R[0][1]);
+  if (res[0] > 0.0f) {
+    res[0] -= pi;
+    res[1] = std::atan2(-R[0][2], -c2);
+  } else {
+    res[1] = std::atan2(-R[0][2], c2);
+  }
+  const float s1 = std::sin(res[0]), c1 = std::cos(res[0]);
+  res[2] = std::atan2(s1 * R[2][0] - c1 * R[1][0], c1 * R[1][1] - s1 * R[2][1]);
+  res[0] = -res[0]; res[1] = -res[1]; res[2] = -res[2];
+}
+
+void gauss_constants(const ndtb200_params& p, double& d1, double& d2, double& d3) {
+  // ndt_omp_impl.hpp:86-93
+  const double c1 = 10.0 * (1 - p.outlier_ratio);
+  const double c2 = p.outlier_ratio / std::pow(static_cast<double>(p.resolution), 3);
+  d3 = -std::log(c2);
+  d1 = -std::log(c1 + c2) - d3;
+  d2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - d3) / d1);
+}
+
+template <int METHOD>
+int query_coop_blocks(ndtb200_handle* h) {
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ndt_align_kernel<METHOD>, kAlignThreads, 0));
+  if (per_sm < 1) { h->err = "align kernel does not fit on an SM"; return NDTB200_ERR_CUDA; }
+  h->coop_blocks[METHOD] = per_sm * h->num_sms;
+  return NDTB200_OK;
+}
+
+// Enqueue one launch of the persistent kernel (no host synchronisation).
+int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0[12], int has_guess, int eval_hessian) {
+  if (!h->has_source || h->n_source == 0) { h->err = "no input source"; return NDTB200_ERR_NO_INPUT; }
+  const int method = h->prm.search_method;
+  if (method < NDTB200_DIRECT26 || method > NDTB200_DIRECT1) {
+    h->err = "search method not implemented (KDTREE)";
+    return NDTB200_ERR_INVALID;
+  }
+  AlignParams prm;
+  gauss_constants(h->prm, prm.d1, prm.d2, prm.d3);
+  prm.step_size = h->prm.step_size;
+  prm.trans_eps = h->prm.trans_eps;
+  prm.max_iterations = h->prm.max_iterations;
+  prm.mode = mode;
+  prm.eval_hessian = eval_hessian;
+  prm.has_guess = has_guess;
+  for (int i = 0; i < 6; ++i) prm.p0[i] = p0[i];
+  for (int i = 0; i < 12; ++i) prm.T0[i] = T0[i];
+  prm.n_source = static_cast<int>(h->n_source);
+  prm.trace_cap = ndtb200_handle::kTraceCap;
+
+  const int max_blocks = h->coop_blocks[method];
+  int blocks = grid_for(h->n_source, kAlignThreads, max_blocks);
+  CK(h->d_partials.ensure((size_t)max_blocks * kNVP * sizeof(double)));
+  CK(h->d_totals.ensure(2 * kNVP * sizeof(double)));
+  CK(h->d_sync.ensure(64));
+  CK(h->d_result.ensure(sizeof(AlignResultDev)));
+  CK(h->d_trace.ensure(ndtb200_handle::kTraceCap * sizeof(TraceRec)));
+  CK(cudaMemsetAsync(h->d_sync.p, 0, 8, h->stream));
+
+  AlignWorkspace ws;
+  ws.partials = h->d_partials.as<double>();
+  ws.totals = h->d_totals.as<double>();
+  ws.sync = h->d_sync.as<unsigned int>();
+  ws.result = h->d_result.as<AlignResultDev>();
+  ws.trace = h->d_trace.as<TraceRec>();
+  MapView map = make_view(h);
+  const float4* src = h->d_source.as<float4>();
+  void* args[] = {(void*)&src, (void*)&map, (void*)&prm, (void*)&ws};
+  const void* fn = method == NDTB200_DIRECT1 ? (const void*)ndt_align_kernel<3>
+                 : method == NDTB200_DIRECT7 ? (const void*)ndt_align_kernel<2>
+                                             : (const void*)ndt_align_kernel<1>;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kAlignThreads), args, 0, h->stream));
+  LAUNCHED(h);
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->result_valid = false;
+  return NDTB200_OK;
+}
+
+int fetch_result(ndtb200_handle* h) {
+  CK(cudaMemcpyAsync(h->h_result, h->d_result.p, sizeof(AlignResultDev), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->result_valid = true;
+  return NDTB200_OK;
+}
+
+void colmajor_to_T(const float* m, float T[12]) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) T[r * 4 + c] = m[c * 4 + r];
+}
+void T_to_colmajor(const float T[12], float* m) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) m[c * 4 + r] = T[r * 4 + c];
+  m[3] = m[7] = m[11] = 0.0f;
+  m[15] = 1.0f;
+}
+bool is_identity_colmajor(const float* m) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c)
+      if (m[c * 4 + r] != ((r == c) ? 1.0f : 0.0f)) return false;
+  return true;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int ndtb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int ndtb200_default_params(ndtb200_params* p) {
+  if (!p) return NDTB200_ERR_INVALID;
+  p->resolution = 1.0f;
+  p->step_size = 0.1;
+  p->outlier_ratio = 0.55;
+  p->trans_eps = 0.1;
+  p->max_iterations = 35;
+  p->search_method = NDTB200_DIRECT7;
+  p->min_points_per_voxel = 6;
+  p->eig_ratio = 0.01;
+  return NDTB200_OK;
+}
+
+int ndtb200_create(ndtb200_handle** out, int device) {
+  if (!out) return NDTB200_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+    return NDTB200_ERR_NO_DEVICE;  // no CPU fallback, by design
+  ndtb200_handle* h = new ndtb200_handle();
+  h->device = device;
+  ndtb200_default_params(&h->prm);
+  auto fail = [&](int code) { delete h; return code; };
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NDTB200_ERR_NO_DEVICE);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(NDTB200_ERR_NO_DEVICE);
+  h->num_sms = prop.multiProcessorCount;
+  if (!prop.cooperativeLaunch) return fail(NDTB200_ERR_NO_DEVICE);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(NDTB200_ERR_CUDA);
+  if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) return fail(NDTB200_ERR_CUDA);
+  if (cudaMallocHost(&h->h_result, sizeof(AlignResultDev)) != cudaSuccess) return fail(NDTB200_ERR_CUDA);
+  std::memset(h->h_result, 0, sizeof(AlignResultDev));
+  int st = query_coop_blocks<1>(h);
+  if (st == NDTB200_OK) st = query_coop_blocks<2>(h);
+  if (st == NDTB200_OK) st = query_coop_blocks<3>(h);
+  if (st == NDTB200_OK) st = ensure_empty_hash(h);
+  if (st == NDTB200_OK && h->d_scalar.ensure(256) != cudaSuccess) st = NDTB200_ERR_CUDA;
+  if (st != NDTB200_OK) {
+    std::fprintf(stderr, "ndtb200_create: %s\n", h->err.c_str());
+    return fail(st);
+  }
+  *out = h;
+  return NDTB200_OK;
+}
+
+int ndtb200_destroy(ndtb200_handle* h) {
+  if (!h) return NDTB200_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->d_target, &h->d_grid, &h->d_mm_partial, &h->d_mm_finite, &h->d_keys_a, &h->d_keys_b,
+                    &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_voxel_key,
+                    &h->d_voxel_start, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_source,
+                    &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp};
+  for (DevBuf* b : bufs) b->release();
+  if (h->h_result) cudaFreeHost(h->h_result);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return NDTB200_OK;
+}
+
+const char* ndtb200_last_error(const ndtb200_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int ndtb200_set_params(ndtb200_handle* h, const ndtb200_params* p) {
+  if (!h || !p) return NDTB200_ERR_INVALID;
+  if (!(p->resolution > 0) || p->search_method < 0 || p->search_method > 3) {
+    h->err = "invalid parameters";
+    return NDTB200_ERR_INVALID;
+  }
+  const bool res_changed = (p->resolution != h->prm.resolution);
+  h->prm = *p;
+  if (h->prm.min_points_per_voxel < 3) h->prm.min_points_per_voxel = 3;  // setMinPointPerVoxel, vgc.h:228-240
+  // setResolution (ndt_omp.h:132-142): rebuild only if the value changed AND a source is set (sic)
+  if (res_changed && h->has_source && h->has_target) {
+    cudaSetDevice(h->device);
+    int st = build_map(h);
+    if (st == NDTB200_ERR_CUDA) return st;
+  }
+  return NDTB200_OK;
+}
+
+int ndtb200_get_params(const ndtb200_handle* h, ndtb200_params* p) {
+  if (!h || !p) return NDTB200_ERR_INVALID;
+  *p = h->prm;
+  return NDTB200_OK;
+}
+
+int ndtb200_set_target(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, int is_dense) {
+  if (!h || (!points && n)) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  int st = upload_points(h, h->d_target, points, n, stride_bytes);
+  if (st != NDTB200_OK) return st;
+  h->n_target = n;
+  h->target_dense = is_dense != 0;
+  h->has_target = true;
+  return build_map(h);
+}
+
+int ndtb200_set_target_device(ndtb200_handle* h, const void* d_points, size_t n, int is_dense) {
+  if (!h || (!d_points && n)) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (n) {
+    CK(h->d_target.ensure(n * sizeof(float4)));
+    CK(cudaMemcpyAsync(h->d_target.p, d_points, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->n_target = n;
+  h->target_dense = is_dense != 0;
+  h->has_target = true;
+  return build_map(h);
+}
+
+int ndtb200_set_source(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes) {
+  if (!h || (!points && n)) return NDTB200_ERR_INVALID;
+  if (n > 0x7FFFFFF0ull) { h->err = "source cloud too large"; return NDTB200_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  int st = upload_points(h, h->d_source, points, n, stride_bytes);
+  if (st != NDTB200_OK) return st;
+  h->n_source = n;
+  h->has_source = true;
+  return NDTB200_OK;
+}
+
+int ndtb200_set_source_device(ndtb200_handle* h, const void* d_points, size_t n) {
+  if (!h || (!d_points && n)) return NDTB200_ERR_INVALID;
+  if (n > 0x7FFFFFF0ull) { h->err = "source cloud too large"; return NDTB200_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  if (n) {
+    CK(h->d_source.ensure(n * sizeof(float4)));
+    CK(cudaMemcpyAsync(h->d_source.p, d_points, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->n_source = n;
+  h->has_source = true;
+  return NDTB200_OK;
+}
+
+int ndtb200_align_async(ndtb200_handle* h, const float* guess) {
+  if (!h) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  float T0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  double p0[6] = {0, 0, 0, 0, 0, 0};
+  int has_guess = 0;
+  if (guess && !is_identity_colmajor(guess)) {
+    has_guess = 1;
+    colmajor_to_T(guess, T0);
+  }
+  // p = [translation, rotation().eulerAngles(0,1,2)] of final_transformation_ (Identity gives -0,0,-0)
+  float R[3][3], ang[3];
+  rotation_polar_host(T0, R);
+  euler_angles_012_host(R, ang);
+  p0[0] = T0[3]; p0[1] = T0[7]; p0[2] = T0[11];
+  p0[3] = ang[0]; p0[4] = ang[1]; p0[5] = ang[2];
+  return launch_align(h, MODE_ALIGN, p0, T0, has_guess, 1);
+}
+
+int ndtb200_sync(ndtb200_handle* h) {
+  if (!h) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  int st = fetch_result(h);
+  if (st != NDTB200_OK) return st;
+  std::memcpy(h->last_final_T, h->h_result->final_T, sizeof(h->last_final_T));
+  return NDTB200_OK;
+}
+
+int ndtb200_align(ndtb200_handle* h, const float* guess, void* out_points, size_t out_stride_bytes) {
+  if (!h) return NDTB200_ERR_INVALID;
+  int st = ndtb200_align_async(h, guess);
+  if (st != NDTB200_OK) return st;
+  if (out_points) {
+    if (out_stride_bytes < 16) { h->err = "out_stride_bytes must be >= 16"; return NDTB200_ERR_INVALID; }
+    const int n = static_cast<int>(h->n_source);
+    CK(h->d_out.ensure((size_t)n * sizeof(float4)));
+    transform_output_kernel<<<grid_for(n, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+        h->d_source.as<float4>(), n, h->d_result.as<AlignResultDev>(), h->d_out.as<float4>());
+    LAUNCHED(h);
+    if (out_stride_bytes == 16)
+      CK(cudaMemcpyAsync(out_points, h->d_out.p, (size_t)n * 16, cudaMemcpyDeviceToHost, h->stream));
+    else
+      CK(cudaMemcpy2DAsync(out_points, out_stride_bytes, h->d_out.p, 16, 16, n, cudaMemcpyDeviceToHost, h->stream));
+  }
+  return ndtb200_sync(h);
+}
+
+int ndtb200_get_result(ndtb200_handle* h, ndtb200_result* out) {
+  if (!h || !out) return NDTB200_ERR_INVALID;
+  if (!h->result_valid) {
+    int st = ndtb200_sync(h);
+    if (st != NDTB200_OK) return st;
+  }
+  const AlignResultDev& r = *h->h_result;
+  T_to_colmajor(r.final_T, out->final_transformation);
+  T_to_colmajor(r.incr_T, out->last_increment);
+  out->converged = r.converged;
+  out->iterations = r.iterations;
+  out->trans_probability = r.trans_probability;
+  for (int i = 0; i < 6; ++i) out->final_pose[i] = r.final_pose[i];
+  out->final_score = r.final_score;
+  out->n_evaluations = r.n_evals;
+  out->n_hessian_passes = r.n_hess;
+  out->n_hits = r.n_hits;
+  return NDTB200_OK;
+}
+
+int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out) {
+  if (!h || !out) return NDTB200_ERR_INVALID;
+  if (!h->has_source || !h->has_target || h->n_source == 0 || h->n_target == 0) {
+    h->err = "fitness needs a source and a target";
+    return NDTB200_ERR_NO_INPUT;
+  }
+  cudaSetDevice(h->device);
+  const int n = static_cast<int>(h->n_source);
+  const int blocks = (n + 255) / 256;
+  CK(h->d_tmp.ensure((size_t)blocks * 16 + 64));
+  double* d_sum = h->d_tmp.as<double>();
+  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(d_sum + blocks);
+  float* d_T = reinterpret_cast<float*>(h->d_scalar.as<char>() + 64);
+  CK(cudaMemcpyAsync(d_T, h->last_final_T, 12 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  fitness_bruteforce_kernel<<<blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), n, h->d_target.as<float4>(),
+                                                           static_cast<int>(h->n_target), d_T, max_range, d_sum, d_cnt);
+  LAUNCHED(h);
+  std::vector<double> hs(blocks);
+  std::vector<unsigned long long> hc(blocks);
+  CK(cudaMemcpyAsync(hs.data(), d_sum, blocks * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(hc.data(), d_cnt, blocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double s = 0;
+  unsigned long long c = 0;
+  for (int b = 0; b < blocks; ++b) { s += hs[b]; c += hc[b]; }
+  *out = c > 0 ? s / static_cast<double>(c) : 1.7976931348623157e308;
+  return NDTB200_OK;
+}
+
+int ndtb200_calculate_score(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, double* out) {
+  if (!h || !out || (!points && n)) return NDTB200_ERR_INVALID;
+  if (n == 0) { *out = 0; return NDTB200_ERR_NO_INPUT; }
+  cudaSetDevice(h->device);
+  int st = upload_points(h, h->d_out, points, n, stride_bytes);
+  if (st != NDTB200_OK) return st;
+  const int blocks = static_cast<int>((n + 255) / 256);
+  CK(h->d_tmp.ensure((size_t)blocks * 8 + 64));
+  double d1, d2, d3;
+  gauss_constants(h->prm, d1, d2, d3);
+  MapView map = make_view(h);
+  const float4* cloud = h->d_out.as<float4>();
+  double* d_sum = h->d_tmp.as<double>();
+  switch (h->prm.search_method) {
+    case NDTB200_DIRECT1: calculate_score_kernel<3><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
+    case NDTB200_DIRECT7: calculate_score_kernel<2><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
+    case NDTB200_DIRECT26: calculate_score_kernel<1><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
+    default: h->err = "search method not implemented (KDTREE)"; return NDTB200_ERR_INVALID;
+  }
+  LAUNCHED(h);
+  std::vector<double> hs(blocks);
+  CK(cudaMemcpyAsync(hs.data(), d_sum, blocks * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double s = 0;
+  for (int b = 0; b < blocks; ++b) s += hs[b];
+  *out = s / static_cast<double>(n);
+  return NDTB200_OK;
+}
+
+int ndtb200_get_map_info(const ndtb200_handle* h, ndtb200_map_info* out) {
+  if (!h || !out) return NDTB200_ERR_INVALID;
+  for (int a = 0; a < 3; ++a) {
+    out->min_b[a] = h->grid.min_b[a];
+    out->max_b[a] = h->grid.max_b[a];
+    out->div_b[a] = h->grid.div_b[a];
+  }
+  out->n_points = static_cast<int64_t>(h->n_target);
+  out->n_voxels = h->n_voxels;
+  out->n_valid = h->n_valid;
+  out->hash_capacity = h->hash_cap;
+  return h->map_status;
+}
+
+int ndtb200_dump_point_keys(ndtb200_handle* h, int32_t* keys) {
+  if (!h || !keys) return NDTB200_ERR_INVALID;
+  if (h->map_status != NDTB200_OK) return h->map_status;
+  cudaSetDevice(h->device);
+  const size_t n = h->n_target;
+  CK(h->d_tmp.ensure(n * sizeof(uint32_t)));
+  voxel_key_kernel<<<grid_for(n, kBuildThreads * 4, h->num_sms * 16), kBuildThreads, 0, h->stream>>>(
+      h->d_target.as<float4>(), n, h->target_dense ? 1 : 0, h->d_grid.as<GridDesc>(), 0xFFFFFFFFu,
+      h->d_tmp.as<uint32_t>(), nullptr);
+  LAUNCHED(h);
+  CK(cudaMemcpyAsync(keys, h->d_tmp.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return NDTB200_OK;
+}
+
+int ndtb200_dump_voxels(ndtb200_handle* h, int32_t* keys, int32_t* counts, double* mean, double* cov, double* icov,
+                        int32_t* inflated) {
+  if (!h) return NDTB200_ERR_INVALID;
+  if (h->map_status != NDTB200_OK) return h->map_status;
+  cudaSetDevice(h->device);
+  const uint32_t V = static_cast<uint32_t>(h->n_voxels);
+  if (V == 0) return NDTB200_OK;
+  DevBuf d_cov, d_icov, d_infl, d_rec, d_ic64;
+  CK(d_cov.ensure((size_t)V * 9 * sizeof(double)));
+  CK(d_icov.ensure((size_t)V * 9 * sizeof(double)));
+  CK(d_infl.ensure((size_t)V * sizeof(int)));
+  CK(d_rec.ensure((size_t)V * sizeof(VoxelRecord)));
+  CK(d_ic64.ensure((size_t)V * 6 * sizeof(double)));
+  unsigned int* d_nvalid = h->d_scalar.as<unsigned int>() + 8;
+  const int vblocks = static_cast<int>(((size_t)V + kBuildThreads - 1) / kBuildThreads);
+  finalize_voxels_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(
+      h->d_moments.as<double>(), h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), V,
+      static_cast<uint32_t>(h->grid.n_finite), h->prm.min_points_per_voxel, h->prm.eig_ratio, d_rec.as<VoxelRecord>(),
+      d_ic64.as<double>(), d_nvalid, d_cov.as<double>(), d_icov.as<double>(), d_infl.as<int>());
+  LAUNCHED(h);
+  std::vector<VoxelRecord> recs(V);
+  CK(cudaMemcpyAsync(recs.data(), d_rec.p, (size_t)V * sizeof(VoxelRecord), cudaMemcpyDeviceToHost, h->stream));
+  if (cov) CK(cudaMemcpyAsync(cov, d_cov.p, (size_t)V * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (icov) CK(cudaMemcpyAsync(icov, d_icov.p, (size_t)V * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (inflated) CK(cudaMemcpyAsync(inflated, d_infl.p, (size_t)V * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (uint32_t v = 0; v < V; ++v) {
+    if (keys) keys[v] = recs[v].key;
+    if (counts) counts[v] = recs[v].count;
+    if (mean) { mean[v * 3 + 0] = recs[v].mean[0]; mean[v * 3 + 1] = recs[v].mean[1]; mean[v * 3 + 2] = recs[v].mean[2]; }
+  }
+  d_cov.release(); d_icov.release(); d_infl.release(); d_rec.release(); d_ic64.release();
+  return NDTB200_OK;
+}
+
+int ndtb200_eval_derivatives(ndtb200_handle* h, const double p[6], const float* T, int compute_hessian,
+                             double out43[43], int64_t* n_hits) {
+  if (!h || !p || !out43) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  float T0[12];
+  if (T) colmajor_to_T(T, T0); else pose_to_matrix(p, T0);
+  int st = launch_align(h, MODE_EVAL, p, T0, 0, compute_hessian);
+  if (st != NDTB200_OK) return st;
+  st = fetch_result(h);
+  if (st != NDTB200_OK) return st;
+  for (int i = 0; i < 43; ++i) out43[i] = h->h_result->totals[i];
+  if (n_hits) *n_hits = h->h_result->n_hits;
+  h->result_valid = false;
+  return NDTB200_OK;
+}
+
+int ndtb200_eval_hessian(ndtb200_handle* h, const double p[6], const float* T, double out36[36]) {
+  if (!h || !p || !out36) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  float T0[12];
+  if (T) colmajor_to_T(T, T0); else pose_to_matrix(p, T0);
+  int st = launch_align(h, MODE_HESSIAN, p, T0, 0, 1);
+  if (st != NDTB200_OK) return st;
+  st = fetch_result(h);
+  if (st != NDTB200_OK) return st;
+  for (int i = 0; i < 36; ++i) out36[i] = h->h_result->totals[7 + i];
+  h->result_valid = false;
+  return NDTB200_OK;
+}
+
+int ndtb200_lookup(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, int search_method,
+                   int32_t* out_keys) {
+  if (!h || !out_keys || (!points && n)) return NDTB200_ERR_INVALID;
+  if (n == 0) return NDTB200_OK;
+  cudaSetDevice(h->device);
+  int st = upload_points(h, h->d_out, points, n, stride_bytes);
+  if (st != NDTB200_OK) return st;
+  CK(h->d_tmp.ensure(n * 26 * sizeof(int32_t)));
+  MapView map = make_view(h);
+  const int blocks = static_cast<int>((n + 255) / 256);
+  const float4* q = h->d_out.as<float4>();
+  int32_t* d_keys = h->d_tmp.as<int32_t>();
+  switch (search_method) {
+    case NDTB200_DIRECT1: lookup_kernel<3><<<blocks, 256, 0, h->stream>>>(q, (int)n, map, d_keys); break;
+    case NDTB200_DIRECT7: lookup_kernel<2><<<blocks, 256, 0, h->stream>>>(q, (int)n, map, d_keys); break;
+    case NDTB200_DIRECT26: lookup_kernel<1><<<blocks, 256, 0, h->stream>>>(q, (int)n, map, d_keys); break;
+    default: h->err = "search method not implemented (KDTREE)"; return NDTB200_ERR_INVALID;
+  }
+  LAUNCHED(h);
+  CK(cudaMemcpyAsync(out_keys, d_keys, n * 26 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return NDTB200_OK;
+}
+
+// parity helper: the on-device line-search trace of the last align (kind, pose, a_t, score per evaluation)
+int ndtb200_get_trace(ndtb200_handle* h, int32_t* kinds, double* x6, double* a_t, double* score, int cap, int* n_out) {
+  if (!h || !n_out) return NDTB200_ERR_INVALID;
+  if (!h->result_valid) {
+    int st = ndtb200_sync(h);
+    if (st != NDTB200_OK) return st;
+  }
+  cudaSetDevice(h->device);
+  int n = h->h_result->n_trace;
+  *n_out = n;
+  if (n > ndtb200_handle::kTraceCap) n = ndtb200_handle::kTraceCap;
+  if (n > cap) n = cap;
+  if (n <= 0) return NDTB200_OK;
+  std::vector<TraceRec> tr(n);
+  CK(cudaMemcpyAsync(tr.data(), h->d_trace.p, n * sizeof(TraceRec), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; ++i) {
+    if (kinds) kinds[i] = tr[i].kind;
+    if (x6) for (int k = 0; k < 6; ++k) x6[i * 6 + k] = tr[i].x[k];
+    if (a_t) a_t[i] = tr[i].a_t;
+    if (score) score[i] = tr[i].score;
+  }
+  return NDTB200_OK;
+}
+
+int ndtb200_clone(const ndtb200_handle* src, ndtb200_handle** out) {
+  if (!src || !out) return NDTB200_ERR_INVALID;
+  ndtb200_handle* h = nullptr;
+  int st = ndtb200_create(&h, src->device);
+  if (st != NDTB200_OK) return st;
+  h->prm = src->prm;
+  if (src->has_target) {
+    cudaStreamSynchronize(src->stream);
+    // the copy keeps the source object's map: build it with the resolution the source map was built with
+    ndtb200_params p = src->prm;
+    if (src->grid.leaf[0] > 0) h->prm.resolution = src->grid.leaf[0];
+    st = ndtb200_set_target_device(h, src->d_target.p, src->n_target, src->target_dense ? 1 : 0);
+    h->prm = p;
+    if (st == NDTB200_ERR_CUDA) { ndtb200_destroy(h); return st; }
+  }
+  if (src->has_source) {
+    st = ndtb200_set_source_device(h, src->d_source.p, src->n_source);
+    if (st != NDTB200_OK) { ndtb200_destroy(h); return st; }
+  }
+  std::memcpy(h->h_result, src->h_result, sizeof(AlignResultDev));
+  h->result_valid = src->result_valid;
+  std::memcpy(h->last_final_T, src->last_final_T, sizeof(h->last_final_T));
+  cudaStreamSynchronize(h->stream);
+  *out = h;
+  return NDTB200_OK;
+}
+
+void* ndtb200_stream(ndtb200_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+int64_t ndtb200_launch_count(const ndtb200_handle* h) { return h ? h->launches : 0; }
+void ndtb200_reset_launch_count(ndtb200_handle* h) { if (h) h->launches = 0; }
+
+int ndtb200_last_align_ms(ndtb200_handle* h, float* ms) {
+  if (!h || !ms) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return NDTB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,489 @@
+// map_build.cuh — target-map build: pclomp::VoxelGridCovariance::applyFilter
+// (ndt_omp/include/pclomp/voxel_grid_covariance_omp_impl.hpp:48-370) re-designed for B200:
+//
+//   minmax3d            -> bounding box (pcl::getMinMax3D, …_impl.hpp:72)
+//   grid_setup          -> min_b/max_b/div_b/divb_mul + int32 overflow guard (…_impl.hpp:75-103)
+//   voxel_key           -> per-point int32 key, bit-exact fp32 arithmetic (…_impl.hpp:218-223)
+//   radix sort          -> hand-written stable LSD radix sort of (key, point index), 8-bit digits
+//   segment heads       -> occupied-voxel list (= leaves_), per-voxel point ranges
+//   voxel_moments       -> per-voxel count, sum x, sum x x^T in fp64 (first pass, …_impl.hpp:233-262)
+//   finalize_voxels     -> mean, covariance, eigen-regularisation, inverse (second pass, …_impl.hpp:282-367)
+//   hash_insert         -> open-addressing HBM hash over the valid voxels
+//
+// All kernels are HBM-bound streaming / gather kernels: no tensor cores on this path.
+#pragma once
+#include "common.cuh"
+
+namespace ndtb200 {
+
+constexpr int kBuildThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// bounding box
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBuildThreads)
+minmax3d_kernel(const float4* __restrict__ pts, size_t n, int is_dense, float* __restrict__ partial,
+                unsigned int* __restrict__ finite_partial) {
+  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+  float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+  unsigned int nf = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float4 p = __ldg(pts + i);
+    bool ok = is_dense || (isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
+    if (ok) {
+      mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+      mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+      mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+      ++nf;
+    }
+  }
+  __shared__ float s_mn[3][kBuildThreads / 32], s_mx[3][kBuildThreads / 32];
+  __shared__ unsigned int s_nf[kBuildThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  }
+  if (lane == 0) {
+    for (int a = 0; a < 3; ++a) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; }
+    s_nf[warp] = nf;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kBuildThreads / 32; ++w) {
+      for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], s_mn[a][w]); mx[a] = fmaxf(mx[a], s_mx[a][w]); }
+      nf += s_nf[w];
+    }
+    for (int a = 0; a < 3; ++a) { partial[blockIdx.x * 6 + a] = mn[a]; partial[blockIdx.x * 6 + 3 + a] = mx[a]; }
+    finite_partial[blockIdx.x] = nf;
+  }
+}
+
+__global__ void grid_setup_kernel(const float* __restrict__ partial, const unsigned int* __restrict__ finite_partial,
+                                  int nblocks, float leaf, GridDesc* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+  float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+  long long nf = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], partial[b * 6 + a]); mx[a] = fmaxf(mx[a], partial[b * 6 + 3 + a]); }
+    nf += finite_partial[b];
+  }
+  GridDesc g;
+  const float inv = __fdiv_rn(1.0f, leaf);  // pcl::VoxelGrid::setLeafSize: inverse_leaf_size_ = 1.0f / leaf
+  long long d[3];
+  for (int a = 0; a < 3; ++a) {
+    g.leaf[a] = leaf;
+    g.inv_leaf[a] = inv;
+    g.min_p[a] = mn[a];
+    g.max_p[a] = mx[a];
+    // …_impl.hpp:75-77  int64((max - min) * inv_leaf) + 1, fp32 arithmetic
+    d[a] = static_cast<long long>(__fmul_rn(__fsub_rn(mx[a], mn[a]), inv)) + 1;
+    // …_impl.hpp:87-92
+    g.min_b[a] = static_cast<int>(floorf(__fmul_rn(mn[a], inv)));
+    g.max_b[a] = static_cast<int>(floorf(__fmul_rn(mx[a], inv)));
+    g.div_b[a] = g.max_b[a] - g.min_b[a] + 1;
+  }
+  g.ncell = d[0] * d[1] * d[2];
+  g.overflow = (nf > 0 && g.ncell > 2147483647ll) ? 1 : 0;
+  g.mul[0] = 1;
+  g.mul[1] = g.div_b[0];
+  g.mul[2] = g.div_b[0] * g.div_b[1];
+  g.n_finite = static_cast<int>(nf);
+  *out = g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// keys  (…_impl.hpp:218-223) — bit-exact: fp32 multiply by inv_leaf, floor, fp32 subtract of min_b
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t voxel_key_of(const float4& p, const GridDesc& g) {
+  int ijk0 = static_cast<int>(__fsub_rn(floorf(__fmul_rn(p.x, g.inv_leaf[0])), static_cast<float>(g.min_b[0])));
+  int ijk1 = static_cast<int>(__fsub_rn(floorf(__fmul_rn(p.y, g.inv_leaf[1])), static_cast<float>(g.min_b[1])));
+  int ijk2 = static_cast<int>(__fsub_rn(floorf(__fmul_rn(p.z, g.inv_leaf[2])), static_cast<float>(g.min_b[2])));
+  return ijk0 * g.mul[0] + ijk1 * g.mul[1] + ijk2 * g.mul[2];
+}
+
+__global__ void __launch_bounds__(kBuildThreads)
+voxel_key_kernel(const float4* __restrict__ pts, size_t n, int is_dense, const GridDesc* __restrict__ gd,
+                 uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+  __shared__ GridDesc g;
+  if (threadIdx.x == 0) g = *gd;
+  __syncthreads();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float4 p = __ldg(pts + i);
+    bool ok = is_dense || (isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
+    keys[i] = ok ? static_cast<uint32_t>(voxel_key_of(p, g)) : sentinel;
+    if (idx) idx[i] = static_cast<uint32_t>(i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic exclusive scan over uint32 (3-kernel, recursive)
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kBuildThreads * kScanItems;
+
+__global__ void __launch_bounds__(kBuildThreads)
+scan_tiles_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n,
+                  uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t smem[kBuildThreads / 32 + 1];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    sum += v[k];
+  }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan(sum, smem, total);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) out[base + k] = off;
+    off += v[k];
+  }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kBuildThreads)
+scan_add_kernel(uint32_t* __restrict__ out, size_t n, const uint32_t* __restrict__ tile_offsets) {
+  const uint32_t add = tile_offsets[blockIdx.x];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (base + k < n) out[base + k] += add;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stable LSD radix sort pass, 8-bit digit.  Tile = 256 threads x 8 keys; warp w owns 256
+// consecutive keys, lane = consecutive key, so global loads are fully coalesced.
+// Ranks come from __match_any_sync (stable inside a warp round) + per-warp digit counters.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kBuildThreads * kSortItems;
+constexpr int kSortWarps = kBuildThreads / 32;
+
+__device__ __forceinline__ void sort_tile_count(const uint32_t* __restrict__ keys, size_t n, int shift,
+                                                uint32_t (*warp_cnt)[256], uint32_t k[kSortItems],
+                                                unsigned int valid_bits[kSortItems]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = threadIdx.x; d < 256 * kSortWarps; d += blockDim.x) (&warp_cnt[0][0])[d] = 0u;
+  __syncthreads();
+  const size_t wbase = (size_t)blockIdx.x * kSortTile + (size_t)warp * (32 * kSortItems);
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const size_t i = wbase + r * 32 + lane;
+    const bool valid = i < n;
+    k[r] = valid ? keys[i] : 0u;
+    const uint32_t d = valid ? ((k[r] >> shift) & 255u) : (256u + lane);
+    const unsigned int m = __match_any_sync(0xffffffffu, d);
+    valid_bits[r] = m;
+    if (valid && lane == (__ffs(m) - 1)) warp_cnt[warp][d] += __popc(m);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kBuildThreads)
+radix_count_kernel(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t* __restrict__ hist, int ntiles) {
+  __shared__ uint32_t warp_cnt[kSortWarps][256];
+  uint32_t k[kSortItems];
+  unsigned int m[kSortItems];
+  sort_tile_count(keys, n, shift, warp_cnt, k, m);
+  __syncthreads();
+  const int d = threadIdx.x;  // blockDim == 256
+  uint32_t s = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) s += warp_cnt[w][d];
+  hist[(size_t)d * ntiles + blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(kBuildThreads)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, size_t n, int shift,
+                     const uint32_t* __restrict__ hist_scanned, int ntiles, uint32_t* __restrict__ keys_out,
+                     uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t warp_cnt[kSortWarps][256];
+  uint32_t k[kSortItems];
+  unsigned int m[kSortItems];
+  sort_tile_count(keys_in, n, shift, warp_cnt, k, m);
+  __syncthreads();
+  {
+    const int d = threadIdx.x;
+    uint32_t base = hist_scanned[(size_t)d * ntiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      uint32_t c = warp_cnt[w][d];
+      warp_cnt[w][d] = base;
+      base += c;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t wbase = (size_t)blockIdx.x * kSortTile + (size_t)warp * (32 * kSortItems);
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const size_t i = wbase + r * 32 + lane;
+    const bool valid = i < n;
+    const uint32_t d = (k[r] >> shift) & 255u;
+    const unsigned int mm = m[r];
+    uint32_t pos = 0;
+    if (valid) pos = warp_cnt[warp][d] + __popc(mm & ((1u << lane) - 1u));
+    __syncwarp();
+    if (valid && lane == (__ffs(mm) - 1)) warp_cnt[warp][d] += __popc(mm);
+    __syncwarp();
+    if (valid) {
+      keys_out[pos] = k[r];
+      vals_out[pos] = vals_in ? vals_in[i] : static_cast<uint32_t>(i);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// segment heads -> occupied voxel list
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBuildThreads)
+head_count_kernel(const uint32_t* __restrict__ skeys, size_t n, uint32_t sentinel, uint32_t* __restrict__ tile_counts) {
+  __shared__ uint32_t smem[kBuildThreads / 32 + 1];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const size_t i = base + k;
+    if (i < n) {
+      uint32_t key = skeys[i];
+      bool head = (key != sentinel) && (i == 0 || skeys[i - 1] != key);
+      c += head ? 1u : 0u;
+    }
+  }
+  uint32_t total;
+  block_exclusive_scan(c, smem, total);
+  if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kBuildThreads)
+head_write_kernel(const uint32_t* __restrict__ skeys, size_t n, uint32_t sentinel,
+                  const uint32_t* __restrict__ tile_offsets, int32_t* __restrict__ voxel_key,
+                  uint32_t* __restrict__ voxel_start) {
+  __shared__ uint32_t smem[kBuildThreads / 32 + 1];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t c = 0;
+  bool head[kScanItems];
+  uint32_t key[kScanItems];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const size_t i = base + k;
+    head[k] = false;
+    key[k] = 0;
+    if (i < n) {
+      key[k] = skeys[i];
+      head[k] = (key[k] != sentinel) && (i == 0 || skeys[i - 1] != key[k]);
+      c += head[k] ? 1u : 0u;
+    }
+  }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan(c, smem, total) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (head[k]) {
+      voxel_key[off] = static_cast<int32_t>(key[k]);
+      voxel_start[off] = static_cast<uint32_t>(base + k);
+      ++off;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-voxel moments: count, sum x, sum x x^T (fp64).  GROUP lanes per voxel stride through the
+// voxel's sorted point range (gather through the sorted index), then a fixed-order shuffle tree.
+// moments layout per voxel: [sx sy sz sxx sxy sxz syy syz szz] (9 doubles)
+// ---------------------------------------------------------------------------------------------
+template <int GROUP>
+__global__ void __launch_bounds__(kBuildThreads)
+voxel_moments_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx,
+                     const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
+                     double* __restrict__ moments) {
+  const uint32_t gid = (blockIdx.x * (uint32_t)blockDim.x + threadIdx.x) / GROUP;
+  const int gl = threadIdx.x % GROUP;
+  const bool active = gid < n_voxels;
+  double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    const uint32_t b = voxel_start[gid];
+    const uint32_t e = (gid + 1 < n_voxels) ? voxel_start[gid + 1] : n_finite;
+    for (uint32_t i = b + gl; i < e; i += GROUP) {
+      const float4 p = __ldg(pts + __ldg(sorted_idx + i));
+      const double x = p.x, y = p.y, z = p.z;
+      s[0] += x; s[1] += y; s[2] += z;
+      s[3] += x * x; s[4] += x * y; s[5] += x * z;
+      s[6] += y * y; s[7] += y * z; s[8] += z * z;
+    }
+  }
+#pragma unroll
+  for (int o = GROUP / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] += __shfl_down_sync(0xffffffffu, s[k], o, GROUP);
+  }
+  if (active && gl == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) moments[(size_t)gid * 9 + k] = s[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: second pass of applyFilter (…_impl.hpp:282-367), one thread per voxel, fp64
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sym_eig3_jacobi(const double A[3][3], double eval[3], double evec[3][3]) {
+  // SelfAdjointEigenSolver<Matrix3d> equivalent: lower triangle in, ascending eigenvalues out.
+  double a00 = A[0][0], a11 = A[1][1], a22 = A[2][2], a01 = A[1][0], a02 = A[2][0], a12 = A[2][1];
+  double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#define NDTB200_ROT(app, aqq, apq, apr, aqr, P, Q)                                                  \
+  if (apq != 0.0) {                                                                                 \
+    double theta = (aqq - app) / (2.0 * apq);                                                       \
+    double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));               \
+    double c = 1.0 / sqrt(t * t + 1.0), s = t * c;                                                  \
+    app -= t * apq;                                                                                 \
+    aqq += t * apq;                                                                                 \
+    apq = 0.0;                                                                                      \
+    double r_p = apr, r_q = aqr;                                                                    \
+    apr = c * r_p - s * r_q;                                                                        \
+    aqr = s * r_p + c * r_q;                                                                        \
+    for (int k = 0; k < 3; ++k) {                                                                   \
+      double vp = v[k][P], vq = v[k][Q];                                                            \
+      v[k][P] = c * vp - s * vq;                                                                    \
+      v[k][Q] = s * vp + c * vq;                                                                    \
+    }                                                                                               \
+  }
+  for (int sweep = 0; sweep < 32; ++sweep) {
+    if (a01 * a01 + a02 * a02 + a12 * a12 == 0.0) break;
+    NDTB200_ROT(a00, a11, a01, a02, a12, 0, 1)
+    NDTB200_ROT(a00, a22, a02, a01, a12, 0, 2)
+    NDTB200_ROT(a11, a22, a12, a01, a02, 1, 2)
+  }
+#undef NDTB200_ROT
+  double d[3] = {a00, a11, a22};
+  int o0 = 0, o1 = 1, o2 = 2, t;
+  if (d[o1] < d[o0]) { t = o0; o0 = o1; o1 = t; }
+  if (d[o2] < d[o1]) { t = o1; o1 = o2; o2 = t; }
+  if (d[o1] < d[o0]) { t = o0; o0 = o1; o1 = t; }
+  const int ord[3] = {o0, o1, o2};
+  for (int j = 0; j < 3; ++j) {
+    eval[j] = d[ord[j]];
+    for (int i = 0; i < 3; ++i) evec[i][j] = v[i][ord[j]];
+  }
+}
+
+__device__ __forceinline__ void inv3_cofactor(const double a[3][3], double r[3][3]) {
+  double c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1];
+  double c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2];
+  double c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+  double det = a[0][0] * c00 + a[0][1] * c01 + a[0][2] * c02;
+  double id = 1.0 / det;
+  r[0][0] = c00 * id; r[1][0] = c01 * id; r[2][0] = c02 * id;
+  r[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id;
+  r[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * id;
+  r[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * id;
+  r[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * id;
+  r[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id;
+  r[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
+}
+
+// dbg_cov / dbg_icov / dbg_inflated: optional full-precision dumps (parity API), NULL in production.
+__global__ void __launch_bounds__(kBuildThreads)
+finalize_voxels_kernel(const double* __restrict__ moments, const int32_t* __restrict__ voxel_key,
+                       const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
+                       int min_points, double eig_ratio, VoxelRecord* __restrict__ records,
+                       double* __restrict__ icov64, unsigned int* __restrict__ n_valid,
+                       double* __restrict__ dbg_cov, double* __restrict__ dbg_icov, int* __restrict__ dbg_inflated) {
+  const uint32_t v = blockIdx.x * (uint32_t)blockDim.x + threadIdx.x;
+  if (v >= n_voxels) return;
+  const uint32_t b = voxel_start[v];
+  const uint32_t e = (v + 1 < n_voxels) ? voxel_start[v + 1] : n_finite;
+  int count = static_cast<int>(e - b);
+  const double n = static_cast<double>(count);
+  double m[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) m[k] = moments[(size_t)v * 9 + k];
+  const double pt_sum[3] = {m[0], m[1], m[2]};
+  const double mean[3] = {m[0] / n, m[1] / n, m[2] / n};
+  // Q1: the reference accumulates x x^T on top of an Identity-initialised cov_ (vgc.h:107)
+  double S[3][3] = {{m[3] + 1.0, m[4], m[5]}, {m[4], m[6] + 1.0, m[7]}, {m[5], m[7], m[8] + 1.0}};
+  double cov[3][3], icov[3][3];
+  bool inflated = false;
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) { cov[a][c] = (a == c) ? 1.0 : 0.0; icov[a][c] = 0.0; }
+  if (count >= min_points) {
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c)  // …_impl.hpp:329
+        cov[a][c] = (S[a][c] - 2 * (pt_sum[a] * mean[c])) / n + mean[a] * mean[c];
+    const double scale = (n - 1.0) / n;  // Q3, …_impl.hpp:330
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) cov[a][c] *= scale;
+    double ev[3], evec[3][3];
+    sym_eig3_jacobi(cov, ev, evec);
+    if (ev[0] < 0 || ev[1] < 0 || ev[2] <= 0) {
+      count = -1;  // …_impl.hpp:337-341
+    } else {
+      const double min_ev = eig_ratio * ev[2];
+      if (ev[0] < min_ev) {  // …_impl.hpp:346-356
+        ev[0] = min_ev;
+        if (ev[1] < min_ev) ev[1] = min_ev;
+        double vinv[3][3], vd[3][3];
+        inv3_cofactor(evec, vinv);
+        for (int a = 0; a < 3; ++a)
+          for (int c = 0; c < 3; ++c) vd[a][c] = evec[a][c] * ev[c];
+        for (int a = 0; a < 3; ++a)
+          for (int c = 0; c < 3; ++c)
+            cov[a][c] = vd[a][0] * vinv[0][c] + vd[a][1] * vinv[1][c] + vd[a][2] * vinv[2][c];
+        inflated = true;
+      }
+      inv3_cofactor(cov, icov);  // …_impl.hpp:359
+      double mxc = icov[0][0], mnc = icov[0][0];
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c) { mxc = fmax(mxc, icov[a][c]); mnc = fmin(mnc, icov[a][c]); }
+      if (isinf(mxc) && mxc > 0) count = -1;  // …_impl.hpp:360-364
+      if (isinf(mnc) && mnc < 0) count = -1;
+    }
+  }
+  VoxelRecord r;
+  r.mean[0] = mean[0]; r.mean[1] = mean[1]; r.mean[2] = mean[2];
+  r.icov[0] = static_cast<float>(icov[0][0]); r.icov[1] = static_cast<float>(icov[0][1]);
+  r.icov[2] = static_cast<float>(icov[0][2]); r.icov[3] = static_cast<float>(icov[1][1]);
+  r.icov[4] = static_cast<float>(icov[1][2]); r.icov[5] = static_cast<float>(icov[2][2]);
+  r.key = voxel_key[v];
+  r.count = count;
+  r.pad[0] = r.pad[1] = 0;
+  records[v] = r;
+  double* ic = icov64 + (size_t)v * 6;
+  ic[0] = icov[0][0]; ic[1] = icov[0][1]; ic[2] = icov[0][2]; ic[3] = icov[1][1]; ic[4] = icov[1][2]; ic[5] = icov[2][2];
+  if (count >= min_points) atomicAdd(n_valid, 1u);
+  if (dbg_cov) {
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c) {
+        dbg_cov[(size_t)v * 9 + a * 3 + c] = cov[a][c];
+        dbg_icov[(size_t)v * 9 + a * 3 + c] = icov[a][c];
+      }
+    dbg_inflated[v] = inflated ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kBuildThreads)
+hash_insert_kernel(const VoxelRecord* __restrict__ records, uint32_t n_voxels, int min_points,
+                   HashSlot* __restrict__ table, uint32_t mask, int shift) {
+  const uint32_t v = blockIdx.x * (uint32_t)blockDim.x + threadIdx.x;
+  if (v >= n_voxels) return;
+  const int count = records[v].count;
+  if (count < min_points) return;  // sparse and rejected leaves are invisible to lookups (…_impl.hpp:395)
+  const uint32_t key = static_cast<uint32_t>(records[v].key);
+  const HashSlot slot = (static_cast<HashSlot>(v) << 32) | key;
+  uint32_t h = hash_key(key, shift);
+  while (true) {
+    HashSlot prev = atomicCAS(table + h, NDTB200_HASH_EMPTY, slot);
+    if (prev == NDTB200_HASH_EMPTY) return;
+    h = (h + 1) & mask;
+  }
+}
+
+}  // namespace ndtb200

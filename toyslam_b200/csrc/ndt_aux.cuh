@@ -1,0 +1,146 @@
+// ndt_aux.cuh — kernels around the hot path: output-cloud transform (pcl::transformPointCloud),
+// getFitnessScore (pcl::Registration), calculateScore (ndt_omp_impl.hpp:935-983), neighbour lookup dump.
+#pragma once
+#include "common.cuh"
+#include "ndt_align.cuh"
+
+namespace ndtb200 {
+
+// align()'s output cloud: source transformed by final_transformation_, data[3] = 1.
+__global__ void __launch_bounds__(256)
+transform_output_kernel(const float4* __restrict__ src, int n, const AlignResultDev* __restrict__ res,
+                        float4* __restrict__ out) {
+  __shared__ float T[12];
+  if (threadIdx.x < 12) T[threadIdx.x] = res->final_T[threadIdx.x];
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(src + i);
+    float4 o;
+    transform_point(T, p.x, p.y, p.z, o.x, o.y, o.z);
+    o.w = 1.0f;
+    out[i] = o;
+  }
+}
+
+// getFitnessScore: exact 1-NN of T*source in the RAW target, squared distance in fp32 with FLANN's
+// L2_Simple order ((dx^2 + dy^2) + dz^2).  Brute force, target streamed through shared memory tiles.
+// One partial (sum of accepted d2 in fp64, count) per CTA; the host adds the partials in CTA order.
+constexpr int kNNTile = 2048;
+__global__ void __launch_bounds__(256)
+fitness_bruteforce_kernel(const float4* __restrict__ src, int n_src, const float4* __restrict__ tgt, int n_tgt,
+                          const float* __restrict__ T_in, double max_range, double* __restrict__ part_sum,
+                          unsigned long long* __restrict__ part_cnt) {
+  __shared__ float4 tile[kNNTile];
+  __shared__ float T[12];
+  __shared__ double s_sum[8];
+  __shared__ unsigned int s_cnt[8];
+  if (threadIdx.x < 12) T[threadIdx.x] = T_in[threadIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float qx = 0, qy = 0, qz = 0;
+  if (i < n_src) {
+    const float4 p = __ldg(src + i);
+    transform_point(T, p.x, p.y, p.z, qx, qy, qz);
+  }
+  float best = __int_as_float(0x7f800000);
+  for (int base = 0; base < n_tgt; base += kNNTile) {
+    const int m = min(kNNTile, n_tgt - base);
+    __syncthreads();
+    for (int k = threadIdx.x; k < m; k += blockDim.x) tile[k] = __ldg(tgt + base + k);
+    __syncthreads();
+    if (i < n_src) {
+#pragma unroll 8
+      for (int k = 0; k < m; ++k) {
+        const float4 t = tile[k];
+        const float dx = qx - t.x, dy = qy - t.y, dz = qz - t.z;
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        best = fminf(best, d);
+      }
+    }
+  }
+  double v = 0;
+  unsigned int c = 0;
+  if (i < n_src && static_cast<double>(best) <= max_range) { v = best; c = 1; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_down_sync(0xffffffffu, v, o);
+    c += __shfl_down_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = v; s_cnt[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    unsigned long long cc = 0;
+    for (int w = 0; w < 8; ++w) { s += s_sum[w]; cc += s_cnt[w]; }
+    part_sum[blockIdx.x] = s;
+    part_cnt[blockIdx.x] = cc;
+  }
+}
+
+// calculateScore (ndt_omp_impl.hpp:935-983): fp64, mean over neighbours of (-d1*e - d3), mean over points.
+template <int METHOD>
+__global__ void __launch_bounds__(256)
+calculate_score_kernel(const float4* __restrict__ cloud, int n, const MapView map, double d1, double d2, double d3,
+                       double* __restrict__ part_sum) {
+  __shared__ double s_sum[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double score = 0;
+  if (i < n) {
+    const float4 p = __ldg(cloud + i);
+    const int ix = static_cast<int>(floorf(__fdiv_rn(p.x, map.leaf[0])));
+    const int iy = static_cast<int>(floorf(__fdiv_rn(p.y, map.leaf[1])));
+    const int iz = static_cast<int>(floorf(__fdiv_rn(p.z, map.leaf[2])));
+    constexpr int K = num_offsets<METHOD>();
+    int recs[K];
+    int cnt = 0;
+    for (int k = 0; k < K; ++k) {
+      int dx, dy, dz;
+      get_offset<METHOD>(k, dx, dy, dz);
+      recs[k] = probe_cell(map, ix + dx, iy + dy, iz + dz);
+      cnt += recs[k] >= 0;
+    }
+    for (int k = 0; k < K; ++k) {
+      if (recs[k] < 0) continue;
+      const VoxelRecord* R = map.records + recs[k];
+      const double* ic = map.icov64 + (size_t)recs[k] * 6;
+      const double r0 = static_cast<double>(p.x) - R->mean[0], r1 = static_cast<double>(p.y) - R->mean[1],
+                   r2 = static_cast<double>(p.z) - R->mean[2];
+      const double u0 = ic[0] * r0 + ic[1] * r1 + ic[2] * r2, u1 = ic[1] * r0 + ic[3] * r1 + ic[4] * r2,
+                   u2 = ic[2] * r0 + ic[4] * r1 + ic[5] * r2;
+      const double e = exp(-d2 * (r0 * u0 + r1 * u1 + r2 * u2) / 2);
+      score += (-d1 * e - d3) / cnt;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) score += __shfl_down_sync(0xffffffffu, score, o);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = score;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += s_sum[w];
+    part_sum[blockIdx.x] = s;
+  }
+}
+
+// getNeighborhoodAtPoint{,7,1} dump: keys of the valid neighbour voxels, reference offset order, -1 padded.
+template <int METHOD>
+__global__ void __launch_bounds__(256)
+lookup_kernel(const float4* __restrict__ q, int n, const MapView map, int32_t* __restrict__ out_keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(q + i);
+  const int ix = static_cast<int>(floorf(__fdiv_rn(p.x, map.leaf[0])));
+  const int iy = static_cast<int>(floorf(__fdiv_rn(p.y, map.leaf[1])));
+  const int iz = static_cast<int>(floorf(__fdiv_rn(p.z, map.leaf[2])));
+  constexpr int K = num_offsets<METHOD>();
+  int w = 0;
+  for (int k = 0; k < K; ++k) {
+    int dx, dy, dz;
+    get_offset<METHOD>(k, dx, dy, dz);
+    const int rec = probe_cell(map, ix + dx, iy + dy, iz + dz);
+    if (rec >= 0) out_keys[(size_t)i * 26 + (w++)] = map.records[rec].key;
+  }
+  for (; w < 26; ++w) out_keys[(size_t)i * 26 + w] = -1;
+}
+
+}  // namespace ndtb200

@@ -1,0 +1,370 @@
+"""ctypes mirror of pclomp::NormalDistributionsTransform over libndt_b200.so (include/ndt_b200.h)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from . import _build
+
+KDTREE, DIRECT26, DIRECT7, DIRECT1 = 0, 1, 2, 3  # pclomp::NeighborSearchMethod (ndt_omp.h:52-57)
+
+OK, ERR_NO_INPUT, ERR_GRID_OVERFLOW, ERR_CUDA, ERR_INVALID, ERR_NO_DEVICE = range(6)
+_STATUS_NAMES = {0: "OK", 1: "NO_INPUT", 2: "GRID_OVERFLOW", 3: "CUDA", 4: "INVALID", 5: "NO_DEVICE"}
+
+
+class NdtError(RuntimeError):
+    def __init__(self, status, msg=""):
+        super().__init__("ndtb200 status %s%s" % (_STATUS_NAMES.get(status, status), (": " + msg) if msg else ""))
+        self.status = status
+
+
+class Params(C.Structure):
+    _fields_ = [("resolution", C.c_float), ("step_size", C.c_double), ("outlier_ratio", C.c_double),
+                ("trans_eps", C.c_double), ("max_iterations", C.c_int32), ("search_method", C.c_int32),
+                ("min_points_per_voxel", C.c_int32), ("eig_ratio", C.c_double)]
+
+
+class Result(C.Structure):
+    _fields_ = [("final_transformation", C.c_float * 16), ("last_increment", C.c_float * 16),
+                ("converged", C.c_int32), ("iterations", C.c_int32), ("trans_probability", C.c_double),
+                ("final_pose", C.c_double * 6), ("final_score", C.c_double), ("n_evaluations", C.c_int32),
+                ("n_hessian_passes", C.c_int32), ("n_hits", C.c_int64)]
+
+
+class MapInfo(C.Structure):
+    _fields_ = [("min_b", C.c_int32 * 3), ("max_b", C.c_int32 * 3), ("div_b", C.c_int32 * 3),
+                ("n_points", C.c_int64), ("n_voxels", C.c_int64), ("n_valid", C.c_int64),
+                ("hash_capacity", C.c_int64)]
+
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def exported_symbols():
+    """Function names declared in include/ndt_b200.h (the drop-in boundary)."""
+    hdr = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "ndt_b200.h")
+    with open(hdr) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"^\s*(?:int|void|void\*|const char\*|int64_t)\s*\*?\s*(ndtb200_[a-z0-9_]+)\s*\(", text, flags=re.M)))
+
+
+def load_library():
+    """Load libndt_b200.so.  Raises if it has not been built — never falls back to anything else."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise NdtError(ERR_NO_DEVICE, "libndt_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(path)
+    vp, f32p, f64p, i32p, i64p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    L.ndtb200_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.ndtb200_destroy.argtypes = [vp]
+    L.ndtb200_clone.argtypes = [vp, C.POINTER(vp)]
+    L.ndtb200_last_error.argtypes = [vp]
+    L.ndtb200_last_error.restype = C.c_char_p
+    L.ndtb200_device_count.restype = C.c_int
+    L.ndtb200_default_params.argtypes = [C.POINTER(Params)]
+    L.ndtb200_set_params.argtypes = [vp, C.POINTER(Params)]
+    L.ndtb200_get_params.argtypes = [vp, C.POINTER(Params)]
+    L.ndtb200_set_target.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int]
+    L.ndtb200_set_source.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
+    L.ndtb200_set_target_device.argtypes = [vp, vp, C.c_size_t, C.c_int]
+    L.ndtb200_set_source_device.argtypes = [vp, vp, C.c_size_t]
+    L.ndtb200_align.argtypes = [vp, f32p, vp, C.c_size_t]
+    L.ndtb200_align_async.argtypes = [vp, f32p]
+    L.ndtb200_sync.argtypes = [vp]
+    L.ndtb200_get_result.argtypes = [vp, C.POINTER(Result)]
+    L.ndtb200_fitness_score.argtypes = [vp, C.c_double, f64p]
+    L.ndtb200_calculate_score.argtypes = [vp, vp, C.c_size_t, C.c_size_t, f64p]
+    L.ndtb200_get_map_info.argtypes = [vp, C.POINTER(MapInfo)]
+    L.ndtb200_dump_point_keys.argtypes = [vp, i32p]
+    L.ndtb200_dump_voxels.argtypes = [vp, i32p, i32p, f64p, f64p, f64p, i32p]
+    L.ndtb200_eval_derivatives.argtypes = [vp, f64p, f32p, C.c_int, f64p, i64p]
+    L.ndtb200_eval_hessian.argtypes = [vp, f64p, f32p, f64p]
+    L.ndtb200_lookup.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, i32p]
+    L.ndtb200_get_trace.argtypes = [vp, i32p, f64p, f64p, f64p, C.c_int, C.POINTER(C.c_int)]
+    L.ndtb200_stream.argtypes = [vp]
+    L.ndtb200_stream.restype = vp
+    L.ndtb200_launch_count.argtypes = [vp]
+    L.ndtb200_launch_count.restype = C.c_int64
+    L.ndtb200_reset_launch_count.argtypes = [vp]
+    L.ndtb200_reset_launch_count.restype = None
+    L.ndtb200_last_align_ms.argtypes = [vp, f32p]
+    _lib = L
+    return L
+
+
+def device_count():
+    return int(load_library().ndtb200_device_count())
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def as_xyzw(points):
+    """(n,3)/(n,4) array -> contiguous (n,4) float32, w = 1: the pcl::PointXYZ 16-byte layout."""
+    p = np.asarray(points)
+    if p.ndim != 2 or p.shape[1] not in (3, 4):
+        raise ValueError("points must be (n,3) or (n,4)")
+    if p.dtype == np.float32 and p.shape[1] == 4 and p.flags["C_CONTIGUOUS"]:
+        return p
+    out = np.ones((p.shape[0], 4), dtype=np.float32)
+    out[:, :3] = p[:, :3]
+    return out
+
+
+def _colmajor(T):
+    return np.ascontiguousarray(np.asarray(T, dtype=np.float32).T).reshape(-1)
+
+
+class NormalDistributionsTransform:
+    """Same method names and meaning as pclomp::NormalDistributionsTransform (ndt_omp.h:70-502)."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        st = self._L.ndtb200_create(C.byref(self._h), int(device))
+        if st != OK:
+            self._h = C.c_void_p()
+            raise NdtError(st, "ndtb200_create failed (no CUDA device? this library has no CPU fallback)")
+        self._p = Params()
+        self._L.ndtb200_get_params(self._h, C.byref(self._p))
+        self._n_source = 0
+        self._n_target = 0
+        self._keep = {}
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.ndtb200_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- helpers ----
+    def _check(self, st, allow=()):
+        if st != OK and st not in allow:
+            raise NdtError(st, self._L.ndtb200_last_error(self._h).decode())
+        return st
+
+    def _push(self):
+        return self._check(self._L.ndtb200_set_params(self._h, C.byref(self._p)), allow=(ERR_NO_INPUT, ERR_GRID_OVERFLOW))
+
+    def clone(self):
+        """Copy construction (the mapping node returns the object by value, ndt_omp_mapping_node.cpp:151-169)."""
+        other = object.__new__(NormalDistributionsTransform)
+        other._L = self._L
+        other._h = C.c_void_p()
+        self._check(self._L.ndtb200_clone(self._h, C.byref(other._h)))
+        other._p = Params()
+        self._L.ndtb200_get_params(other._h, C.byref(other._p))
+        other._n_source, other._n_target, other._keep = self._n_source, self._n_target, {}
+        return other
+
+    # ---- setters / getters (reference names) ----
+    def setResolution(self, r):
+        self._p.resolution = float(r); self._push()
+
+    def getResolution(self):
+        return float(self._p.resolution)
+
+    def setStepSize(self, s):
+        self._p.step_size = float(s); self._push()
+
+    def getStepSize(self):
+        return float(self._p.step_size)
+
+    def setOutlierRatio(self, o):
+        self._p.outlier_ratio = float(o); self._push()
+
+    def getOutlierRatio(self):
+        return float(self._p.outlier_ratio)
+
+    def setTransformationEpsilon(self, e):
+        self._p.trans_eps = float(e); self._push()
+
+    def setMaximumIterations(self, n):
+        self._p.max_iterations = int(n); self._push()
+
+    def setNeighborhoodSearchMethod(self, m):
+        self._p.search_method = int(m); self._push()
+
+    def setNumThreads(self, n):
+        """Accepted and ignored: the device path has no host thread count (ndt_omp.h:115-117)."""
+
+    def setMinPointPerVoxel(self, n):
+        self._p.min_points_per_voxel = int(n); self._push()
+
+    def setCovEigValueInflationRatio(self, r):
+        self._p.eig_ratio = float(r); self._push()
+
+    def setInputTarget(self, points, is_dense=True):
+        p = as_xyzw(points)
+        self._n_target = p.shape[0]
+        st = self._L.ndtb200_set_target(self._h, p.ctypes.data, p.shape[0], 16, 1 if is_dense else 0)
+        self.build_status = self._check(st, allow=(ERR_NO_INPUT, ERR_GRID_OVERFLOW))
+        return self.build_status
+
+    def setInputSource(self, points):
+        p = as_xyzw(points)
+        self._n_source = p.shape[0]
+        self._check(self._L.ndtb200_set_source(self._h, p.ctypes.data, p.shape[0], 16))
+
+    def set_target_raw(self, ptr, n, stride, is_dense=True):
+        """Host pointer + stride, exactly as the C ABI takes it (pinned buffers, 32-byte point types...)."""
+        self._n_target = int(n)
+        self.build_status = self._check(self._L.ndtb200_set_target(self._h, ptr, n, stride, 1 if is_dense else 0),
+                                        allow=(ERR_NO_INPUT, ERR_GRID_OVERFLOW))
+        return self.build_status
+
+    def set_source_raw(self, ptr, n, stride):
+        self._n_source = int(n)
+        self._check(self._L.ndtb200_set_source(self._h, ptr, n, stride))
+
+    def set_target_device(self, dev_ptr, n, is_dense=True):
+        self._n_target = int(n)
+        self.build_status = self._check(self._L.ndtb200_set_target_device(self._h, dev_ptr, n, 1 if is_dense else 0),
+                                        allow=(ERR_NO_INPUT, ERR_GRID_OVERFLOW))
+        return self.build_status
+
+    def set_source_device(self, dev_ptr, n):
+        self._n_source = int(n)
+        self._check(self._L.ndtb200_set_source_device(self._h, dev_ptr, n))
+
+    # ---- registration ----
+    def align(self, guess=None, want_output=True, out=None):
+        """align(output[, guess]).  Returns the (n,4) transformed source (or None)."""
+        g = _colmajor(guess) if guess is not None else None
+        if want_output and out is None:
+            out = np.empty((self._n_source, 4), dtype=np.float32)
+        self._check(self._L.ndtb200_align(self._h, _ptr(g, C.c_float) if g is not None else None,
+                                          out.ctypes.data if want_output else None, 16))
+        return out if want_output else None
+
+    def align_raw(self, guess_ptr, out_ptr, out_stride):
+        self._check(self._L.ndtb200_align(self._h, guess_ptr, out_ptr, out_stride))
+
+    def align_async(self, guess=None):
+        g = _colmajor(guess) if guess is not None else None
+        self._check(self._L.ndtb200_align_async(self._h, _ptr(g, C.c_float) if g is not None else None))
+
+    def sync(self):
+        self._check(self._L.ndtb200_sync(self._h))
+
+    def result(self):
+        r = Result()
+        self._check(self._L.ndtb200_get_result(self._h, C.byref(r)))
+        return {"final": np.array(r.final_transformation, dtype=np.float32).reshape(4, 4).T.copy(),
+                "last_increment": np.array(r.last_increment, dtype=np.float32).reshape(4, 4).T.copy(),
+                "converged": bool(r.converged), "iterations": int(r.iterations),
+                "trans_probability": float(r.trans_probability), "final_pose": np.array(r.final_pose),
+                "final_score": float(r.final_score), "n_evaluations": int(r.n_evaluations),
+                "n_hessian_passes": int(r.n_hessian_passes), "n_hits": int(r.n_hits)}
+
+    def getFinalTransformation(self):
+        return self.result()["final"]
+
+    def hasConverged(self):
+        return self.result()["converged"]
+
+    def getFinalNumIteration(self):
+        return self.result()["iterations"]
+
+    def getTransformationProbability(self):
+        return self.result()["trans_probability"]
+
+    def getFitnessScore(self, max_range=np.finfo(np.float64).max):
+        v = C.c_double()
+        self._check(self._L.ndtb200_fitness_score(self._h, float(max_range), C.byref(v)))
+        return v.value
+
+    def calculateScore(self, points):
+        p = as_xyzw(points)
+        v = C.c_double()
+        self._check(self._L.ndtb200_calculate_score(self._h, p.ctypes.data, p.shape[0], 16, C.byref(v)))
+        return v.value
+
+    # ---- stage dumps (parity API) ----
+    def map_info(self):
+        m = MapInfo()
+        st = self._L.ndtb200_get_map_info(self._h, C.byref(m))
+        return {"status": st, "min_b": np.array(m.min_b), "max_b": np.array(m.max_b), "div_b": np.array(m.div_b),
+                "n_points": m.n_points, "n_voxels": m.n_voxels, "n_valid": m.n_valid, "hash_capacity": m.hash_capacity}
+
+    def point_keys(self):
+        k = np.empty(self._n_target, dtype=np.int32)
+        self._check(self._L.ndtb200_dump_point_keys(self._h, _ptr(k, C.c_int32)))
+        return k
+
+    def dump_voxels(self):
+        n = self.map_info()["n_voxels"]
+        keys = np.empty(n, dtype=np.int32)
+        counts = np.empty(n, dtype=np.int32)
+        mean = np.empty((n, 3), dtype=np.float64)
+        cov = np.empty((n, 3, 3), dtype=np.float64)
+        icov = np.empty((n, 3, 3), dtype=np.float64)
+        infl = np.empty(n, dtype=np.int32)
+        self._check(self._L.ndtb200_dump_voxels(self._h, _ptr(keys, C.c_int32), _ptr(counts, C.c_int32),
+                                                _ptr(mean, C.c_double), _ptr(cov, C.c_double), _ptr(icov, C.c_double),
+                                                _ptr(infl, C.c_int32)))
+        return {"keys": keys, "counts": counts, "mean": mean, "cov": cov, "icov": icov, "inflated": infl}
+
+    def eval_derivatives(self, p, T=None, compute_hessian=True):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        Tc = None if T is None else _colmajor(T)
+        out = np.empty(43, dtype=np.float64)
+        hits = C.c_int64()
+        self._check(self._L.ndtb200_eval_derivatives(self._h, _ptr(p, C.c_double),
+                                                     _ptr(Tc, C.c_float) if Tc is not None else None,
+                                                     1 if compute_hessian else 0, _ptr(out, C.c_double), C.byref(hits)))
+        return {"score": out[0], "gradient": out[1:7].copy(), "hessian": out[7:].reshape(6, 6).copy(), "hits": hits.value}
+
+    def eval_hessian(self, p, T=None):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        Tc = None if T is None else _colmajor(T)
+        out = np.empty(36, dtype=np.float64)
+        self._check(self._L.ndtb200_eval_hessian(self._h, _ptr(p, C.c_double),
+                                                 _ptr(Tc, C.c_float) if Tc is not None else None, _ptr(out, C.c_double)))
+        return out.reshape(6, 6)
+
+    def lookup(self, points, method=None):
+        p = as_xyzw(points)
+        keys = np.empty((p.shape[0], 26), dtype=np.int32)
+        self._check(self._L.ndtb200_lookup(self._h, p.ctypes.data, p.shape[0], 16,
+                                           self._p.search_method if method is None else int(method),
+                                           _ptr(keys, C.c_int32)))
+        return keys
+
+    def trace(self):
+        cap = 1024
+        kinds = np.empty(cap, dtype=np.int32)
+        x = np.empty((cap, 6), dtype=np.float64)
+        a = np.empty(cap, dtype=np.float64)
+        s = np.empty(cap, dtype=np.float64)
+        n = C.c_int()
+        self._check(self._L.ndtb200_get_trace(self._h, _ptr(kinds, C.c_int32), _ptr(x, C.c_double), _ptr(a, C.c_double),
+                                              _ptr(s, C.c_double), cap, C.byref(n)))
+        m = min(n.value, cap)
+        return {"kind": kinds[:m].copy(), "x": x[:m].copy(), "a_t": a[:m].copy(), "score": s[:m].copy()}
+
+    # ---- plumbing ----
+    def stream_ptr(self):
+        return int(self._L.ndtb200_stream(self._h) or 0)
+
+    def launch_count(self):
+        return int(self._L.ndtb200_launch_count(self._h))
+
+    def reset_launch_count(self):
+        self._L.ndtb200_reset_launch_count(self._h)
+
+    def last_align_ms(self):
+        v = C.c_float()
+        self._check(self._L.ndtb200_last_align_ms(self._h, C.byref(v)))
+        return v.value
