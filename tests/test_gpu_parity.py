@@ -101,6 +101,16 @@ def test_map_build_degenerate_voxels(nb):
     tgt = np.concatenate(pts).astype(np.float32)
     ref, gpu = make_pair(nb, tgt, tgt[:10])
     check_map(ref, gpu)
+    # Q1 adds I/n to every covariance, so at 1 m no voxel needs inflation; at a 10 m leaf thin structures do
+    # (eigenvalue inflation branch, voxel_grid_covariance_omp_impl.hpp:345-356)
+    t = rng.uniform(-4, 4, size=(60, 1))
+    line = np.array([5.0, 5.0, 5.0]) + t * np.array([1.0, 0.5, 0.2])
+    uv = rng.uniform(-4, 4, size=(80, 2))
+    plane = np.array([15.0, 5.0, 5.0]) + np.c_[uv, 0.01 * rng.normal(size=80)]
+    blob = np.array([25.0, 5.0, 5.0]) + rng.uniform(-4, 4, size=(40, 3))
+    tgt = np.concatenate([line, plane, blob]).astype(np.float32)
+    ref, gpu = make_pair(nb, tgt, tgt[:10], res=10.0)
+    check_map(ref, gpu)
     assert gpu.dump_voxels()["inflated"].sum() >= 2
 
 

@@ -47,8 +47,10 @@ def transform_delta(Ta, Tb):
     Tb = np.asarray(Tb, dtype=np.float64)
     dt = float(np.linalg.norm(Ta[:3, 3] - Tb[:3, 3]))
     R = Ta[:3, :3].T @ Tb[:3, :3]
-    c = np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)
-    return dt, float(np.arccos(c))
+    # angle from the skew part (sin) and the trace (cos): arccos alone has only sqrt(eps) resolution near 0
+    w = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    c = (np.trace(R) - 1.0) / 2.0
+    return dt, float(np.arctan2(np.linalg.norm(w), c))
 
 
 def synthetic_scene(n_target=40000, n_source=8000, seed=0, offset=(0.0, 0.0, 0.0), extent=40.0):
