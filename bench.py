@@ -1,0 +1,363 @@
+#!/usr/bin/env python3
+"""bench.py — NDT registration hot path on B200 (BASELINE.json metric: aligns/s and source-point·iterations/s,
+achieved HBM GB/s vs peak), next to the reference's OpenMP CPU path (the oracle port) on the same box.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference CPU path (oracle port, all host threads)
+
+Workload (config.workload): BASELINE.json configs[1] — a synthetic 64-beam LiDAR scan (~120 k points) against a
+1 M-point target map, resolution 1.0, DIRECT7, class defaults, identity guess.  A "step" is one align() of that
+pair (the `10times` loop of ndt_omp/apps/align.cpp:25-27: target map built once outside the timer).
+N > 1: one process per GPU, each rank aligns its own independent scan against its own copy of the map
+(independent scan pairs are the unit that shards; no data-path collective) -> weak scaling.
+
+`value`  : aligns/s with inputs resident in HBM; every timed step is one launch of the persistent solve kernel,
+           timed with CUDA events on the handle's stream; L2 is flushed (256 MiB write) between timed steps.
+`e2e`    : the same align through the C ABI with HOST buffers: per step H2D of the source cloud from pinned
+           memory, the solve, D2H of the transformed cloud and of the result block.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METHODS = {"DIRECT1": 3, "DIRECT7": 2, "DIRECT26": 1}
+KPROBE = {"DIRECT1": 1, "DIRECT7": 7, "DIRECT26": 26}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo",
+                                device_id=torch.device("cuda", local) if torch.cuda.is_available() else None)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x, world, device):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world, device):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def make_workload(args, rank):
+    import workloads
+    return workloads.config2(map_points=args.map_points, n_map_scans=args.map_scans, scan_seed=rank,
+                             azimuth_steps=args.azimuth_steps)
+
+
+def workload_name(args, n_src, n_tgt):
+    return ("c2: synthetic 64-beam LiDAR scan (%d pts) vs %d-pt target map, resolution 1.0, %s, class defaults, "
+            "identity guess; step = one align() (target map prebuilt, as apps/align.cpp 10times loop)" %
+            (n_src, n_tgt, args.method))
+
+
+def cpu_baseline(w, args, max_seconds=25.0):
+    """The oracle port (C++/OpenMP restatement of the reference) on the host cores: same pair, same parameters."""
+    import oracle
+    ref = oracle.NormalDistributionsTransform()
+    ref.setNeighborhoodSearchMethod({"DIRECT1": oracle.DIRECT1, "DIRECT7": oracle.DIRECT7, "DIRECT26": oracle.DIRECT26}[args.method])
+    t0 = time.perf_counter()
+    ref.setInputTarget(w["target"])
+    t_build = time.perf_counter() - t0
+    ref.setInputSource(w["source"])
+    ref.align()  # warm-up
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 5 and (time.perf_counter() - t_start) < max_seconds:
+        t0 = time.perf_counter()
+        ref.align()
+        times.append(time.perf_counter() - t0)
+    r = ref.result()
+    per = float(np.mean(times))
+    return {"value": 1.0 / per, "unit": "aligns/s", "cores": oracle.max_threads(), "kind": "port",
+            "sample": "%d full aligns of the same pair (oracle C++/OpenMP port of ndt_omp; the reference itself needs "
+                      "PCL/Eigen and cannot be built here)" % len(times),
+            "ms_per_align": per * 1e3, "map_build_ms": t_build * 1e3,
+            "src_pt_iters_per_s": len(w["source"]) * r["n_evaluations"] / per}, ref
+
+
+def run_reference(args):
+    rank, world, local = dist_setup(args.gpus)
+    if rank != 0:
+        return 0
+    import oracle
+    w = make_workload(args, 0)
+    ref = oracle.NormalDistributionsTransform()
+    ref.setNeighborhoodSearchMethod({"DIRECT1": oracle.DIRECT1, "DIRECT7": oracle.DIRECT7, "DIRECT26": oracle.DIRECT26}[args.method])
+    ref.setInputTarget(w["target"])
+    ref.setInputSource(w["source"])
+    steps = min(args.steps, 20)          # bounded sample: each step is one full align of the same workload
+    warm = min(args.warmup, 3)
+    for _ in range(warm):
+        ref.align()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.align()
+    dt = time.perf_counter() - t0
+    r = ref.result()
+    val = steps / dt
+    line = {"impl": "reference", "metric": "ndt_aligns_per_s", "value": val, "unit": "aligns/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args, len(w["source"]), len(w["target"])),
+                       "note": "reference CPU path = oracle port (C++/OpenMP restatement), all host threads"},
+            "cpu_baseline": {"value": val, "unit": "aligns/s", "cores": oracle.max_threads(), "kind": "port",
+                             "sample": "%d full aligns of the c2 pair" % steps},
+            "e2e": {"value": val, "unit": "aligns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "src_pt_iters_per_s": len(w["source"]) * r["n_evaluations"] * val,
+            "evaluations_per_align": r["n_evaluations"]}
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args):
+    import torch
+    import toyslam_b200 as nb
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    w = make_workload(args, rank)
+    n_src, n_tgt = len(w["source"]), len(w["target"])
+    ndt = nb.NormalDistributionsTransform(device=local)
+    ndt.setNeighborhoodSearchMethod(METHODS[args.method])
+
+    # inputs resident in HBM before the timed region
+    tgt_host = torch.ones((n_tgt, 4), dtype=torch.float32).pin_memory()
+    tgt_host[:, :3] = torch.from_numpy(w["target"])
+    src_host = torch.ones((n_src, 4), dtype=torch.float32).pin_memory()
+    src_host[:, :3] = torch.from_numpy(w["source"])
+    out_host = torch.empty((n_src, 4), dtype=torch.float32).pin_memory()
+    t0 = time.perf_counter()
+    ndt.set_target_raw(tgt_host.data_ptr(), n_tgt, 16)
+    map_build_ms = (time.perf_counter() - t0) * 1e3
+    ndt.set_source_raw(src_host.data_ptr(), n_src, 16)
+    info = ndt.map_info()
+
+    stream = torch.cuda.ExternalStream(ndt.stream_ptr(), device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def one_step(timed):
+        with torch.cuda.stream(stream):
+            flush.fill_(1)  # evict L2 (not timed)
+            if timed:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ndt.align_async()
+                e1.record(stream)
+                return e0, e1
+            ndt.align_async()
+            return None
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(False)
+    ndt.sync()
+    res = ndt.result()
+
+    sampler = ClockSampler(local)
+    barrier(world)
+    torch.cuda.synchronize()
+    sampler.start()
+    ndt.reset_launch_count()
+    t_wall0 = time.perf_counter()
+    events = [one_step(True) for _ in range(args.steps)]
+    ndt.sync()
+    torch.cuda.synchronize()
+    barrier(world)
+    wall = time.perf_counter() - t_wall0
+    launches = ndt.launch_count()
+    clocks = sampler.stop()
+    step_ms = np.array([a.elapsed_time(b) for a, b in events], dtype=np.float64)
+    total_ms = float(step_ms.sum())
+    total_ms_max = max_over_ranks(total_ms, world, dev)
+    aligns_total = args.steps * world
+    value = aligns_total / (total_ms_max * 1e-3)
+    ms_per_step = total_ms_max / args.steps
+    res = ndt.result()
+    evals = res["n_evaluations"]
+    hess = res["n_hessian_passes"]
+    hits_per_align = res["n_hits"]
+    pt_iters = sum_over_ranks(n_src * evals * args.steps, world, dev) / (total_ms_max * 1e-3)
+
+    # roofline of the dominant (only) kernel in the timed region: ndt_align_kernel
+    kprobe = KPROBE[args.method]
+    alg_bytes = (evals + hess) * n_src * (16 + 4 * kprobe) + 64 * hits_per_align  # SURVEY §8d, per launch
+    kernel_ms = float(step_ms.mean())
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        try:
+            peak = float(json.load(open(pk))["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "align_kernel_ncu.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get(args.method, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "ndt_align_kernel<%s>" % args.method, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
+                "formula": "(evals+hessian passes)*N*(16+4K) + 64*hits"}
+
+    # end-to-end through the C ABI with host buffers (H2D source, solve, D2H cloud + result)
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    for _ in range(3):
+        ndt.set_source_raw(src_host.data_ptr(), n_src, 16)
+        ndt.align_raw(None, out_host.data_ptr(), 16)
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ndt.set_source_raw(src_host.data_ptr(), n_src, 16)
+        ndt.align_raw(None, out_host.data_ptr(), 16)
+        ndt.result()
+    torch.cuda.synchronize()
+    barrier(world)
+    e2e_dt = max_over_ranks(time.perf_counter() - t0, world, dev)
+    e2e = {"value": e2e_steps * world / e2e_dt, "unit": "aligns/s", "h2d_bytes_per_step": n_src * 16,
+           "d2h_bytes_per_step": n_src * 16 + 416, "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3}
+
+    line = {"metric": "ndt_aligns_per_s", "value": value, "unit": "aligns/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args, n_src, n_tgt),
+                       "l2": "flushed between timed iterations (256 MiB device write, untimed)",
+                       "parallelism": "replicas: one independent scan pair per GPU, no collective",
+                       "arith": "fp32 per-hit math, fp64 accumulation (as the reference)",
+                       "map": {"voxels": info["n_voxels"], "valid": info["n_valid"], "build_ms_incl_h2d": map_build_ms}},
+            "src_pt_iters_per_s": pt_iters, "evaluations_per_align": evals, "hessian_passes_per_align": hess,
+            "hits_per_point_eval": hits_per_align / float(max(1, (evals + hess) * n_src)),
+            "newton_iterations": res["iterations"], "converged": res["converged"],
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "wall_s_timed_region": wall}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            cb, ref = cpu_baseline(w, args)
+            rr = ref.result()
+            line["cpu_baseline"] = cb
+            dT = float(np.abs(rr["final"] - res["final"]).max())
+            line["parity_vs_oracle"] = {"max_abs_dT": dT, "iterations_equal": rr["iterations"] == res["iterations"],
+                                        "evaluations_equal": rr["n_evaluations"] == evals}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--method", default="DIRECT7", choices=list(METHODS))
+    ap.add_argument("--map-points", type=int, default=1_000_000)
+    ap.add_argument("--map-scans", type=int, default=31)
+    ap.add_argument("--azimuth-steps", type=int, default=1875)
+    ap.add_argument("--e2e-steps", type=int, default=300)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
