@@ -126,9 +126,21 @@ def sum_over_ranks(x, world, device):
 
 
 def make_workload(args, rank):
+    """The c2 pair of this rank.  --cache DIR keeps the generated arrays so a profiler run (ncu) of the same
+    command does not see the generator's kernels."""
     import workloads
-    return workloads.config2(map_points=args.map_points, n_map_scans=args.map_scans, scan_seed=rank,
-                             azimuth_steps=args.azimuth_steps)
+    path = None
+    if args.cache:
+        os.makedirs(args.cache, exist_ok=True)
+        path = os.path.join(args.cache, "c2_%d_%d_%d_r%d.npz" % (args.map_points, args.map_scans, args.azimuth_steps, rank))
+        if os.path.exists(path):
+            d = np.load(path)
+            return {"target": d["target"], "source": d["source"], "truth": d["truth"]}
+    w = workloads.config2(map_points=args.map_points, n_map_scans=args.map_scans, scan_seed=rank,
+                          azimuth_steps=args.azimuth_steps)
+    if path:
+        np.savez(path, target=w["target"], source=w["source"], truth=w["truth"])
+    return w
 
 
 def workload_name(args, n_src, n_tgt):
@@ -353,6 +365,7 @@ def main():
     ap.add_argument("--azimuth-steps", type=int, default=1875)
     ap.add_argument("--e2e-steps", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cache", default=None, help="directory for cached workload arrays")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

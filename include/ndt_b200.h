@@ -144,6 +144,10 @@ int ndtb200_lookup(ndtb200_handle* h, const void* points, size_t n, size_t strid
  * n_out receives the number of evaluations; at most `cap` entries are written. */
 int ndtb200_get_trace(ndtb200_handle* h, int32_t* kinds, double* x6, double* a_t, double* score, int cap, int* n_out);
 
+/* Profiling: CTA-0 timeline of the last solve, 4 stamps per evaluation in ns since the first evaluation
+ * started: evaluation start, local work done, reduced totals available, next step decided. */
+int ndtb200_get_timeline(ndtb200_handle* h, double* t4, int cap, int* n_out);
+
 /* ---- plumbing for benchmarks ----------------------------------------------------------------- */
 /* The handle's cudaStream_t (as void*), so a caller can record CUDA events on it. */
 void* ndtb200_stream(ndtb200_handle* h);

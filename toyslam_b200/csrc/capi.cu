@@ -2,6 +2,7 @@
 // See include/ndt_b200.h for the contract of every entry point and the reference method it replaces.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -277,7 +278,7 @@ int build_map(ndtb200_handle* h) {
   finalize_voxels_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(
       h->d_moments.as<double>(), h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), n_vox, n_finite,
       h->prm.min_points_per_voxel, h->prm.eig_ratio, h->d_records.as<VoxelRecord>(), h->d_icov64.as<double>(),
-      d_nvalid, nullptr, nullptr, nullptr);
+      d_nvalid, nullptr, nullptr, nullptr, nullptr);
   LAUNCHED(h);
   unsigned int n_valid = 0;
   CK(cudaMemcpyAsync(&n_valid, d_nvalid, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
@@ -418,10 +419,12 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   int blocks = grid_for(h->n_source, kAlignThreads, max_blocks);
   CK(h->d_partials.ensure((size_t)max_blocks * kNVP * sizeof(double)));
   CK(h->d_totals.ensure(2 * kNVP * sizeof(double)));
-  CK(h->d_sync.ensure(64));
+  if (h->d_sync.p == nullptr) {  // barrier words: zeroed once; every launch leaves them zeroed again
+    CK(h->d_sync.ensure(64));
+    CK(cudaMemsetAsync(h->d_sync.p, 0, 64, h->stream));
+  }
   CK(h->d_result.ensure(sizeof(AlignResultDev)));
   CK(h->d_trace.ensure(ndtb200_handle::kTraceCap * sizeof(TraceRec)));
-  CK(cudaMemsetAsync(h->d_sync.p, 0, 8, h->stream));
 
   AlignWorkspace ws;
   ws.partials = h->d_partials.as<double>();
@@ -777,7 +780,8 @@ int ndtb200_dump_voxels(ndtb200_handle* h, int32_t* keys, int32_t* counts, doubl
   cudaSetDevice(h->device);
   const uint32_t V = static_cast<uint32_t>(h->n_voxels);
   if (V == 0) return NDTB200_OK;
-  DevBuf d_cov, d_icov, d_infl, d_rec, d_ic64;
+  DevBuf d_mean, d_cov, d_icov, d_infl, d_rec, d_ic64;
+  CK(d_mean.ensure((size_t)V * 3 * sizeof(double)));
   CK(d_cov.ensure((size_t)V * 9 * sizeof(double)));
   CK(d_icov.ensure((size_t)V * 9 * sizeof(double)));
   CK(d_infl.ensure((size_t)V * sizeof(int)));
@@ -788,10 +792,11 @@ int ndtb200_dump_voxels(ndtb200_handle* h, int32_t* keys, int32_t* counts, doubl
   finalize_voxels_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(
       h->d_moments.as<double>(), h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), V,
       static_cast<uint32_t>(h->grid.n_finite), h->prm.min_points_per_voxel, h->prm.eig_ratio, d_rec.as<VoxelRecord>(),
-      d_ic64.as<double>(), d_nvalid, d_cov.as<double>(), d_icov.as<double>(), d_infl.as<int>());
+      d_ic64.as<double>(), d_nvalid, d_mean.as<double>(), d_cov.as<double>(), d_icov.as<double>(), d_infl.as<int>());
   LAUNCHED(h);
   std::vector<VoxelRecord> recs(V);
   CK(cudaMemcpyAsync(recs.data(), d_rec.p, (size_t)V * sizeof(VoxelRecord), cudaMemcpyDeviceToHost, h->stream));
+  if (mean) CK(cudaMemcpyAsync(mean, d_mean.p, (size_t)V * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (cov) CK(cudaMemcpyAsync(cov, d_cov.p, (size_t)V * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (icov) CK(cudaMemcpyAsync(icov, d_icov.p, (size_t)V * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (inflated) CK(cudaMemcpyAsync(inflated, d_infl.p, (size_t)V * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -799,9 +804,8 @@ int ndtb200_dump_voxels(ndtb200_handle* h, int32_t* keys, int32_t* counts, doubl
   for (uint32_t v = 0; v < V; ++v) {
     if (keys) keys[v] = recs[v].key;
     if (counts) counts[v] = recs[v].count;
-    if (mean) { mean[v * 3 + 0] = recs[v].mean[0]; mean[v * 3 + 1] = recs[v].mean[1]; mean[v * 3 + 2] = recs[v].mean[2]; }
   }
-  d_cov.release(); d_icov.release(); d_infl.release(); d_rec.release(); d_ic64.release();
+  d_mean.release(); d_cov.release(); d_icov.release(); d_infl.release(); d_rec.release(); d_ic64.release();
   return NDTB200_OK;
 }
 
@@ -860,6 +864,37 @@ int ndtb200_lookup(ndtb200_handle* h, const void* points, size_t n, size_t strid
 }
 
 // parity helper: the on-device line-search trace of the last align (kind, pose, a_t, score per evaluation)
+// profiling helper: CTA-0 timeline (ns since the first evaluation started) of the last solve, 4 stamps per evaluation
+int ndtb200_get_timeline(ndtb200_handle* h, double* t4, int cap, int* n_out) {
+  // t4 rows: start, local, reduced, advanced (contract) — debug stamps are printed to stderr when NDTB200_DEBUG_STEP is set
+  if (!h || !n_out || !t4) return NDTB200_ERR_INVALID;
+  if (!h->result_valid) {
+    int st = ndtb200_sync(h);
+    if (st != NDTB200_OK) return st;
+  }
+  cudaSetDevice(h->device);
+  int n = h->h_result->n_trace;
+  *n_out = n;
+  if (n > ndtb200_handle::kTraceCap) n = ndtb200_handle::kTraceCap;
+  if (n > cap) n = cap;
+  if (n <= 0) return NDTB200_OK;
+  std::vector<TraceRec> tr(n);
+  CK(cudaMemcpyAsync(tr.data(), h->d_trace.p, n * sizeof(TraceRec), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const unsigned long long t0 = tr[0].t_start;
+  for (int i = 0; i < n; ++i) {
+    t4[i * 4 + 0] = static_cast<double>(tr[i].t_start - t0);
+    t4[i * 4 + 1] = static_cast<double>(tr[i].t_local - t0);
+    t4[i * 4 + 2] = static_cast<double>(tr[i].t_reduced - t0);
+    t4[i * 4 + 3] = static_cast<double>(tr[i].t_advanced - t0);
+    if (getenv("NDTB200_DEBUG_STEP"))
+      std::fprintf(stderr, "  step %d: advance %.2f us, solve %.2f us, post %.2f us, pose setup %.2f us\n", i,
+                   (tr[i].t_dbg[0] - tr[i].t_reduced) * 1e-3, (tr[i].t_dbg[1] - tr[i].t_dbg[0]) * 1e-3,
+                   (tr[i].t_dbg[2] - tr[i].t_dbg[1]) * 1e-3, (tr[i].t_advanced - tr[i].t_dbg[2]) * 1e-3);
+  }
+  return NDTB200_OK;
+}
+
 int ndtb200_get_trace(ndtb200_handle* h, int32_t* kinds, double* x6, double* a_t, double* score, int cap, int* n_out) {
   if (!h || !n_out) return NDTB200_ERR_INVALID;
   if (!h->result_valid) {
@@ -920,6 +955,9 @@ int ndtb200_last_align_ms(ndtb200_handle* h, float* ms) {
   cudaSetDevice(h->device);
   CK(cudaEventSynchronize(h->ev1));
   CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  if (getenv("NDTB200_DEBUG_STEP") && h->result_valid)
+    std::fprintf(stderr, "  kernel body (CTA 0, globaltimer): %.2f us\n",
+                 (h->h_result->t_kernel_end - h->h_result->t_kernel_begin) * 1e-3);
   return NDTB200_OK;
 }
 

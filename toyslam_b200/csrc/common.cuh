@@ -9,17 +9,25 @@ namespace ndtb200 {
 // HBM layout of the target map (replaces std::map<size_t, Leaf>, voxel_grid_covariance_omp.h:98-201)
 // ---------------------------------------------------------------------------------------------
 // One 64-byte record per occupied voxel, sorted by voxel key (x fastest), so neighbouring cells
-// along x are neighbouring records.  mean stays fp64 (map-scale coordinates need it, SURVEY §7
-// hard part 2); icov is fp32 because the derivative pass casts it to fp32 anyway
-// (ndt_omp_impl.hpp:493-494).  Four 16-byte loads fetch a record.
+// along x are neighbouring records.  The fp64 mean (map-scale coordinates need more than fp32,
+// SURVEY §7 hard part 2) is stored as an exact hi + lo pair of fp32 (mean = hi + lo to 2^-48), so the
+// derivative pass forms x' - mean without touching the fp64 / conversion pipes:
+// (x' - hi) - lo equals fl32(double(x') - mean) up to one ulp of the (sub-voxel-sized) result.
+// icov is fp32 because the derivative pass casts it to fp32 anyway (ndt_omp_impl.hpp:493-494).
+// Three 16-byte loads fetch the 48 bytes the hot loop needs.
 struct __align__(16) VoxelRecord {
-  double mean[3];  // Leaf::mean_
-  float icov[6];   // Leaf::icov_ as fp32: c00 c01 c02 c11 c12 c22
-  int32_t key;     // linear voxel index (voxel_grid_covariance_omp_impl.hpp:223)
-  int32_t count;   // Leaf::nr_points; -1 = rejected leaf (…_impl.hpp:337-341, 360-364)
+  float mean_hi[3];  // fl32(Leaf::mean_)
+  float mean_lo[3];  // fl32(Leaf::mean_ - mean_hi)
+  float icov[6];     // Leaf::icov_ as fp32: c00 c01 c02 c11 c12 c22
+  int32_t key;       // linear voxel index (voxel_grid_covariance_omp_impl.hpp:223)
+  int32_t count;     // Leaf::nr_points; -1 = rejected leaf (…_impl.hpp:337-341, 360-364)
   int32_t pad[2];
 };
 static_assert(sizeof(VoxelRecord) == 64, "VoxelRecord must be 64 bytes");
+
+__host__ __device__ __forceinline__ double record_mean(const VoxelRecord& r, int a) {
+  return static_cast<double>(r.mean_hi[a]) + static_cast<double>(r.mean_lo[a]);
+}
 
 // Open-addressing hash over the VALID voxels only (count >= min_points, not rejected): the only ones a
 // lookup may return (…_impl.hpp:395).  Slot = {key (low 32), record index (high 32)}, linear probing,

@@ -396,7 +396,8 @@ finalize_voxels_kernel(const double* __restrict__ moments, const int32_t* __rest
                        const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
                        int min_points, double eig_ratio, VoxelRecord* __restrict__ records,
                        double* __restrict__ icov64, unsigned int* __restrict__ n_valid,
-                       double* __restrict__ dbg_cov, double* __restrict__ dbg_icov, int* __restrict__ dbg_inflated) {
+                       double* __restrict__ dbg_mean, double* __restrict__ dbg_cov, double* __restrict__ dbg_icov,
+                       int* __restrict__ dbg_inflated) {
   const uint32_t v = blockIdx.x * (uint32_t)blockDim.x + threadIdx.x;
   if (v >= n_voxels) return;
   const uint32_t b = voxel_start[v];
@@ -448,7 +449,10 @@ finalize_voxels_kernel(const double* __restrict__ moments, const int32_t* __rest
     }
   }
   VoxelRecord r;
-  r.mean[0] = mean[0]; r.mean[1] = mean[1]; r.mean[2] = mean[2];
+  for (int a = 0; a < 3; ++a) {
+    r.mean_hi[a] = static_cast<float>(mean[a]);
+    r.mean_lo[a] = static_cast<float>(mean[a] - static_cast<double>(r.mean_hi[a]));
+  }
   r.icov[0] = static_cast<float>(icov[0][0]); r.icov[1] = static_cast<float>(icov[0][1]);
   r.icov[2] = static_cast<float>(icov[0][2]); r.icov[3] = static_cast<float>(icov[1][1]);
   r.icov[4] = static_cast<float>(icov[1][2]); r.icov[5] = static_cast<float>(icov[2][2]);
@@ -460,6 +464,7 @@ finalize_voxels_kernel(const double* __restrict__ moments, const int32_t* __rest
   ic[0] = icov[0][0]; ic[1] = icov[0][1]; ic[2] = icov[0][2]; ic[3] = icov[1][1]; ic[4] = icov[1][2]; ic[5] = icov[2][2];
   if (count >= min_points) atomicAdd(n_valid, 1u);
   if (dbg_cov) {
+    for (int a = 0; a < 3; ++a) dbg_mean[(size_t)v * 3 + a] = mean[a];
     for (int a = 0; a < 3; ++a)
       for (int c = 0; c < 3; ++c) {
         dbg_cov[(size_t)v * 9 + a * 3 + c] = cov[a][c];

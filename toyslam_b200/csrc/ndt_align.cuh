@@ -1,19 +1,25 @@
 // ndt_align.cuh — the registration hot path as ONE persistent kernel:
 //
 //   derivative pass   computeDerivatives / updateDerivatives / computePointDerivatives
-//                     (ndt_omp_impl.hpp:179-285, 398-440, 484-537), fp32 per-hit math, fp64 accumulation
+//                     (ndt_omp_impl.hpp:179-285, 398-440, 484-537), fp32 per-hit math
 //   Hessian-only pass computeHessian / updateHessian (ndt_omp_impl.hpp:540-645), fp64 math, fp64 tables
 //   Newton + line search  computeTransformation / computeStepLengthMT (ndt_omp_impl.hpp:80-171, 772-932)
 //
 // Design (B200-first, not the reference's per-point-slot + serial-sum structure):
 //   * one thread per source point, float4 loads, in-register fp32 transform (never materialises
-//     trans_cloud), DIRECT1/7/26 probes into the HBM voxel hash, 64-byte Gaussian records;
-//   * 28 (+1 hit counter) fp64 accumulators per thread -> warp shuffle tree -> shared memory ->
-//     one partial per CTA -> the LAST-ARRIVING CTA sums the partials in CTA order (bit-reproducible)
-//     and publishes the 28 totals; every CTA then runs the identical Newton / More-Thuente step
-//     redundantly, so a single grid barrier per evaluation is the only synchronisation and the
-//     whole align() never returns to the host;
-//   * the kernel is launched cooperatively (all CTAs co-resident) with gridDim = #SMs x occupancy.
+//     trans_cloud), DIRECT1/7/26 probes into the HBM voxel hash (all probes of a point issued
+//     together), 64-byte Gaussian records prefetched, then consumed hit by hit;
+//   * warps take 32-point groups interleaved over the whole grid, so every CTA sees the same mix of
+//     dense and empty regions of the scan (static, deterministic load balance);
+//   * accumulation: a thread adds the (fp32) contributions of at most kFlushPoints points in fp32,
+//     then the warp folds them into fp64 (shuffle tree) — fp64 everywhere a long sum is formed,
+//     without the fp32->fp64 conversion per hit that saturated the XU pipe in the first version;
+//     warp sums -> one fp64 partial per CTA -> the LAST-ARRIVING CTA sums the partials in CTA order
+//     (bit-reproducible) and publishes the 28 totals;
+//   * every CTA then runs the identical Newton / More-Thuente step (scalar part in one thread, the
+//     trigonometry and the 69 table entries spread over a warp), so ONE grid barrier per evaluation
+//     is the only synchronisation and the whole align() never returns to the host;
+//   * launched cooperatively (all CTAs co-resident), gridDim = #SMs x occupancy.
 #pragma once
 #include "common.cuh"
 #include "ndt_solve.cuh"
@@ -21,10 +27,12 @@
 namespace ndtb200 {
 
 constexpr int kAlignThreads = 256;
-constexpr int kNV = 29;   // score, g[6], H upper triangle[21], hit count
-constexpr int kNVP = 32;  // padded row length of the partial / total buffers
+constexpr int kAlignWarps = kAlignThreads / 32;
+constexpr int kNV = 29;          // score, g[6], H upper triangle[21], hit count
+constexpr int kNVP = 32;         // padded row length of the partial / total buffers
+constexpr int kFlushPoints = 8;  // fp32 run length (points per thread) before folding into fp64
 
-enum { ACT_DONE = 0, ACT_EVAL_FULL = 1, ACT_EVAL_NOHESS = 2, ACT_HESS_ONLY = 3 };
+enum { ACT_DONE = 0, ACT_EVAL_FULL = 1, ACT_EVAL_NOHESS = 2, ACT_HESS_ONLY = 3, ACT_SOLVE = 4 };
 enum { ST_INITIAL = 0, ST_MT_FIRST = 1, ST_MT_LOOP = 2, ST_MT_HESS = 3, ST_SINGLE = 4 };
 enum { MODE_ALIGN = 0, MODE_EVAL = 1, MODE_HESSIAN = 2 };
 
@@ -34,6 +42,9 @@ struct TraceRec {
   double x[6];
   double a_t;
   double score;
+  // CTA-0 timeline of this evaluation (globaltimer ns): start, local work done, totals available, step decided
+  unsigned long long t_start, t_local, t_reduced, t_advanced;
+  unsigned long long t_dbg[4];  // step breakdown: after advance(), after the warp solve, after newton_post(), (spare)
 };
 
 struct AlignResultDev {
@@ -46,6 +57,7 @@ struct AlignResultDev {
   double totals[43];  // score, g[6], H[36] of the last evaluation
   long long n_hits;
   int32_t n_trace, pad;
+  unsigned long long t_kernel_begin, t_kernel_end;  // globaltimer ns, CTA 0
 };
 
 struct AlignParams {
@@ -84,18 +96,24 @@ struct SolverState {
   long long n_hits;
   int32_t step_iterations, interval_converged, open_interval;
   int32_t nr_iterations, converged, state, n_evals, n_hess, n_trace;
-  float final_T[12], incr_T[12];
+  int32_t need_pose;  // 1 => ctx (matrix + tables) must be rebuilt from x_t before the next evaluation
+  double last_dp[6];  // last Newton increment (transformation_ is built from it once, at the end)
+  double delta[6];    // Newton step H^-1 (-g), written by the warp solver
+  float final_T[12];
 };
 
 // ---------------------------------------------------------------------------------------------
-// one (point, voxel) contribution: updateDerivatives (fp32, T=float) / updateHessian (fp64, T=double)
+// one (point, voxel) contribution: updateDerivatives (T = float) / updateHessian (T = double)
 // pj = j_ang * x (8 values), ph = h_ang * x (15 values); r = x' - mean; c = inverse covariance.
 // acc layout: [0] score, [1..6] gradient, [7..27] Hessian upper triangle row-major.
+// d1 is passed in T: for the fp32 path the reference forms -d1*e and d1*(d2*e) in fp64 and rounds
+// to fp32 (ndt_omp_impl.hpp:501, 510); multiplying by fl32(d1) in fp32 differs from that by at most
+// 1.2e-7 relative, and keeps the per-hit path free of fp64 and conversion instructions.
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool SCORE_GRAD, bool HESS>
 __device__ __forceinline__ void hit_contribution(const T r0, const T r1, const T r2, const T c00, const T c01,
                                                  const T c02, const T c11, const T c12, const T c22, const T* pj,
-                                                 const T* ph, const T d2, const double d1, double* acc) {
+                                                 const T* ph, const T d2, const T d1, T* acc) {
   const T u0 = c00 * r0 + c01 * r1 + c02 * r2;
   const T u1 = c01 * r0 + c11 * r1 + c12 * r2;
   const T u2 = c02 * r0 + c12 * r1 + c22 * r2;
@@ -106,8 +124,8 @@ __device__ __forceinline__ void hit_contribution(const T r0, const T r1, const T
     const float e = expf(-d2 * q * 0.5f);
     const float e2 = d2 * e;
     if (!(e2 <= 1.0f && e2 >= 0.0f)) return;  // e2 > 1 || e2 < 0 || NaN  -> contributes nothing
-    if (SCORE_GRAD) acc[0] += static_cast<double>(e) * (-d1);
-    w = static_cast<float>(static_cast<double>(e2) * d1);
+    if (SCORE_GRAD) acc[0] -= d1 * e;
+    w = e2 * d1;
   } else {
     // ndt_omp_impl.hpp:622-629
     const double e2 = d2 * exp(-d2 * q / 2);
@@ -119,12 +137,12 @@ __device__ __forceinline__ void hit_contribution(const T r0, const T r1, const T
   const T s4 = u0 * pj[2] + u1 * pj[3] + u2 * pj[4];
   const T s5 = u0 * pj[5] + u1 * pj[6] + u2 * pj[7];
   if (SCORE_GRAD) {
-    acc[1] += static_cast<double>(w * s0);
-    acc[2] += static_cast<double>(w * s1);
-    acc[3] += static_cast<double>(w * s2);
-    acc[4] += static_cast<double>(w * s3);
-    acc[5] += static_cast<double>(w * s4);
-    acc[6] += static_cast<double>(w * s5);
+    acc[1] += w * s0;
+    acc[2] += w * s1;
+    acc[3] += w * s2;
+    acc[4] += w * s3;
+    acc[5] += w * s4;
+    acc[6] += w * s5;
   }
   if (HESS) {
     // C * J_i for the three rotational columns (J_3 = (0,j0,j1), J_4 = (j2,j3,j4), J_5 = (j5,j6,j7))
@@ -134,7 +152,7 @@ __device__ __forceinline__ void hit_contribution(const T r0, const T r1, const T
     const T v5x = c00 * pj[5] + c01 * pj[6] + c02 * pj[7], v5y = c01 * pj[5] + c11 * pj[6] + c12 * pj[7],
             v5z = c02 * pj[5] + c12 * pj[6] + c22 * pj[7];
     const T md2 = -d2;
-#define NDTB200_H(idx, si, sj, extra) acc[7 + idx] += static_cast<double>(w * (md2 * si * sj + (extra)));
+#define NDTB200_H(idx, si, sj, extra) acc[7 + idx] += w * (md2 * si * sj + (extra));
     NDTB200_H(0, s0, s0, c00)
     NDTB200_H(1, s0, s1, c01)
     NDTB200_H(2, s0, s2, c02)
@@ -167,18 +185,24 @@ __constant__ int8_t c_off26[26][3] = {
     {-1, -1, 0}, {0, -1, 0}, {1, -1, 0}, {-1, 0, 0},
     {1, 1, 1}, {1, 0, 1}, {1, -1, 1}, {0, 1, 1}, {0, 0, 1}, {0, -1, 1}, {-1, 1, 1}, {-1, 0, 1}, {-1, -1, 1},
     {1, 1, 0}, {0, 1, 0}, {-1, 1, 0}, {1, 0, 0}};
-__constant__ int8_t c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
 
 template <int METHOD>
 __device__ __forceinline__ constexpr int num_offsets() {
   return METHOD == 3 ? 1 : (METHOD == 2 ? 7 : 26);
 }
 
+// DIRECT7 order (voxel_grid_covariance_omp_impl.hpp:423-430): centre, +x, -x, +y, -y, +z, -z
 template <int METHOD>
 __device__ __forceinline__ void get_offset(int k, int& dx, int& dy, int& dz) {
-  if (METHOD == 3) { dx = dy = dz = 0; }
-  else if (METHOD == 2) { dx = c_off7[k][0]; dy = c_off7[k][1]; dz = c_off7[k][2]; }
-  else { dx = c_off26[k][0]; dy = c_off26[k][1]; dz = c_off26[k][2]; }
+  if (METHOD == 3) {
+    dx = dy = dz = 0;
+  } else if (METHOD == 2) {
+    dx = (k == 1) - (k == 2);
+    dy = (k == 3) - (k == 4);
+    dz = (k == 5) - (k == 6);
+  } else {
+    dx = c_off26[k][0]; dy = c_off26[k][1]; dz = c_off26[k][2];
+  }
 }
 
 // Probe one neighbour cell (voxel_grid_covariance_omp_impl.hpp:388-400): bounds test, key, hash find.
@@ -189,45 +213,106 @@ __device__ __forceinline__ int probe_cell(const MapView& m, int cx, int cy, int 
   return map_find(m, key);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// All K probes of a point with their first hash slots in flight together (memory-level parallelism),
+// then resolved; collisions (rare at load <= 0.25) continue with the plain linear probe.
+template <int K>
+__device__ __forceinline__ void probe_cells(const MapView& m, int ix, int iy, int iz, int (&rec)[K]) {
+  static_assert(K == 1 || K == 7, "unrolled probe is for DIRECT1 / DIRECT7");
+  HashSlot slot[K];
+  uint32_t key[K], h[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int dx, dy, dz;
+    get_offset<(K == 1 ? 3 : 2)>(k, dx, dy, dz);
+    const int cx = ix + dx, cy = iy + dy, cz = iz + dz;
+    const bool inside = !(cx < m.min_b[0] || cx > m.max_b[0] || cy < m.min_b[1] || cy > m.max_b[1] ||
+                          cz < m.min_b[2] || cz > m.max_b[2]);
+    key[k] = static_cast<uint32_t>((cx - m.min_b[0]) * m.mul[0] + (cy - m.min_b[1]) * m.mul[1] + (cz - m.min_b[2]) * m.mul[2]);
+    h[k] = hash_key(key[k], m.hash_shift);
+    slot[k] = inside ? __ldg(m.hash + h[k]) : NDTB200_HASH_EMPTY;
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int r = -1;
+    HashSlot s = slot[k];
+    uint32_t hh = h[k];
+    while (s != NDTB200_HASH_EMPTY) {
+      if (static_cast<uint32_t>(s) == key[k]) { r = static_cast<int>(s >> 32); break; }
+      hh = (hh + 1) & m.hash_mask;
+      s = __ldg(m.hash + hh);
+    }
+    rec[k] = r;
+    if (r >= 0) prefetch_l2(m.records + r);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // all hits of one source point, fp32 path (computeDerivatives inner loop, ndt_omp_impl.hpp:207-275)
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hit_from_record_f32(const VoxelRecord* R, float tx, float ty, float tz, float& r0,
+                                                    float& r1, float& r2, float (&c)[6]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(R));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(R) + 1);
+  const float4 cc = __ldg(reinterpret_cast<const float4*>(R) + 2);
+  // x_trans = fl32(double(x') - mean) (ndt_omp_impl.hpp:259-262, 492) via the exact hi/lo split of the mean
+  r0 = __fsub_rn(__fsub_rn(tx, a.x), a.w);
+  r1 = __fsub_rn(__fsub_rn(ty, a.y), b.x);
+  r2 = __fsub_rn(__fsub_rn(tz, a.z), b.y);
+  c[0] = b.z; c[1] = b.w; c[2] = cc.x; c[3] = cc.y; c[4] = cc.z; c[5] = cc.w;
+}
+
 template <int METHOD, bool HESS>
 __device__ __forceinline__ void eval_point_f32(const float4 pt, const EvalCtx& c, const MapView& m, const float d2f,
-                                               const double d1, double* acc) {
+                                               const float d1f, float* acc) {
   float tx, ty, tz;
   transform_point(c.T, pt.x, pt.y, pt.z, tx, ty, tz);
   // getNeighborhoodAtPoint (…_impl.hpp:379-381): cell = floor(x' / leaf), fp32 DIVISION (Q8)
   const int ix = static_cast<int>(floorf(__fdiv_rn(tx, m.leaf[0])));
   const int iy = static_cast<int>(floorf(__fdiv_rn(ty, m.leaf[1])));
   const int iz = static_cast<int>(floorf(__fdiv_rn(tz, m.leaf[2])));
-  // computePointDerivatives (fp32 overload, ndt_omp_impl.hpp:398-440): depends on the ORIGINAL point only
-  float pj[8], ph[15];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) pj[r] = c.tab.jf[r][0] * pt.x + c.tab.jf[r][1] * pt.y + c.tab.jf[r][2] * pt.z;
-  if (HESS) {
-#pragma unroll
-    for (int r = 0; r < 15; ++r) ph[r] = c.tab.hf[r][0] * pt.x + c.tab.hf[r][1] * pt.y + c.tab.hf[r][2] * pt.z;
-  }
-  const double dtx = tx, dty = ty, dtz = tz;
   constexpr int K = num_offsets<METHOD>();
-#pragma unroll(METHOD == 1 ? 1 : K)
-  for (int k = 0; k < K; ++k) {
-    int dx, dy, dz;
-    get_offset<METHOD>(k, dx, dy, dz);
-    const int rec = probe_cell(m, ix + dx, iy + dy, iz + dz);
-    if (rec < 0) continue;
-    const VoxelRecord* R = m.records + rec;
-    const double2 m01 = __ldg(reinterpret_cast<const double2*>(R));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(R) + 1);
-    const float4 cc = __ldg(reinterpret_cast<const float4*>(R) + 2);
-    const double m2 = __hiloint2double(__float_as_int(b.y), __float_as_int(b.x));
-    // x_trans = double(x') - mean, THEN cast to fp32 (ndt_omp_impl.hpp:259-262, 492)
-    const float r0 = static_cast<float>(dtx - m01.x);
-    const float r1 = static_cast<float>(dty - m01.y);
-    const float r2 = static_cast<float>(dtz - m2);
-    hit_contribution<float, true, HESS>(r0, r1, r2, b.z, b.w, cc.x, cc.y, cc.z, cc.w, pj, ph, d2f, d1, acc);
-    acc[28] += 1.0;
+  if constexpr (METHOD != 1) {
+    int rec[K];
+    probe_cells<K>(m, ix, iy, iz, rec);
+    // computePointDerivatives (fp32 overload, ndt_omp_impl.hpp:398-440): depends on the ORIGINAL point only
+    float pj[8], ph[15];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) pj[r] = c.tab.jf[r][0] * pt.x + c.tab.jf[r][1] * pt.y + c.tab.jf[r][2] * pt.z;
+    if (HESS) {
+#pragma unroll
+      for (int r = 0; r < 15; ++r) ph[r] = c.tab.hf[r][0] * pt.x + c.tab.hf[r][1] * pt.y + c.tab.hf[r][2] * pt.z;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (rec[k] < 0) continue;
+      float r0, r1, r2, cv[6];
+      hit_from_record_f32(m.records + rec[k], tx, ty, tz, r0, r1, r2, cv);
+      acc[28] += 1.0f;
+      hit_contribution<float, true, HESS>(r0, r1, r2, cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], pj, ph, d2f, d1f, acc);
+    }
+  } else {
+    float pj[8], ph[15];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) pj[r] = c.tab.jf[r][0] * pt.x + c.tab.jf[r][1] * pt.y + c.tab.jf[r][2] * pt.z;
+    if (HESS) {
+#pragma unroll
+      for (int r = 0; r < 15; ++r) ph[r] = c.tab.hf[r][0] * pt.x + c.tab.hf[r][1] * pt.y + c.tab.hf[r][2] * pt.z;
+    }
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      int dx, dy, dz;
+      get_offset<METHOD>(k, dx, dy, dz);
+      const int rec = probe_cell(m, ix + dx, iy + dy, iz + dz);
+      if (rec < 0) continue;
+      float r0, r1, r2, cv[6];
+      hit_from_record_f32(m.records + rec, tx, ty, tz, r0, r1, r2, cv);
+      acc[28] += 1.0f;
+      hit_contribution<float, true, HESS>(r0, r1, r2, cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], pj, ph, d2f, d1f, acc);
+    }
   }
 }
 
@@ -255,42 +340,42 @@ __device__ __forceinline__ void eval_point_f64(const float4 pt, const EvalCtx& c
     if (rec < 0) continue;
     const VoxelRecord* R = m.records + rec;
     const double* ic = m.icov64 + (size_t)rec * 6;
-    const double r0 = static_cast<double>(tx) - __ldg(&R->mean[0]);
-    const double r1 = static_cast<double>(ty) - __ldg(&R->mean[1]);
-    const double r2 = static_cast<double>(tz) - __ldg(&R->mean[2]);
+    const double r0 = static_cast<double>(tx) - (static_cast<double>(__ldg(&R->mean_hi[0])) + static_cast<double>(__ldg(&R->mean_lo[0])));
+    const double r1 = static_cast<double>(ty) - (static_cast<double>(__ldg(&R->mean_hi[1])) + static_cast<double>(__ldg(&R->mean_lo[1])));
+    const double r2 = static_cast<double>(tz) - (static_cast<double>(__ldg(&R->mean_hi[2])) + static_cast<double>(__ldg(&R->mean_lo[2])));
+    acc[28] += 1.0;
     hit_contribution<double, false, true>(r0, r1, r2, __ldg(ic), __ldg(ic + 1), __ldg(ic + 2), __ldg(ic + 3),
                                           __ldg(ic + 4), __ldg(ic + 5), pj, ph, d2, d1, acc);
-    acc[28] += 1.0;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
-// acc[kNV] per thread -> s_block[kNV] (block sum, fixed order)
-__device__ __forceinline__ void block_reduce(double* acc, double (*s_warp)[kNVP], double* s_block) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Fold the per-thread accumulators of a warp into the warp's fp64 sums (fixed shuffle tree) and clear them.
+template <typename A>
+__device__ __forceinline__ void warp_flush(A* acc, double* s_warp_row) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < kNV; ++k) {
-    double v = acc[k];
+    double v = static_cast<double>(acc[k]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_warp[warp][k] = v;
+    if (lane == 0) s_warp_row[k] += v;
+    acc[k] = A(0);
   }
-  __syncthreads();
-  if (threadIdx.x < kNV) {
-    double s = 0;
-#pragma unroll
-    for (int w = 0; w < kAlignThreads / 32; ++w) s += s_warp[w][threadIdx.x];
-    s_block[threadIdx.x] = s;
-  }
-  __syncthreads();
 }
 
 // s_block (this CTA's sums) -> s_tot (sum over all CTAs, identical bits in every CTA).
@@ -315,12 +400,19 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
   const int par = epoch & 1u;
   if (*s_flag) {  // last CTA to arrive: every partial is visible
     __threadfence();
-    if (threadIdx.x < kNV) {
-      double s = 0;
-      const double* p = ws.partials + threadIdx.x;
-#pragma unroll 8
-      for (unsigned int b = 0; b < G; ++b) s += __ldcg(p + (size_t)b * kNVP);
-      ws.totals[par * kNVP + threadIdx.x] = s;
+    // 8 lanes per value, each summing a strided subset of the CTAs, then a fixed tree: order is
+    // independent of which CTA happens to be last, so totals are bit-reproducible
+    const int k = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    double s = 0;
+    if (k < kNV) {
+      const double* p = ws.partials + k;
+      for (unsigned int b = sub; b < G; b += 8) s += __ldcg(p + (size_t)b * kNVP);
+    }
+    s += __shfl_down_sync(0xffffffffu, s, 4, 8);
+    s += __shfl_down_sync(0xffffffffu, s, 2, 8);
+    s += __shfl_down_sync(0xffffffffu, s, 1, 8);
+    if (k < kNV && sub == 0) {
+      ws.totals[par * kNVP + k] = s;
       __threadfence();
     }
     __syncthreads();
@@ -337,21 +429,177 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
 }
 
 // ---------------------------------------------------------------------------------------------
-// optimiser state machine (thread 0 of every CTA, identical inputs -> identical decisions)
+// pose -> (fp32 matrix, fp32 + fp64 angle tables), spread over one warp.
+// Table entries are sums of at most two signed products of {1,cx,sx,cy,sy,cz,sz}; each lane evaluates
+// its entries from a compact term list with un-fused fp64 multiplies/adds — the same values the
+// straight-line formulas of computeAngleDerivatives give (ndt_omp_impl.hpp:329-393).
 // ---------------------------------------------------------------------------------------------
-__device__ inline void set_eval_pose(SolverState& st, EvalCtx& ctx, const double x_t[6]) {
-  // final_transformation_ = T(x_t) in fp32 (ndt_omp_impl.hpp:827-830, 871-874)
-  pose_to_matrix(x_t, ctx.T);
-  for (int i = 0; i < 12; ++i) st.final_T[i] = ctx.T[i];
-  compute_angle_tables(x_t, ctx.tab);
+// factor codes: 0:1  1:cx 2:sx 3:cy 4:sy 5:cz 6:sz ; term = sign * (f[a]*f[b])*f[c]; sign 0 => absent
+struct TableTerm { int8_t s1, a1, b1, c1, s2, a2, b2, c2; };
+#define TT(s1, a1, b1, c1, s2, a2, b2, c2) {s1, a1, b1, c1, s2, a2, b2, c2}
+__device__ const TableTerm g_table_terms[69] = {
+    // j_ang rows a..h (8 x 3)
+    TT(-1, 2, 6, 0, +1, 1, 4, 5), TT(-1, 2, 5, 0, -1, 1, 4, 6), TT(-1, 1, 3, 0, 0, 0, 0, 0),   // a
+    TT(+1, 1, 6, 0, +1, 2, 4, 5), TT(+1, 1, 5, 0, -1, 2, 4, 6), TT(-1, 2, 3, 0, 0, 0, 0, 0),   // b
+    TT(-1, 4, 5, 0, 0, 0, 0, 0), TT(+1, 4, 6, 0, 0, 0, 0, 0), TT(+1, 3, 0, 0, 0, 0, 0, 0),     // c
+    TT(+1, 2, 3, 5, 0, 0, 0, 0), TT(-1, 2, 3, 6, 0, 0, 0, 0), TT(+1, 2, 4, 0, 0, 0, 0, 0),     // d
+    TT(-1, 1, 3, 5, 0, 0, 0, 0), TT(+1, 1, 3, 6, 0, 0, 0, 0), TT(-1, 1, 4, 0, 0, 0, 0, 0),     // e
+    TT(-1, 3, 6, 0, 0, 0, 0, 0), TT(-1, 3, 5, 0, 0, 0, 0, 0), TT(0, 0, 0, 0, 0, 0, 0, 0),      // f
+    TT(+1, 1, 5, 0, -1, 2, 4, 6), TT(-1, 1, 6, 0, -1, 2, 4, 5), TT(0, 0, 0, 0, 0, 0, 0, 0),    // g
+    TT(+1, 2, 5, 0, +1, 1, 4, 6), TT(+1, 1, 4, 5, -1, 2, 6, 0), TT(0, 0, 0, 0, 0, 0, 0, 0),    // h
+    // h_ang rows a2 a3 b2 b3 c2 c3 d1 d2 d3 e1 e2 e3 f1 f2 f3 (15 x 3), fp64 table (d1.z = -sy)
+    TT(-1, 1, 6, 0, -1, 2, 4, 5), TT(-1, 1, 5, 0, +1, 2, 4, 6), TT(+1, 2, 3, 0, 0, 0, 0, 0),   // a2
+    TT(-1, 2, 6, 0, +1, 1, 4, 5), TT(-1, 1, 4, 6, -1, 2, 5, 0), TT(-1, 1, 3, 0, 0, 0, 0, 0),   // a3
+    TT(+1, 1, 3, 5, 0, 0, 0, 0), TT(-1, 1, 3, 6, 0, 0, 0, 0), TT(+1, 1, 4, 0, 0, 0, 0, 0),     // b2
+    TT(+1, 2, 3, 5, 0, 0, 0, 0), TT(-1, 2, 3, 6, 0, 0, 0, 0), TT(+1, 2, 4, 0, 0, 0, 0, 0),     // b3
+    TT(-1, 2, 5, 0, -1, 1, 4, 6), TT(+1, 2, 6, 0, -1, 1, 4, 5), TT(0, 0, 0, 0, 0, 0, 0, 0),    // c2
+    TT(+1, 1, 5, 0, -1, 2, 4, 6), TT(-1, 2, 4, 5, -1, 1, 6, 0), TT(0, 0, 0, 0, 0, 0, 0, 0),    // c3
+    TT(-1, 3, 5, 0, 0, 0, 0, 0), TT(+1, 3, 6, 0, 0, 0, 0, 0), TT(-1, 4, 0, 0, 0, 0, 0, 0),     // d1
+    TT(-1, 2, 4, 5, 0, 0, 0, 0), TT(+1, 2, 4, 6, 0, 0, 0, 0), TT(+1, 2, 3, 0, 0, 0, 0, 0),     // d2
+    TT(+1, 1, 4, 5, 0, 0, 0, 0), TT(-1, 1, 4, 6, 0, 0, 0, 0), TT(-1, 1, 3, 0, 0, 0, 0, 0),     // d3
+    TT(+1, 4, 6, 0, 0, 0, 0, 0), TT(+1, 4, 5, 0, 0, 0, 0, 0), TT(0, 0, 0, 0, 0, 0, 0, 0),      // e1
+    TT(-1, 2, 3, 6, 0, 0, 0, 0), TT(-1, 2, 3, 5, 0, 0, 0, 0), TT(0, 0, 0, 0, 0, 0, 0, 0),      // e2
+    TT(+1, 1, 3, 6, 0, 0, 0, 0), TT(+1, 1, 3, 5, 0, 0, 0, 0), TT(0, 0, 0, 0, 0, 0, 0, 0),      // e3
+    TT(-1, 3, 5, 0, 0, 0, 0, 0), TT(+1, 3, 6, 0, 0, 0, 0, 0), TT(0, 0, 0, 0, 0, 0, 0, 0),      // f1
+    TT(-1, 1, 6, 0, -1, 2, 4, 5), TT(-1, 1, 5, 0, +1, 2, 4, 6), TT(0, 0, 0, 0, 0, 0, 0, 0),    // f2
+    TT(-1, 2, 6, 0, +1, 1, 4, 5), TT(-1, 1, 4, 6, -1, 2, 5, 0), TT(0, 0, 0, 0, 0, 0, 0, 0)};   // f3
+#undef TT
+
+// Called by all threads of warp 0 (others return immediately).  s_trig: 16 doubles of shared scratch.
+__device__ __forceinline__ void setup_pose_warp(const double* x_t, EvalCtx& ctx, float* final_T, double* s_trig,
+                                                const TableTerm* s_terms, bool build_matrix) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  // lanes 0..5 : fp64 cos/sin of the three angles with the small-angle snap (ndt_omp_impl.hpp:292-326)
+  // lanes 6..11: fp32 sin/cos of the fp32-cast angles for the matrix (Eigen::AngleAxis<float>)
+  if (lane < 6) {
+    const double a = x_t[3 + (lane >> 1)];
+    double v;
+    if (fabs(a) < 10e-5) v = (lane & 1) ? 0.0 : 1.0;
+    else v = (lane & 1) ? sin(a) : cos(a);
+    s_trig[1 + lane] = v;  // order cx sx cy sy cz sz = factor codes 1..6
+  } else if (lane < 12) {
+    const int l = lane - 6;
+    const double a = static_cast<double>(static_cast<float>(x_t[3 + (l >> 1)]));
+    s_trig[8 + l] = static_cast<double>(static_cast<float>((l & 1) ? sin(a) : cos(a)));  // cx sx cy sy cz sz (fp32 values)
+  } else if (lane == 12) {
+    s_trig[0] = 1.0;
+  }
+  __syncwarp();
+  for (int e = lane; e < 69; e += 32) {
+    const TableTerm t = s_terms[e];
+    double v = 0.0;
+    if (t.s1) v = __dmul_rn(__dmul_rn(s_trig[t.a1], s_trig[t.b1]), s_trig[t.c1]) * static_cast<double>(t.s1);
+    if (t.s2) v = __dadd_rn(v, __dmul_rn(__dmul_rn(s_trig[t.a2], s_trig[t.b2]), s_trig[t.c2]) * static_cast<double>(t.s2));
+    if (e < 24) {
+      ctx.tab.jd[e / 3][e % 3] = v;
+      ctx.tab.jf[e / 3][e % 3] = static_cast<float>(v);
+    } else {
+      const int r = (e - 24) / 3, c = (e - 24) % 3;
+      ctx.tab.hd[r][c] = v;
+      // Q2: the fp32 table carries +sy in row d1 (ndt_omp_impl.hpp:383), the fp64 table -sy (:361)
+      ctx.tab.hf[r][c] = (r == 6 && c == 2) ? static_cast<float>(s_trig[4]) : static_cast<float>(v);
+    }
+  }
+  if (build_matrix && lane == 0) {
+    // Translation * Rx * Ry * Rz in fp32 from the fp32 trig values (same arithmetic as pose_to_matrix)
+    const float cx = static_cast<float>(s_trig[8]), sx = static_cast<float>(s_trig[9]);
+    const float cy = static_cast<float>(s_trig[10]), sy = static_cast<float>(s_trig[11]);
+    const float cz = static_cast<float>(s_trig[12]), sz = static_cast<float>(s_trig[13]);
+    float Rx[3][3], Ry[3][3], Rz[3][3], Rxy[3][3], R[3][3];
+    angle_axis_from_sc(sx, cx, 0, Rx);
+    angle_axis_from_sc(sy, cy, 1, Ry);
+    angle_axis_from_sc(sz, cz, 2, Rz);
+    mul33f(Rx, Ry, Rxy);
+    mul33f(Rxy, Rz, R);
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) ctx.T[i * 4 + j] = R[i][j];
+      ctx.T[i * 4 + 3] = static_cast<float>(x_t[i]);
+    }
+    for (int i = 0; i < 12; ++i) final_T[i] = ctx.T[i];  // final_transformation_ = T(x_t) (ndt_omp_impl.hpp:827-830)
+  }
+  __syncwarp();
 }
 
-// Newton step + start of the line search (ndt_omp_impl.hpp:121-142, 772-837).  Returns the next action.
-__device__ inline int newton_top(SolverState& st, EvalCtx& ctx, const AlignParams& prm) {
+// ---------------------------------------------------------------------------------------------
+// optimiser state machine — scalar part (thread 0 of every CTA, identical inputs -> identical decisions)
+// ---------------------------------------------------------------------------------------------
+// Newton step H * delta = -g (ndt_omp_impl.hpp:127-129), rows spread over the lanes of warp 0:
+// Gaussian elimination with partial pivoting in registers + shuffles (~1k cycles instead of the ~10k a
+// single thread spends walking a 6x7 array in local memory).  A (numerically) rank-deficient H falls
+// back to the one-sided Jacobi SVD pseudo-inverse (Eigen's JacobiSVD::solve semantics) in lane 0.
+__device__ __forceinline__ void warp_newton_solve(SolverState& st) {
+  const int lane = threadIdx.x & 31;
+  const int r = lane < 6 ? lane : 5;
+  double a[7];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) a[j] = st.H[r * 6 + j];
+  a[6] = -st.g[r];
+  double pmin = 1e300, pmax = 0.0, amax = 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    double v = (lane >= c && lane < 6) ? fabs(a[c]) : -1.0;
+    int idx = lane;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    const int piv = __shfl_sync(0xffffffffu, idx, 0);
+    const double best = __shfl_sync(0xffffffffu, v, 0);
+    if (!(best > 0.0) || isinf(best)) ok = false;
+    pmin = fmin(pmin, best);
+    pmax = fmax(pmax, best);
+    amax = fmax(amax, best);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      if (j < c) continue;
+      const double from_piv = __shfl_sync(0xffffffffu, a[j], piv);
+      const double from_c = __shfl_sync(0xffffffffu, a[j], c);
+      if (lane == c) a[j] = from_piv;
+      else if (lane == piv) a[j] = from_c;
+    }
+    const double pc = __shfl_sync(0xffffffffu, a[c], c);
+    const double f = a[c] * (1.0 / pc);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      if (j < c) continue;
+      const double pj = __shfl_sync(0xffffffffu, a[j], c);
+      if (lane > c && lane < 6) a[j] = (j == c) ? 0.0 : a[j] - f * pj;
+    }
+  }
+  ok = ok && (pmin > 1e-9 * pmax);
+  double x[6];
+  double dinv = 1.0;  // 1 / diagonal of this lane's row, all lanes at once
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    if (j == r) dinv = 1.0 / a[j];
+#pragma unroll
+  for (int rr = 5; rr >= 0; --rr) {
+    const double xr = __shfl_sync(0xffffffffu, a[6] * dinv, rr);
+    x[rr] = xr;
+    if (lane < rr) a[6] -= a[rr] * xr;
+  }
+  if (lane == 0) {
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) st.delta[i] = x[i];
+    } else {
+      double neg_g[6];
+      for (int i = 0; i < 6; ++i) neg_g[i] = -st.g[i];
+      svd_solve6(st.H, neg_g, st.delta);
+    }
+  }
+  __syncwarp();
+}
+
+// After the Newton solve: step-length bookkeeping and start of the line search
+// (ndt_omp_impl.hpp:131-142, 772-837).  Returns the next action.
+__device__ __noinline__ int newton_post(SolverState& st, const AlignParams& prm) {
   while (true) {
-    double neg_g[6], delta[6];
-    for (int i = 0; i < 6; ++i) neg_g[i] = -st.g[i];
-    newton_solve6(st.H, neg_g, delta);
+    const double* delta = st.delta;  // a zero-length step leaves H and g unchanged: same solution next round
     double nrm = 0;
     for (int i = 0; i < 6; ++i) nrm += delta[i] * delta[i];
     nrm = sqrt(nrm);
@@ -367,7 +615,7 @@ __device__ inline int newton_top(SolverState& st, EvalCtx& ctx, const AlignParam
     double dphi = 0;
     for (int i = 0; i < 6; ++i) dphi += st.g[i] * st.dir[i];
     st.d_phi_0 = -dphi;
-    double a_ret;
+    double a_ret = 0;
     bool evaluate = true;
     if (st.d_phi_0 >= 0) {
       if (st.d_phi_0 == 0) {
@@ -393,15 +641,13 @@ __device__ inline int newton_top(SolverState& st, EvalCtx& ctx, const AlignParam
       a_t = std_max(a_t, st.step_min);
       st.a_t = a_t;
       for (int i = 0; i < 6; ++i) st.x_t[i] = st.p[i] + st.dir[i] * a_t;
-      set_eval_pose(st, ctx, st.x_t);
+      st.need_pose = 1;
       st.state = ST_MT_FIRST;
       return ACT_EVAL_FULL;
     }
     // zero-length step: finish this Newton iteration without an evaluation
-    double dp[6];
-    for (int i = 0; i < 6; ++i) dp[i] = st.dir[i] * a_ret;
-    pose_to_matrix(dp, st.incr_T);
-    for (int i = 0; i < 6; ++i) st.p[i] += dp[i];
+    for (int i = 0; i < 6; ++i) st.last_dp[i] = st.dir[i] * a_ret;
+    for (int i = 0; i < 6; ++i) st.p[i] += st.last_dp[i];
     if (st.nr_iterations > prm.max_iterations || (st.nr_iterations && (fabs(a_ret) < prm.trans_eps))) st.converged = 1;
     st.nr_iterations++;
     if (st.converged) return ACT_DONE;
@@ -409,9 +655,8 @@ __device__ inline int newton_top(SolverState& st, EvalCtx& ctx, const AlignParam
 }
 
 // Called after every evaluation with the reduced totals; returns the next action.
-__device__ inline int advance(SolverState& st, EvalCtx& ctx, const AlignParams& prm, const double* tot, int kind,
-                              TraceRec* trace) {
-  // unpack totals
+__device__ __noinline__ int advance(SolverState& st, const AlignParams& prm, const double* tot, int kind, TraceRec* trace) {
+  st.need_pose = 0;
   if (kind != ACT_HESS_ONLY) {
     st.score = tot[0];
     for (int i = 0; i < 6; ++i) st.g[i] = tot[1 + i];
@@ -440,7 +685,7 @@ __device__ inline int advance(SolverState& st, EvalCtx& ctx, const AlignParams& 
     case ST_SINGLE:
       return ACT_DONE;
     case ST_INITIAL:
-      return newton_top(st, ctx, prm);
+      return ACT_SOLVE;
     case ST_MT_FIRST: {
       st.phi_t = -st.score;
       double d = 0;
@@ -485,7 +730,7 @@ __device__ inline int advance(SolverState& st, EvalCtx& ctx, const AlignParams& 
     a_t = std_max(a_t, st.step_min);
     st.a_t = a_t;
     for (int i = 0; i < 6; ++i) st.x_t[i] = st.p[i] + st.dir[i] * a_t;
-    set_eval_pose(st, ctx, st.x_t);
+    st.need_pose = 1;
     st.state = ST_MT_LOOP;
     return ACT_EVAL_NOHESS;
   }
@@ -496,14 +741,12 @@ __device__ inline int advance(SolverState& st, EvalCtx& ctx, const AlignParams& 
 mt_finish: {
     // back in computeTransformation (ndt_omp_impl.hpp:143-164)
     const double a = st.a_t;
-    double dp[6];
-    for (int i = 0; i < 6; ++i) dp[i] = st.dir[i] * a;
-    pose_to_matrix(dp, st.incr_T);
-    for (int i = 0; i < 6; ++i) st.p[i] = st.p[i] + dp[i];
+    for (int i = 0; i < 6; ++i) st.last_dp[i] = st.dir[i] * a;
+    for (int i = 0; i < 6; ++i) st.p[i] = st.p[i] + st.last_dp[i];
     if (st.nr_iterations > prm.max_iterations || (st.nr_iterations && (fabs(a) < prm.trans_eps))) st.converged = 1;
     st.nr_iterations++;
     if (st.converged) return ACT_DONE;
-    return newton_top(st, ctx, prm);
+    return ACT_SOLVE;
   }
 }
 
@@ -511,21 +754,25 @@ mt_finish: {
 // the persistent kernel
 // ---------------------------------------------------------------------------------------------
 template <int METHOD>
-__global__ void __launch_bounds__(kAlignThreads)
+__global__ void __launch_bounds__(kAlignThreads, 2)
 ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignParams prm, const AlignWorkspace ws) {
   __shared__ SolverState st;
   __shared__ EvalCtx ctx;
-  __shared__ double s_warp[kAlignThreads / 32][kNVP];
+  __shared__ double s_warp[kAlignWarps][kNVP];
   __shared__ double s_block[kNVP];
   __shared__ double s_tot[kNVP];
+  __shared__ double s_trig[16];
+  __shared__ TableTerm s_terms[69];
   __shared__ int s_action;
   __shared__ int s_flag;
 
+  const unsigned long long t_kernel_begin = globaltimer_ns();
   const int n = prm.n_source;
-  // contiguous chunk of source points per CTA (multiple of 32 so warps stay coalesced)
-  const int chunk = ((n + gridDim.x - 1) / gridDim.x + 31) & ~31;
-  const int begin = min(n, (int)blockIdx.x * chunk);
-  const int end = min(n, begin + chunk);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // 32-point groups interleaved over all warps of the grid (deterministic static balance)
+  const int n_groups = (n + 31) >> 5;
+  const int warp_global = blockIdx.x * kAlignWarps + warp;
+  const int warps_total = gridDim.x * kAlignWarps;
   unsigned int epoch = 0;
 
   if (threadIdx.x == 0) {
@@ -539,13 +786,13 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     st.converged = 0;
     st.n_evals = st.n_hess = st.n_trace = 0;
     st.a_t = 0;
+    st.need_pose = 0;
     for (int i = 0; i < 6; ++i) st.x_t[i] = prm.p0[i];
     for (int i = 0; i < 12; ++i) {
-      ctx.T[i] = prm.T0[i];     // first evaluation: source transformed by the guess matrix itself (:100)
+      ctx.T[i] = prm.T0[i];       // first evaluation: source transformed by the guess matrix itself (:100)
       st.final_T[i] = prm.T0[i];  // final_transformation_ = guess (:98) or Identity (align())
-      st.incr_T[i] = (i % 5 == 0) ? 1.0f : 0.0f;
     }
-    compute_angle_tables(prm.p0, ctx.tab);
+    for (int i = 0; i < 6; ++i) st.last_dp[i] = 0.0;
     if (prm.mode == MODE_ALIGN) {
       st.state = ST_INITIAL;
       s_action = ACT_EVAL_FULL;
@@ -557,34 +804,90 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
       s_action = ACT_HESS_ONLY;
     }
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 69) s_terms[threadIdx.x - 64] = g_table_terms[threadIdx.x - 64];
+  __syncthreads();
+  setup_pose_warp(st.x_t, ctx, st.final_T, s_trig, s_terms, /*build_matrix=*/false);  // tables for p0; matrix = T0
   __syncthreads();
 
   const float d2f = static_cast<float>(prm.d2);
+  const float d1f = static_cast<float>(prm.d1);
   while (true) {
     const int action = s_action;
     if (action == ACT_DONE) break;
-    double acc[kNV];
+    unsigned long long t_start = 0, t_local = 0, t_reduced = 0;
+    const bool timing = (blockIdx.x == 0 && threadIdx.x == 0 && ws.trace != nullptr);
+    if (timing) t_start = globaltimer_ns();
+    if (threadIdx.x < kAlignWarps * kNVP) (&s_warp[0][0])[threadIdx.x] = 0.0;
+    __syncthreads();
+
+    if (action == ACT_HESS_ONLY) {
+      double acc[kNV];
 #pragma unroll
-    for (int k = 0; k < kNV; ++k) acc[k] = 0.0;
-    if (action == ACT_EVAL_FULL) {
-      for (int i = begin + threadIdx.x; i < end; i += kAlignThreads)
-        eval_point_f32<METHOD, true>(__ldg(src + i), ctx, map, d2f, prm.d1, acc);
-    } else if (action == ACT_EVAL_NOHESS) {
-      for (int i = begin + threadIdx.x; i < end; i += kAlignThreads)
-        eval_point_f32<METHOD, false>(__ldg(src + i), ctx, map, d2f, prm.d1, acc);
+      for (int k = 0; k < kNV; ++k) acc[k] = 0.0;
+      for (int g = warp_global; g < n_groups; g += warps_total) {
+        const int i = (g << 5) + lane;
+        if (i < n) eval_point_f64<METHOD>(__ldg(src + i), ctx, map, prm.d2, prm.d1, acc);
+      }
+      warp_flush(acc, s_warp[warp]);
     } else {
-      for (int i = begin + threadIdx.x; i < end; i += kAlignThreads)
-        eval_point_f64<METHOD>(__ldg(src + i), ctx, map, prm.d2, prm.d1, acc);
+      float acc[kNV];
+#pragma unroll
+      for (int k = 0; k < kNV; ++k) acc[k] = 0.0f;
+      int since = 0;
+      for (int g = warp_global; g < n_groups; g += warps_total) {
+        const int i = (g << 5) + lane;
+        if (i < n) {
+          const float4 pt = __ldg(src + i);
+          if (action == ACT_EVAL_FULL) eval_point_f32<METHOD, true>(pt, ctx, map, d2f, d1f, acc);
+          else eval_point_f32<METHOD, false>(pt, ctx, map, d2f, d1f, acc);
+        }
+        if (++since == kFlushPoints) {  // bound the fp32 run, fold into fp64
+          warp_flush(acc, s_warp[warp]);
+          since = 0;
+        }
+      }
+      warp_flush(acc, s_warp[warp]);
     }
-    block_reduce(acc, s_warp, s_block);
+    __syncthreads();
+    if (threadIdx.x < kNV) {
+      double s = 0;
+#pragma unroll
+      for (int w = 0; w < kAlignWarps; ++w) s += s_warp[w][threadIdx.x];
+      s_block[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (timing) t_local = globaltimer_ns();
     grid_allreduce(s_block, s_tot, ws, epoch, &s_flag);
-    if (threadIdx.x == 0) s_action = advance(st, ctx, prm, s_tot, action, blockIdx.x == 0 ? ws.trace : nullptr);
+    if (timing) t_reduced = globaltimer_ns();
+    int slot = 0;
+    unsigned long long t_d0 = 0, t_d1 = 0, t_d2 = 0;
+    if (threadIdx.x == 0) {
+      slot = st.n_trace;
+      s_action = advance(st, prm, s_tot, action, blockIdx.x == 0 ? ws.trace : nullptr);
+    }
+    __syncthreads();
+    if (timing) t_d0 = t_d1 = t_d2 = globaltimer_ns();
+    if (s_action == ACT_SOLVE) {  // block-uniform
+      if (warp == 0) warp_newton_solve(st);
+      __syncthreads();
+      if (timing) t_d1 = globaltimer_ns();
+      if (threadIdx.x == 0) s_action = newton_post(st, prm);
+      __syncthreads();
+      if (timing) t_d2 = globaltimer_ns();
+    }
+    if (st.need_pose) setup_pose_warp(st.x_t, ctx, st.final_T, s_trig, s_terms, /*build_matrix=*/true);
+    if (timing && slot < prm.trace_cap) {
+      TraceRec& r = ws.trace[slot];
+      r.t_start = t_start; r.t_local = t_local; r.t_reduced = t_reduced; r.t_advanced = globaltimer_ns();
+      r.t_dbg[0] = t_d0; r.t_dbg[1] = t_d1; r.t_dbg[2] = t_d2; r.t_dbg[3] = 0;
+    }
     __syncthreads();
   }
 
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     AlignResultDev& r = *ws.result;
-    for (int i = 0; i < 12; ++i) { r.final_T[i] = st.final_T[i]; r.incr_T[i] = st.incr_T[i]; }
+    for (int i = 0; i < 12; ++i) r.final_T[i] = st.final_T[i];
+    pose_to_matrix(st.last_dp, r.incr_T);  // transformation_ (ndt_omp_impl.hpp:146-149); Identity if no step was taken
     r.converged = st.converged;
     r.iterations = st.nr_iterations;
     r.n_evals = st.n_evals;
@@ -599,6 +902,18 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     r.n_hits = st.n_hits;
     r.n_trace = st.n_trace;
     r.pad = 0;
+    r.t_kernel_begin = t_kernel_begin;
+    r.t_kernel_end = globaltimer_ns();
+  }
+  // Leave the barrier words zeroed for the next launch: the LAST CTA to get here resets them (every other
+  // CTA has finished its last barrier by then); sync[2] is a wrapping exit counter that resets itself.
+  if (threadIdx.x == 0 && gridDim.x > 1) {
+    const unsigned int old = atomicInc(&ws.sync[2], gridDim.x - 1);
+    if (old == gridDim.x - 1) {
+      ws.sync[0] = 0u;
+      ws.sync[1] = 0u;
+      __threadfence();
+    }
   }
 }
 

@@ -103,8 +103,8 @@ calculate_score_kernel(const float4* __restrict__ cloud, int n, const MapView ma
       if (recs[k] < 0) continue;
       const VoxelRecord* R = map.records + recs[k];
       const double* ic = map.icov64 + (size_t)recs[k] * 6;
-      const double r0 = static_cast<double>(p.x) - R->mean[0], r1 = static_cast<double>(p.y) - R->mean[1],
-                   r2 = static_cast<double>(p.z) - R->mean[2];
+      const double r0 = static_cast<double>(p.x) - record_mean(*R, 0), r1 = static_cast<double>(p.y) - record_mean(*R, 1),
+                   r2 = static_cast<double>(p.z) - record_mean(*R, 2);
       const double u0 = ic[0] * r0 + ic[1] * r1 + ic[2] * r2, u1 = ic[1] * r0 + ic[3] * r1 + ic[4] * r2,
                    u2 = ic[2] * r0 + ic[4] * r1 + ic[5] * r2;
       const double e = exp(-d2 * (r0 * u0 + r1 * u1 + r2 * u2) / 2);

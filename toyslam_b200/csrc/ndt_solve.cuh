@@ -36,6 +36,31 @@ __host__ __device__ inline void angle_axis_unit(float angle, int axis, float R[3
 #endif
 }
 
+// Same rotation matrix from precomputed fp32 sine / cosine (the persistent kernel computes the
+// trigonometry in parallel lanes).
+__host__ __device__ inline void angle_axis_from_sc(float s, float c, int axis, float R[3][3]) {
+  float ax[3] = {0.f, 0.f, 0.f};
+  ax[axis] = 1.0f;
+  const float sin_axis[3] = {s * ax[0], s * ax[1], s * ax[2]};
+  const float c1 = 1.0f - c;
+  const float cos1_axis[3] = {c1 * ax[0], c1 * ax[1], c1 * ax[2]};
+  float tmp;
+  tmp = cos1_axis[0] * ax[1];
+  R[0][1] = tmp - sin_axis[2];
+  R[1][0] = tmp + sin_axis[2];
+  tmp = cos1_axis[0] * ax[2];
+  R[0][2] = tmp + sin_axis[1];
+  R[2][0] = tmp - sin_axis[1];
+  tmp = cos1_axis[1] * ax[2];
+  R[1][2] = tmp - sin_axis[0];
+  R[2][1] = tmp + sin_axis[0];
+#ifdef __CUDA_ARCH__
+  for (int i = 0; i < 3; ++i) R[i][i] = __fadd_rn(__fmul_rn(cos1_axis[i], ax[i]), c);
+#else
+  for (int i = 0; i < 3; ++i) { volatile float t = cos1_axis[i] * ax[i]; R[i][i] = t + c; }
+#endif
+}
+
 __host__ __device__ inline void mul33f(const float A[3][3], const float B[3][3], float C[3][3]) {
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) {

@@ -89,6 +89,7 @@ def load_library():
     L.ndtb200_eval_hessian.argtypes = [vp, f64p, f32p, f64p]
     L.ndtb200_lookup.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, i32p]
     L.ndtb200_get_trace.argtypes = [vp, i32p, f64p, f64p, f64p, C.c_int, C.POINTER(C.c_int)]
+    L.ndtb200_get_timeline.argtypes = [vp, f64p, C.c_int, C.POINTER(C.c_int)]
     L.ndtb200_stream.argtypes = [vp]
     L.ndtb200_stream.restype = vp
     L.ndtb200_launch_count.argtypes = [vp]
@@ -353,6 +354,13 @@ class NormalDistributionsTransform:
                                               _ptr(s, C.c_double), cap, C.byref(n)))
         m = min(n.value, cap)
         return {"kind": kinds[:m].copy(), "x": x[:m].copy(), "a_t": a[:m].copy(), "score": s[:m].copy()}
+
+    def timeline(self):
+        cap = 1024
+        t = np.empty((cap, 4), dtype=np.float64)
+        n = C.c_int()
+        self._check(self._L.ndtb200_get_timeline(self._h, _ptr(t, C.c_double), cap, C.byref(n)))
+        return t[:min(n.value, cap)].copy()
 
     # ---- plumbing ----
     def stream_ptr(self):
