@@ -1,5 +1,6 @@
 // capi.cu — host side of libndt_b200.so: handle, device memory, kernel orchestration, C ABI.
 // See include/ndt_b200.h for the contract of every entry point and the reference method it replaces.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -47,6 +48,8 @@ struct ndtb200_handle {
   std::string err;
   ndtb200_params prm{};
   long long launches = 0;
+  uint32_t launch_seq = 0;
+  int last_blocks = 0;
 
   // target cloud + map
   DevBuf d_target;
@@ -388,7 +391,9 @@ void gauss_constants(const ndtb200_params& p, double& d1, double& d2, double& d3
 template <int METHOD>
 int query_coop_blocks(ndtb200_handle* h) {
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ndt_align_kernel<METHOD>, kAlignThreads, 0));
+  const size_t smem = eval_smem_bytes<METHOD>();
+  CK(cudaFuncSetAttribute(ndt_align_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ndt_align_kernel<METHOD>, kAlignThreads, smem));
   if (per_sm < 1) { h->err = "align kernel does not fit on an SM"; return NDTB200_ERR_CUDA; }
   h->coop_blocks[METHOD] = per_sm * h->num_sms;
   return NDTB200_OK;
@@ -414,11 +419,16 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   for (int i = 0; i < 12; ++i) prm.T0[i] = T0[i];
   prm.n_source = static_cast<int>(h->n_source);
   prm.trace_cap = ndtb200_handle::kTraceCap;
+  prm.launch_tag = (++h->launch_seq) << 10;
+  compute_angle_tables(p0, prm.tab0);
 
   const int max_blocks = h->coop_blocks[method];
   int blocks = grid_for(h->n_source, kAlignThreads, max_blocks);
   CK(h->d_partials.ensure((size_t)max_blocks * kNVP * sizeof(double)));
-  CK(h->d_totals.ensure(2 * kNVP * sizeof(double)));
+  if (h->d_totals.p == nullptr) {
+    CK(h->d_totals.ensure(3 * kNVP * sizeof(double)));
+    CK(cudaMemsetAsync(h->d_totals.p, 0, 3 * kNVP * sizeof(double), h->stream));
+  }
   if (h->d_sync.p == nullptr) {  // barrier words: zeroed once; every launch leaves them zeroed again
     CK(h->d_sync.ensure(64));
     CK(cudaMemsetAsync(h->d_sync.p, 0, 64, h->stream));
@@ -438,8 +448,13 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   const void* fn = method == NDTB200_DIRECT1 ? (const void*)ndt_align_kernel<3>
                  : method == NDTB200_DIRECT7 ? (const void*)ndt_align_kernel<2>
                                              : (const void*)ndt_align_kernel<1>;
+  h->last_blocks = blocks;
   CK(cudaEventRecord(h->ev0, h->stream));
-  CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kAlignThreads), args, 0, h->stream));
+  const size_t smem = method == NDTB200_DIRECT1 ? eval_smem_bytes<3>()
+                    : method == NDTB200_DIRECT7 ? eval_smem_bytes<2>() : eval_smem_bytes<1>();
+  static const bool plain_launch = getenv("NDTB200_PLAIN_LAUNCH") != nullptr;  // experiment only: no co-residency guarantee
+  if (plain_launch) CK(cudaLaunchKernel(fn, dim3(blocks), dim3(kAlignThreads), args, smem, h->stream));
+  else CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kAlignThreads), args, smem, h->stream));
   LAUNCHED(h);
   CK(cudaEventRecord(h->ev1, h->stream));
   h->result_valid = false;
@@ -674,7 +689,9 @@ int ndtb200_get_result(ndtb200_handle* h, ndtb200_result* out) {
   }
   const AlignResultDev& r = *h->h_result;
   T_to_colmajor(r.final_T, out->final_transformation);
-  T_to_colmajor(r.incr_T, out->last_increment);
+  float incr[12];
+  pose_to_matrix(r.last_dp, incr);  // transformation_ (ndt_omp_impl.hpp:146-149); Identity if no step was taken
+  T_to_colmajor(incr, out->last_increment);
   out->converged = r.converged;
   out->iterations = r.iterations;
   out->trans_probability = r.trans_probability;
@@ -882,13 +899,35 @@ int ndtb200_get_timeline(ndtb200_handle* h, double* t4, int cap, int* n_out) {
   CK(cudaMemcpyAsync(tr.data(), h->d_trace.p, n * sizeof(TraceRec), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   const unsigned long long t0 = tr[0].t_start;
+  if (getenv("NDTB200_DEBUG_STEP")) {  // arrival-time spread of the CTAs at the LAST barrier
+    const int G = static_cast<int>(h->last_blocks);
+    std::vector<double> part((size_t)G * kNVP);
+    CK(cudaMemcpyAsync(part.data(), h->d_partials.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<double> arr(G);
+    const unsigned long long tl = tr[n - 1].t_start;
+    for (int b = 0; b < G; ++b) {
+      long long bits; std::memcpy(&bits, &part[(size_t)b * kNVP + 31], 8);
+      arr[b] = (double)((long long)bits - (long long)tl) * 1e-3;
+    }
+    std::vector<double> s(arr); std::sort(s.begin(), s.end());
+    std::fprintf(stderr, "  last eval: CTA arrival after eval start [us]: min %.2f p10 %.2f p50 %.2f p90 %.2f p99 %.2f max %.2f (CTA0 %.2f, G=%d)\n",
+                 s[0], s[G / 10], s[G / 2], s[G * 9 / 10], s[G * 99 / 100], s[G - 1], arr[0], G);
+    // by SM pairing: CTAs b and b+148 usually share an SM
+    double mx_lo = 0, mx_hi = 0; for (int b = 0; b < G; ++b) { if (b < G / 2) mx_lo = std::max(mx_lo, arr[b]); else mx_hi = std::max(mx_hi, arr[b]); }
+    std::fprintf(stderr, "  max arrival first half of CTAs %.2f, second half %.2f\n", mx_lo, mx_hi);
+  }
   for (int i = 0; i < n; ++i) {
     t4[i * 4 + 0] = static_cast<double>(tr[i].t_start - t0);
     t4[i * 4 + 1] = static_cast<double>(tr[i].t_local - t0);
     t4[i * 4 + 2] = static_cast<double>(tr[i].t_reduced - t0);
     t4[i * 4 + 3] = static_cast<double>(tr[i].t_advanced - t0);
     if (getenv("NDTB200_DEBUG_STEP"))
-      std::fprintf(stderr, "  step %d: advance %.2f us, solve %.2f us, post %.2f us, pose setup %.2f us\n", i,
+      std::fprintf(stderr, "  eval %d CTA0: phase A %.2f us, phase B %.2f us, fold %.2f us\n", i, (double)((long long)tr[i].t_phase[0] - (long long)tr[i].t_start) * 1e-3,
+                   (double)((long long)tr[i].t_phase[1] - (long long)tr[i].t_phase[0]) * 1e-3, (double)((long long)tr[i].t_local - (long long)tr[i].t_phase[1]) * 1e-3);
+    if (getenv("NDTB200_DEBUG_STEP"))
+      std::fprintf(stderr, "  step %d: last CTA arrived %.2f us after CTA 0 finished, totals %.2f us later; advance %.2f us, solve %.2f us, post %.2f us, pose setup %.2f us\n", i,
+                   (double)((long long)tr[i].t_dbg[3] - (long long)tr[i].t_local) * 1e-3, (double)((long long)tr[i].t_reduced - (long long)tr[i].t_dbg[3]) * 1e-3,
                    (tr[i].t_dbg[0] - tr[i].t_reduced) * 1e-3, (tr[i].t_dbg[1] - tr[i].t_dbg[0]) * 1e-3,
                    (tr[i].t_dbg[2] - tr[i].t_dbg[1]) * 1e-3, (tr[i].t_advanced - tr[i].t_dbg[2]) * 1e-3);
   }

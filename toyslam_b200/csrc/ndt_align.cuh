@@ -44,12 +44,13 @@ struct TraceRec {
   double score;
   // CTA-0 timeline of this evaluation (globaltimer ns): start, local work done, totals available, step decided
   unsigned long long t_start, t_local, t_reduced, t_advanced;
+  unsigned long long t_phase[2];  // CTA 0: first chunk's phase A done, phase B done
   unsigned long long t_dbg[4];  // step breakdown: after advance(), after the warp solve, after newton_post(), (spare)
 };
 
 struct AlignResultDev {
   float final_T[12];
-  float incr_T[12];
+  double last_dp[6];
   int32_t converged, iterations, n_evals, n_hess;
   double trans_probability;
   double final_pose[6];
@@ -71,6 +72,8 @@ struct AlignParams {
   float T0[12];
   int32_t n_source;
   int32_t trace_cap;
+  uint32_t launch_tag;  // launch sequence number << 10: makes the tags of the published totals unique per launch
+  AngleTables tab0;     // angle tables of p0 (host-computed: the kernel prologue has no trigonometry)
 };
 
 struct AlignWorkspace {
@@ -366,7 +369,7 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 
 // Fold the per-thread accumulators of a warp into the warp's fp64 sums (fixed shuffle tree) and clear them.
 template <typename A>
-__device__ __forceinline__ void warp_flush(A* acc, double* s_warp_row) {
+__device__ __noinline__ void warp_flush(A* acc, double* s_warp_row) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < kNV; ++k) {
@@ -378,52 +381,80 @@ __device__ __forceinline__ void warp_flush(A* acc, double* s_warp_row) {
   }
 }
 
-// s_block (this CTA's sums) -> s_tot (sum over all CTAs, identical bits in every CTA).
+// ---- grid-wide sum of the CTA partials: ONE barrier per evaluation ---------------------------------
+// 1. every CTA publishes its 29 fp64 partials, then one acq_rel atomic "arrive";
+// 2. the LAST CTA to arrive (whichever it is) sums the partials in a fixed (slice, row) order — totals are
+//    bit-reproducible — and publishes each total as two 64-bit words that carry a 32-bit tag next to each
+//    32-bit half of the double (flag-in-data, as NCCL's LL protocol): readers need a single round trip;
+// 3. 29 threads of every CTA poll their own total until both tags match this evaluation.
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr int kRedRows = 20;  // partial rows per thread in flight while the last CTA reduces
+
 __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_tot, const AlignWorkspace& ws,
-                                               unsigned int& epoch, int* s_flag) {
+                                               unsigned int& epoch, int* s_flag, double (*s_red8)[kNVP],
+                                               unsigned int launch_tag) {
   const unsigned int G = gridDim.x;
   if (G == 1) {
     if (threadIdx.x < kNV) s_tot[threadIdx.x] = s_block[threadIdx.x];
     __syncthreads();
     return;
   }
-  if (threadIdx.x < kNV) {
-    ws.partials[(size_t)blockIdx.x * kNVP + threadIdx.x] = s_block[threadIdx.x];
-    __threadfence();
-  }
+  const unsigned int tag = launch_tag + epoch + 1u;
+  if (threadIdx.x < kNV) ws.partials[(size_t)blockIdx.x * kNVP + threadIdx.x] = s_block[threadIdx.x];
+  if (threadIdx.x == 31) ws.partials[(size_t)blockIdx.x * kNVP + 31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: arrival time of this CTA
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int ticket = atomicAdd(&ws.sync[0], 1u);
+    const unsigned int ticket = atom_add_acq_rel_gpu(&ws.sync[0], 1u);  // release: the CTA's partials; acquire: everyone's
     *s_flag = (ticket == (epoch + 1u) * G - 1u) ? 1 : 0;
   }
   __syncthreads();
-  const int par = epoch & 1u;
+  unsigned long long* slots = reinterpret_cast<unsigned long long*>(ws.totals);
   if (*s_flag) {  // last CTA to arrive: every partial is visible
-    __threadfence();
-    // 8 lanes per value, each summing a strided subset of the CTAs, then a fixed tree: order is
-    // independent of which CTA happens to be last, so totals are bit-reproducible
-    const int k = threadIdx.x >> 3, sub = threadIdx.x & 7;
-    double s = 0;
-    if (k < kNV) {
-      const double* p = ws.partials + k;
-      for (unsigned int b = sub; b < G; b += 8) s += __ldcg(p + (size_t)b * kNVP);
+    if (threadIdx.x == 0) ws.totals[2 * kNVP + (epoch & 1u)] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling stamp
+    const int k = threadIdx.x & 31, slice = threadIdx.x >> 5;  // lane = value, warp = slice of the CTA rows
+    double s = 0.0;
+    for (unsigned int b0 = 0; b0 < G; b0 += kAlignWarps * kRedRows) {
+      double v[kRedRows];
+#pragma unroll
+      for (int i = 0; i < kRedRows; ++i) {
+        const unsigned int b = b0 + slice + kAlignWarps * i;
+        v[i] = (b < G && k < kNV) ? __ldcg(ws.partials + (size_t)b * kNVP + k) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < kRedRows; ++i) s += v[i];
     }
-    s += __shfl_down_sync(0xffffffffu, s, 4, 8);
-    s += __shfl_down_sync(0xffffffffu, s, 2, 8);
-    s += __shfl_down_sync(0xffffffffu, s, 1, 8);
-    if (k < kNV && sub == 0) {
-      ws.totals[par * kNVP + k] = s;
-      __threadfence();
-    }
+    s_red8[slice][k] = s;
     __syncthreads();
-    if (threadIdx.x == 0) atomicExch(&ws.sync[1], epoch + 1u);
-  }
-  if (threadIdx.x == 0) {
-    while (ld_acquire_u32(&ws.sync[1]) < epoch + 1u) {
+    if (threadIdx.x < kNV) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kAlignWarps; ++w) t += s_red8[w][threadIdx.x];
+      const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(t));
+      st_volatile_u64(slots + 2 * threadIdx.x, (static_cast<unsigned long long>(tag) << 32) | (bits & 0xffffffffull));
+      st_volatile_u64(slots + 2 * threadIdx.x + 1, (static_cast<unsigned long long>(tag) << 32) | (bits >> 32));
     }
   }
-  __syncthreads();
-  if (threadIdx.x < kNV) s_tot[threadIdx.x] = __ldcg(ws.totals + par * kNVP + threadIdx.x);
+  if (threadIdx.x < kNV) {
+    unsigned long long w0, w1;
+    do {
+      w0 = ld_volatile_u64(slots + 2 * threadIdx.x);
+      w1 = ld_volatile_u64(slots + 2 * threadIdx.x + 1);
+    } while (static_cast<unsigned int>(w0 >> 32) != tag || static_cast<unsigned int>(w1 >> 32) != tag);
+    s_tot[threadIdx.x] = __longlong_as_double(static_cast<long long>(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
+  }
   __syncthreads();
   ++epoch;
 }
@@ -751,6 +782,190 @@ mt_finish: {
 }
 
 // ---------------------------------------------------------------------------------------------
+// fp32 derivative pass of one CTA — two phases per chunk of kChunk points ("hit queue"):
+//   A  one thread per point: float4 load, transform, cell, all K hash probes in flight together, record
+//      prefetch; the point's transformed position and its J_E / H_E coefficients are staged in shared
+//      memory; every (point, voxel) hit is appended to the warp's queue segment (ballot compaction,
+//      deterministic order);
+//   B  the CTA's 256 threads consume the pooled queue densely, one hit per thread per round, so lanes
+//      stay ~100 % busy whatever the per-point hit count (0..K) and the work is balanced over the CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPtVec = 7;              // float4 per staged point: x'(3) + pj(8) + ph(15) = 26 floats
+constexpr int kRedStride = kAlignThreads + 8;  // padded row of the final fold (conflict-free banks)
+constexpr int kFlushChunks = 2;        // fp32 run length bound: chunks before folding into fp64 (large clouds only)
+
+// 32-point groups per warp per chunk: 2 for DIRECT1/7 (512 points staged per CTA: ~86 KB of shared memory, two
+// CTAs per SM), 1 for DIRECT26 whose queue is 3.7x larger.
+template <int METHOD>
+__host__ __device__ constexpr int groups_per_warp() { return METHOD == 1 ? 1 : 2; }
+template <int METHOD>
+__host__ __device__ constexpr int queue_cap_per_warp() {
+  return groups_per_warp<METHOD>() * 32 * (METHOD == 3 ? 1 : (METHOD == 2 ? 7 : 26));
+}
+template <int METHOD>
+__host__ __device__ constexpr size_t eval_smem_bytes() {
+  return (size_t)groups_per_warp<METHOD>() * kAlignThreads * kPtVec * 16 + (size_t)kAlignWarps * queue_cap_per_warp<METHOD>() * 8;
+}
+
+struct HitOperands {  // what phase B needs for one hit before the arithmetic starts
+  uint2 e;
+  float4 a, b, c;  // the 48 hot bytes of the voxel record
+};
+
+// q-th entry of the pooled queue: the per-warp segments are walked forward only (q grows by 256 per round)
+__device__ __forceinline__ HitOperands fetch_hit(const uint2* s_q, const int* s_wcount, int qcap, int q, int& seg, int& base,
+                                                 const VoxelRecord* records) {
+  while (q >= base + s_wcount[seg]) { base += s_wcount[seg]; ++seg; }
+  HitOperands h;
+  h.e = s_q[seg * qcap + (q - base)];
+  const float4* R = reinterpret_cast<const float4*>(records + h.e.x);
+  h.a = __ldg(R);
+  h.b = __ldg(R + 1);
+  h.c = __ldg(R + 2);
+  return h;
+}
+
+template <int METHOD, bool HESS>
+__device__ __forceinline__ void eval_chunked_f32(const float4* __restrict__ src, int n, int n_groups, const EvalCtx& ctx,
+                                                 const MapView& m, float d2f, float d1f, float4* s_pts, uint2* s_q,
+                                                 int* s_wcount, double (*s_warp)[kNVP], double* s_extra,
+                                                 unsigned long long* s_dbg) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int K = num_offsets<METHOD>();
+  constexpr int GPW = groups_per_warp<METHOD>();
+  constexpr int QCAP = queue_cap_per_warp<METHOD>();
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  float acc[kNV];
+#pragma unroll
+  for (int k = 0; k < kNV; ++k) acc[k] = 0.0f;
+  int chunks_since = 0;
+  // this CTA's 32-point groups: g = blockIdx.x + j * gridDim.x (interleaved over the grid)
+  const int groups_mine = (n_groups > (int)blockIdx.x) ? (n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  for (int j0 = 0; j0 < groups_mine; j0 += kAlignWarps * GPW) {
+    // ---------------- phase A ----------------
+    int wcount = 0;
+    uint2* qw = s_q + warp * QCAP;
+#pragma unroll
+    for (int s = 0; s < GPW; ++s) {
+      const int j = j0 + s * kAlignWarps + warp;
+      if (j < groups_mine) {  // warp-uniform
+        const int i = ((blockIdx.x + j * gridDim.x) << 5) + lane;
+        const int slot = s * kAlignThreads + threadIdx.x;
+        const bool valid = i < n;
+        const float4 pt = valid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float tx, ty, tz;
+        transform_point(ctx.T, pt.x, pt.y, pt.z, tx, ty, tz);
+        // getNeighborhoodAtPoint (…_impl.hpp:379-381): cell = floor(x' / leaf), fp32 DIVISION (Q8)
+        const int ix = static_cast<int>(floorf(__fdiv_rn(tx, m.leaf[0])));
+        const int iy = static_cast<int>(floorf(__fdiv_rn(ty, m.leaf[1])));
+        const int iz = static_cast<int>(floorf(__fdiv_rn(tz, m.leaf[2])));
+        if constexpr (METHOD != 1) {
+          int rec[K];
+          probe_cells<K>(m, ix, iy, iz, rec);
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const bool hit = valid && rec[k] >= 0;
+            const unsigned int mask = __ballot_sync(0xffffffffu, hit);
+            if (hit) qw[wcount + __popc(mask & lt_mask)] = make_uint2(static_cast<unsigned int>(rec[k]), slot);
+            wcount += __popc(mask);
+          }
+        } else {
+#pragma unroll 1
+          for (int k = 0; k < K; ++k) {
+            int dx, dy, dz;
+            get_offset<METHOD>(k, dx, dy, dz);
+            const int rec = valid ? probe_cell(m, ix + dx, iy + dy, iz + dz) : -1;
+            const bool hit = rec >= 0;
+            const unsigned int mask = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+              qw[wcount + __popc(mask & lt_mask)] = make_uint2(static_cast<unsigned int>(rec), slot);
+              prefetch_l2(m.records + rec);
+            }
+            wcount += __popc(mask);
+          }
+        }
+        // computePointDerivatives (fp32 overload, ndt_omp_impl.hpp:398-440): depends on the ORIGINAL point only
+        float pj[8], ph[15];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) pj[r] = ctx.tab.jf[r][0] * pt.x + ctx.tab.jf[r][1] * pt.y + ctx.tab.jf[r][2] * pt.z;
+        float4* P = s_pts + slot * kPtVec;
+        P[0] = make_float4(tx, ty, tz, pj[0]);
+        P[1] = make_float4(pj[1], pj[2], pj[3], pj[4]);
+        if (HESS) {
+#pragma unroll
+          for (int r = 0; r < 15; ++r) ph[r] = ctx.tab.hf[r][0] * pt.x + ctx.tab.hf[r][1] * pt.y + ctx.tab.hf[r][2] * pt.z;
+          P[2] = make_float4(pj[5], pj[6], pj[7], ph[0]);
+          P[3] = make_float4(ph[1], ph[2], ph[3], ph[4]);
+          P[4] = make_float4(ph[5], ph[6], ph[7], ph[8]);
+          P[5] = make_float4(ph[9], ph[10], ph[11], ph[12]);
+          P[6] = make_float4(ph[13], ph[14], 0.f, 0.f);
+        } else {
+          P[2] = make_float4(pj[5], pj[6], pj[7], 0.f);
+        }
+      }
+    }
+    if (lane == 0) s_wcount[warp] = wcount;
+    __syncthreads();
+    if (threadIdx.x == 0 && j0 == 0) s_dbg[0] = globaltimer_ns();
+    // ---------------- phase B ----------------
+    int Q = 0;
+#pragma unroll
+    for (int w = 0; w < kAlignWarps; ++w) Q += s_wcount[w];
+    int seg = 0, base = 0;
+    for (int q = threadIdx.x; q < Q; q += kAlignThreads) {
+      const HitOperands cur = fetch_hit(s_q, s_wcount, QCAP, q, seg, base, m.records);
+      const float4* P = s_pts + cur.e.y * kPtVec;
+      const float4 v0 = P[0], v1 = P[1], v2 = P[2];
+      float pj[8] = {v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z};
+      float ph[15];
+      if (HESS) {
+        const float4 v3 = P[3], v4 = P[4], v5 = P[5], v6 = P[6];
+        ph[0] = v2.w; ph[1] = v3.x; ph[2] = v3.y; ph[3] = v3.z; ph[4] = v3.w; ph[5] = v4.x; ph[6] = v4.y; ph[7] = v4.z;
+        ph[8] = v4.w; ph[9] = v5.x; ph[10] = v5.y; ph[11] = v5.z; ph[12] = v5.w; ph[13] = v6.x; ph[14] = v6.y;
+      }
+      // x_trans = fl32(double(x') - mean) (ndt_omp_impl.hpp:259-262, 492) via the exact hi/lo split of the mean
+      const float r0 = __fsub_rn(__fsub_rn(v0.x, cur.a.x), cur.a.w);
+      const float r1 = __fsub_rn(__fsub_rn(v0.y, cur.a.y), cur.b.x);
+      const float r2 = __fsub_rn(__fsub_rn(v0.z, cur.a.z), cur.b.y);
+      acc[28] += 1.0f;
+      hit_contribution<float, true, HESS>(r0, r1, r2, cur.b.z, cur.b.w, cur.c.x, cur.c.y, cur.c.z, cur.c.w, pj, ph, d2f, d1f, acc);
+    }
+    __syncthreads();  // the next chunk overwrites the staging buffers
+    if (threadIdx.x == 0 && j0 == 0) s_dbg[1] = globaltimer_ns();
+    if (++chunks_since == kFlushChunks) {  // only reached by large clouds
+      warp_flush(acc, s_warp[warp]);
+      chunks_since = 0;
+    }
+  }
+  // final fold of the per-thread fp32 partials into fp64 CTA sums through shared memory (the staging buffers
+  // are free again): thread (k, sub) adds 32 of the 256 partials of value k in fp64, 8 lanes combine in a fixed tree.
+  // ~8x fewer instructions than a 29-value warp shuffle tree per warp.
+  float* s_red = reinterpret_cast<float*>(s_pts);
+#pragma unroll
+  for (int k = 0; k < kNV; ++k) s_red[k * kRedStride + threadIdx.x] = acc[k];
+  __syncthreads();
+  {
+    const int k = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    double s = 0.0;
+    if (k < kNV) {
+      // partials of 4 threads are first added in fp32 (their fp32 runs are short), then everything is fp64
+      const float* row = s_red + k * kRedStride + sub;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        s0 += static_cast<double>((row[8 * i] + row[8 * (i + 1)]) + (row[8 * (i + 2)] + row[8 * (i + 3)]));
+        s1 += static_cast<double>((row[8 * (i + 4)] + row[8 * (i + 5)]) + (row[8 * (i + 6)] + row[8 * (i + 7)]));
+      }
+      s = s0 + s1;
+    }
+    s += __shfl_down_sync(0xffffffffu, s, 4, 8);
+    s += __shfl_down_sync(0xffffffffu, s, 2, 8);
+    s += __shfl_down_sync(0xffffffffu, s, 1, 8);
+    if (k < kNV && sub == 0) s_extra[k] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------------------------
 template <int METHOD>
@@ -761,10 +976,16 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
   __shared__ double s_warp[kAlignWarps][kNVP];
   __shared__ double s_block[kNVP];
   __shared__ double s_tot[kNVP];
+  __shared__ double s_extra[kNVP];
+  __shared__ unsigned long long s_dbg[4];
   __shared__ double s_trig[16];
   __shared__ TableTerm s_terms[69];
   __shared__ int s_action;
   __shared__ int s_flag;
+  __shared__ int s_wcount[kAlignWarps];
+  extern __shared__ float4 dyn_smem[];
+  float4* s_pts = dyn_smem;                                                                      // [GPW * 256][kPtVec]
+  uint2* s_q = reinterpret_cast<uint2*>(dyn_smem + groups_per_warp<METHOD>() * kAlignThreads * kPtVec);  // [kAlignWarps][QCAP]
 
   const unsigned long long t_kernel_begin = globaltimer_ns();
   const int n = prm.n_source;
@@ -805,8 +1026,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     }
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 69) s_terms[threadIdx.x - 64] = g_table_terms[threadIdx.x - 64];
-  __syncthreads();
-  setup_pose_warp(st.x_t, ctx, st.final_T, s_trig, s_terms, /*build_matrix=*/false);  // tables for p0; matrix = T0
+  if (threadIdx.x == 32) ctx.tab = prm.tab0;  // tables for p0 (computed on the host); matrix = T0
   __syncthreads();
 
   const float d2f = static_cast<float>(prm.d2);
@@ -818,6 +1038,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     const bool timing = (blockIdx.x == 0 && threadIdx.x == 0 && ws.trace != nullptr);
     if (timing) t_start = globaltimer_ns();
     if (threadIdx.x < kAlignWarps * kNVP) (&s_warp[0][0])[threadIdx.x] = 0.0;
+    if (threadIdx.x < kNVP) s_extra[threadIdx.x] = 0.0;
     __syncthreads();
 
     if (action == ACT_HESS_ONLY) {
@@ -829,36 +1050,24 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
         if (i < n) eval_point_f64<METHOD>(__ldg(src + i), ctx, map, prm.d2, prm.d1, acc);
       }
       warp_flush(acc, s_warp[warp]);
+    } else if (action == ACT_EVAL_FULL) {
+      eval_chunked_f32<METHOD, true>(src, n, n_groups, ctx, map, d2f, d1f, s_pts, s_q, s_wcount, s_warp, s_extra, s_dbg);
     } else {
-      float acc[kNV];
-#pragma unroll
-      for (int k = 0; k < kNV; ++k) acc[k] = 0.0f;
-      int since = 0;
-      for (int g = warp_global; g < n_groups; g += warps_total) {
-        const int i = (g << 5) + lane;
-        if (i < n) {
-          const float4 pt = __ldg(src + i);
-          if (action == ACT_EVAL_FULL) eval_point_f32<METHOD, true>(pt, ctx, map, d2f, d1f, acc);
-          else eval_point_f32<METHOD, false>(pt, ctx, map, d2f, d1f, acc);
-        }
-        if (++since == kFlushPoints) {  // bound the fp32 run, fold into fp64
-          warp_flush(acc, s_warp[warp]);
-          since = 0;
-        }
-      }
-      warp_flush(acc, s_warp[warp]);
+      eval_chunked_f32<METHOD, false>(src, n, n_groups, ctx, map, d2f, d1f, s_pts, s_q, s_wcount, s_warp, s_extra, s_dbg);
     }
     __syncthreads();
     if (threadIdx.x < kNV) {
       double s = 0;
 #pragma unroll
       for (int w = 0; w < kAlignWarps; ++w) s += s_warp[w][threadIdx.x];
-      s_block[threadIdx.x] = s;
+      s_block[threadIdx.x] = s + s_extra[threadIdx.x];
     }
     __syncthreads();
     if (timing) t_local = globaltimer_ns();
-    grid_allreduce(s_block, s_tot, ws, epoch, &s_flag);
+    grid_allreduce(s_block, s_tot, ws, epoch, &s_flag, s_warp, prm.launch_tag);
     if (timing) t_reduced = globaltimer_ns();
+    unsigned long long t_last_arrive = 0;
+    if (timing && gridDim.x > 1) t_last_arrive = static_cast<unsigned long long>(__double_as_longlong(__ldcg(ws.totals + 2 * kNVP + ((epoch - 1u) & 1u))));
     int slot = 0;
     unsigned long long t_d0 = 0, t_d1 = 0, t_d2 = 0;
     if (threadIdx.x == 0) {
@@ -879,7 +1088,8 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     if (timing && slot < prm.trace_cap) {
       TraceRec& r = ws.trace[slot];
       r.t_start = t_start; r.t_local = t_local; r.t_reduced = t_reduced; r.t_advanced = globaltimer_ns();
-      r.t_dbg[0] = t_d0; r.t_dbg[1] = t_d1; r.t_dbg[2] = t_d2; r.t_dbg[3] = 0;
+      r.t_dbg[0] = t_d0; r.t_dbg[1] = t_d1; r.t_dbg[2] = t_d2; r.t_dbg[3] = t_last_arrive;
+      r.t_phase[0] = s_dbg[0]; r.t_phase[1] = s_dbg[1];
     }
     __syncthreads();
   }
@@ -887,7 +1097,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     AlignResultDev& r = *ws.result;
     for (int i = 0; i < 12; ++i) r.final_T[i] = st.final_T[i];
-    pose_to_matrix(st.last_dp, r.incr_T);  // transformation_ (ndt_omp_impl.hpp:146-149); Identity if no step was taken
+    for (int i = 0; i < 6; ++i) r.last_dp[i] = st.last_dp[i];  // transformation_ = T(last_dp) is formed on the host
     r.converged = st.converged;
     r.iterations = st.nr_iterations;
     r.n_evals = st.n_evals;
@@ -911,7 +1121,6 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     const unsigned int old = atomicInc(&ws.sync[2], gridDim.x - 1);
     if (old == gridDim.x - 1) {
       ws.sync[0] = 0u;
-      ws.sync[1] = 0u;
       __threadfence();
     }
   }

@@ -121,6 +121,37 @@ def pose_matrix(p):
     return T
 
 
+def config2_scan(scene, scan_seed, seed=SEED_C2, azimuth_steps=1875):
+    """One perturbed scan (source cloud) of the c2 scene and the transform that maps it onto the map."""
+    rng = np.random.default_rng(seed + 7919 * (scan_seed + 1))
+    sx = float(rng.uniform(-25.0, 25.0))
+    _, pw = scene.scan((sx, float(rng.uniform(-1.0, 1.0)), float(rng.uniform(-0.05, 0.05))), seed=seed + 5000 + scan_seed,
+                       azimuth_steps=azimuth_steps)
+    d2r = np.pi / 180.0
+    pert = [rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5),
+            rng.uniform(-0.5, 0.5) * d2r, rng.uniform(-0.5, 0.5) * d2r, rng.uniform(-2.0, 2.0) * d2r]
+    centre = np.array([sx, 0.0, 0.0])  # perturb about the scan's own position so the correction stays a small pose
+    T = pose_matrix(pert)
+    inv = np.linalg.inv(T)
+    local = pw.astype(np.float64) - centre
+    src = local @ inv[:3, :3].T + inv[:3, 3] + centre
+    truth = np.eye(4)
+    truth[:3, :3] = T[:3, :3]
+    truth[:3, 3] = T[:3, 3] + centre - T[:3, :3] @ centre
+    return src.astype(np.float32), truth
+
+
+def config2_map(map_points=1_000_000, n_map_scans=31, seed=SEED_C2, azimuth_steps=1875):
+    """The c2 target map: union of scans taken every 2 m along the street, voxel-thinned to ~map_points."""
+    scene = Scene(seed)
+    xs = np.linspace(-30.0, 30.0, n_map_scans)
+    world = []
+    for i, x in enumerate(xs):
+        _, pw = scene.scan((float(x), 0.0, 0.0), seed=seed + 1000 + i, azimuth_steps=azimuth_steps)
+        world.append(pw)
+    return scene, voxel_thin(np.concatenate(world), 0.1, map_points, seed + 1)
+
+
 def config2(map_points=1_000_000, n_map_scans=31, scan_seed=0, seed=SEED_C2, azimuth_steps=1875, offset=(0.0, 0.0, 0.0)):
     """BASELINE.json configs[1]: one 64-beam scan (~120 k points) against a ~1 M-point target map.
 
