@@ -1,0 +1,107 @@
+// apps/align_b200.cpp — the NDT part of ndt_omp/apps/align.cpp (:15-33, 83-105) on the B200 library, through the
+// header-only shim with the reference's method names.  Same measurement protocol: setInputTarget/Source once,
+// time one align ("single"), then ten more ("10times"), then print getFitnessScore().
+//
+//   align_b200 target.{pcd|bin} source.{pcd|bin} [--leaf 0.1]
+//
+// .pcd: PCD v0.7 "DATA binary" files with float32 x y z first (the format of ndt_omp/data/*.pcd);
+// .bin: raw float32 x,y,z triples.  The reference app first downsamples both clouds with a 0.1 m pcl::VoxelGrid
+// (:57-69); pass clouds that are already downsampled (tests/golden/pair_ds0p1.npz exported as .bin), or see
+// INTEGRATION.md for the PCL build where pcl::VoxelGrid is available.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <pclomp_b200/ndt_b200.hpp>
+
+typedef pcl::PointCloud<pcl::PointXYZ> Cloud;
+
+static bool load_cloud(const std::string& path, Cloud& cloud) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) return false;
+  std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  size_t off = 0, stride = 12, npts = 0;
+  if (path.size() > 4 && path.substr(path.size() - 4) == ".pcd") {
+    const std::string marker = "DATA binary\n";
+    std::string head(raw.begin(), raw.begin() + std::min<size_t>(raw.size(), 4096));
+    const size_t pos = head.find(marker);
+    if (pos == std::string::npos) return false;
+    off = pos + marker.size();
+    std::istringstream hs(head.substr(0, pos));
+    std::string line;
+    size_t nfields = 0;
+    while (std::getline(hs, line)) {
+      std::istringstream ls(line);
+      std::string key;
+      ls >> key;
+      if (key == "FIELDS") { std::string t; while (ls >> t) ++nfields; }
+      if (key == "POINTS") ls >> npts;
+    }
+    stride = 4 * nfields;
+  } else {
+    npts = raw.size() / 12;
+  }
+  if (off + npts * stride > raw.size()) return false;
+  cloud.points.resize(npts);
+  for (size_t i = 0; i < npts; ++i) {
+    float xyz[3];
+    std::memcpy(xyz, raw.data() + off + i * stride, 12);
+    cloud.points[i] = pcl::PointXYZ(xyz[0], xyz[1], xyz[2]);
+  }
+  cloud.width = static_cast<uint32_t>(npts);
+  cloud.height = 1;
+  cloud.is_dense = true;
+  return true;
+}
+
+// align point clouds and measure processing time (ndt_omp/apps/align.cpp:15-33)
+template <typename Registration>
+static void align(Registration& registration, const Cloud::Ptr& target_cloud, const Cloud::Ptr& source_cloud) {
+  registration.setInputTarget(target_cloud);
+  registration.setInputSource(source_cloud);
+  Cloud aligned;
+  auto t1 = std::chrono::steady_clock::now();
+  registration.align(aligned);
+  auto t2 = std::chrono::steady_clock::now();
+  std::cout << "single : " << std::chrono::duration<double, std::milli>(t2 - t1).count() << "[msec]" << std::endl;
+  for (int i = 0; i < 10; i++) registration.align(aligned);
+  auto t3 = std::chrono::steady_clock::now();
+  std::cout << "10times: " << std::chrono::duration<double, std::milli>(t3 - t2).count() << "[msec]" << std::endl;
+  std::cout.precision(6);
+  std::cout << "fitness: " << registration.getFitnessScore() << std::endl << std::endl;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) {
+    std::cout << "usage: align_b200 target.{pcd|bin} source.{pcd|bin}" << std::endl;
+    return 0;
+  }
+  Cloud::Ptr target_cloud(new Cloud()), source_cloud(new Cloud());
+  if (!load_cloud(argv[1], *target_cloud)) { std::cerr << "failed to load " << argv[1] << std::endl; return 1; }
+  if (!load_cloud(argv[2], *source_cloud)) { std::cerr << "failed to load " << argv[2] << std::endl; return 1; }
+  std::cout << "target " << target_cloud->size() << " pts, source " << source_cloud->size() << " pts" << std::endl;
+
+  pclomp_b200::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ> ndt;
+  if (!ndt.handle()) return 2;
+  ndt.setResolution(1.0);
+  const std::pair<const char*, pclomp_b200::NeighborSearchMethod> methods[] = {
+      {"DIRECT7", pclomp_b200::DIRECT7}, {"DIRECT1", pclomp_b200::DIRECT1}, {"DIRECT26", pclomp_b200::DIRECT26}};
+  for (const auto& m : methods) {
+    std::cout << "--- pclomp_b200::NDT (" << m.first << ") ---" << std::endl;
+    ndt.setNeighborhoodSearchMethod(m.second);
+    align(ndt, target_cloud, source_cloud);
+  }
+  // the mapping nodes copy the object (ndt_omp_mapping_node.cpp:151-169): a copy must give the same answer
+  auto copy = ndt;
+  copy.setNeighborhoodSearchMethod(pclomp_b200::DIRECT7);
+  Cloud out;
+  copy.align(out);
+  std::cout << "copy converged: " << copy.hasConverged() << ", iterations " << copy.getFinalNumIteration() << std::endl;
+  return 0;
+}

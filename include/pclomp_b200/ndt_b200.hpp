@@ -1,0 +1,172 @@
+// ndt_b200.hpp — header-only C++ shim: the public method set of pclomp::NormalDistributionsTransform
+// (ndt_omp/include/pclomp/ndt_omp.h:96-238, 499) forwarded to the C ABI of libndt_b200.so (include/ndt_b200.h).
+//
+// A caller of the reference switches by changing
+//     #include <pclomp/ndt_omp.h>                      ->  #include <pclomp_b200/ndt_b200.hpp>
+//     pclomp::NormalDistributionsTransform<P, P>        ->  pclomp_b200::NormalDistributionsTransform<P, P>
+// and linking -lndt_b200 instead of -lndt_omp.  Methods, argument meaning and observable behaviour
+// (setInputTarget builds the map immediately, setResolution rebuilds only if the value changed and a source is set,
+// align() may be repeated, final transform = pose of the last line-search trial, hasConverged() is also true at the
+// iteration cap, copies are independent objects) follow the reference; errors are reported like PCL does
+// (a message on stderr + empty map / converged == false), never by exception.
+#pragma once
+#include <cstdio>
+#include <limits>
+#include <memory>
+#include <utility>
+
+#include "../ndt_b200.h"
+#include "pcl_compat.hpp"
+
+namespace pclomp_b200 {
+
+enum NeighborSearchMethod { KDTREE = NDTB200_KDTREE, DIRECT26 = NDTB200_DIRECT26, DIRECT7 = NDTB200_DIRECT7, DIRECT1 = NDTB200_DIRECT1 };
+
+template <typename PointSource, typename PointTarget = PointSource>
+class NormalDistributionsTransform {
+ public:
+  typedef pcl::PointCloud<PointSource> PointCloudSource;
+  typedef typename PointCloudSource::Ptr PointCloudSourcePtr;
+  typedef typename PointCloudSource::ConstPtr PointCloudSourceConstPtr;
+  typedef pcl::PointCloud<PointTarget> PointCloudTarget;
+  typedef typename PointCloudTarget::ConstPtr PointCloudTargetConstPtr;
+  typedef std::shared_ptr<NormalDistributionsTransform<PointSource, PointTarget>> Ptr;
+  typedef std::shared_ptr<const NormalDistributionsTransform<PointSource, PointTarget>> ConstPtr;
+
+  explicit NormalDistributionsTransform(int device = 0) : search_method(DIRECT7), h_(nullptr), device_(device) {
+    const int st = ndtb200_create(&h_, device);
+    if (st != NDTB200_OK) {
+      std::fprintf(stderr, "[pclomp_b200::NormalDistributionsTransform] no usable CUDA device (status %d); "
+                           "this library has no CPU fallback\n", st);
+      h_ = nullptr;
+    }
+    ndtb200_default_params(&prm_);
+  }
+  ~NormalDistributionsTransform() { if (h_) ndtb200_destroy(h_); }
+
+  // copy construction / assignment: the mapping node returns the object by value (ndt_omp_mapping_node.cpp:151-169)
+  NormalDistributionsTransform(const NormalDistributionsTransform& o)
+      : search_method(o.search_method), h_(nullptr), device_(o.device_), prm_(o.prm_), target_(o.target_), input_(o.input_) {
+    if (o.h_) ndtb200_clone(o.h_, &h_);
+  }
+  NormalDistributionsTransform& operator=(const NormalDistributionsTransform& o) {
+    if (this != &o) {
+      if (h_) ndtb200_destroy(h_);
+      h_ = nullptr;
+      search_method = o.search_method; device_ = o.device_; prm_ = o.prm_; target_ = o.target_; input_ = o.input_;
+      if (o.h_) ndtb200_clone(o.h_, &h_);
+    }
+    return *this;
+  }
+  NormalDistributionsTransform(NormalDistributionsTransform&& o) noexcept
+      : search_method(o.search_method), h_(o.h_), device_(o.device_), prm_(o.prm_), target_(std::move(o.target_)), input_(std::move(o.input_)) {
+    o.h_ = nullptr;
+  }
+
+  // ---- setters / getters (ndt_omp.h:115-209 + pcl::Registration) ----
+  void setNumThreads(int) {}  // accepted, meaningless on the device path
+  void setResolution(float resolution) { prm_.resolution = resolution; push(); }
+  float getResolution() const { return prm_.resolution; }
+  double getStepSize() const { return prm_.step_size; }
+  void setStepSize(double step_size) { prm_.step_size = step_size; push(); }
+  double getOutlierRatio() const { return prm_.outlier_ratio; }
+  void setOutlierRatio(double outlier_ratio) { prm_.outlier_ratio = outlier_ratio; push(); }
+  void setNeighborhoodSearchMethod(NeighborSearchMethod method) { search_method = method; }
+  void setTransformationEpsilon(double epsilon) { prm_.trans_eps = epsilon; push(); }
+  double getTransformationEpsilon() const { return prm_.trans_eps; }
+  void setMaximumIterations(int nr_iterations) { prm_.max_iterations = nr_iterations; push(); }
+  int getMaximumIterations() const { return prm_.max_iterations; }
+
+  void setInputTarget(const PointCloudTargetConstPtr& cloud) {
+    target_ = cloud;
+    if (!h_) return;
+    const void* p = (cloud && !cloud->points.empty()) ? static_cast<const void*>(cloud->points.data()) : nullptr;
+    const size_t n = cloud ? cloud->points.size() : 0;
+    const int st = ndtb200_set_target(h_, p, n, sizeof(PointTarget), cloud ? (cloud->is_dense ? 1 : 0) : 1);
+    if (st == NDTB200_ERR_NO_INPUT)
+      std::fprintf(stderr, "[pclomp_b200::VoxelGridCovariance::applyFilter] No input dataset given!\n");
+    else if (st == NDTB200_ERR_GRID_OVERFLOW)
+      std::fprintf(stderr, "[pclomp_b200::VoxelGridCovariance::applyFilter] Leaf size is too small for the input dataset. "
+                           "Integer indices would overflow.\n");
+    else if (st != NDTB200_OK)
+      std::fprintf(stderr, "[pclomp_b200] setInputTarget failed: %s\n", ndtb200_last_error(h_));
+  }
+  void setInputSource(const PointCloudSourceConstPtr& cloud) {
+    input_ = cloud;
+    if (!h_) return;
+    const void* p = (cloud && !cloud->points.empty()) ? static_cast<const void*>(cloud->points.data()) : nullptr;
+    const int st = ndtb200_set_source(h_, p, cloud ? cloud->points.size() : 0, sizeof(PointSource));
+    if (st != NDTB200_OK) std::fprintf(stderr, "[pclomp_b200] setInputSource failed: %s\n", ndtb200_last_error(h_));
+  }
+  PointCloudTargetConstPtr getInputTarget() const { return target_; }
+  PointCloudSourceConstPtr getInputSource() const { return input_; }
+
+  // ---- registration (pcl::Registration::align -> computeTransformation, ndt_omp_impl.hpp:80-171) ----
+  void align(PointCloudSource& output) { align(output, Eigen::Matrix4f::Identity()); }
+  void align(PointCloudSource& output, const Eigen::Matrix4f& guess) {
+    if (!h_ || !input_) return;
+    prm_.search_method = static_cast<int32_t>(search_method);  // public field, read at align time like the reference
+    ndtb200_set_params(h_, &prm_);
+    output.points.resize(input_->points.size());
+    output.width = static_cast<uint32_t>(output.points.size());
+    output.height = 1;
+    output.is_dense = input_->is_dense;
+    for (size_t i = 0; i < output.points.size(); ++i) output.points[i] = input_->points[i];  // copies the non-xyz fields
+    const int st = ndtb200_align(h_, guess.data(), output.points.empty() ? nullptr : output.points.data(), sizeof(PointSource));
+    if (st != NDTB200_OK) std::fprintf(stderr, "[pclomp_b200] align failed: %s\n", ndtb200_last_error(h_));
+  }
+
+  Eigen::Matrix4f getFinalTransformation() { return matrix_of(true); }
+  Eigen::Matrix4f getLastIncrementalTransformation() { return matrix_of(false); }
+  bool hasConverged() { ndtb200_result r; return h_ && ndtb200_get_result(h_, &r) == NDTB200_OK && r.converged != 0; }
+  int getFinalNumIteration() { ndtb200_result r; return (h_ && ndtb200_get_result(h_, &r) == NDTB200_OK) ? r.iterations : 0; }
+  double getTransformationProbability() {
+    ndtb200_result r;
+    return (h_ && ndtb200_get_result(h_, &r) == NDTB200_OK) ? r.trans_probability : 0.0;
+  }
+  double getFitnessScore(double max_range = std::numeric_limits<double>::max()) {
+    double v = std::numeric_limits<double>::max();
+    if (h_) ndtb200_fitness_score(h_, max_range, &v);
+    return v;
+  }
+  // negative log likelihood of an already transformed cloud (ndt_omp_impl.hpp:935-983)
+  double calculateScore(const PointCloudSource& cloud) {
+    double v = 0.0;
+    if (h_ && !cloud.points.empty()) {
+      prm_.search_method = static_cast<int32_t>(search_method);
+      ndtb200_set_params(h_, &prm_);
+      ndtb200_calculate_score(h_, cloud.points.data(), cloud.points.size(), sizeof(PointSource), &v);
+    }
+    return v;
+  }
+
+  ndtb200_handle* handle() { return h_; }
+
+  NeighborSearchMethod search_method;  // public in the reference too (ndt_omp.h:499)
+
+ private:
+  void push() {
+    if (!h_) return;
+    prm_.search_method = static_cast<int32_t>(search_method);
+    const int st = ndtb200_set_params(h_, &prm_);
+    if (st == NDTB200_ERR_CUDA) std::fprintf(stderr, "[pclomp_b200] set_params failed: %s\n", ndtb200_last_error(h_));
+  }
+  Eigen::Matrix4f matrix_of(bool final_not_increment) {
+    Eigen::Matrix4f M = Eigen::Matrix4f::Identity();
+    ndtb200_result r;
+    if (h_ && ndtb200_get_result(h_, &r) == NDTB200_OK) {
+      const float* src = final_not_increment ? r.final_transformation : r.last_increment;
+      for (int c = 0; c < 4; ++c)
+        for (int rr = 0; rr < 4; ++rr) M(rr, c) = src[c * 4 + rr];
+    }
+    return M;
+  }
+
+  ndtb200_handle* h_;
+  int device_;
+  ndtb200_params prm_;
+  PointCloudTargetConstPtr target_;
+  PointCloudSourceConstPtr input_;
+};
+
+}  // namespace pclomp_b200

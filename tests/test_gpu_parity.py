@@ -295,3 +295,24 @@ def test_point_strides(nb):
     b.align_raw(None, out.ctypes.data, 32)
     assert np.array_equal(a.result()["final"], b.result()["final"])
     assert np.all(out[:, 3] == 1.0) and np.all(out[:, 4:] == 0.0)
+
+
+def test_cpp_shim_app_reproduces_golden_fitness(nb, tmp_path):
+    """apps/align_b200 (the reference's apps/align.cpp NDT section over the header-only C++ shim) prints the
+    reference's published fitness values (ndt_omp/README.md:26,31)."""
+    import os
+    import re
+    import subprocess
+    from toyslam_b200 import _build
+    app = _build.build_apps()
+    tgt, src = load_pair()
+    tp, sp = str(tmp_path / "t.bin"), str(tmp_path / "s.bin")
+    np.ascontiguousarray(tgt, dtype=np.float32).tofile(tp)
+    np.ascontiguousarray(src, dtype=np.float32).tofile(sp)
+    out = subprocess.run([os.path.abspath(app), tp, sp], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    fit = re.findall(r"fitness: ([0-9.]+)", out.stdout)
+    assert len(fit) == 3, out.stdout
+    assert abs(float(fit[0]) - golden()["fitness"]["DIRECT7"]) < 1e-6
+    assert abs(float(fit[1]) - golden()["fitness"]["DIRECT1"]) < 1e-6
+    assert "copy converged: 1, iterations 5" in out.stdout

@@ -142,3 +142,13 @@ def test_product_does_not_import_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                     text = open(os.path.join(dirpath, f)).read()
                     assert "import oracle" not in text and "ndt_oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_cpp_shim_compiles_and_links():
+    """The header-only shim with the reference's method names builds against the C ABI (no GPU needed to link)."""
+    from toyslam_b200 import _build
+    app = _build.build_apps()
+    assert os.path.exists(app)
+    import subprocess
+    out = subprocess.run([os.path.abspath(app)], capture_output=True, text=True, timeout=60)
+    assert "usage: align_b200" in out.stdout

@@ -45,5 +45,22 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+APP_SRC = os.path.join(_HERE, "..", "apps", "align_b200.cpp")
+APP_BIN = os.path.join(_HERE, "..", "apps", "align_b200")
+
+
+def build_apps(force=False):
+    """The C++ demo over the header-only shim (apps/align_b200.cpp): proves the reference-named API compiles and links."""
+    hdrs = [os.path.join(_HERE, "..", "include", "pclomp_b200", h) for h in ("ndt_b200.hpp", "pcl_compat.hpp")]
+    deps = [APP_SRC, LIB_PATH] + hdrs
+    if not force and os.path.exists(APP_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(APP_BIN) for d in deps):
+        return APP_BIN
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-I", os.path.join(_HERE, "..", "include"), APP_SRC, "-o", APP_BIN,
+           "-L", LIB_DIR, "-lndt_b200", "-Wl,-rpath,$ORIGIN/../toyslam_b200/lib"]
+    subprocess.check_call(cmd)
+    return APP_BIN
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

@@ -178,7 +178,7 @@ int build_map(ndtb200_handle* h) {
   minmax3d_kernel<<<mm_blocks, kBuildThreads, 0, h->stream>>>(pts, n, dense, h->d_mm_partial.as<float>(),
                                                                h->d_mm_finite.as<unsigned int>());
   LAUNCHED(h);
-  grid_setup_kernel<<<1, 32, 0, h->stream>>>(h->d_mm_partial.as<float>(), h->d_mm_finite.as<unsigned int>(),
+  grid_setup_kernel<<<1, kBuildThreads, 0, h->stream>>>(h->d_mm_partial.as<float>(), h->d_mm_finite.as<unsigned int>(),
                                               mm_blocks, h->prm.resolution, h->d_grid.as<GridDesc>());
   LAUNCHED(h);
   CK(cudaMemcpyAsync(&h->grid, h->d_grid.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, h->stream));
@@ -683,6 +683,12 @@ int ndtb200_align(ndtb200_handle* h, const float* guess, void* out_points, size_
 
 int ndtb200_get_result(ndtb200_handle* h, ndtb200_result* out) {
   if (!h || !out) return NDTB200_ERR_INVALID;
+  if (!h->result_valid && h->d_result.p == nullptr) {  // nothing aligned yet: pcl::Registration's initial state
+    std::memset(out, 0, sizeof(*out));
+    out->final_transformation[0] = out->final_transformation[5] = out->final_transformation[10] = out->final_transformation[15] = 1.0f;
+    out->last_increment[0] = out->last_increment[5] = out->last_increment[10] = out->last_increment[15] = 1.0f;
+    return NDTB200_OK;
+  }
   if (!h->result_valid) {
     int st = ndtb200_sync(h);
     if (st != NDTB200_OK) return st;

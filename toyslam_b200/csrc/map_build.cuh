@@ -64,15 +64,37 @@ minmax3d_kernel(const float4* __restrict__ pts, size_t n, int is_dense, float* _
   }
 }
 
-__global__ void grid_setup_kernel(const float* __restrict__ partial, const unsigned int* __restrict__ finite_partial,
-                                  int nblocks, float leaf, GridDesc* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(kBuildThreads)
+grid_setup_kernel(const float* __restrict__ partial, const unsigned int* __restrict__ finite_partial,
+                  int nblocks, float leaf, GridDesc* __restrict__ out) {
+  // one CTA: strided reduction of the per-CTA partials, then thread 0 derives the grid description
+  __shared__ float s_mn[3][kBuildThreads / 32], s_mx[3][kBuildThreads / 32];
+  __shared__ unsigned long long s_nf[kBuildThreads / 32];
   float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
   float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-  long long nf = 0;
-  for (int b = 0; b < nblocks; ++b) {
+  unsigned long long nf = 0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
     for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], partial[b * 6 + a]); mx[a] = fmaxf(mx[a], partial[b * 6 + 3 + a]); }
     nf += finite_partial[b];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    for (int a = 0; a < 3; ++a) { s_mn[a][threadIdx.x >> 5] = mn[a]; s_mx[a][threadIdx.x >> 5] = mx[a]; }
+    s_nf[threadIdx.x >> 5] = nf;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int w = 1; w < kBuildThreads / 32; ++w) {
+    for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], s_mn[a][w]); mx[a] = fmaxf(mx[a], s_mx[a][w]); }
+    nf += s_nf[w];
   }
   GridDesc g;
   const float inv = __fdiv_rn(1.0f, leaf);  // pcl::VoxelGrid::setLeafSize: inverse_leaf_size_ = 1.0f / leaf

@@ -355,6 +355,28 @@ __device__ __forceinline__ void eval_point_f64(const float4 pt, const EvalCtx& c
 // ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------
+template <typename A>
+__device__ __forceinline__ void warp_flush(A* acc, double* s_warp_row);
+
+// The whole fp64 Hessian-only pass of one warp.  Rare (only after a multi-trial line search) and register hungry
+// (46 fp64 coefficients + 22 fp64 accumulators): kept out of line so its register pressure and spills never touch the
+// fp32 hot path.
+template <int METHOD>
+__device__ __noinline__ void eval_hessian_f64(const float4* __restrict__ src, int n, int n_groups, const EvalCtx* ctx,
+                                              const MapView* map, double d2, double d1, double* s_warp_row) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * kAlignWarps + (threadIdx.x >> 5);
+  const int warps_total = gridDim.x * kAlignWarps;
+  double acc[kNV];
+#pragma unroll
+  for (int k = 0; k < kNV; ++k) acc[k] = 0.0;
+  for (int g = warp_global; g < n_groups; g += warps_total) {
+    const int i = (g << 5) + lane;
+    if (i < n) eval_point_f64<METHOD>(__ldg(src + i), *ctx, *map, d2, d1, acc);
+  }
+  warp_flush(acc, s_warp_row);
+}
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -369,7 +391,7 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 
 // Fold the per-thread accumulators of a warp into the warp's fp64 sums (fixed shuffle tree) and clear them.
 template <typename A>
-__device__ __noinline__ void warp_flush(A* acc, double* s_warp_row) {
+__device__ __forceinline__ void warp_flush(A* acc, double* s_warp_row) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < kNV; ++k) {
@@ -807,6 +829,32 @@ __host__ __device__ constexpr size_t eval_smem_bytes() {
   return (size_t)groups_per_warp<METHOD>() * kAlignThreads * kPtVec * 16 + (size_t)kAlignWarps * queue_cap_per_warp<METHOD>() * 8;
 }
 
+// Fold the per-thread fp32 partials into the fp64 CTA sums through shared memory (the staging buffers are free when
+// this is called): thread (k, sub) adds 32 of the 256 partials of value k — groups of 4 in fp32 (short runs), then
+// fp64 — and 8 lanes combine in a fixed tree.  ~8x fewer instructions than a 29-value warp shuffle tree per warp.
+// Clears acc.  Must be called by all threads of the CTA.
+__device__ __forceinline__ void fold_partials(float (&acc)[kNV], float* s_red, double* s_extra) {
+#pragma unroll
+  for (int k = 0; k < kNV; ++k) { s_red[k * kRedStride + threadIdx.x] = acc[k]; acc[k] = 0.0f; }
+  __syncthreads();
+  const int k = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  double s = 0.0;
+  if (k < kNV) {
+    const float* row = s_red + k * kRedStride + sub;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      s0 += static_cast<double>((row[8 * i] + row[8 * (i + 1)]) + (row[8 * (i + 2)] + row[8 * (i + 3)]));
+      s1 += static_cast<double>((row[8 * (i + 4)] + row[8 * (i + 5)]) + (row[8 * (i + 6)] + row[8 * (i + 7)]));
+    }
+    s = s0 + s1;
+  }
+  s += __shfl_down_sync(0xffffffffu, s, 4, 8);
+  s += __shfl_down_sync(0xffffffffu, s, 2, 8);
+  s += __shfl_down_sync(0xffffffffu, s, 1, 8);
+  if (k < kNV && sub == 0) s_extra[k] += s;
+}
+
 struct HitOperands {  // what phase B needs for one hit before the arithmetic starts
   uint2 e;
   float4 a, b, c;  // the 48 hot bytes of the voxel record
@@ -932,37 +980,13 @@ __device__ __forceinline__ void eval_chunked_f32(const float4* __restrict__ src,
     }
     __syncthreads();  // the next chunk overwrites the staging buffers
     if (threadIdx.x == 0 && j0 == 0) s_dbg[1] = globaltimer_ns();
-    if (++chunks_since == kFlushChunks) {  // only reached by large clouds
-      warp_flush(acc, s_warp[warp]);
+    if (++chunks_since == kFlushChunks) {  // only reached by large clouds: bound the fp32 run length
+      fold_partials(acc, reinterpret_cast<float*>(s_pts), s_extra);
+      __syncthreads();
       chunks_since = 0;
     }
   }
-  // final fold of the per-thread fp32 partials into fp64 CTA sums through shared memory (the staging buffers
-  // are free again): thread (k, sub) adds 32 of the 256 partials of value k in fp64, 8 lanes combine in a fixed tree.
-  // ~8x fewer instructions than a 29-value warp shuffle tree per warp.
-  float* s_red = reinterpret_cast<float*>(s_pts);
-#pragma unroll
-  for (int k = 0; k < kNV; ++k) s_red[k * kRedStride + threadIdx.x] = acc[k];
-  __syncthreads();
-  {
-    const int k = threadIdx.x >> 3, sub = threadIdx.x & 7;
-    double s = 0.0;
-    if (k < kNV) {
-      // partials of 4 threads are first added in fp32 (their fp32 runs are short), then everything is fp64
-      const float* row = s_red + k * kRedStride + sub;
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        s0 += static_cast<double>((row[8 * i] + row[8 * (i + 1)]) + (row[8 * (i + 2)] + row[8 * (i + 3)]));
-        s1 += static_cast<double>((row[8 * (i + 4)] + row[8 * (i + 5)]) + (row[8 * (i + 6)] + row[8 * (i + 7)]));
-      }
-      s = s0 + s1;
-    }
-    s += __shfl_down_sync(0xffffffffu, s, 4, 8);
-    s += __shfl_down_sync(0xffffffffu, s, 2, 8);
-    s += __shfl_down_sync(0xffffffffu, s, 1, 8);
-    if (k < kNV && sub == 0) s_extra[k] = s;
-  }
+  fold_partials(acc, reinterpret_cast<float*>(s_pts), s_extra);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1042,14 +1066,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     __syncthreads();
 
     if (action == ACT_HESS_ONLY) {
-      double acc[kNV];
-#pragma unroll
-      for (int k = 0; k < kNV; ++k) acc[k] = 0.0;
-      for (int g = warp_global; g < n_groups; g += warps_total) {
-        const int i = (g << 5) + lane;
-        if (i < n) eval_point_f64<METHOD>(__ldg(src + i), ctx, map, prm.d2, prm.d1, acc);
-      }
-      warp_flush(acc, s_warp[warp]);
+      eval_hessian_f64<METHOD>(src, n, n_groups, &ctx, &map, prm.d2, prm.d1, s_warp[warp]);
     } else if (action == ACT_EVAL_FULL) {
       eval_chunked_f32<METHOD, true>(src, n, n_groups, ctx, map, d2f, d1f, s_pts, s_q, s_wcount, s_warp, s_extra, s_dbg);
     } else {
