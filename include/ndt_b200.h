@@ -119,6 +119,16 @@ int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out);
 /* calculateScore(cloud) (ndt_omp_impl.hpp:935-983). */
 int ndtb200_calculate_score(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, double* out);
 
+/* ---- multi-GPU source sharding (one process + one handle per GPU of an NVSwitch node; not in the reference) ----
+ * Every rank holds the full target map and a contiguous slice of the source; each derivative evaluation exchanges the
+ * 29 partial sums by direct stores into every peer's mailbox over NVLink inside the persistent kernel, summed in rank
+ * order, so all ranks take the identical Newton step.  Like a collective: every rank must issue the same sequence of
+ * align / eval calls.  Usage: export -> exchange the 64-byte handles out of band (e.g. torch.distributed) -> attach. */
+#define NDTB200_COMM_HANDLE_BYTES 64
+int ndtb200_comm_export(ndtb200_handle* h, void* handle_out64);
+int ndtb200_comm_attach(ndtb200_handle* h, int rank, int world, const void* all_handles, int64_t n_source_total);
+int ndtb200_comm_detach(ndtb200_handle* h);
+
 /* ---- parity / inspection (stage dumps; used by tests, not by callers) ------------------------ */
 int ndtb200_get_map_info(const ndtb200_handle* h, ndtb200_map_info* out);
 /* voxel key of every target point, input order (-1 = skipped non-finite point). */

@@ -1,0 +1,39 @@
+"""Source-sharded multi-GPU align on >= 2 GPUs: one process per GPU via torchrun; the 29 per-evaluation
+sums are exchanged inside the persistent kernel through P2P mailboxes.  Skipped on single-GPU boxes."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_align_matches_oracle(world):
+    if _gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + world), os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    line = [l for l in out.stdout.splitlines() if l.startswith("MGPU_RESULT ")][0]
+    res = json.loads(line[len("MGPU_RESULT "):])
+    assert res["world"] == world
+    for c in res["cases"]:
+        assert c["identical_across_ranks"], c
+        assert c["hits_equal"], c
+        assert c["score_rel"] < 1e-5 and c["grad_rel"] < 1e-5 and c["hess_rel"] < 1e-5, c
+        assert c["iterations"][0] == c["iterations"][1] and c["evaluations"][0] == c["evaluations"][1], c
+        assert c["hessian_passes"][0] == c["hessian_passes"][1], c
+        assert c["dt"] < 1e-4 and c["dr"] < 1e-4 and c["tp_rel"] < 1e-5, c

@@ -51,6 +51,13 @@ struct ndtb200_handle {
   uint32_t launch_seq = 0;
   int last_blocks = 0;
 
+  // multi-GPU source sharding
+  int comm_world = 1, comm_rank = 0;
+  long long comm_n_total = 0;
+  DevBuf d_mail;                               // own mailbox: [2][kMaxRanks][kNVP][2] uint64
+  unsigned long long* mail_ptrs[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool mail_opened[kMaxRanks] = {false, false, false, false, false, false, false, false};
+
   // target cloud + map
   DevBuf d_target;
   size_t n_target = 0;
@@ -401,7 +408,7 @@ int query_coop_blocks(ndtb200_handle* h) {
 
 // Enqueue one launch of the persistent kernel (no host synchronisation).
 int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0[12], int has_guess, int eval_hessian) {
-  if (!h->has_source || h->n_source == 0) { h->err = "no input source"; return NDTB200_ERR_NO_INPUT; }
+  if (!h->has_source || (h->n_source == 0 && h->comm_world == 1)) { h->err = "no input source"; return NDTB200_ERR_NO_INPUT; }
   const int method = h->prm.search_method;
   if (method < NDTB200_DIRECT26 || method > NDTB200_DIRECT1) {
     h->err = "search method not implemented (KDTREE)";
@@ -419,7 +426,7 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   for (int i = 0; i < 12; ++i) prm.T0[i] = T0[i];
   prm.n_source = static_cast<int>(h->n_source);
   prm.trace_cap = ndtb200_handle::kTraceCap;
-  prm.launch_tag = (++h->launch_seq) << 10;
+  prm.launch_tag = (++h->launch_seq) << 12;  // 4096 evaluations per launch before tags could repeat
   compute_angle_tables(p0, prm.tab0);
 
   const int max_blocks = h->coop_blocks[method];
@@ -442,6 +449,10 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   ws.sync = h->d_sync.as<unsigned int>();
   ws.result = h->d_result.as<AlignResultDev>();
   ws.trace = h->d_trace.as<TraceRec>();
+  ws.world = h->comm_world;
+  ws.rank = h->comm_rank;
+  ws.n_source_total = h->comm_world > 1 ? h->comm_n_total : static_cast<long long>(h->n_source);
+  for (int r = 0; r < kMaxRanks; ++r) ws.mail[r] = h->mail_ptrs[r];
   MapView map = make_view(h);
   const float4* src = h->d_source.as<float4>();
   void* args[] = {(void*)&src, (void*)&map, (void*)&prm, (void*)&ws};
@@ -547,10 +558,11 @@ int ndtb200_destroy(ndtb200_handle* h) {
   if (!h) return NDTB200_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  ndtb200_comm_detach(h);
   DevBuf* bufs[] = {&h->d_target, &h->d_grid, &h->d_mm_partial, &h->d_mm_finite, &h->d_keys_a, &h->d_keys_b,
                     &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_voxel_key,
                     &h->d_voxel_start, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_source,
-                    &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp};
+                    &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail};
   for (DevBuf* b : bufs) b->release();
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -659,6 +671,7 @@ int ndtb200_sync(ndtb200_handle* h) {
   int st = fetch_result(h);
   if (st != NDTB200_OK) return st;
   std::memcpy(h->last_final_T, h->h_result->final_T, sizeof(h->last_final_T));
+  if (h->h_result->aborted) { h->err = "sharded solve aborted: a peer rank did not answer within 10 s"; return NDTB200_ERR_CUDA; }
   return NDTB200_OK;
 }
 
@@ -961,6 +974,63 @@ int ndtb200_get_trace(ndtb200_handle* h, int32_t* kinds, double* x6, double* a_t
     if (a_t) a_t[i] = tr[i].a_t;
     if (score) score[i] = tr[i].score;
   }
+  return NDTB200_OK;
+}
+
+// ---- multi-GPU source sharding -----------------------------------------------------------------------------
+static constexpr size_t kMailBytes = (size_t)2 * kMaxRanks * kNVP * 2 * sizeof(unsigned long long);
+
+int ndtb200_comm_export(ndtb200_handle* h, void* handle_out64) {
+  if (!h || !handle_out64) return NDTB200_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == NDTB200_COMM_HANDLE_BYTES, "IPC handle size");
+  cudaSetDevice(h->device);
+  if (h->d_mail.p == nullptr) {
+    CK(cudaMalloc(&h->d_mail.p, kMailBytes));   // a dedicated allocation: IPC handles cover whole allocations
+    h->d_mail.cap = kMailBytes;
+    CK(cudaMemset(h->d_mail.p, 0, kMailBytes));
+  }
+  cudaIpcMemHandle_t ipc;
+  CK(cudaIpcGetMemHandle(&ipc, h->d_mail.p));
+  std::memcpy(handle_out64, &ipc, sizeof(ipc));
+  return NDTB200_OK;
+}
+
+int ndtb200_comm_detach(ndtb200_handle* h) {
+  if (!h) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (h->mail_opened[r] && h->mail_ptrs[r]) cudaIpcCloseMemHandle(h->mail_ptrs[r]);
+    h->mail_opened[r] = false;
+    h->mail_ptrs[r] = nullptr;
+  }
+  h->comm_world = 1;
+  h->comm_rank = 0;
+  h->comm_n_total = 0;
+  return NDTB200_OK;
+}
+
+int ndtb200_comm_attach(ndtb200_handle* h, int rank, int world, const void* all_handles, int64_t n_source_total) {
+  if (!h || !all_handles || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return NDTB200_ERR_INVALID;
+  if (h->d_mail.p == nullptr) { h->err = "call ndtb200_comm_export first"; return NDTB200_ERR_INVALID; }
+  ndtb200_comm_detach(h);
+  cudaSetDevice(h->device);
+  CK(cudaMemset(h->d_mail.p, 0, kMailBytes));
+  const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      h->mail_ptrs[r] = h->d_mail.as<unsigned long long>();
+    } else {
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess));
+      h->mail_ptrs[r] = static_cast<unsigned long long*>(p);
+      h->mail_opened[r] = true;
+    }
+  }
+  h->comm_world = world;
+  h->comm_rank = rank;
+  h->comm_n_total = n_source_total;
+  h->launch_seq = 0;  // tags are compared across ranks: all ranks restart the launch sequence together
   return NDTB200_OK;
 }
 

@@ -57,7 +57,7 @@ struct AlignResultDev {
   double final_score;
   double totals[43];  // score, g[6], H[36] of the last evaluation
   long long n_hits;
-  int32_t n_trace, pad;
+  int32_t n_trace, aborted;
   unsigned long long t_kernel_begin, t_kernel_end;  // globaltimer ns, CTA 0
 };
 
@@ -76,12 +76,19 @@ struct AlignParams {
   AngleTables tab0;     // angle tables of p0 (host-computed: the kernel prologue has no trigonometry)
 };
 
+constexpr int kMaxRanks = 8;  // GPUs of one NVSwitch node
+
 struct AlignWorkspace {
   double* partials;      // [gridDim][kNVP]
   double* totals;        // [2][kNVP]
-  unsigned int* sync;    // [0] arrive counter, [1] epoch flag   (zeroed before each launch)
+  unsigned int* sync;    // [0] arrive counter, [2] wrapping exit counter, [3] abort flag (zeroed once, self-resetting)
   AlignResultDev* result;
   TraceRec* trace;
+  // source-sharded multi-GPU solve: every rank holds a slice of the source and the full map; the
+  // 29 per-evaluation sums are exchanged by direct stores into every peer's mailbox over NVLink.
+  int32_t world, rank;
+  unsigned long long* mail[kMaxRanks];  // mail[r]: rank r's mailbox [2 parities][kMaxRanks][kNVP][2 words] (own or IPC-mapped peer memory)
+  long long n_source_total;              // points of the whole (unsharded) source cloud
 };
 
 struct EvalCtx {
@@ -425,59 +432,119 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
 
 constexpr int kRedRows = 20;  // partial rows per thread in flight while the last CTA reduces
 
+__device__ __forceinline__ unsigned long long pack_lo(unsigned int tag, unsigned long long bits) {
+  return (static_cast<unsigned long long>(tag) << 32) | (bits & 0xffffffffull);
+}
+__device__ __forceinline__ unsigned long long pack_hi(unsigned int tag, unsigned long long bits) {
+  return (static_cast<unsigned long long>(tag) << 32) | (bits >> 32);
+}
+
+// Poll one tagged (lo, hi) word pair until both carry `tag`.  With peers involved the spin is bounded (10 s): a rank
+// that never launches must not hang the GPU; on timeout the abort flag is raised and the solve ends with an error.
+__device__ __forceinline__ double poll_tagged(const unsigned long long* slot, unsigned int tag, bool bounded,
+                                              unsigned int* abort_flag) {
+  unsigned long long w0, w1;
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
+  while (true) {
+    w0 = ld_volatile_u64(slot);
+    w1 = ld_volatile_u64(slot + 1);
+    if (static_cast<unsigned int>(w0 >> 32) == tag && static_cast<unsigned int>(w1 >> 32) == tag) break;
+    if (bounded && ((++spins) & 0x3ffu) == 0u) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 10000000000ull || *reinterpret_cast<volatile unsigned int*>(abort_flag) != 0u) {
+        atomicExch(abort_flag, 1u);
+        return 0.0;
+      }
+    }
+  }
+  return __longlong_as_double(static_cast<long long>(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
+}
+
 __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_tot, const AlignWorkspace& ws,
                                                unsigned int& epoch, int* s_flag, double (*s_red8)[kNVP],
                                                unsigned int launch_tag) {
   const unsigned int G = gridDim.x;
-  if (G == 1) {
+  const int W = ws.world;
+  if (G == 1 && W == 1) {
     if (threadIdx.x < kNV) s_tot[threadIdx.x] = s_block[threadIdx.x];
     __syncthreads();
+    ++epoch;
     return;
   }
   const unsigned int tag = launch_tag + epoch + 1u;
-  if (threadIdx.x < kNV) ws.partials[(size_t)blockIdx.x * kNVP + threadIdx.x] = s_block[threadIdx.x];
-  if (threadIdx.x == 31) ws.partials[(size_t)blockIdx.x * kNVP + 31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: arrival time of this CTA
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int ticket = atom_add_acq_rel_gpu(&ws.sync[0], 1u);  // release: the CTA's partials; acquire: everyone's
-    *s_flag = (ticket == (epoch + 1u) * G - 1u) ? 1 : 0;
-  }
-  __syncthreads();
-  unsigned long long* slots = reinterpret_cast<unsigned long long*>(ws.totals);
-  if (*s_flag) {  // last CTA to arrive: every partial is visible
-    if (threadIdx.x == 0) ws.totals[2 * kNVP + (epoch & 1u)] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling stamp
-    const int k = threadIdx.x & 31, slice = threadIdx.x >> 5;  // lane = value, warp = slice of the CTA rows
-    double s = 0.0;
-    for (unsigned int b0 = 0; b0 < G; b0 += kAlignWarps * kRedRows) {
-      double v[kRedRows];
-#pragma unroll
-      for (int i = 0; i < kRedRows; ++i) {
-        const unsigned int b = b0 + slice + kAlignWarps * i;
-        v[i] = (b < G && k < kNV) ? __ldcg(ws.partials + (size_t)b * kNVP + k) : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < kRedRows; ++i) s += v[i];
-    }
-    s_red8[slice][k] = s;
+  const int par = epoch & 1u;
+  bool last = true;
+  if (G > 1) {
+    if (threadIdx.x < kNV) ws.partials[(size_t)blockIdx.x * kNVP + threadIdx.x] = s_block[threadIdx.x];
+    if (threadIdx.x == 31) ws.partials[(size_t)blockIdx.x * kNVP + 31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: arrival time of this CTA
     __syncthreads();
-    if (threadIdx.x < kNV) {
-      double t = 0.0;
+    if (threadIdx.x == 0) {
+      const unsigned int ticket = atom_add_acq_rel_gpu(&ws.sync[0], 1u);  // release: the CTA's partials; acquire: everyone's
+      *s_flag = (ticket == (epoch + 1u) * G - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    last = (*s_flag != 0);
+  }
+  unsigned long long* slots = reinterpret_cast<unsigned long long*>(ws.totals);
+  if (last) {  // last CTA of this GPU to arrive: every partial is visible
+    double t = 0.0;
+    if (G > 1) {
+      if (threadIdx.x == 0) ws.totals[2 * kNVP + (epoch & 1u)] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling stamp
+      const int k = threadIdx.x & 31, slice = threadIdx.x >> 5;  // lane = value, warp = slice of the CTA rows
+      double s = 0.0;
+      for (unsigned int b0 = 0; b0 < G; b0 += kAlignWarps * kRedRows) {
+        double v[kRedRows];
 #pragma unroll
-      for (int w = 0; w < kAlignWarps; ++w) t += s_red8[w][threadIdx.x];
+        for (int i = 0; i < kRedRows; ++i) {
+          const unsigned int b = b0 + slice + kAlignWarps * i;
+          v[i] = (b < G && k < kNV) ? __ldcg(ws.partials + (size_t)b * kNVP + k) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < kRedRows; ++i) s += v[i];
+      }
+      s_red8[slice][k] = s;
+      __syncthreads();
+      if (threadIdx.x < kNV) {
+#pragma unroll
+        for (int w = 0; w < kAlignWarps; ++w) t += s_red8[w][threadIdx.x];
+      }
+      __syncthreads();
+    } else if (threadIdx.x < kNV) {
+      t = s_block[threadIdx.x];
+    }
+    if (threadIdx.x < kNV) {
       const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(t));
-      st_volatile_u64(slots + 2 * threadIdx.x, (static_cast<unsigned long long>(tag) << 32) | (bits & 0xffffffffull));
-      st_volatile_u64(slots + 2 * threadIdx.x + 1, (static_cast<unsigned long long>(tag) << 32) | (bits >> 32));
+      if (W == 1) {
+        st_volatile_u64(slots + 2 * threadIdx.x, pack_lo(tag, bits));
+        st_volatile_u64(slots + 2 * threadIdx.x + 1, pack_hi(tag, bits));
+      } else {
+        // this GPU's sums go straight into every rank's mailbox (P2P stores over NVLink; each 64-bit word is
+        // self-validating, so no ordering between them is needed)
+        const size_t off = (((size_t)par * kMaxRanks + ws.rank) * kNVP + threadIdx.x) * 2;
+        for (int r = 0; r < W; ++r) {
+          st_volatile_u64(ws.mail[r] + off, pack_lo(tag, bits));
+          st_volatile_u64(ws.mail[r] + off + 1, pack_hi(tag, bits));
+        }
+      }
     }
   }
-  if (threadIdx.x < kNV) {
-    unsigned long long w0, w1;
-    do {
-      w0 = ld_volatile_u64(slots + 2 * threadIdx.x);
-      w1 = ld_volatile_u64(slots + 2 * threadIdx.x + 1);
-    } while (static_cast<unsigned int>(w0 >> 32) != tag || static_cast<unsigned int>(w1 >> 32) != tag);
-    s_tot[threadIdx.x] = __longlong_as_double(static_cast<long long>(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
+  if (W == 1) {
+    if (threadIdx.x < kNV) s_tot[threadIdx.x] = poll_tagged(slots + 2 * threadIdx.x, tag, false, &ws.sync[3]);
+    __syncthreads();
+  } else {
+    const int r = threadIdx.x >> 5, k = threadIdx.x & 31;
+    if (r < W && k < kNV)
+      s_red8[r][k] = poll_tagged(ws.mail[ws.rank] + (((size_t)par * kMaxRanks + r) * kNVP + k) * 2, tag, true, &ws.sync[3]);
+    __syncthreads();
+    if (threadIdx.x < kNV) {  // rank order: every GPU forms identical bits and takes the identical Newton step
+      double t = 0.0;
+      for (int rr = 0; rr < W; ++rr) t += s_red8[rr][threadIdx.x];
+      s_tot[threadIdx.x] = t;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   ++epoch;
 }
 
@@ -1082,6 +1149,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     __syncthreads();
     if (timing) t_local = globaltimer_ns();
     grid_allreduce(s_block, s_tot, ws, epoch, &s_flag, s_warp, prm.launch_tag);
+    if (ws.world > 1 && *reinterpret_cast<volatile unsigned int*>(&ws.sync[3]) != 0u) break;  // a peer never answered (uniform: checked after a barrier)
     if (timing) t_reduced = globaltimer_ns();
     unsigned long long t_last_arrive = 0;
     if (timing && gridDim.x > 1) t_last_arrive = static_cast<unsigned long long>(__double_as_longlong(__ldcg(ws.totals + 2 * kNVP + ((epoch - 1u) & 1u))));
@@ -1119,7 +1187,8 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     r.iterations = st.nr_iterations;
     r.n_evals = st.n_evals;
     r.n_hess = st.n_hess;
-    r.trans_probability = st.score / static_cast<double>(n);  // ndt_omp_impl.hpp:136, 170
+    r.trans_probability = st.score / static_cast<double>(ws.world > 1 ? ws.n_source_total : (long long)n);  // ndt_omp_impl.hpp:136, 170
+    r.aborted = (ws.world > 1) ? static_cast<int32_t>(*reinterpret_cast<volatile unsigned int*>(&ws.sync[3])) : 0;
     const bool trial = (st.n_evals > 1) || prm.mode != MODE_ALIGN;
     for (int i = 0; i < 6; ++i) r.final_pose[i] = trial ? st.x_t[i] : prm.p0[i];
     r.final_score = st.score;
@@ -1128,7 +1197,6 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     for (int i = 0; i < 36; ++i) r.totals[7 + i] = st.H[i];
     r.n_hits = st.n_hits;
     r.n_trace = st.n_trace;
-    r.pad = 0;
     r.t_kernel_begin = t_kernel_begin;
     r.t_kernel_end = globaltimer_ns();
   }
@@ -1138,6 +1206,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     const unsigned int old = atomicInc(&ws.sync[2], gridDim.x - 1);
     if (old == gridDim.x - 1) {
       ws.sync[0] = 0u;
+      ws.sync[3] = 0u;
       __threadfence();
     }
   }

@@ -90,6 +90,9 @@ def load_library():
     L.ndtb200_lookup.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, i32p]
     L.ndtb200_get_trace.argtypes = [vp, i32p, f64p, f64p, f64p, C.c_int, C.POINTER(C.c_int)]
     L.ndtb200_get_timeline.argtypes = [vp, f64p, C.c_int, C.POINTER(C.c_int)]
+    L.ndtb200_comm_export.argtypes = [vp, vp]
+    L.ndtb200_comm_attach.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64]
+    L.ndtb200_comm_detach.argtypes = [vp]
     L.ndtb200_stream.argtypes = [vp]
     L.ndtb200_stream.restype = vp
     L.ndtb200_launch_count.argtypes = [vp]
@@ -361,6 +364,20 @@ class NormalDistributionsTransform:
         n = C.c_int()
         self._check(self._L.ndtb200_get_timeline(self._h, _ptr(t, C.c_double), cap, C.byref(n)))
         return t[:min(n.value, cap)].copy()
+
+    # ---- multi-GPU source sharding ----
+    def comm_export(self):
+        buf = C.create_string_buffer(64)
+        self._check(self._L.ndtb200_comm_export(self._h, buf))
+        return buf.raw
+
+    def comm_attach(self, rank, world, handles, n_source_total):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._check(self._L.ndtb200_comm_attach(self._h, int(rank), int(world), blob, int(n_source_total)))
+
+    def comm_detach(self):
+        self._check(self._L.ndtb200_comm_detach(self._h))
 
     # ---- plumbing ----
     def stream_ptr(self):
