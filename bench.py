@@ -389,6 +389,77 @@ def run_b200(args):
     return 0
 
 
+def run_c4(args):
+    """BASELINE configs[3] (scaled to what the generator can build quickly): one large source cloud (16 merged scans,
+    ~1.9 M points) against a multi-million-point map, the source sharded over the N GPUs by contiguous ranges, one
+    29-value in-kernel exchange per evaluation.  Strong scaling: total work is fixed."""
+    import torch
+    import torch.distributed as dist
+    import toyslam_b200 as nb
+    import workloads
+    from toyslam_b200.sharding import ShardedNdt, source_range
+    rank, world, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world == 1:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29655", rank=0, world_size=1, device_id=dev)
+    box = [None]
+    if rank == 0:
+        scene, target = workloads.config2_map(map_points=args.map_points, n_map_scans=args.map_scans, azimuth_steps=args.azimuth_steps,
+                                              thin_leaf=args.thin_leaf)
+        srcs = [workloads.config2_scan(scene, 100 + i, azimuth_steps=args.azimuth_steps, perturb_seed=100)[0] for i in range(args.c4_scans)]
+        box[0] = (target, np.concatenate(srcs))
+    dist.broadcast_object_list(box, src=0)
+    target, source = box[0]
+    ndt = nb.NormalDistributionsTransform(device=local)
+    ndt.setNeighborhoodSearchMethod(METHODS[args.method])
+    sh = ShardedNdt(ndt, dist)
+    t0 = time.perf_counter()
+    sh.setInputTarget(target)
+    build_ms = (time.perf_counter() - t0) * 1e3
+    sh.setInputSource(source)
+    lo, hi = source_range(len(source), rank, world)
+    for _ in range(max(3, args.warmup)):
+        sh.align()
+    res = sh.result()
+    steps = min(args.steps, 200)
+    times = []
+    for _ in range(steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        ndt.align_async()
+        ndt.sync()
+        times.append(ndt.last_align_ms())
+    t = torch.tensor([float(np.sum(times))], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    evals, hess = res["n_evaluations"], res["n_hessian_passes"]
+    kprobe = KPROBE[args.method]
+    alg_bytes = (evals + hess) * len(source) * (16 + 4 * kprobe) + 64 * res["n_hits"]
+    peak = 6454.9
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    if rank == 0:
+        info = ndt.map_info()
+        line = {"metric": "ndt_aligns_per_s", "workload": "c4", "value": steps / (total_ms * 1e-3), "unit": "aligns/s", "n_gpus": world,
+                "steps": steps, "ms_per_step": total_ms / steps, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+                "src_pt_iters_per_s": len(source) * evals * steps / (total_ms * 1e-3), "evaluations_per_align": evals,
+                "hessian_passes_per_align": hess, "hits_per_point_eval": res["n_hits"] / float((evals + hess) * len(source)),
+                "config": {"workload": "c4: %d-pt source (%d merged scans) sharded by contiguous ranges over %d GPU(s) vs %d-pt map "
+                                       "(%d voxels, %d valid), res 1.0, %s; one in-kernel 29-value P2P exchange per evaluation" %
+                                       (len(source), args.c4_scans, world, len(target), info["n_voxels"], info["n_valid"], args.method),
+                           "map_build_ms_incl_h2d": build_ms, "points_this_rank": hi - lo},
+                "roofline": {"bound": "hbm", "achieved": alg_bytes / (total_ms / steps * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
+                             "frac": alg_bytes / (total_ms / steps * 1e-3) / 1e9 / world / peak, "algorithmic_bytes_per_launch": alg_bytes},
+                "converged": res["converged"], "iterations": res["iterations"]}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -405,7 +476,12 @@ def main():
     ap.add_argument("--l2", default="inputs", choices=["inputs", "flush"],
                     help="how timed steps see a cold L2: inputs larger than L2 (default) or a 256 MiB flush write")
     ap.add_argument("--cache", default=None, help="directory for cached workload arrays")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--c4-scans", type=int, default=16)
+    ap.add_argument("--thin-leaf", type=float, default=0.1)
     args = ap.parse_args()
+    if args.workload == "c4" and args.impl == "b200":
+        return run_c4(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -121,12 +121,16 @@ def pose_matrix(p):
     return T
 
 
-def config2_scan(scene, scan_seed, seed=SEED_C2, azimuth_steps=1875):
-    """One perturbed scan (source cloud) of the c2 scene and the transform that maps it onto the map."""
+def config2_scan(scene, scan_seed, seed=SEED_C2, azimuth_steps=1875, perturb_seed=None):
+    """One perturbed scan (source cloud) of the c2 scene and the transform that maps it onto the map.
+    perturb_seed: use one common perturbation (about the origin) for several scans that are merged into one source."""
     rng = np.random.default_rng(seed + 7919 * (scan_seed + 1))
     sx = float(rng.uniform(-25.0, 25.0))
     _, pw = scene.scan((sx, float(rng.uniform(-1.0, 1.0)), float(rng.uniform(-0.05, 0.05))), seed=seed + 5000 + scan_seed,
                        azimuth_steps=azimuth_steps)
+    if perturb_seed is not None:
+        rng = np.random.default_rng(seed + 104729 * (perturb_seed + 1))
+        sx = 0.0
     d2r = np.pi / 180.0
     pert = [rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5),
             rng.uniform(-0.5, 0.5) * d2r, rng.uniform(-0.5, 0.5) * d2r, rng.uniform(-2.0, 2.0) * d2r]
@@ -141,7 +145,7 @@ def config2_scan(scene, scan_seed, seed=SEED_C2, azimuth_steps=1875):
     return src.astype(np.float32), truth
 
 
-def config2_map(map_points=1_000_000, n_map_scans=31, seed=SEED_C2, azimuth_steps=1875):
+def config2_map(map_points=1_000_000, n_map_scans=31, seed=SEED_C2, azimuth_steps=1875, thin_leaf=0.1):
     """The c2 target map: union of scans taken every 2 m along the street, voxel-thinned to ~map_points."""
     scene = Scene(seed)
     xs = np.linspace(-30.0, 30.0, n_map_scans)
@@ -149,7 +153,7 @@ def config2_map(map_points=1_000_000, n_map_scans=31, seed=SEED_C2, azimuth_step
     for i, x in enumerate(xs):
         _, pw = scene.scan((float(x), 0.0, 0.0), seed=seed + 1000 + i, azimuth_steps=azimuth_steps)
         world.append(pw)
-    return scene, voxel_thin(np.concatenate(world), 0.1, map_points, seed + 1)
+    return scene, voxel_thin(np.concatenate(world), thin_leaf, map_points, seed + 1)
 
 
 def config2(map_points=1_000_000, n_map_scans=31, scan_seed=0, seed=SEED_C2, azimuth_steps=1875, offset=(0.0, 0.0, 0.0)):
