@@ -149,6 +149,26 @@ def test_lookup(nb, method):
     assert np.array_equal(a, b)   # same keys in the same (reference offset) order
 
 
+@pytest.mark.parametrize("method", [oracle.DIRECT1, oracle.DIRECT7, oracle.DIRECT26])
+def test_hash_index_fallback(nb, method, monkeypatch):
+    """The voxel index has two interchangeable forms (direct-mapped cell table / open-addressing hash for grids whose
+    table would not fit): both must return the same voxels and the same derivatives."""
+    tgt, src = load_pair()
+    monkeypatch.setenv("NDTB200_FORCE_HASH", "1")
+    ref, gpu_hash = make_pair(nb, tgt, src, method=method)
+    monkeypatch.delenv("NDTB200_FORCE_HASH")
+    _, gpu_dense = make_pair(nb, tgt, src, method=method)
+    q = np.concatenate([src[:4000], np.round(src[:500])]).astype(np.float32)
+    assert np.array_equal(gpu_hash.lookup(q, method), ref.lookup(q, method))
+    assert np.array_equal(gpu_dense.lookup(q, method), ref.lookup(q, method))
+    p = np.array([0.4, 0.1, -0.02, 0.005, -0.001, -0.01])
+    a, b = gpu_hash.eval_derivatives(p, True), gpu_dense.eval_derivatives(p, True)
+    assert a["score"] == b["score"] and np.array_equal(a["gradient"], b["gradient"]) and np.array_equal(a["hessian"], b["hessian"])
+    gpu_hash.align()
+    gpu_dense.align()
+    assert np.array_equal(gpu_hash.result()["final"], gpu_dense.result()["final"])
+
+
 POSES = [np.zeros(6),
          np.array([0.4, 0.1, -0.02, 0.005, -0.001, -0.01]),
          np.array([0.1, -0.3, 0.05, 0.3, -0.25, 0.6]),        # large angles: exposes Q2 (+sy / -sy)

@@ -68,7 +68,8 @@ struct ndtb200_handle {
   uint32_t hash_cap = 0;
   int hash_shift = 0;
   DevBuf d_grid, d_mm_partial, d_mm_finite, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_scan_tmp, d_scalar;
-  DevBuf d_voxel_key, d_voxel_start, d_moments, d_records, d_icov64, d_hash;
+  DevBuf d_voxel_key, d_voxel_start, d_moments, d_records, d_icov64, d_hash, d_dense;
+  bool use_dense = false;
 
   // source cloud
   DevBuf d_source;
@@ -159,6 +160,7 @@ int ensure_empty_hash(ndtb200_handle* h) {
   CK(cudaMemsetAsync(h->d_hash.p, 0xFF, h->hash_cap * sizeof(HashSlot), h->stream));
   CK(h->d_records.ensure(sizeof(VoxelRecord)));
   CK(h->d_icov64.ensure(6 * sizeof(double)));
+  h->use_dense = false;
   return NDTB200_OK;
 }
 
@@ -307,6 +309,28 @@ int build_map(ndtb200_handle* h) {
                                                                h->prm.min_points_per_voxel, h->d_hash.as<HashSlot>(),
                                                                cap - 1, h->hash_shift);
   LAUNCHED(h);
+
+  // 7. direct-mapped cell table (one 4-byte load per probe, no collisions) when dx*dy*dz int32 entries fit the budget:
+  //    <= 4 GiB and <= 1/4 of the free device memory; otherwise lookups go through the hash
+  h->use_dense = false;
+  {
+    // cells actually addressed by keys: div_b product (the guard's dx*dy*dz, grid.ncell, is computed from the float
+    // extents and can be smaller by one per axis)
+    const unsigned long long ncell = static_cast<unsigned long long>(h->grid.div_b[0]) * static_cast<unsigned long long>(h->grid.div_b[1]) *
+                                     static_cast<unsigned long long>(h->grid.div_b[2]);
+    const unsigned long long bytes = ncell * sizeof(int32_t);
+    size_t free_b = 0, total_b = 0;
+    const bool forced_hash = getenv("NDTB200_FORCE_HASH") != nullptr;
+    if (!forced_hash && ncell > 0 && bytes <= (4ull << 30) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+        bytes <= (free_b + h->d_dense.cap) / 4) {
+      CK(h->d_dense.ensure(bytes));
+      CK(cudaMemsetAsync(h->d_dense.p, 0xFF, bytes, h->stream));
+      dense_fill_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
+                                                                  h->prm.min_points_per_voxel, h->d_dense.as<int32_t>());
+      LAUNCHED(h);
+      h->use_dense = true;
+    }
+  }
   h->map_status = NDTB200_OK;
   return NDTB200_OK;
 }
@@ -316,6 +340,7 @@ MapView make_view(const ndtb200_handle* h) {
   m.records = h->d_records.as<VoxelRecord>();
   m.icov64 = h->d_icov64.as<double>();
   m.hash = h->d_hash.as<HashSlot>();
+  m.dense = (h->use_dense && h->n_voxels > 0) ? h->d_dense.as<int32_t>() : nullptr;
   m.hash_mask = h->hash_cap - 1;
   m.hash_shift = h->hash_shift;
   for (int a = 0; a < 3; ++a) {
@@ -398,8 +423,7 @@ void gauss_constants(const ndtb200_params& p, double& d1, double& d2, double& d3
 template <int METHOD>
 int query_coop_blocks(ndtb200_handle* h) {
   int per_sm = 0;
-  const size_t smem = eval_smem_bytes<METHOD>();
-  CK(cudaFuncSetAttribute(ndt_align_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const size_t smem = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ndt_align_kernel<METHOD>, kAlignThreads, smem));
   if (per_sm < 1) { h->err = "align kernel does not fit on an SM"; return NDTB200_ERR_CUDA; }
   h->coop_blocks[METHOD] = per_sm * h->num_sms;
@@ -426,11 +450,14 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   for (int i = 0; i < 12; ++i) prm.T0[i] = T0[i];
   prm.n_source = static_cast<int>(h->n_source);
   prm.trace_cap = ndtb200_handle::kTraceCap;
+  static const int rot_env = getenv("NDTB200_ROTATE") ? atoi(getenv("NDTB200_ROTATE")) : 0;
+  prm.rot = rot_env;
   prm.launch_tag = (++h->launch_seq) << 12;  // 4096 evaluations per launch before tags could repeat
   compute_angle_tables(p0, prm.tab0);
 
   const int max_blocks = h->coop_blocks[method];
-  int blocks = grid_for(h->n_source, kAlignThreads, max_blocks);
+  // every SM takes part as soon as there is one 32-point group per CTA (the kernel deals groups to warps round-robin)
+  int blocks = grid_for(h->n_source, 32, max_blocks);
   CK(h->d_partials.ensure((size_t)max_blocks * kNVP * sizeof(double)));
   if (h->d_totals.p == nullptr) {
     CK(h->d_totals.ensure(3 * kNVP * sizeof(double)));
@@ -461,8 +488,7 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
                                              : (const void*)ndt_align_kernel<1>;
   h->last_blocks = blocks;
   CK(cudaEventRecord(h->ev0, h->stream));
-  const size_t smem = method == NDTB200_DIRECT1 ? eval_smem_bytes<3>()
-                    : method == NDTB200_DIRECT7 ? eval_smem_bytes<2>() : eval_smem_bytes<1>();
+  const size_t smem = 0;
   static const bool plain_launch = getenv("NDTB200_PLAIN_LAUNCH") != nullptr;  // experiment only: no co-residency guarantee
   if (plain_launch) CK(cudaLaunchKernel(fn, dim3(blocks), dim3(kAlignThreads), args, smem, h->stream));
   else CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kAlignThreads), args, smem, h->stream));
@@ -561,7 +587,7 @@ int ndtb200_destroy(ndtb200_handle* h) {
   ndtb200_comm_detach(h);
   DevBuf* bufs[] = {&h->d_target, &h->d_grid, &h->d_mm_partial, &h->d_mm_finite, &h->d_keys_a, &h->d_keys_b,
                     &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_voxel_key,
-                    &h->d_voxel_start, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_source,
+                    &h->d_voxel_start, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_dense, &h->d_source,
                     &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail};
   for (DevBuf* b : bufs) b->release();
   if (h->h_result) cudaFreeHost(h->h_result);
@@ -932,6 +958,16 @@ int ndtb200_get_timeline(ndtb200_handle* h, double* t4, int cap, int* n_out) {
     std::vector<double> s(arr); std::sort(s.begin(), s.end());
     std::fprintf(stderr, "  last eval: CTA arrival after eval start [us]: min %.2f p10 %.2f p50 %.2f p90 %.2f p99 %.2f max %.2f (CTA0 %.2f, G=%d)\n",
                  s[0], s[G / 10], s[G / 2], s[G * 9 / 10], s[G * 99 / 100], s[G - 1], arr[0], G);
+    {  // the slowest CTAs and the SMs they ran on (hardware position vs data: do the same SMs repeat?)
+      std::vector<int> order(G);
+      for (int b = 0; b < G; ++b) order[b] = b;
+      std::sort(order.begin(), order.end(), [&](int x, int y) { return arr[x] > arr[y]; });
+      std::fprintf(stderr, "  slowest CTAs (cta:sm:us):");
+      for (int i = 0; i < std::min(G, 8); ++i) std::fprintf(stderr, " %d:%d:%.2f(h%.0f)", order[i], (int)part[(size_t)order[i] * kNVP + 30], arr[order[i]], part[(size_t)order[i] * kNVP + 28]);
+      std::vector<double> hh(G); for (int b = 0; b < G; ++b) hh[b] = part[(size_t)b * kNVP + 28];
+      std::sort(hh.begin(), hh.end());
+      std::fprintf(stderr, "\n  hits per CTA: min %.0f p50 %.0f max %.0f\n", hh[0], hh[G / 2], hh[G - 1]);
+    }
     // by SM pairing: CTAs b and b+148 usually share an SM
     double mx_lo = 0, mx_hi = 0; for (int b = 0; b < G; ++b) { if (b < G / 2) mx_lo = std::max(mx_lo, arr[b]); else mx_hi = std::max(mx_hi, arr[b]); }
     std::fprintf(stderr, "  max arrival first half of CTAs %.2f, second half %.2f\n", mx_lo, mx_hi);
@@ -942,7 +978,7 @@ int ndtb200_get_timeline(ndtb200_handle* h, double* t4, int cap, int* n_out) {
     t4[i * 4 + 2] = static_cast<double>(tr[i].t_reduced - t0);
     t4[i * 4 + 3] = static_cast<double>(tr[i].t_advanced - t0);
     if (getenv("NDTB200_DEBUG_STEP"))
-      std::fprintf(stderr, "  eval %d CTA0: phase A %.2f us, phase B %.2f us, fold %.2f us\n", i, (double)((long long)tr[i].t_phase[0] - (long long)tr[i].t_start) * 1e-3,
+      std::fprintf(stderr, "  eval %d CTA0: thread 0 points + warp sum %.2f us, (unused %.2f,) CTA fold %.2f us\n", i, (double)((long long)tr[i].t_phase[0] - (long long)tr[i].t_start) * 1e-3,
                    (double)((long long)tr[i].t_phase[1] - (long long)tr[i].t_phase[0]) * 1e-3, (double)((long long)tr[i].t_local - (long long)tr[i].t_phase[1]) * 1e-3);
     if (getenv("NDTB200_DEBUG_STEP"))
       std::fprintf(stderr, "  step %d: last CTA arrived %.2f us after CTA 0 finished, totals %.2f us later; advance %.2f us, solve %.2f us, post %.2f us, pose setup %.2f us\n", i,

@@ -52,6 +52,7 @@ struct MapView {  // what the kernels need to probe the map
   const VoxelRecord* records;
   const double* icov64;  // [n_voxels][6] fp64 inverse covariance for the fp64 Hessian-only pass
   const HashSlot* hash;
+  const int32_t* dense;  // direct-mapped cell table [dx*dy*dz] -> record index or -1 (nullptr: use the hash)
   uint32_t hash_mask;
   int32_t hash_shift;
   int32_t min_b[3], max_b[3], mul[3];
@@ -59,7 +60,12 @@ struct MapView {  // what the kernels need to probe the map
   int32_t min_points;
 };
 
+// key -> record index of a VALID voxel, or -1.  Two interchangeable indexes over the same records:
+//   * dense: one 4-byte load from a direct-mapped table over the grid's dx*dy*dz cells (x-neighbours share a 32-byte
+//     sector) — a single round trip, no compare, no collision chain; used whenever the table fits the memory budget;
+//   * hash: open addressing over the valid voxels, for huge sparse grids (up to the int32 key guard, Q9).
 __device__ __forceinline__ int map_find(const MapView& m, int32_t key) {
+  if (m.dense != nullptr) return __ldg(m.dense + key);
   uint32_t h = hash_key(static_cast<uint32_t>(key), m.hash_shift);
   while (true) {
     HashSlot s = __ldg(m.hash + h);

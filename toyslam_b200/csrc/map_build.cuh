@@ -513,4 +513,13 @@ hash_insert_kernel(const VoxelRecord* __restrict__ records, uint32_t n_voxels, i
   }
 }
 
+// direct-mapped cell table: table[key] = record index of every VALID voxel (the table is pre-filled with -1)
+__global__ void __launch_bounds__(kBuildThreads)
+dense_fill_kernel(const VoxelRecord* __restrict__ records, uint32_t n_voxels, int min_points, int32_t* __restrict__ table) {
+  const uint32_t v = blockIdx.x * (uint32_t)blockDim.x + threadIdx.x;
+  if (v >= n_voxels) return;
+  if (records[v].count < min_points) return;  // sparse and rejected leaves are invisible to lookups (…_impl.hpp:395)
+  table[records[v].key] = static_cast<int32_t>(v);
+}
+
 }  // namespace ndtb200

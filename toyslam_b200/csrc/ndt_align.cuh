@@ -26,7 +26,16 @@
 
 namespace ndtb200 {
 
-constexpr int kAlignThreads = 256;
+// CTA shape of the persistent kernel: one CTA of 1024 threads per SM (148 CTAs: fewer rows in the grid reduction,
+// fewer arrivals on the barrier word), 64 registers per thread.
+#ifndef NDTB200_ALIGN_THREADS
+#define NDTB200_ALIGN_THREADS 1024
+#endif
+#ifndef NDTB200_ALIGN_MIN_BLOCKS
+#define NDTB200_ALIGN_MIN_BLOCKS 1
+#endif
+constexpr int kAlignThreads = NDTB200_ALIGN_THREADS;
+constexpr int kAlignMinBlocks = NDTB200_ALIGN_MIN_BLOCKS;
 constexpr int kAlignWarps = kAlignThreads / 32;
 constexpr int kNV = 29;          // score, g[6], H upper triangle[21], hit count
 constexpr int kNVP = 32;         // padded row length of the partial / total buffers
@@ -72,6 +81,7 @@ struct AlignParams {
   float T0[12];
   int32_t n_source;
   int32_t trace_cap;
+  int32_t rot;          // profiling: rotate the CTA -> point-group assignment by this many CTAs
   uint32_t launch_tag;  // launch sequence number << 10: makes the tags of the published totals unique per launch
   AngleTables tab0;     // angle tables of p0 (host-computed: the kernel prologue has no trigonometry)
 };
@@ -93,6 +103,7 @@ struct AlignWorkspace {
 
 struct EvalCtx {
   float T[12];
+  float4 tf[23];  // the fp32 tables as (c0, c1, c2, 0) rows: j_ang rows 0..7, h_ang rows 8..22 (one LDS.128 per row)
   AngleTables tab;
 };
 
@@ -110,84 +121,11 @@ struct SolverState {
   double last_dp[6];  // last Newton increment (transformation_ is built from it once, at the end)
   double delta[6];    // Newton step H^-1 (-g), written by the warp solver
   float final_T[12];
+  // copies of the launch parameters the step functions need (the parameter struct itself is never address-taken, so it
+  // stays in the constant bank instead of being copied to every thread's local memory)
+  double step_size, trans_eps;
+  int32_t max_iterations, trace_cap;
 };
-
-// ---------------------------------------------------------------------------------------------
-// one (point, voxel) contribution: updateDerivatives (T = float) / updateHessian (T = double)
-// pj = j_ang * x (8 values), ph = h_ang * x (15 values); r = x' - mean; c = inverse covariance.
-// acc layout: [0] score, [1..6] gradient, [7..27] Hessian upper triangle row-major.
-// d1 is passed in T: for the fp32 path the reference forms -d1*e and d1*(d2*e) in fp64 and rounds
-// to fp32 (ndt_omp_impl.hpp:501, 510); multiplying by fl32(d1) in fp32 differs from that by at most
-// 1.2e-7 relative, and keeps the per-hit path free of fp64 and conversion instructions.
-// ---------------------------------------------------------------------------------------------
-template <typename T, bool SCORE_GRAD, bool HESS>
-__device__ __forceinline__ void hit_contribution(const T r0, const T r1, const T r2, const T c00, const T c01,
-                                                 const T c02, const T c11, const T c12, const T c22, const T* pj,
-                                                 const T* ph, const T d2, const T d1, T* acc) {
-  const T u0 = c00 * r0 + c01 * r1 + c02 * r2;
-  const T u1 = c01 * r0 + c11 * r1 + c12 * r2;
-  const T u2 = c02 * r0 + c12 * r1 + c22 * r2;
-  const T q = r0 * u0 + r1 * u1 + r2 * u2;
-  T w;
-  if constexpr (sizeof(T) == 4) {
-    // ndt_omp_impl.hpp:499-510
-    const float e = expf(-d2 * q * 0.5f);
-    const float e2 = d2 * e;
-    if (!(e2 <= 1.0f && e2 >= 0.0f)) return;  // e2 > 1 || e2 < 0 || NaN  -> contributes nothing
-    if (SCORE_GRAD) acc[0] -= d1 * e;
-    w = e2 * d1;
-  } else {
-    // ndt_omp_impl.hpp:622-629
-    const double e2 = d2 * exp(-d2 * q / 2);
-    if (!(e2 <= 1.0 && e2 >= 0.0)) return;
-    w = e2 * d1;
-  }
-  const T s0 = u0, s1 = u1, s2 = u2;
-  const T s3 = u1 * pj[0] + u2 * pj[1];
-  const T s4 = u0 * pj[2] + u1 * pj[3] + u2 * pj[4];
-  const T s5 = u0 * pj[5] + u1 * pj[6] + u2 * pj[7];
-  if (SCORE_GRAD) {
-    acc[1] += w * s0;
-    acc[2] += w * s1;
-    acc[3] += w * s2;
-    acc[4] += w * s3;
-    acc[5] += w * s4;
-    acc[6] += w * s5;
-  }
-  if (HESS) {
-    // C * J_i for the three rotational columns (J_3 = (0,j0,j1), J_4 = (j2,j3,j4), J_5 = (j5,j6,j7))
-    const T v3x = c01 * pj[0] + c02 * pj[1], v3y = c11 * pj[0] + c12 * pj[1], v3z = c12 * pj[0] + c22 * pj[1];
-    const T v4x = c00 * pj[2] + c01 * pj[3] + c02 * pj[4], v4y = c01 * pj[2] + c11 * pj[3] + c12 * pj[4],
-            v4z = c02 * pj[2] + c12 * pj[3] + c22 * pj[4];
-    const T v5x = c00 * pj[5] + c01 * pj[6] + c02 * pj[7], v5y = c01 * pj[5] + c11 * pj[6] + c12 * pj[7],
-            v5z = c02 * pj[5] + c12 * pj[6] + c22 * pj[7];
-    const T md2 = -d2;
-#define NDTB200_H(idx, si, sj, extra) acc[7 + idx] += w * (md2 * si * sj + (extra));
-    NDTB200_H(0, s0, s0, c00)
-    NDTB200_H(1, s0, s1, c01)
-    NDTB200_H(2, s0, s2, c02)
-    NDTB200_H(3, s0, s3, v3x)
-    NDTB200_H(4, s0, s4, v4x)
-    NDTB200_H(5, s0, s5, v5x)
-    NDTB200_H(6, s1, s1, c11)
-    NDTB200_H(7, s1, s2, c12)
-    NDTB200_H(8, s1, s3, v3y)
-    NDTB200_H(9, s1, s4, v4y)
-    NDTB200_H(10, s1, s5, v5y)
-    NDTB200_H(11, s2, s2, c22)
-    NDTB200_H(12, s2, s3, v3z)
-    NDTB200_H(13, s2, s4, v4z)
-    NDTB200_H(14, s2, s5, v5z)
-    // rotational block: u . H_E[i][j]  +  J_j . (C J_i)
-    NDTB200_H(15, s3, s3, (u1 * ph[0] + u2 * ph[1]) + (pj[0] * v3y + pj[1] * v3z))
-    NDTB200_H(16, s3, s4, (u1 * ph[2] + u2 * ph[3]) + (pj[2] * v3x + pj[3] * v3y + pj[4] * v3z))
-    NDTB200_H(17, s3, s5, (u1 * ph[4] + u2 * ph[5]) + (pj[5] * v3x + pj[6] * v3y + pj[7] * v3z))
-    NDTB200_H(18, s4, s4, (u0 * ph[6] + u1 * ph[7] + u2 * ph[8]) + (pj[2] * v4x + pj[3] * v4y + pj[4] * v4z))
-    NDTB200_H(19, s4, s5, (u0 * ph[9] + u1 * ph[10] + u2 * ph[11]) + (pj[5] * v4x + pj[6] * v4y + pj[7] * v4z))
-    NDTB200_H(20, s5, s5, (u0 * ph[12] + u1 * ph[13] + u2 * ph[14]) + (pj[5] * v5x + pj[6] * v5y + pj[7] * v5z))
-#undef NDTB200_H
-  }
-}
 
 __constant__ int8_t c_off26[26][3] = {
     // pcl::getAllNeighborCellIndices(): 13 "half" offsets then their negations (centre excluded, Q7)
@@ -227,163 +165,72 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-// All K probes of a point with their first hash slots in flight together (memory-level parallelism),
-// then resolved; collisions (rare at load <= 0.25) continue with the plain linear probe.
+// All K probes of a point (DIRECT1 / DIRECT7) with their loads in flight together.  In-bounds tests are unsigned
+// compares of the min-relative cell coordinates; neighbour keys are key0 +- mul[axis].
 template <int K>
 __device__ __forceinline__ void probe_cells(const MapView& m, int ix, int iy, int iz, int (&rec)[K]) {
   static_assert(K == 1 || K == 7, "unrolled probe is for DIRECT1 / DIRECT7");
-  HashSlot slot[K];
-  uint32_t key[K], h[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    int dx, dy, dz;
-    get_offset<(K == 1 ? 3 : 2)>(k, dx, dy, dz);
-    const int cx = ix + dx, cy = iy + dy, cz = iz + dz;
-    const bool inside = !(cx < m.min_b[0] || cx > m.max_b[0] || cy < m.min_b[1] || cy > m.max_b[1] ||
-                          cz < m.min_b[2] || cz > m.max_b[2]);
-    key[k] = static_cast<uint32_t>((cx - m.min_b[0]) * m.mul[0] + (cy - m.min_b[1]) * m.mul[1] + (cz - m.min_b[2]) * m.mul[2]);
-    h[k] = hash_key(key[k], m.hash_shift);
-    slot[k] = inside ? __ldg(m.hash + h[k]) : NDTB200_HASH_EMPTY;
+  const int rx = ix - m.min_b[0], ry = iy - m.min_b[1], rz = iz - m.min_b[2];
+  const unsigned int ex = static_cast<unsigned int>(m.max_b[0] - m.min_b[0]);
+  const unsigned int ey = static_cast<unsigned int>(m.max_b[1] - m.min_b[1]);
+  const unsigned int ez = static_cast<unsigned int>(m.max_b[2] - m.min_b[2]);
+  // (unsigned)(r + d) <= e  <=>  min_b <= i + d <= max_b ; an empty map has max_b < min_b: e wraps to 0xffffffff only
+  // if max_b - min_b == -1, so the empty view sets mul = 0 and its table holds -1 everywhere (see make_view)
+  const bool inx = static_cast<unsigned int>(rx) <= ex, iny = static_cast<unsigned int>(ry) <= ey,
+             inz = static_cast<unsigned int>(rz) <= ez;
+  const int key0 = rx * m.mul[0] + ry * m.mul[1] + rz * m.mul[2];
+  bool ok[K];
+  int key[K];
+  ok[0] = inx && iny && inz;
+  key[0] = key0;
+  if constexpr (K == 7) {
+    // DIRECT7 order (voxel_grid_covariance_omp_impl.hpp:423-430): centre, +x, -x, +y, -y, +z, -z
+    ok[1] = (static_cast<unsigned int>(rx + 1) <= ex) && iny && inz; key[1] = key0 + m.mul[0];
+    ok[2] = (static_cast<unsigned int>(rx - 1) <= ex) && iny && inz; key[2] = key0 - m.mul[0];
+    ok[3] = inx && (static_cast<unsigned int>(ry + 1) <= ey) && inz; key[3] = key0 + m.mul[1];
+    ok[4] = inx && (static_cast<unsigned int>(ry - 1) <= ey) && inz; key[4] = key0 - m.mul[1];
+    ok[5] = inx && iny && (static_cast<unsigned int>(rz + 1) <= ez); key[5] = key0 + m.mul[2];
+    ok[6] = inx && iny && (static_cast<unsigned int>(rz - 1) <= ez); key[6] = key0 - m.mul[2];
   }
+  if (m.dense != nullptr) {  // uniform
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    int r = -1;
-    HashSlot s = slot[k];
-    uint32_t hh = h[k];
-    while (s != NDTB200_HASH_EMPTY) {
-      if (static_cast<uint32_t>(s) == key[k]) { r = static_cast<int>(s >> 32); break; }
-      hh = (hh + 1) & m.hash_mask;
-      s = __ldg(m.hash + hh);
-    }
-    rec[k] = r;
-    if (r >= 0) prefetch_l2(m.records + r);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// all hits of one source point, fp32 path (computeDerivatives inner loop, ndt_omp_impl.hpp:207-275)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hit_from_record_f32(const VoxelRecord* R, float tx, float ty, float tz, float& r0,
-                                                    float& r1, float& r2, float (&c)[6]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(R));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(R) + 1);
-  const float4 cc = __ldg(reinterpret_cast<const float4*>(R) + 2);
-  // x_trans = fl32(double(x') - mean) (ndt_omp_impl.hpp:259-262, 492) via the exact hi/lo split of the mean
-  r0 = __fsub_rn(__fsub_rn(tx, a.x), a.w);
-  r1 = __fsub_rn(__fsub_rn(ty, a.y), b.x);
-  r2 = __fsub_rn(__fsub_rn(tz, a.z), b.y);
-  c[0] = b.z; c[1] = b.w; c[2] = cc.x; c[3] = cc.y; c[4] = cc.z; c[5] = cc.w;
-}
-
-template <int METHOD, bool HESS>
-__device__ __forceinline__ void eval_point_f32(const float4 pt, const EvalCtx& c, const MapView& m, const float d2f,
-                                               const float d1f, float* acc) {
-  float tx, ty, tz;
-  transform_point(c.T, pt.x, pt.y, pt.z, tx, ty, tz);
-  // getNeighborhoodAtPoint (…_impl.hpp:379-381): cell = floor(x' / leaf), fp32 DIVISION (Q8)
-  const int ix = static_cast<int>(floorf(__fdiv_rn(tx, m.leaf[0])));
-  const int iy = static_cast<int>(floorf(__fdiv_rn(ty, m.leaf[1])));
-  const int iz = static_cast<int>(floorf(__fdiv_rn(tz, m.leaf[2])));
-  constexpr int K = num_offsets<METHOD>();
-  if constexpr (METHOD != 1) {
-    int rec[K];
-    probe_cells<K>(m, ix, iy, iz, rec);
-    // computePointDerivatives (fp32 overload, ndt_omp_impl.hpp:398-440): depends on the ORIGINAL point only
-    float pj[8], ph[15];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) pj[r] = c.tab.jf[r][0] * pt.x + c.tab.jf[r][1] * pt.y + c.tab.jf[r][2] * pt.z;
-    if (HESS) {
-#pragma unroll
-      for (int r = 0; r < 15; ++r) ph[r] = c.tab.hf[r][0] * pt.x + c.tab.hf[r][1] * pt.y + c.tab.hf[r][2] * pt.z;
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      if (rec[k] < 0) continue;
-      float r0, r1, r2, cv[6];
-      hit_from_record_f32(m.records + rec[k], tx, ty, tz, r0, r1, r2, cv);
-      acc[28] += 1.0f;
-      hit_contribution<float, true, HESS>(r0, r1, r2, cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], pj, ph, d2f, d1f, acc);
-    }
+    for (int k = 0; k < K; ++k) rec[k] = ok[k] ? __ldg(m.dense + key[k]) : -1;
   } else {
-    float pj[8], ph[15];
+    HashSlot slot[K];
+    uint32_t h[K];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) pj[r] = c.tab.jf[r][0] * pt.x + c.tab.jf[r][1] * pt.y + c.tab.jf[r][2] * pt.z;
-    if (HESS) {
-#pragma unroll
-      for (int r = 0; r < 15; ++r) ph[r] = c.tab.hf[r][0] * pt.x + c.tab.hf[r][1] * pt.y + c.tab.hf[r][2] * pt.z;
-    }
-#pragma unroll 1
     for (int k = 0; k < K; ++k) {
-      int dx, dy, dz;
-      get_offset<METHOD>(k, dx, dy, dz);
-      const int rec = probe_cell(m, ix + dx, iy + dy, iz + dz);
-      if (rec < 0) continue;
-      float r0, r1, r2, cv[6];
-      hit_from_record_f32(m.records + rec, tx, ty, tz, r0, r1, r2, cv);
-      acc[28] += 1.0f;
-      hit_contribution<float, true, HESS>(r0, r1, r2, cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], pj, ph, d2f, d1f, acc);
+      h[k] = hash_key(static_cast<uint32_t>(key[k]), m.hash_shift);
+      slot[k] = ok[k] ? __ldg(m.hash + h[k]) : NDTB200_HASH_EMPTY;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      int r = -1;
+      HashSlot sl = slot[k];
+      uint32_t hh = h[k];
+      while (sl != NDTB200_HASH_EMPTY) {
+        if (static_cast<uint32_t>(sl) == static_cast<uint32_t>(key[k])) { r = static_cast<int>(sl >> 32); break; }
+        hh = (hh + 1) & m.hash_mask;
+        sl = __ldg(m.hash + hh);
+      }
+      rec[k] = r;
     }
   }
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    if (rec[k] >= 0) prefetch_l2(m.records + rec[k]);
 }
 
-// fp64 Hessian-only path (computeHessian inner loop, ndt_omp_impl.hpp:565-609)
-template <int METHOD>
-__device__ __forceinline__ void eval_point_f64(const float4 pt, const EvalCtx& c, const MapView& m, const double d2,
-                                               const double d1, double* acc) {
-  float tx, ty, tz;
-  transform_point(c.T, pt.x, pt.y, pt.z, tx, ty, tz);
-  const int ix = static_cast<int>(floorf(__fdiv_rn(tx, m.leaf[0])));
-  const int iy = static_cast<int>(floorf(__fdiv_rn(ty, m.leaf[1])));
-  const int iz = static_cast<int>(floorf(__fdiv_rn(tz, m.leaf[2])));
-  const double x = pt.x, y = pt.y, z = pt.z;
-  double pj[8], ph[15];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) pj[r] = x * c.tab.jd[r][0] + y * c.tab.jd[r][1] + z * c.tab.jd[r][2];
-#pragma unroll
-  for (int r = 0; r < 15; ++r) ph[r] = x * c.tab.hd[r][0] + y * c.tab.hd[r][1] + z * c.tab.hd[r][2];
-  constexpr int K = num_offsets<METHOD>();
-#pragma unroll 1
-  for (int k = 0; k < K; ++k) {
-    int dx, dy, dz;
-    get_offset<METHOD>(k, dx, dy, dz);
-    const int rec = probe_cell(m, ix + dx, iy + dy, iz + dz);
-    if (rec < 0) continue;
-    const VoxelRecord* R = m.records + rec;
-    const double* ic = m.icov64 + (size_t)rec * 6;
-    const double r0 = static_cast<double>(tx) - (static_cast<double>(__ldg(&R->mean_hi[0])) + static_cast<double>(__ldg(&R->mean_lo[0])));
-    const double r1 = static_cast<double>(ty) - (static_cast<double>(__ldg(&R->mean_hi[1])) + static_cast<double>(__ldg(&R->mean_lo[1])));
-    const double r2 = static_cast<double>(tz) - (static_cast<double>(__ldg(&R->mean_hi[2])) + static_cast<double>(__ldg(&R->mean_lo[2])));
-    acc[28] += 1.0;
-    hit_contribution<double, false, true>(r0, r1, r2, __ldg(ic), __ldg(ic + 1), __ldg(ic + 2), __ldg(ic + 3),
-                                          __ldg(ic + 4), __ldg(ic + 5), pj, ph, d2, d1, acc);
-  }
-}
+// The optimiser state and the evaluation context of the CTA live in file-scope shared memory, so the out-of-line step
+// functions reach them with shared-space loads/stores at fixed addresses (not generic pointers).
+__shared__ SolverState g_st;
+__shared__ EvalCtx g_ctx;
 
 // ---------------------------------------------------------------------------------------------
-// reductions
+// fp64 Hessian-only pass (computeHessian / updateHessian, ndt_omp_impl.hpp:540-645): fp64 math, fp64 tables (Q2: -sy),
+// same per-point factorisation as the fp32 pass (see point_f32 below): A = sum w u, M = sum w (C - d2 u u^T),
+// H_ij = J_i^T M J_j + A . H_E[i][j].
 // ---------------------------------------------------------------------------------------------
-template <typename A>
-__device__ __forceinline__ void warp_flush(A* acc, double* s_warp_row);
-
-// The whole fp64 Hessian-only pass of one warp.  Rare (only after a multi-trial line search) and register hungry
-// (46 fp64 coefficients + 22 fp64 accumulators): kept out of line so its register pressure and spills never touch the
-// fp32 hot path.
-template <int METHOD>
-__device__ __noinline__ void eval_hessian_f64(const float4* __restrict__ src, int n, int n_groups, const EvalCtx* ctx,
-                                              const MapView* map, double d2, double d1, double* s_warp_row) {
-  const int lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * kAlignWarps + (threadIdx.x >> 5);
-  const int warps_total = gridDim.x * kAlignWarps;
-  double acc[kNV];
-#pragma unroll
-  for (int k = 0; k < kNV; ++k) acc[k] = 0.0;
-  for (int g = warp_global; g < n_groups; g += warps_total) {
-    const int i = (g << 5) + lane;
-    if (i < n) eval_point_f64<METHOD>(__ldg(src + i), *ctx, *map, d2, d1, acc);
-  }
-  warp_flush(acc, s_warp_row);
-}
-
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -396,17 +243,94 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
-// Fold the per-thread accumulators of a warp into the warp's fp64 sums (fixed shuffle tree) and clear them.
-template <typename A>
-__device__ __forceinline__ void warp_flush(A* acc, double* s_warp_row) {
-  const int lane = threadIdx.x & 31;
+template <int METHOD>
+__device__ __forceinline__ void point_hessian_f64(const float4 pt, const EvalCtx& c, const MapView& m, const double d2,
+                                                  const double d1, double* acc /*[22]: H upper triangle, hits*/) {
+  float tx, ty, tz;
+  transform_point(c.T, pt.x, pt.y, pt.z, tx, ty, tz);
+  const int ix = static_cast<int>(floorf(__fdiv_rn(tx, m.leaf[0])));
+  const int iy = static_cast<int>(floorf(__fdiv_rn(ty, m.leaf[1])));
+  const int iz = static_cast<int>(floorf(__fdiv_rn(tz, m.leaf[2])));
+  constexpr int K = num_offsets<METHOD>();
+  double A[3] = {0, 0, 0}, M[6] = {0, 0, 0, 0, 0, 0};
+  int nh = 0;
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    int dx, dy, dz;
+    get_offset<METHOD>(k, dx, dy, dz);
+    const int rec = probe_cell(m, ix + dx, iy + dy, iz + dz);
+    if (rec < 0) continue;
+    ++nh;
+    const VoxelRecord* R = m.records + rec;
+    const double* ic = m.icov64 + (size_t)rec * 6;
+    const double r0 = static_cast<double>(tx) - (static_cast<double>(__ldg(&R->mean_hi[0])) + static_cast<double>(__ldg(&R->mean_lo[0])));
+    const double r1 = static_cast<double>(ty) - (static_cast<double>(__ldg(&R->mean_hi[1])) + static_cast<double>(__ldg(&R->mean_lo[1])));
+    const double r2 = static_cast<double>(tz) - (static_cast<double>(__ldg(&R->mean_hi[2])) + static_cast<double>(__ldg(&R->mean_lo[2])));
+    const double c00 = __ldg(ic), c01 = __ldg(ic + 1), c02 = __ldg(ic + 2), c11 = __ldg(ic + 3), c12 = __ldg(ic + 4), c22 = __ldg(ic + 5);
+    const double u0 = c00 * r0 + c01 * r1 + c02 * r2;
+    const double u1 = c01 * r0 + c11 * r1 + c12 * r2;
+    const double u2 = c02 * r0 + c12 * r1 + c22 * r2;
+    const double q = r0 * u0 + r1 * u1 + r2 * u2;
+    const double e2 = d2 * exp(-d2 * q / 2);  // ndt_omp_impl.hpp:622-626
+    if (!(e2 <= 1.0 && e2 >= 0.0)) continue;
+    const double w = e2 * d1;
+    A[0] += w * u0; A[1] += w * u1; A[2] += w * u2;
+    const double kk = -d2 * w;
+    const double t0 = kk * u0, t1 = kk * u1, t2 = kk * u2;
+    M[0] += w * c00 + t0 * u0;
+    M[1] += w * c01 + t0 * u1;
+    M[2] += w * c02 + t0 * u2;
+    M[3] += w * c11 + t1 * u1;
+    M[4] += w * c12 + t1 * u2;
+    M[5] += w * c22 + t2 * u2;
+  }
+  if (nh == 0) return;
+  acc[21] += static_cast<double>(nh);
+  const double x = pt.x, y = pt.y, z = pt.z;
+  double pj[8];
 #pragma unroll
-  for (int k = 0; k < kNV; ++k) {
-    double v = static_cast<double>(acc[k]);
+  for (int r = 0; r < 8; ++r) pj[r] = x * c.tab.jd[r][0] + y * c.tab.jd[r][1] + z * c.tab.jd[r][2];
+  const double m3x = M[1] * pj[0] + M[2] * pj[1], m3y = M[3] * pj[0] + M[4] * pj[1], m3z = M[4] * pj[0] + M[5] * pj[1];
+  const double m4x = M[0] * pj[2] + M[1] * pj[3] + M[2] * pj[4], m4y = M[1] * pj[2] + M[3] * pj[3] + M[4] * pj[4],
+               m4z = M[2] * pj[2] + M[4] * pj[3] + M[5] * pj[4];
+  const double m5x = M[0] * pj[5] + M[1] * pj[6] + M[2] * pj[7], m5y = M[1] * pj[5] + M[3] * pj[6] + M[4] * pj[7],
+               m5z = M[2] * pj[5] + M[4] * pj[6] + M[5] * pj[7];
+  acc[0] += M[0]; acc[1] += M[1]; acc[2] += M[2]; acc[3] += m3x; acc[4] += m4x; acc[5] += m5x;
+  acc[6] += M[3]; acc[7] += M[4]; acc[8] += m3y; acc[9] += m4y; acc[10] += m5y;
+  acc[11] += M[5]; acc[12] += m3z; acc[13] += m4z; acc[14] += m5z;
+#define NDTB200_PH(r) (x * c.tab.hd[r][0] + y * c.tab.hd[r][1] + z * c.tab.hd[r][2])
+  acc[15] += (pj[0] * m3y + pj[1] * m3z) + (A[1] * NDTB200_PH(0) + A[2] * NDTB200_PH(1));
+  acc[16] += (pj[0] * m4y + pj[1] * m4z) + (A[1] * NDTB200_PH(2) + A[2] * NDTB200_PH(3));
+  acc[17] += (pj[0] * m5y + pj[1] * m5z) + (A[1] * NDTB200_PH(4) + A[2] * NDTB200_PH(5));
+  acc[18] += (pj[2] * m4x + pj[3] * m4y + pj[4] * m4z) + (A[0] * NDTB200_PH(6) + A[1] * NDTB200_PH(7) + A[2] * NDTB200_PH(8));
+  acc[19] += (pj[2] * m5x + pj[3] * m5y + pj[4] * m5z) + (A[0] * NDTB200_PH(9) + A[1] * NDTB200_PH(10) + A[2] * NDTB200_PH(11));
+  acc[20] += (pj[5] * m5x + pj[6] * m5y + pj[7] * m5z) + (A[0] * NDTB200_PH(12) + A[1] * NDTB200_PH(13) + A[2] * NDTB200_PH(14));
+#undef NDTB200_PH
+}
+
+// The whole fp64 Hessian-only pass of one warp.  Rare (only after a multi-trial line search) and register hungry:
+// kept out of line so its register pressure never touches the fp32 hot path.  Writes the warp's fp64 sums
+// (fixed shuffle tree) to s_warp_row[0..31] (entries 0..6: score / gradient are not produced by this pass).
+template <int METHOD>
+__device__ __noinline__ void eval_hessian_f64(const float4* __restrict__ src, int n, int n_groups, int warp_global,
+                                              int warps_total, const EvalCtx* ctx, const MapView* map, double d2, double d1,
+                                              double* s_warp_row) {
+  const int lane = threadIdx.x & 31;
+  double acc[22];
+#pragma unroll
+  for (int k = 0; k < 22; ++k) acc[k] = 0.0;
+  for (int g = warp_global; g < n_groups; g += warps_total) {
+    const int i = (g << 5) + lane;
+    if (i < n) point_hessian_f64<METHOD>(__ldg(src + i), *ctx, *map, d2, d1, acc);
+  }
+  if (lane < 7) s_warp_row[lane] = 0.0;
+  if (lane >= 29) s_warp_row[lane] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 22; ++k) {
+    double v = acc[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_warp_row[k] += v;
-    acc[k] = A(0);
+    if (lane == 0) s_warp_row[7 + k] = v;
   }
 }
 
@@ -430,7 +354,7 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-constexpr int kRedRows = 20;  // partial rows per thread in flight while the last CTA reduces
+constexpr int kRedRows = (kAlignThreads >= 1024) ? 8 : 20;  // partial rows per thread in flight while the last CTA reduces
 
 __device__ __forceinline__ unsigned long long pack_lo(unsigned int tag, unsigned long long bits) {
   return (static_cast<unsigned long long>(tag) << 32) | (bits & 0xffffffffull);
@@ -479,6 +403,7 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
   if (G > 1) {
     if (threadIdx.x < kNV) ws.partials[(size_t)blockIdx.x * kNVP + threadIdx.x] = s_block[threadIdx.x];
     if (threadIdx.x == 31) ws.partials[(size_t)blockIdx.x * kNVP + 31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: arrival time of this CTA
+    if (threadIdx.x == 30) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); ws.partials[(size_t)blockIdx.x * kNVP + 30] = static_cast<double>(smid); }
     __syncthreads();
     if (threadIdx.x == 0) {
       const unsigned int ticket = atom_add_acq_rel_gpu(&ws.sync[0], 1u);  // release: the CTA's partials; acquire: everyone's
@@ -613,12 +538,12 @@ __device__ __forceinline__ void setup_pose_warp(const double* x_t, EvalCtx& ctx,
     if (t.s2) v = __dadd_rn(v, __dmul_rn(__dmul_rn(s_trig[t.a2], s_trig[t.b2]), s_trig[t.c2]) * static_cast<double>(t.s2));
     if (e < 24) {
       ctx.tab.jd[e / 3][e % 3] = v;
-      ctx.tab.jf[e / 3][e % 3] = static_cast<float>(v);
+      reinterpret_cast<float*>(&ctx.tf[e / 3])[e % 3] = static_cast<float>(v);
     } else {
       const int r = (e - 24) / 3, c = (e - 24) % 3;
       ctx.tab.hd[r][c] = v;
       // Q2: the fp32 table carries +sy in row d1 (ndt_omp_impl.hpp:383), the fp64 table -sy (:361)
-      ctx.tab.hf[r][c] = (r == 6 && c == 2) ? static_cast<float>(s_trig[4]) : static_cast<float>(v);
+      reinterpret_cast<float*>(&ctx.tf[8 + r])[c] = (r == 6 && c == 2) ? static_cast<float>(s_trig[4]) : static_cast<float>(v);
     }
   }
   if (build_matrix && lane == 0) {
@@ -715,9 +640,74 @@ __device__ __forceinline__ void warp_newton_solve(SolverState& st) {
   __syncwarp();
 }
 
+// H (6x6, both triangles) from the 21 reduced upper-triangle totals, one or two entries per lane.
+// computeDerivatives(..., false) leaves H zeroed (ndt_omp_impl.hpp:186, 218).
+__device__ __forceinline__ void unpack_hessian_warp(const double* tot, int kind) {
+  const int lane = threadIdx.x & 31;
+  for (int idx = lane; idx < 36; idx += 32) {
+    const int i = idx / 6, j = idx - i * 6;
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    const int k = 7 + a * 6 - (a * (a - 1)) / 2 + (b - a);
+    g_st.H[idx] = (kind == ACT_EVAL_NOHESS) ? 0.0 : tot[k];
+  }
+  __syncwarp();
+}
+
+// Fast path of the Newton solve: elimination WITHOUT pivot search / row swaps, rows spread over lanes 0..5.  Accepted
+// only when every pivot has the same sign (H definite — the normal case near the optimum, where no-pivot elimination
+// is backward stable) and the pivots span less than 1e9; otherwise the caller runs the pivoted solver.  Either way
+// the solution equals JacobiSVD::solve (ndt_omp_impl.hpp:127-129) up to cond(H) * eps.
+__device__ __forceinline__ bool warp_solve_definite() {
+  SolverState& st = g_st;
+  const int lane = threadIdx.x & 31;
+  const int r = lane < 6 ? lane : 5;
+  double a[7];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) a[j] = st.H[r * 6 + j];
+  a[6] = -st.g[r];
+  double pmin = 1e300, pmax = 0.0;
+  int npos = 0, nneg = 0;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const double pc = __shfl_sync(0xffffffffu, a[c], c);
+    npos += (pc > 0.0);
+    nneg += (pc < 0.0);
+    pmin = fmin(pmin, fabs(pc));
+    pmax = fmax(pmax, fabs(pc));
+    const double f = a[c] * (1.0 / pc);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      if (j <= c) continue;
+      const double pj = __shfl_sync(0xffffffffu, a[j], c);
+      if (lane > c && lane < 6) a[j] -= f * pj;
+    }
+  }
+  const bool ok = (npos == 6 || nneg == 6) && (pmin > 1e-9 * pmax) && !isinf(pmax);
+  if (!ok) return false;  // warp-uniform
+  double dinv = 1.0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    if (j == r) dinv = 1.0 / a[j];
+  double x[6];
+#pragma unroll
+  for (int rr = 5; rr >= 0; --rr) {
+    const double xr = __shfl_sync(0xffffffffu, a[6] * dinv, rr);
+    x[rr] = xr;
+    if (lane < rr) a[6] -= a[rr] * xr;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) st.delta[i] = x[i];
+  }
+  __syncwarp();
+  return true;
+}
+
 // After the Newton solve: step-length bookkeeping and start of the line search
 // (ndt_omp_impl.hpp:131-142, 772-837).  Returns the next action.
-__device__ __noinline__ int newton_post(SolverState& st, const AlignParams& prm) {
+__device__ __noinline__ int newton_post() {
+  SolverState& st = g_st;
+  const SolverState& prm = g_st;
   while (true) {
     const double* delta = st.delta;  // a zero-length step leaves H and g unchanged: same solution next round
     double nrm = 0;
@@ -727,6 +717,7 @@ __device__ __noinline__ int newton_post(SolverState& st, const AlignParams& prm)
       st.converged = (nrm == nrm) ? 1 : 0;
       return ACT_DONE;
     }
+#pragma unroll
     for (int i = 0; i < 6; ++i) st.dir[i] = delta[i] / nrm;
     // computeStepLengthMT(p, dir, nrm, step_size, eps/2, ...)
     st.step_max = prm.step_size;
@@ -775,19 +766,16 @@ __device__ __noinline__ int newton_post(SolverState& st, const AlignParams& prm)
 }
 
 // Called after every evaluation with the reduced totals; returns the next action.
-__device__ __noinline__ int advance(SolverState& st, const AlignParams& prm, const double* tot, int kind, TraceRec* trace) {
+__device__ __noinline__ int advance(const double* tot, int kind, TraceRec* trace) {
+  SolverState& st = g_st;
+  const SolverState& prm = g_st;
   st.need_pose = 0;
   if (kind != ACT_HESS_ONLY) {
     st.score = tot[0];
+#pragma unroll
     for (int i = 0; i < 6; ++i) st.g[i] = tot[1 + i];
   }
-  if (kind == ACT_EVAL_NOHESS) {
-    for (int i = 0; i < 36; ++i) st.H[i] = 0.0;  // computeDerivatives(..., false) leaves H zeroed
-  } else {
-    int k = 7;
-    for (int i = 0; i < 6; ++i)
-      for (int j = i; j < 6; ++j) { st.H[i * 6 + j] = tot[k]; st.H[j * 6 + i] = tot[k]; ++k; }
-  }
+  // st.H was filled by the lanes of the warp (unpack_hessian_warp) before this call
   st.n_hits += static_cast<long long>(tot[28]);
   if (kind == ACT_HESS_ONLY) st.n_hess++; else st.n_evals++;
   if (trace && st.n_trace < prm.trace_cap) {
@@ -871,221 +859,218 @@ mt_finish: {
 }
 
 // ---------------------------------------------------------------------------------------------
-// fp32 derivative pass of one CTA — two phases per chunk of kChunk points ("hit queue"):
-//   A  one thread per point: float4 load, transform, cell, all K hash probes in flight together, record
-//      prefetch; the point's transformed position and its J_E / H_E coefficients are staged in shared
-//      memory; every (point, voxel) hit is appended to the warp's queue segment (ballot compaction,
-//      deterministic order);
-//   B  the CTA's 256 threads consume the pooled queue densely, one hit per thread per round, so lanes
-//      stay ~100 % busy whatever the per-point hit count (0..K) and the work is balanced over the CTA.
+// fp32 derivative pass: ONE THREAD PER SOURCE POINT, contributions factorised per point.
+//
+// The reference adds, for every (point, voxel) hit, 6 gradient and 36 Hessian terms (ndt_omp_impl.hpp:512-534).  All of
+// them are linear in three per-hit quantities once the point's J_E / H_E are factored out (they depend on the point
+// only, :267):
+//     A = sum_hits w u                (3)      u = C (x' - mean),  w = d1 d2 exp(-d2/2 (x'-mean)^T u)
+//     M = sum_hits w (C - d2 u u^T)   (6, symmetric)
+//     S = sum_hits -d1 e              (1)
+//     g_i  = J_i . A                      H_ij = J_i^T M J_j + A . H_E[i][j]
+// so a hit costs ~45 fp32 instructions (u, q, exp, 3 + 12 FMAs) instead of ~220, and the 21 Hessian / 6 gradient terms
+// are formed once per point (~90 instructions).  J_E / H_E are only needed in that epilogue, which keeps the hit loop's
+// register footprint small.  Same validity test per hit (e2 > 1 || e2 < 0 || NaN contributes nothing, :506-507).
 // ---------------------------------------------------------------------------------------------
-constexpr int kPtVec = 7;              // float4 per staged point: x'(3) + pj(8) + ph(15) = 26 floats
-constexpr int kRedStride = kAlignThreads + 8;  // padded row of the final fold (conflict-free banks)
-constexpr int kFlushChunks = 2;        // fp32 run length bound: chunks before folding into fp64 (large clouds only)
-
-// 32-point groups per warp per chunk: 2 for DIRECT1/7 (512 points staged per CTA: ~86 KB of shared memory, two
-// CTAs per SM), 1 for DIRECT26 whose queue is 3.7x larger.
-template <int METHOD>
-__host__ __device__ constexpr int groups_per_warp() { return METHOD == 1 ? 1 : 2; }
-template <int METHOD>
-__host__ __device__ constexpr int queue_cap_per_warp() {
-  return groups_per_warp<METHOD>() * 32 * (METHOD == 3 ? 1 : (METHOD == 2 ? 7 : 26));
-}
-template <int METHOD>
-__host__ __device__ constexpr size_t eval_smem_bytes() {
-  return (size_t)groups_per_warp<METHOD>() * kAlignThreads * kPtVec * 16 + (size_t)kAlignWarps * queue_cap_per_warp<METHOD>() * 8;
-}
-
-// Fold the per-thread fp32 partials into the fp64 CTA sums through shared memory (the staging buffers are free when
-// this is called): thread (k, sub) adds 32 of the 256 partials of value k — groups of 4 in fp32 (short runs), then
-// fp64 — and 8 lanes combine in a fixed tree.  ~8x fewer instructions than a 29-value warp shuffle tree per warp.
-// Clears acc.  Must be called by all threads of the CTA.
-__device__ __forceinline__ void fold_partials(float (&acc)[kNV], float* s_red, double* s_extra) {
-#pragma unroll
-  for (int k = 0; k < kNV; ++k) { s_red[k * kRedStride + threadIdx.x] = acc[k]; acc[k] = 0.0f; }
-  __syncthreads();
-  const int k = threadIdx.x >> 3, sub = threadIdx.x & 7;
-  double s = 0.0;
-  if (k < kNV) {
-    const float* row = s_red + k * kRedStride + sub;
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      s0 += static_cast<double>((row[8 * i] + row[8 * (i + 1)]) + (row[8 * (i + 2)] + row[8 * (i + 3)]));
-      s1 += static_cast<double>((row[8 * (i + 4)] + row[8 * (i + 5)]) + (row[8 * (i + 6)] + row[8 * (i + 7)]));
-    }
-    s = s0 + s1;
+template <bool HESS>
+__device__ __forceinline__ void hit_f32(const VoxelRecord* R, float tx, float ty, float tz, float d2f, float d1f,
+                                        float& S, float (&A)[3], float (&M)[6]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(R));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(R) + 1);
+  const float4 c = __ldg(reinterpret_cast<const float4*>(R) + 2);
+  // x_trans = fl32(double(x') - mean) (ndt_omp_impl.hpp:259-262, 492) via the exact hi/lo split of the mean
+  const float r0 = __fsub_rn(__fsub_rn(tx, a.x), a.w);
+  const float r1 = __fsub_rn(__fsub_rn(ty, a.y), b.x);
+  const float r2 = __fsub_rn(__fsub_rn(tz, a.z), b.y);
+  const float c00 = b.z, c01 = b.w, c02 = c.x, c11 = c.y, c12 = c.z, c22 = c.w;
+  const float u0 = c00 * r0 + c01 * r1 + c02 * r2;
+  const float u1 = c01 * r0 + c11 * r1 + c12 * r2;
+  const float u2 = c02 * r0 + c12 * r1 + c22 * r2;
+  const float q = r0 * u0 + r1 * u1 + r2 * u2;
+  const float e = expf(-d2f * q * 0.5f);  // ndt_omp_impl.hpp:499
+  const float e2 = d2f * e;
+  if (!(e2 <= 1.0f && e2 >= 0.0f)) return;  // :506-507
+  S -= d1f * e;
+  const float w = e2 * d1f;
+  A[0] += w * u0;
+  A[1] += w * u1;
+  A[2] += w * u2;
+  if (HESS) {
+    const float k = -d2f * w;
+    const float t0 = k * u0, t1 = k * u1, t2 = k * u2;
+    M[0] += w * c00; M[0] += t0 * u0;
+    M[1] += w * c01; M[1] += t0 * u1;
+    M[2] += w * c02; M[2] += t0 * u2;
+    M[3] += w * c11; M[3] += t1 * u1;
+    M[4] += w * c12; M[4] += t1 * u2;
+    M[5] += w * c22; M[5] += t2 * u2;
   }
-  s += __shfl_down_sync(0xffffffffu, s, 4, 8);
-  s += __shfl_down_sync(0xffffffffu, s, 2, 8);
-  s += __shfl_down_sync(0xffffffffu, s, 1, 8);
-  if (k < kNV && sub == 0) s_extra[k] += s;
 }
 
-struct HitOperands {  // what phase B needs for one hit before the arithmetic starts
-  uint2 e;
-  float4 a, b, c;  // the 48 hot bytes of the voxel record
-};
-
-// q-th entry of the pooled queue: the per-warp segments are walked forward only (q grows by 256 per round)
-__device__ __forceinline__ HitOperands fetch_hit(const uint2* s_q, const int* s_wcount, int qcap, int q, int& seg, int& base,
-                                                 const VoxelRecord* records) {
-  while (q >= base + s_wcount[seg]) { base += s_wcount[seg]; ++seg; }
-  HitOperands h;
-  h.e = s_q[seg * qcap + (q - base)];
-  const float4* R = reinterpret_cast<const float4*>(records + h.e.x);
-  h.a = __ldg(R);
-  h.b = __ldg(R + 1);
-  h.c = __ldg(R + 2);
-  return h;
-}
-
+// acc: [0] score, [1..6] gradient, [7..27] Hessian upper triangle row-major, [28] hits found, [29..31] unused (zero)
 template <int METHOD, bool HESS>
-__device__ __forceinline__ void eval_chunked_f32(const float4* __restrict__ src, int n, int n_groups, const EvalCtx& ctx,
-                                                 const MapView& m, float d2f, float d1f, float4* s_pts, uint2* s_q,
-                                                 int* s_wcount, double (*s_warp)[kNVP], double* s_extra,
-                                                 unsigned long long* s_dbg) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void point_f32(float px, float py, float pz, const EvalCtx& ctx, const MapView& m, float d2f,
+                                          float d1f, float (&acc)[32]) {
+  float tx, ty, tz;
+  transform_point(ctx.T, px, py, pz, tx, ty, tz);
+  // getNeighborhoodAtPoint (…_impl.hpp:379-381): cell = floor(x' / leaf), fp32 DIVISION (Q8)
+  const int ix = static_cast<int>(floorf(__fdiv_rn(tx, m.leaf[0])));
+  const int iy = static_cast<int>(floorf(__fdiv_rn(ty, m.leaf[1])));
+  const int iz = static_cast<int>(floorf(__fdiv_rn(tz, m.leaf[2])));
   constexpr int K = num_offsets<METHOD>();
-  constexpr int GPW = groups_per_warp<METHOD>();
-  constexpr int QCAP = queue_cap_per_warp<METHOD>();
-  const unsigned int lt_mask = (1u << lane) - 1u;
-  float acc[kNV];
+  float S = 0.f, A[3] = {0.f, 0.f, 0.f}, M[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int nh = 0;
+  if constexpr (METHOD != 1) {
+    int rec[K];
+    probe_cells<K>(m, ix, iy, iz, rec);
 #pragma unroll
-  for (int k = 0; k < kNV; ++k) acc[k] = 0.0f;
-  int chunks_since = 0;
-  // this CTA's 32-point groups: g = blockIdx.x + j * gridDim.x (interleaved over the grid)
-  const int groups_mine = (n_groups > (int)blockIdx.x) ? (n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  for (int j0 = 0; j0 < groups_mine; j0 += kAlignWarps * GPW) {
-    // ---------------- phase A ----------------
-    int wcount = 0;
-    uint2* qw = s_q + warp * QCAP;
-#pragma unroll
-    for (int s = 0; s < GPW; ++s) {
-      const int j = j0 + s * kAlignWarps + warp;
-      if (j < groups_mine) {  // warp-uniform
-        const int i = ((blockIdx.x + j * gridDim.x) << 5) + lane;
-        const int slot = s * kAlignThreads + threadIdx.x;
-        const bool valid = i < n;
-        const float4 pt = valid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float tx, ty, tz;
-        transform_point(ctx.T, pt.x, pt.y, pt.z, tx, ty, tz);
-        // getNeighborhoodAtPoint (…_impl.hpp:379-381): cell = floor(x' / leaf), fp32 DIVISION (Q8)
-        const int ix = static_cast<int>(floorf(__fdiv_rn(tx, m.leaf[0])));
-        const int iy = static_cast<int>(floorf(__fdiv_rn(ty, m.leaf[1])));
-        const int iz = static_cast<int>(floorf(__fdiv_rn(tz, m.leaf[2])));
-        if constexpr (METHOD != 1) {
-          int rec[K];
-          probe_cells<K>(m, ix, iy, iz, rec);
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-            const bool hit = valid && rec[k] >= 0;
-            const unsigned int mask = __ballot_sync(0xffffffffu, hit);
-            if (hit) qw[wcount + __popc(mask & lt_mask)] = make_uint2(static_cast<unsigned int>(rec[k]), slot);
-            wcount += __popc(mask);
-          }
-        } else {
+    for (int k = 0; k < K; ++k) {
+      if (rec[k] < 0) continue;
+      ++nh;
+      hit_f32<HESS>(m.records + rec[k], tx, ty, tz, d2f, d1f, S, A, M);
+    }
+  } else {
 #pragma unroll 1
-          for (int k = 0; k < K; ++k) {
-            int dx, dy, dz;
-            get_offset<METHOD>(k, dx, dy, dz);
-            const int rec = valid ? probe_cell(m, ix + dx, iy + dy, iz + dz) : -1;
-            const bool hit = rec >= 0;
-            const unsigned int mask = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
-              qw[wcount + __popc(mask & lt_mask)] = make_uint2(static_cast<unsigned int>(rec), slot);
-              prefetch_l2(m.records + rec);
-            }
-            wcount += __popc(mask);
-          }
-        }
-        // computePointDerivatives (fp32 overload, ndt_omp_impl.hpp:398-440): depends on the ORIGINAL point only
-        float pj[8], ph[15];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) pj[r] = ctx.tab.jf[r][0] * pt.x + ctx.tab.jf[r][1] * pt.y + ctx.tab.jf[r][2] * pt.z;
-        float4* P = s_pts + slot * kPtVec;
-        P[0] = make_float4(tx, ty, tz, pj[0]);
-        P[1] = make_float4(pj[1], pj[2], pj[3], pj[4]);
-        if (HESS) {
-#pragma unroll
-          for (int r = 0; r < 15; ++r) ph[r] = ctx.tab.hf[r][0] * pt.x + ctx.tab.hf[r][1] * pt.y + ctx.tab.hf[r][2] * pt.z;
-          P[2] = make_float4(pj[5], pj[6], pj[7], ph[0]);
-          P[3] = make_float4(ph[1], ph[2], ph[3], ph[4]);
-          P[4] = make_float4(ph[5], ph[6], ph[7], ph[8]);
-          P[5] = make_float4(ph[9], ph[10], ph[11], ph[12]);
-          P[6] = make_float4(ph[13], ph[14], 0.f, 0.f);
-        } else {
-          P[2] = make_float4(pj[5], pj[6], pj[7], 0.f);
-        }
-      }
-    }
-    if (lane == 0) s_wcount[warp] = wcount;
-    __syncthreads();
-    if (threadIdx.x == 0 && j0 == 0) s_dbg[0] = globaltimer_ns();
-    // ---------------- phase B ----------------
-    int Q = 0;
-#pragma unroll
-    for (int w = 0; w < kAlignWarps; ++w) Q += s_wcount[w];
-    int seg = 0, base = 0;
-    for (int q = threadIdx.x; q < Q; q += kAlignThreads) {
-      const HitOperands cur = fetch_hit(s_q, s_wcount, QCAP, q, seg, base, m.records);
-      const float4* P = s_pts + cur.e.y * kPtVec;
-      const float4 v0 = P[0], v1 = P[1], v2 = P[2];
-      float pj[8] = {v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z};
-      float ph[15];
-      if (HESS) {
-        const float4 v3 = P[3], v4 = P[4], v5 = P[5], v6 = P[6];
-        ph[0] = v2.w; ph[1] = v3.x; ph[2] = v3.y; ph[3] = v3.z; ph[4] = v3.w; ph[5] = v4.x; ph[6] = v4.y; ph[7] = v4.z;
-        ph[8] = v4.w; ph[9] = v5.x; ph[10] = v5.y; ph[11] = v5.z; ph[12] = v5.w; ph[13] = v6.x; ph[14] = v6.y;
-      }
-      // x_trans = fl32(double(x') - mean) (ndt_omp_impl.hpp:259-262, 492) via the exact hi/lo split of the mean
-      const float r0 = __fsub_rn(__fsub_rn(v0.x, cur.a.x), cur.a.w);
-      const float r1 = __fsub_rn(__fsub_rn(v0.y, cur.a.y), cur.b.x);
-      const float r2 = __fsub_rn(__fsub_rn(v0.z, cur.a.z), cur.b.y);
-      acc[28] += 1.0f;
-      hit_contribution<float, true, HESS>(r0, r1, r2, cur.b.z, cur.b.w, cur.c.x, cur.c.y, cur.c.z, cur.c.w, pj, ph, d2f, d1f, acc);
-    }
-    __syncthreads();  // the next chunk overwrites the staging buffers
-    if (threadIdx.x == 0 && j0 == 0) s_dbg[1] = globaltimer_ns();
-    if (++chunks_since == kFlushChunks) {  // only reached by large clouds: bound the fp32 run length
-      fold_partials(acc, reinterpret_cast<float*>(s_pts), s_extra);
-      __syncthreads();
-      chunks_since = 0;
+    for (int k = 0; k < K; ++k) {
+      int dx, dy, dz;
+      get_offset<METHOD>(k, dx, dy, dz);
+      const int rec = probe_cell(m, ix + dx, iy + dy, iz + dz);
+      if (rec < 0) continue;
+      ++nh;
+      hit_f32<HESS>(m.records + rec, tx, ty, tz, d2f, d1f, S, A, M);
     }
   }
-  fold_partials(acc, reinterpret_cast<float*>(s_pts), s_extra);
+  if (nh == 0) return;
+  acc[28] += static_cast<float>(nh);
+  acc[0] += S;
+  // computePointDerivatives (fp32 overload, ndt_omp_impl.hpp:398-440): J_E entries pj[0..7], H_E entries ph[0..14]
+  float pj[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const float4 t = ctx.tf[r];
+    pj[r] = t.x * px + t.y * py + t.z * pz;
+  }
+  acc[1] += A[0];
+  acc[2] += A[1];
+  acc[3] += A[2];
+  acc[4] += A[1] * pj[0] + A[2] * pj[1];
+  acc[5] += A[0] * pj[2] + A[1] * pj[3] + A[2] * pj[4];
+  acc[6] += A[0] * pj[5] + A[1] * pj[6] + A[2] * pj[7];
+  if (HESS) {
+    float ph[15];
+#pragma unroll
+    for (int r = 0; r < 15; ++r) {
+      const float4 t = ctx.tf[8 + r];
+      ph[r] = t.x * px + t.y * py + t.z * pz;
+    }
+    // M J_i for the rotational columns J_3 = (0,pj0,pj1), J_4 = (pj2,pj3,pj4), J_5 = (pj5,pj6,pj7)
+    const float m3x = M[1] * pj[0] + M[2] * pj[1], m3y = M[3] * pj[0] + M[4] * pj[1], m3z = M[4] * pj[0] + M[5] * pj[1];
+    const float m4x = M[0] * pj[2] + M[1] * pj[3] + M[2] * pj[4], m4y = M[1] * pj[2] + M[3] * pj[3] + M[4] * pj[4],
+                m4z = M[2] * pj[2] + M[4] * pj[3] + M[5] * pj[4];
+    const float m5x = M[0] * pj[5] + M[1] * pj[6] + M[2] * pj[7], m5y = M[1] * pj[5] + M[3] * pj[6] + M[4] * pj[7],
+                m5z = M[2] * pj[5] + M[4] * pj[6] + M[5] * pj[7];
+    acc[7] += M[0];  acc[8] += M[1];  acc[9] += M[2];  acc[10] += m3x; acc[11] += m4x; acc[12] += m5x;
+    acc[13] += M[3]; acc[14] += M[4]; acc[15] += m3y;  acc[16] += m4y; acc[17] += m5y;
+    acc[18] += M[5]; acc[19] += m3z;  acc[20] += m4z;  acc[21] += m5z;
+    acc[22] += (pj[0] * m3y + pj[1] * m3z) + (A[1] * ph[0] + A[2] * ph[1]);
+    acc[23] += (pj[0] * m4y + pj[1] * m4z) + (A[1] * ph[2] + A[2] * ph[3]);
+    acc[24] += (pj[0] * m5y + pj[1] * m5z) + (A[1] * ph[4] + A[2] * ph[5]);
+    acc[25] += (pj[2] * m4x + pj[3] * m4y + pj[4] * m4z) + (A[0] * ph[6] + A[1] * ph[7] + A[2] * ph[8]);
+    acc[26] += (pj[2] * m5x + pj[3] * m5y + pj[4] * m5z) + (A[0] * ph[9] + A[1] * ph[10] + A[2] * ph[11]);
+    acc[27] += (pj[5] * m5x + pj[6] * m5y + pj[7] * m5z) + (A[0] * ph[12] + A[1] * ph[13] + A[2] * ph[14]);
+  }
+}
+
+// Sum 32 per-lane quantities over the 32 lanes of a warp with 31 shuffles (recursive halving: at every level a lane
+// keeps one half of its values and sends the other half to its partner).  Lane l returns the warp sum of v[l].
+// Fixed pairwise tree: deterministic, error <= 5 ulp of sum|v| — not a long fp32 run.
+template <typename T>
+__device__ __forceinline__ T warp_transpose_sum(T (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const T send = upper ? v[i] : v[i + half];
+      const T keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+// The fp32 derivative pass of one warp over its 32-point groups g = warp_global + j * warps_total.  The first two
+// points of every thread live in registers for the whole solve (the source never changes between evaluations; clouds
+// of up to 2 x (threads in the grid) points are never re-read from memory after the first evaluation).
+// Returns (lane k) the warp's fp64 sum of quantity k.
+template <int METHOD, bool HESS>
+__device__ __forceinline__ double eval_warp_f32(const float4* __restrict__ src, int n, int n_groups, int warp_global,
+                                                int warps_total, const float (&cached)[2][3], const EvalCtx& ctx,
+                                                const MapView& m, float d2f, float d1f) {
+  const int lane = threadIdx.x & 31;
+  float acc[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc[k] = 0.0f;
+  double wsum = 0.0;
+  int since = 0;
+  int j = 0;
+  for (int g = warp_global; g < n_groups; g += warps_total, ++j) {
+    const int i = (g << 5) + lane;
+    if (i < n) {
+      float px, py, pz;
+      if (j == 0) { px = cached[0][0]; py = cached[0][1]; pz = cached[0][2]; }
+      else if (j == 1) { px = cached[1][0]; py = cached[1][1]; pz = cached[1][2]; }
+      else { const float4 pt = __ldg(src + i); px = pt.x; py = pt.y; pz = pt.z; }
+      point_f32<METHOD, HESS>(px, py, pz, ctx, m, d2f, d1f, acc);
+    }
+    if (++since == kFlushPoints) {  // bound the fp32 run length of a thread (large clouds only)
+      wsum += static_cast<double>(warp_transpose_sum(acc));
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc[k] = 0.0f;
+      since = 0;
+    }
+  }
+  if (since) wsum += static_cast<double>(warp_transpose_sum(acc));
+  return wsum;
 }
 
 // ---------------------------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------------------------
 template <int METHOD>
-__global__ void __launch_bounds__(kAlignThreads, 2)
+__global__ void __launch_bounds__(kAlignThreads, kAlignMinBlocks)
 ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignParams prm, const AlignWorkspace ws) {
-  __shared__ SolverState st;
-  __shared__ EvalCtx ctx;
+  SolverState& st = g_st;
+  EvalCtx& ctx = g_ctx;
   __shared__ double s_warp[kAlignWarps][kNVP];
   __shared__ double s_block[kNVP];
   __shared__ double s_tot[kNVP];
-  __shared__ double s_extra[kNVP];
   __shared__ unsigned long long s_dbg[4];
   __shared__ double s_trig[16];
   __shared__ TableTerm s_terms[69];
   __shared__ int s_action;
   __shared__ int s_flag;
-  __shared__ int s_wcount[kAlignWarps];
-  extern __shared__ float4 dyn_smem[];
-  float4* s_pts = dyn_smem;                                                                      // [GPW * 256][kPtVec]
-  uint2* s_q = reinterpret_cast<uint2*>(dyn_smem + groups_per_warp<METHOD>() * kAlignThreads * kPtVec);  // [kAlignWarps][QCAP]
+  __shared__ MapView s_map;  // for the out-of-line fp64 pass (taking the parameter's address would copy it to local memory)
 
   const unsigned long long t_kernel_begin = globaltimer_ns();
   const int n = prm.n_source;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // 32-point groups interleaved over all warps of the grid (deterministic static balance)
   const int n_groups = (n + 31) >> 5;
-  const int warp_global = blockIdx.x * kAlignWarps + warp;
+  const int warp_global = warp * gridDim.x + (blockIdx.x + prm.rot) % gridDim.x;  // consecutive groups go to different SMs
   const int warps_total = gridDim.x * kAlignWarps;
   unsigned int epoch = 0;
+
+  // this thread's first two source points stay in registers for the whole solve
+  float cached[2][3];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const long long i = (static_cast<long long>(warp_global + j * warps_total) << 5) + lane;
+    float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) pt = __ldg(src + i);
+    cached[j][0] = pt.x; cached[j][1] = pt.y; cached[j][2] = pt.z;
+  }
 
   if (threadIdx.x == 0) {
     // align() prologue + computeTransformation up to the first computeDerivatives (ndt_omp_impl.hpp:83-119)
@@ -1105,6 +1090,10 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
       st.final_T[i] = prm.T0[i];  // final_transformation_ = guess (:98) or Identity (align())
     }
     for (int i = 0; i < 6; ++i) st.last_dp[i] = 0.0;
+    st.step_size = prm.step_size;
+    st.trans_eps = prm.trans_eps;
+    st.max_iterations = prm.max_iterations;
+    st.trace_cap = prm.trace_cap;
     if (prm.mode == MODE_ALIGN) {
       st.state = ST_INITIAL;
       s_action = ACT_EVAL_FULL;
@@ -1117,7 +1106,14 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     }
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 69) s_terms[threadIdx.x - 64] = g_table_terms[threadIdx.x - 64];
-  if (threadIdx.x == 32) ctx.tab = prm.tab0;  // tables for p0 (computed on the host); matrix = T0
+  if (threadIdx.x == 33) s_map = map;
+  if (threadIdx.x == 32) {  // tables for p0 (computed on the host); matrix = T0
+    ctx.tab = prm.tab0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ctx.tf[r] = make_float4(prm.tab0.jf[r][0], prm.tab0.jf[r][1], prm.tab0.jf[r][2], 0.f);
+#pragma unroll
+    for (int r = 0; r < 15; ++r) ctx.tf[8 + r] = make_float4(prm.tab0.hf[r][0], prm.tab0.hf[r][1], prm.tab0.hf[r][2], 0.f);
+  }
   __syncthreads();
 
   const float d2f = static_cast<float>(prm.d2);
@@ -1128,25 +1124,25 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     unsigned long long t_start = 0, t_local = 0, t_reduced = 0;
     const bool timing = (blockIdx.x == 0 && threadIdx.x == 0 && ws.trace != nullptr);
     if (timing) t_start = globaltimer_ns();
-    if (threadIdx.x < kAlignWarps * kNVP) (&s_warp[0][0])[threadIdx.x] = 0.0;
-    if (threadIdx.x < kNVP) s_extra[threadIdx.x] = 0.0;
-    __syncthreads();
 
     if (action == ACT_HESS_ONLY) {
-      eval_hessian_f64<METHOD>(src, n, n_groups, &ctx, &map, prm.d2, prm.d1, s_warp[warp]);
-    } else if (action == ACT_EVAL_FULL) {
-      eval_chunked_f32<METHOD, true>(src, n, n_groups, ctx, map, d2f, d1f, s_pts, s_q, s_wcount, s_warp, s_extra, s_dbg);
+      eval_hessian_f64<METHOD>(src, n, n_groups, warp_global, warps_total, &ctx, &s_map, prm.d2, prm.d1, s_warp[warp]);
     } else {
-      eval_chunked_f32<METHOD, false>(src, n, n_groups, ctx, map, d2f, d1f, s_pts, s_q, s_wcount, s_warp, s_extra, s_dbg);
+      double wsum;
+      if (action == ACT_EVAL_FULL)
+        wsum = eval_warp_f32<METHOD, true>(src, n, n_groups, warp_global, warps_total, cached, ctx, map, d2f, d1f);
+      else
+        wsum = eval_warp_f32<METHOD, false>(src, n, n_groups, warp_global, warps_total, cached, ctx, map, d2f, d1f);
+      s_warp[warp][lane] = wsum;
     }
+    if (timing) s_dbg[0] = globaltimer_ns();
     __syncthreads();
-    if (threadIdx.x < kNV) {
+    if (threadIdx.x < kNV) {  // fp64 sum over the CTA's warps, fixed order
       double s = 0;
-#pragma unroll
+#pragma unroll 8
       for (int w = 0; w < kAlignWarps; ++w) s += s_warp[w][threadIdx.x];
-      s_block[threadIdx.x] = s + s_extra[threadIdx.x];
+      s_block[threadIdx.x] = s;
     }
-    __syncthreads();
     if (timing) t_local = globaltimer_ns();
     grid_allreduce(s_block, s_tot, ws, epoch, &s_flag, s_warp, prm.launch_tag);
     if (ws.world > 1 && *reinterpret_cast<volatile unsigned int*>(&ws.sync[3]) != 0u) break;  // a peer never answered (uniform: checked after a barrier)
@@ -1155,26 +1151,29 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     if (timing && gridDim.x > 1) t_last_arrive = static_cast<unsigned long long>(__double_as_longlong(__ldcg(ws.totals + 2 * kNVP + ((epoch - 1u) & 1u))));
     int slot = 0;
     unsigned long long t_d0 = 0, t_d1 = 0, t_d2 = 0;
-    if (threadIdx.x == 0) {
-      slot = st.n_trace;
-      s_action = advance(st, prm, s_tot, action, blockIdx.x == 0 ? ws.trace : nullptr);
-    }
-    __syncthreads();
-    if (timing) t_d0 = t_d1 = t_d2 = globaltimer_ns();
-    if (s_action == ACT_SOLVE) {  // block-uniform
-      if (warp == 0) warp_newton_solve(st);
-      __syncthreads();
-      if (timing) t_d1 = globaltimer_ns();
-      if (threadIdx.x == 0) s_action = newton_post(st, prm);
-      __syncthreads();
-      if (timing) t_d2 = globaltimer_ns();
-    }
-    if (st.need_pose) setup_pose_warp(st.x_t, ctx, st.final_T, s_trig, s_terms, /*build_matrix=*/true);
-    if (timing && slot < prm.trace_cap) {
-      TraceRec& r = ws.trace[slot];
-      r.t_start = t_start; r.t_local = t_local; r.t_reduced = t_reduced; r.t_advanced = globaltimer_ns();
-      r.t_dbg[0] = t_d0; r.t_dbg[1] = t_d1; r.t_dbg[2] = t_d2; r.t_dbg[3] = t_last_arrive;
-      r.t_phase[0] = s_dbg[0]; r.t_phase[1] = s_dbg[1];
+    // the step: warp 0 of every CTA runs the identical Newton / More-Thuente state machine on the identical totals
+    if (warp == 0) {
+      unpack_hessian_warp(s_tot, action);
+      if (lane == 0) {
+        slot = st.n_trace;
+        s_action = advance(s_tot, action, blockIdx.x == 0 ? ws.trace : nullptr);
+      }
+      __syncwarp();
+      if (timing) t_d0 = t_d1 = t_d2 = globaltimer_ns();
+      if (s_action == ACT_SOLVE) {  // warp-uniform
+        if (!warp_solve_definite()) warp_newton_solve(st);
+        if (timing) t_d1 = globaltimer_ns();
+        if (lane == 0) s_action = newton_post();
+        __syncwarp();
+        if (timing) t_d2 = globaltimer_ns();
+      }
+      if (st.need_pose) setup_pose_warp(st.x_t, ctx, st.final_T, s_trig, s_terms, /*build_matrix=*/true);
+      if (timing && slot < prm.trace_cap) {
+        TraceRec& r = ws.trace[slot];
+        r.t_start = t_start; r.t_local = t_local; r.t_reduced = t_reduced; r.t_advanced = globaltimer_ns();
+        r.t_dbg[0] = t_d0; r.t_dbg[1] = t_d1; r.t_dbg[2] = t_d2; r.t_dbg[3] = t_last_arrive;
+        r.t_phase[0] = s_dbg[0]; r.t_phase[1] = t_local;
+      }
     }
     __syncthreads();
   }

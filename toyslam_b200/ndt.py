@@ -42,7 +42,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB_PATH
+    # NDTB200_LIB: development only — lets a tuning run load an alternative build of the SAME library (other CTA shape)
+    return os.environ.get("NDTB200_LIB") or _build.LIB_PATH
 
 
 def exported_symbols():
