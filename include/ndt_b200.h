@@ -113,6 +113,21 @@ int ndtb200_align_async(ndtb200_handle* h, const float* guess);
 /* ... and wait for it + fetch the result block (one small D2H copy). */
 int ndtb200_sync(ndtb200_handle* h);
 int ndtb200_get_result(ndtb200_handle* h, ndtb200_result* out);
+/* Throughput mode (not in the reference): the solve kernel of this handle uses small CTAs (one per SM), so the solves
+ * of up to four handles — launched on their own streams before anyone waits — are co-resident on every SM and cover
+ * each other's barrier / Newton-step latency.  Default off: one solve owns the whole GPU (lowest latency). */
+int ndtb200_set_throughput_mode(ndtb200_handle* h, int on);
+/* Batched scan pairs (the ndt_rosbag_mapping_node sequence, ndt_rosbag_mapping_node.cpp:99-144, when the pairs are
+ * independent): n handles, each with its own target map and source already set, are aligned together in throughput
+ * mode.  guesses: n column-major 4x4 matrices or NULL (identity); out_points: n host buffers for the aligned clouds
+ * (out_stride_bytes each record) or NULL; results: n entries or NULL.  Returns after all solves have finished; the
+ * first non-OK status is reported. */
+int ndtb200_align_batch(ndtb200_handle* const* hs, int n, const float* guesses, void* const* out_points,
+                        size_t out_stride_bytes, ndtb200_result* results);
+/* Enqueue-only half (every solve, output cloud and result copy goes onto its handle's stream; no host wait):
+ * finish each handle with ndtb200_sync.  out_points: n host buffers (or NULL) as in ndtb200_align. */
+int ndtb200_align_batch_async(ndtb200_handle* const* hs, int n, const float* guesses, void* const* out_points,
+                              size_t out_stride_bytes);
 /* getFitnessScore(max_range) (pcl::Registration): mean squared distance of T*source to its exact
  * nearest raw target point. */
 int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out);

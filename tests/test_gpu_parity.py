@@ -249,6 +249,48 @@ def test_align_config1_golden_fitness(nb, method, name):
     assert np.array_equal(gpu.result()["final"], rg["final"])
 
 
+@pytest.mark.parametrize("method", [oracle.DIRECT7, oracle.DIRECT1, oracle.DIRECT26])
+def test_align_throughput_shape(nb, method):
+    """The small-CTA (throughput) shape of the solve kernel must meet the same parity bar as the default shape."""
+    tgt, src = load_pair("pair_ds0p3.npz")
+    ref, gpu = make_pair(nb, tgt, src, method=method, eps=0.01, max_iter=64)
+    gpu.set_throughput_mode(True)
+    check_align(ref, gpu)
+    for p in POSES[:3]:
+        a, b = gpu.eval_derivatives(p, True), ref.eval_derivatives(p, True)
+        assert rel_err(a["gradient"], b["gradient"]) < REL and rel_err(a["hessian"], b["hessian"]) < REL
+        assert rel_err(gpu.eval_hessian(p), ref.eval_hessian(p)) < REL
+
+
+def test_align_batch_independent_pairs(nb):
+    """ndtb200_align_batch: several independent scan pairs in flight together give each pair the result its own
+    align() gives (oracle parity per pair; pairs differ in source, perturbation and guess)."""
+    tgt, src = load_pair("pair_ds0p3.npz")
+    rng = np.random.default_rng(5)
+    refs, gpus, guesses = [], [], []
+    for i in range(6):
+        p = np.concatenate([rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.02, 0.02, 3)])
+        s_i = oracle.transform_points(pose_matrix(p), src)[:, :3].astype(np.float32)
+        t_i = tgt if i % 2 == 0 else (tgt + np.float32(0.37 * i)).astype(np.float32)
+        s_i = s_i if i % 2 == 0 else (s_i + np.float32(0.37 * i)).astype(np.float32)
+        ref, gpu = make_pair(nb, t_i, s_i, eps=0.01, max_iter=64)
+        refs.append(ref); gpus.append(gpu)
+        guesses.append(pose_matrix(np.array([0.05 * i, 0, 0, 0, 0, 0.002 * i])) if i >= 3 else np.eye(4))
+    results = nb.align_batch(gpus, guesses)
+    assert len(results) == 6
+    for ref, gpu, g, rg in zip(refs, gpus, guesses, results):
+        ref.align(g)
+        rr = ref.result()
+        assert rg["iterations"] == rr["iterations"] and rg["n_evaluations"] == rr["n_evaluations"]
+        assert rg["n_hessian_passes"] == rr["n_hessian_passes"] and rg["converged"] == rr["converged"]
+        dt, dr = transform_delta(rg["final"], rr["final"])
+        assert dt < TRANS_TOL and dr < ROT_TOL, (dt, dr)
+    # the default (latency) shape is back after the batch call
+    gpus[0].align(guesses[0])
+    dt, dr = transform_delta(gpus[0].result()["final"], results[0]["final"])
+    assert dt < 1e-6 and dr < 1e-6
+
+
 def test_align_direct26(nb):
     tgt, src = load_pair()
     ref, gpu = make_pair(nb, tgt, src, method=oracle.DIRECT26)

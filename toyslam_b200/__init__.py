@@ -13,7 +13,9 @@ from .ndt import (  # noqa: F401
     DIRECT26,
     KDTREE,
     NdtError,
+    Batch,
     NormalDistributionsTransform,
+    align_batch,
     device_count,
     exported_symbols,
     library_path,
@@ -21,4 +23,4 @@ from .ndt import (  # noqa: F401
 )
 
 __all__ = ["NormalDistributionsTransform", "NdtError", "KDTREE", "DIRECT26", "DIRECT7", "DIRECT1",
-           "device_count", "load_library", "library_path", "exported_symbols"]
+           "Batch", "align_batch", "device_count", "load_library", "library_path", "exported_symbols"]

@@ -50,6 +50,7 @@ struct ndtb200_handle {
   long long launches = 0;
   uint32_t launch_seq = 0;
   int last_blocks = 0;
+  bool result_copy_enqueued = false;
 
   // multi-GPU source sharding
   int comm_world = 1, comm_rank = 0;
@@ -78,7 +79,8 @@ struct ndtb200_handle {
 
   // align workspace
   DevBuf d_partials, d_totals, d_sync, d_result, d_trace, d_out, d_tmp;
-  int coop_blocks[4] = {0, 0, 0, 0};  // max co-resident CTAs per search method
+  int coop_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // grid size per search method and CTA shape
+  int shape = 0;  // 0 = latency shape (1024 threads, the whole GPU for one solve), 1 = throughput shape (256 threads, 1 CTA / SM)
   AlignResultDev* h_result = nullptr;  // pinned
   bool result_valid = false;
   float last_final_T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -423,10 +425,12 @@ void gauss_constants(const ndtb200_params& p, double& d1, double& d2, double& d3
 template <int METHOD>
 int query_coop_blocks(ndtb200_handle* h) {
   int per_sm = 0;
-  const size_t smem = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ndt_align_kernel<METHOD>, kAlignThreads, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ndt_align_kernel<METHOD, kThreadsLatency>, kThreadsLatency, 0));
   if (per_sm < 1) { h->err = "align kernel does not fit on an SM"; return NDTB200_ERR_CUDA; }
-  h->coop_blocks[METHOD] = per_sm * h->num_sms;
+  h->coop_blocks[METHOD][0] = h->num_sms;  // one 1024-thread CTA per SM
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ndt_align_kernel<METHOD, kThreadsThroughput>, kThreadsThroughput, 0));
+  if (per_sm < 1) { h->err = "align kernel (throughput shape) does not fit on an SM"; return NDTB200_ERR_CUDA; }
+  h->coop_blocks[METHOD][1] = h->num_sms;  // one 256-thread CTA per SM per solve: per_sm solves can be co-resident
   return NDTB200_OK;
 }
 
@@ -455,7 +459,8 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   prm.launch_tag = (++h->launch_seq) << 12;  // 4096 evaluations per launch before tags could repeat
   compute_angle_tables(p0, prm.tab0);
 
-  const int max_blocks = h->coop_blocks[method];
+  const int shape = (h->comm_world > 1) ? 0 : h->shape;  // the sharded exchange needs >= 8 warps per CTA
+  const int max_blocks = h->coop_blocks[method][shape];
   // every SM takes part as soon as there is one 32-point group per CTA (the kernel deals groups to warps round-robin)
   int blocks = grid_for(h->n_source, 32, max_blocks);
   CK(h->d_partials.ensure((size_t)max_blocks * kNVP * sizeof(double)));
@@ -483,24 +488,42 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   MapView map = make_view(h);
   const float4* src = h->d_source.as<float4>();
   void* args[] = {(void*)&src, (void*)&map, (void*)&prm, (void*)&ws};
-  const void* fn = method == NDTB200_DIRECT1 ? (const void*)ndt_align_kernel<3>
-                 : method == NDTB200_DIRECT7 ? (const void*)ndt_align_kernel<2>
-                                             : (const void*)ndt_align_kernel<1>;
+  const void* fn;
+  if (shape == 0)
+    fn = method == NDTB200_DIRECT1 ? (const void*)ndt_align_kernel<3, kThreadsLatency>
+       : method == NDTB200_DIRECT7 ? (const void*)ndt_align_kernel<2, kThreadsLatency>
+                                   : (const void*)ndt_align_kernel<1, kThreadsLatency>;
+  else
+    fn = method == NDTB200_DIRECT1 ? (const void*)ndt_align_kernel<3, kThreadsThroughput>
+       : method == NDTB200_DIRECT7 ? (const void*)ndt_align_kernel<2, kThreadsThroughput>
+                                   : (const void*)ndt_align_kernel<1, kThreadsThroughput>;
+  const int threads = shape == 0 ? kThreadsLatency : kThreadsThroughput;
   h->last_blocks = blocks;
   CK(cudaEventRecord(h->ev0, h->stream));
   const size_t smem = 0;
   static const bool plain_launch = getenv("NDTB200_PLAIN_LAUNCH") != nullptr;  // experiment only: no co-residency guarantee
-  if (plain_launch) CK(cudaLaunchKernel(fn, dim3(blocks), dim3(kAlignThreads), args, smem, h->stream));
-  else CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kAlignThreads), args, smem, h->stream));
+  if (plain_launch) CK(cudaLaunchKernel(fn, dim3(blocks), dim3(threads), args, smem, h->stream));
+  else CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(threads), args, smem, h->stream));
   LAUNCHED(h);
   CK(cudaEventRecord(h->ev1, h->stream));
   h->result_valid = false;
+  h->result_copy_enqueued = false;
+  return NDTB200_OK;
+}
+
+int enqueue_result_copy(ndtb200_handle* h) {
+  CK(cudaMemcpyAsync(h->h_result, h->d_result.p, sizeof(AlignResultDev), cudaMemcpyDeviceToHost, h->stream));
+  h->result_copy_enqueued = true;
   return NDTB200_OK;
 }
 
 int fetch_result(ndtb200_handle* h) {
-  CK(cudaMemcpyAsync(h->h_result, h->d_result.p, sizeof(AlignResultDev), cudaMemcpyDeviceToHost, h->stream));
+  if (!h->result_copy_enqueued) {
+    int st = enqueue_result_copy(h);
+    if (st != NDTB200_OK) return st;
+  }
   CK(cudaStreamSynchronize(h->stream));
+  h->result_copy_enqueued = false;
   h->result_valid = true;
   return NDTB200_OK;
 }
@@ -701,22 +724,29 @@ int ndtb200_sync(ndtb200_handle* h) {
   return NDTB200_OK;
 }
 
+// align()'s output cloud (pcl::Registration::align: source transformed by the final pose), enqueued behind the solve
+static int enqueue_output(ndtb200_handle* h, void* out_points, size_t out_stride_bytes) {
+  if (!out_points) return NDTB200_OK;
+  if (out_stride_bytes < 16) { h->err = "out_stride_bytes must be >= 16"; return NDTB200_ERR_INVALID; }
+  const int n = static_cast<int>(h->n_source);
+  if (n == 0) return NDTB200_OK;
+  CK(h->d_out.ensure((size_t)n * sizeof(float4)));
+  transform_output_kernel<<<grid_for(n, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+      h->d_source.as<float4>(), n, h->d_result.as<AlignResultDev>(), h->d_out.as<float4>());
+  LAUNCHED(h);
+  if (out_stride_bytes == 16)
+    CK(cudaMemcpyAsync(out_points, h->d_out.p, (size_t)n * 16, cudaMemcpyDeviceToHost, h->stream));
+  else
+    CK(cudaMemcpy2DAsync(out_points, out_stride_bytes, h->d_out.p, 16, 16, n, cudaMemcpyDeviceToHost, h->stream));
+  return NDTB200_OK;
+}
+
 int ndtb200_align(ndtb200_handle* h, const float* guess, void* out_points, size_t out_stride_bytes) {
   if (!h) return NDTB200_ERR_INVALID;
   int st = ndtb200_align_async(h, guess);
   if (st != NDTB200_OK) return st;
-  if (out_points) {
-    if (out_stride_bytes < 16) { h->err = "out_stride_bytes must be >= 16"; return NDTB200_ERR_INVALID; }
-    const int n = static_cast<int>(h->n_source);
-    CK(h->d_out.ensure((size_t)n * sizeof(float4)));
-    transform_output_kernel<<<grid_for(n, 256, h->num_sms * 8), 256, 0, h->stream>>>(
-        h->d_source.as<float4>(), n, h->d_result.as<AlignResultDev>(), h->d_out.as<float4>());
-    LAUNCHED(h);
-    if (out_stride_bytes == 16)
-      CK(cudaMemcpyAsync(out_points, h->d_out.p, (size_t)n * 16, cudaMemcpyDeviceToHost, h->stream));
-    else
-      CK(cudaMemcpy2DAsync(out_points, out_stride_bytes, h->d_out.p, 16, 16, n, cudaMemcpyDeviceToHost, h->stream));
-  }
+  st = enqueue_output(h, out_points, out_stride_bytes);
+  if (st != NDTB200_OK) return st;
   return ndtb200_sync(h);
 }
 
@@ -1095,6 +1125,44 @@ int ndtb200_clone(const ndtb200_handle* src, ndtb200_handle** out) {
   cudaStreamSynchronize(h->stream);
   *out = h;
   return NDTB200_OK;
+}
+
+int ndtb200_set_throughput_mode(ndtb200_handle* h, int on) {
+  if (!h) return NDTB200_ERR_INVALID;
+  h->shape = on ? 1 : 0;
+  return NDTB200_OK;
+}
+
+// Independent scan pairs in flight together (SURVEY §8b "align_batch", §8e "batched scan pairs"): every handle owns
+// its map, source and stream; all solves are enqueued with the throughput CTA shape before the first wait, so up to
+// four persistent kernels share every SM and each one's barrier / Newton-step latency is covered by the others.
+int ndtb200_align_batch_async(ndtb200_handle* const* hs, int n, const float* guesses, void* const* out_points,
+                              size_t out_stride_bytes) {
+  if (!hs || n < 0) return NDTB200_ERR_INVALID;
+  int rc = NDTB200_OK;
+  for (int i = 0; i < n; ++i) {
+    if (!hs[i]) return NDTB200_ERR_INVALID;
+    const int keep = hs[i]->shape;
+    hs[i]->shape = 1;
+    int st = ndtb200_align_async(hs[i], guesses ? guesses + 16 * (size_t)i : nullptr);
+    hs[i]->shape = keep;
+    if (st == NDTB200_OK && out_points) st = enqueue_output(hs[i], out_points[i], out_stride_bytes);
+    if (st == NDTB200_OK) st = enqueue_result_copy(hs[i]);
+    if (st != NDTB200_OK && rc == NDTB200_OK) rc = st;
+  }
+  return rc;
+}
+
+int ndtb200_align_batch(ndtb200_handle* const* hs, int n, const float* guesses, void* const* out_points,
+                        size_t out_stride_bytes, ndtb200_result* results) {
+  int rc = ndtb200_align_batch_async(hs, n, guesses, out_points, out_stride_bytes);
+  if (rc == NDTB200_ERR_INVALID) return rc;
+  for (int i = 0; i < n; ++i) {
+    int st = ndtb200_sync(hs[i]);
+    if (st == NDTB200_OK && results) st = ndtb200_get_result(hs[i], results + i);
+    if (st != NDTB200_OK && rc == NDTB200_OK) rc = st;
+  }
+  return rc;
 }
 
 void* ndtb200_stream(ndtb200_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }

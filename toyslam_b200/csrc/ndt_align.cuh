@@ -26,17 +26,15 @@
 
 namespace ndtb200 {
 
-// CTA shape of the persistent kernel: one CTA of 1024 threads per SM (148 CTAs: fewer rows in the grid reduction,
-// fewer arrivals on the barrier word), 64 registers per thread.
-#ifndef NDTB200_ALIGN_THREADS
-#define NDTB200_ALIGN_THREADS 1024
-#endif
-#ifndef NDTB200_ALIGN_MIN_BLOCKS
-#define NDTB200_ALIGN_MIN_BLOCKS 1
-#endif
-constexpr int kAlignThreads = NDTB200_ALIGN_THREADS;
-constexpr int kAlignMinBlocks = NDTB200_ALIGN_MIN_BLOCKS;
-constexpr int kAlignWarps = kAlignThreads / 32;
+// CTA shapes of the persistent kernel (template parameter THREADS), always 64 registers per thread:
+//   latency shape    1024 threads, one CTA per SM: a single align() owns the GPU (148 CTAs: few rows in the grid
+//                    reduction, few arrivals on the barrier word);
+//   throughput shape  256 threads, one CTA per SM PER KERNEL: up to four independent aligns (different handles /
+//                    streams) are co-resident on every SM, so one solve's barrier + Newton-step latency is covered by
+//                    the others' derivative passes (ndtb200_align_batch).
+constexpr int kThreadsLatency = 1024;
+constexpr int kThreadsThroughput = 256;
+__host__ __device__ constexpr int min_blocks_for(int threads) { return 1024 / threads; }
 constexpr int kNV = 29;          // score, g[6], H upper triangle[21], hit count
 constexpr int kNVP = 32;         // padded row length of the partial / total buffers
 constexpr int kFlushPoints = 8;  // fp32 run length (points per thread) before folding into fp64
@@ -354,7 +352,8 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-constexpr int kRedRows = (kAlignThreads >= 1024) ? 8 : 20;  // partial rows per thread in flight while the last CTA reduces
+// partial rows per thread in flight while the last CTA reduces
+__host__ __device__ constexpr int red_rows_for(int nwarps) { return nwarps >= 32 ? 8 : 20; }
 
 __device__ __forceinline__ unsigned long long pack_lo(unsigned int tag, unsigned long long bits) {
   return (static_cast<unsigned long long>(tag) << 32) | (bits & 0xffffffffull);
@@ -386,6 +385,7 @@ __device__ __forceinline__ double poll_tagged(const unsigned long long* slot, un
   return __longlong_as_double(static_cast<long long>(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
 }
 
+template <int NW>
 __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_tot, const AlignWorkspace& ws,
                                                unsigned int& epoch, int* s_flag, double (*s_red8)[kNVP],
                                                unsigned int launch_tag) {
@@ -419,11 +419,12 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
       if (threadIdx.x == 0) ws.totals[2 * kNVP + (epoch & 1u)] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling stamp
       const int k = threadIdx.x & 31, slice = threadIdx.x >> 5;  // lane = value, warp = slice of the CTA rows
       double s = 0.0;
-      for (unsigned int b0 = 0; b0 < G; b0 += kAlignWarps * kRedRows) {
+      constexpr int kRedRows = red_rows_for(NW);
+      for (unsigned int b0 = 0; b0 < G; b0 += NW * kRedRows) {
         double v[kRedRows];
 #pragma unroll
         for (int i = 0; i < kRedRows; ++i) {
-          const unsigned int b = b0 + slice + kAlignWarps * i;
+          const unsigned int b = b0 + slice + NW * i;
           v[i] = (b < G && k < kNV) ? __ldcg(ws.partials + (size_t)b * kNVP + k) : 0.0;
         }
 #pragma unroll
@@ -433,7 +434,7 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
       __syncthreads();
       if (threadIdx.x < kNV) {
 #pragma unroll
-        for (int w = 0; w < kAlignWarps; ++w) t += s_red8[w][threadIdx.x];
+        for (int w = 0; w < NW; ++w) t += s_red8[w][threadIdx.x];
       }
       __syncthreads();
     } else if (threadIdx.x < kNV) {
@@ -1038,9 +1039,10 @@ __device__ __forceinline__ double eval_warp_f32(const float4* __restrict__ src, 
 // ---------------------------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------------------------
-template <int METHOD>
-__global__ void __launch_bounds__(kAlignThreads, kAlignMinBlocks)
+template <int METHOD, int THREADS>
+__global__ void __launch_bounds__(THREADS, min_blocks_for(THREADS))
 ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignParams prm, const AlignWorkspace ws) {
+  constexpr int kAlignWarps = THREADS / 32;
   SolverState& st = g_st;
   EvalCtx& ctx = g_ctx;
   __shared__ double s_warp[kAlignWarps][kNVP];
@@ -1105,7 +1107,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
       s_action = ACT_HESS_ONLY;
     }
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 69) s_terms[threadIdx.x - 64] = g_table_terms[threadIdx.x - 64];
+  for (int i = threadIdx.x; i < 69; i += THREADS) s_terms[i] = g_table_terms[i];
   if (threadIdx.x == 33) s_map = map;
   if (threadIdx.x == 32) {  // tables for p0 (computed on the host); matrix = T0
     ctx.tab = prm.tab0;
@@ -1144,7 +1146,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
       s_block[threadIdx.x] = s;
     }
     if (timing) t_local = globaltimer_ns();
-    grid_allreduce(s_block, s_tot, ws, epoch, &s_flag, s_warp, prm.launch_tag);
+    grid_allreduce<kAlignWarps>(s_block, s_tot, ws, epoch, &s_flag, s_warp, prm.launch_tag);
     if (ws.world > 1 && *reinterpret_cast<volatile unsigned int*>(&ws.sync[3]) != 0u) break;  // a peer never answered (uniform: checked after a barrier)
     if (timing) t_reduced = globaltimer_ns();
     unsigned long long t_last_arrive = 0;

@@ -80,6 +80,9 @@ def load_library():
     L.ndtb200_align.argtypes = [vp, f32p, vp, C.c_size_t]
     L.ndtb200_align_async.argtypes = [vp, f32p]
     L.ndtb200_sync.argtypes = [vp]
+    L.ndtb200_set_throughput_mode.argtypes = [vp, C.c_int]
+    L.ndtb200_align_batch.argtypes = [C.POINTER(vp), C.c_int, f32p, C.POINTER(vp), C.c_size_t, C.POINTER(Result)]
+    L.ndtb200_align_batch_async.argtypes = [C.POINTER(vp), C.c_int, f32p, C.POINTER(vp), C.c_size_t]
     L.ndtb200_get_result.argtypes = [vp, C.POINTER(Result)]
     L.ndtb200_fitness_score.argtypes = [vp, C.c_double, f64p]
     L.ndtb200_calculate_score.argtypes = [vp, vp, C.c_size_t, C.c_size_t, f64p]
@@ -103,6 +106,55 @@ def load_library():
     L.ndtb200_last_align_ms.argtypes = [vp, f32p]
     _lib = L
     return L
+
+
+class Batch:
+    """A fixed set of NDT objects aligned together (ndtb200_align_batch): ctypes arrays are built once."""
+
+    def __init__(self, ndts):
+        self.ndts = list(ndts)
+        self.n = len(self.ndts)
+        self._L = load_library()
+        self._arr = (C.c_void_p * max(1, self.n))(*[d._h for d in self.ndts])
+        self._res = (Result * max(1, self.n))()
+
+    def _guess(self, guesses):
+        if guesses is None:
+            return None
+        return np.concatenate([_colmajor(T) for T in guesses]).astype(np.float32)
+
+    def _outs(self, out_ptrs):
+        if out_ptrs is None:
+            return None
+        return (C.c_void_p * self.n)(*[int(p) for p in out_ptrs])
+
+    def align_async(self, guesses=None, out_ptrs=None, out_stride=16):
+        g = self._guess(guesses)
+        st = self._L.ndtb200_align_batch_async(self._arr, self.n, _ptr(g, C.c_float) if g is not None else None,
+                                               self._outs(out_ptrs), out_stride)
+        if st != 0:
+            raise NdtError(st, "ndtb200_align_batch_async failed")
+
+    def sync(self):
+        for d in self.ndts:
+            d.sync()
+
+    def align(self, guesses=None, out_ptrs=None, out_stride=16):
+        g = self._guess(guesses)
+        st = self._L.ndtb200_align_batch(self._arr, self.n, _ptr(g, C.c_float) if g is not None else None,
+                                         self._outs(out_ptrs), out_stride, self._res)
+        if st != 0:
+            raise NdtError(st, "ndtb200_align_batch failed: " + "; ".join(
+                self._L.ndtb200_last_error(d._h).decode() for d in self.ndts[:4]))
+        return [d.result() for d in self.ndts]
+
+
+def align_batch(ndts, guesses=None):
+    """ndtb200_align_batch: align n independent (target, source) pairs — one object each — together.
+    guesses: optional list of 4x4 matrices.  Returns the list of result dicts."""
+    if len(ndts) == 0:
+        return []
+    return Batch(ndts).align(guesses)
 
 
 def device_count():
@@ -259,6 +311,10 @@ class NormalDistributionsTransform:
     def align_async(self, guess=None):
         g = _colmajor(guess) if guess is not None else None
         self._check(self._L.ndtb200_align_async(self._h, _ptr(g, C.c_float) if g is not None else None))
+
+    def set_throughput_mode(self, on=True):
+        """Small-CTA solve kernel: several handles' solves share every SM (see ndtb200_set_throughput_mode)."""
+        self._check(self._L.ndtb200_set_throughput_mode(self._h, 1 if on else 0))
 
     def sync(self):
         self._check(self._L.ndtb200_sync(self._h))
