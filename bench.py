@@ -284,7 +284,8 @@ def run_b200(args):
         if i >= 3:
             lat_events.append((e0, e1))
     torch.cuda.synchronize()
-    lat_ms = float(np.mean([a.elapsed_time(b) for a, b in lat_events]))
+    lat_all = [a.elapsed_time(b) for a, b in lat_events]
+    lat_ms = float(np.median(lat_all))
 
     # ---- throughput arm (the headline `value`): independent pairs in flight together, ndtb200_align_batch ------------
     # a step = one align() of one pair; the R pairs of a batch are enqueued on their own streams (throughput CTA shape,
@@ -419,7 +420,8 @@ def run_b200(args):
             "src_pt_iters_per_s": pt_iters, "evaluations_per_align": evals, "hessian_passes_per_align": hess,
             "hits_per_point_eval": hits_total / float(max(1.0, (evals + hess) * n_src)),
             "latency": {"ms_per_align": lat_ms, "aligns_per_s": 1e3 / lat_ms,
-                        "note": "one align in flight at a time, default CTA shape, inputs resident, CUDA events per launch"},
+                        "ms_max": float(np.max(lat_all)), "ms_mean": float(np.mean(lat_all)), "steps": len(lat_all),
+                        "note": "one align in flight at a time, default CTA shape, inputs resident, CUDA events per launch (median)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "wall_s_timed_region": wall}
     if rank == 0:
@@ -509,6 +511,227 @@ def run_c4(args):
     return 0
 
 
+def c3_workload(args, rank):
+    """Consecutive scan pairs of the simulated drive (BASELINE configs[2]); `--c3-distinct` distinct pairs per rank,
+    cycled to the requested number of pairs.  Cached like the c2 workload."""
+    import workloads
+    n = args.c3_distinct
+    path = None
+    if args.cache:
+        os.makedirs(args.cache, exist_ok=True)
+        path = os.path.join(args.cache, "c3_%d_%d_r%d.npz" % (n, args.azimuth_steps, rank))
+        if os.path.exists(path):
+            d = np.load(path)
+            return [d["scan_%d" % i] for i in range(n + 1)], [tuple(p) for p in d["poses"]]
+    scans, poses = workloads.config3_sequence(n + 1, seed=workloads.SEED_C3 + 1000 * rank, azimuth_steps=args.azimuth_steps)
+    if path:
+        np.savez(path, poses=np.asarray(poses), **{"scan_%d" % i: s for i, s in enumerate(scans)})
+    return scans, poses
+
+
+C3_PARAMS = dict(eps=0.01, max_iter=64, step=0.1, res=1.0)  # ndt_rosbag_mapping_node.cpp:83-88
+
+
+def run_c3(args):
+    """BASELINE configs[2]: batched scan-to-scan odometry.  A step = one pair: build the target map of scan k
+    (setInputTarget, inside the timed region as the node does), setInputSource(scan k+1), align(guess = true motion of
+    the previous pair).  Pairs are independent units: round-robin over the GPUs (ranks), and inside a GPU over
+    `--c3-lanes` handles driven by one host thread each, so builds, copies and solves of different pairs overlap."""
+    import threading
+    import torch
+    import toyslam_b200 as nb
+    import workloads
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    scans, poses = c3_workload(args, rank)
+    nd = args.c3_distinct
+    pairs_total = args.steps
+    pairs_rank = pairs_total // world
+    hosts = []
+    for sc in scans:
+        hb = torch.ones((len(sc), 4), dtype=torch.float32).pin_memory()
+        hb[:, :3] = torch.from_numpy(sc)
+        hosts.append(hb)
+    guesses = [np.eye(4)] + [workloads.relative_pose_matrix(poses[k - 1], poses[k]) for k in range(1, nd)]
+    truths = [workloads.relative_pose_matrix(poses[k], poses[k + 1]) for k in range(nd)]
+    L = args.c3_lanes
+    lanes = []
+    for _ in range(L):
+        ndt = nb.NormalDistributionsTransform(device=local)
+        ndt.setNeighborhoodSearchMethod(METHODS[args.method])
+        ndt.setTransformationEpsilon(C3_PARAMS["eps"])
+        ndt.setMaximumIterations(C3_PARAMS["max_iter"])
+        ndt.setStepSize(C3_PARAMS["step"])
+        ndt.setResolution(C3_PARAMS["res"])
+        ndt.set_throughput_mode(True)
+        lanes.append(ndt)
+    results = [None] * nd
+
+    def lane_loop(li, first, count):
+        torch.cuda.set_device(local)
+        hd = lanes[li]
+        for j in range(first + li, first + count, L):
+            k = j % nd
+            hd.set_target_raw(hosts[k].data_ptr(), len(scans[k]), 16)          # H2D + voxel-map build
+            hd.set_source_raw(hosts[k + 1].data_ptr(), len(scans[k + 1]), 16)  # H2D
+            hd.align_async(guesses[k])
+            hd.sync()                                                            # the node reads every pose
+            results[k] = hd.result()
+
+    def run(first, count):
+        th = [threading.Thread(target=lane_loop, args=(li, first, count)) for li in range(L)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    run(0, max(args.warmup, L))  # warm-up: allocations, first launches
+    torch.cuda.synchronize()
+    for hd in lanes:
+        hd.reset_launch_count()
+    sampler = ClockSampler(local)
+    barrier(world)
+    torch.cuda.synchronize()
+    sampler.start()
+    master = torch.cuda.Stream(device=dev)
+    streams = [torch.cuda.ExternalStream(hd.stream_ptr(), device=dev) for hd in lanes]
+    e_start = torch.cuda.Event(enable_timing=True)
+    e_end = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e_start.record(master)
+    for st in streams:
+        st.wait_event(e_start)
+    run(0, pairs_rank)
+    for st in streams:
+        e = torch.cuda.Event()
+        e.record(st)
+        master.wait_event(e)
+    e_end.record(master)
+    torch.cuda.synchronize()
+    barrier(world)
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(float(e_start.elapsed_time(e_end)), world, dev)
+    launches = sum(hd.launch_count() for hd in lanes)
+    done = [r for r in results if r is not None]
+    err_t = []
+    for k, r in enumerate(results):
+        if r is not None:
+            err_t.append(float(np.linalg.norm(r["final"][:3, 3] - truths[k][:3, 3])))
+    evals = float(np.mean([r["n_evaluations"] for r in done]))
+    pts = float(np.mean([len(s) for s in scans]))
+    value = pairs_rank * world / (total_ms * 1e-3)
+    line = {"metric": "ndt_aligns_per_s", "workload": "c3", "value": value, "unit": "aligns/s", "n_gpus": world, "steps": pairs_rank * world,
+            "warmup": max(args.warmup, L), "ms_per_step": total_ms / pairs_rank, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c3: %d consecutive scan pairs of a simulated drive (%d distinct pairs per GPU cycled), scans downsampled "
+                                   "0.3 m (%.0f pts mean), per pair: target-map build + align, node parameters (eps 0.01, max_iter 64, "
+                                   "step 0.1, res 1.0, %s), guess = true motion of the previous pair; %d lanes (handles + host threads) per GPU"
+                                   % (pairs_rank * world, nd, pts, args.method, L),
+                       "parallelism": "pairs round-robin over GPUs and lanes; no collective"},
+            "src_pt_iters_per_s": value * pts * evals, "evaluations_per_align": evals,
+            "hessian_passes_per_align": float(np.mean([r["n_hessian_passes"] for r in done])),
+            "iterations_per_align": float(np.mean([r["iterations"] for r in done])),
+            "mean_translation_error_vs_truth_m": float(np.mean(err_t)), "max_translation_error_vs_truth_m": float(np.max(err_t)),
+            "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": wall,
+            "e2e": {"value": pairs_rank * world / max_over_ranks(wall, world, dev), "unit": "aligns/s",
+                    "h2d_bytes_per_step": int(2 * pts * 16), "d2h_bytes_per_step": 416,
+                    "note": "the timed region IS end to end here: host scans (pinned) in, poses out, wall clock"}}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], line["parity_vs_oracle"] = c3_cpu(args, scans, guesses, results, max_pairs=24)
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def c3_cpu(args, scans, guesses, gpu_results, max_pairs=24, max_seconds=25.0):
+    import oracle
+    ref = oracle.NormalDistributionsTransform()
+    ref.setNeighborhoodSearchMethod({"DIRECT1": oracle.DIRECT1, "DIRECT7": oracle.DIRECT7, "DIRECT26": oracle.DIRECT26}[args.method])
+    ref.setTransformationEpsilon(C3_PARAMS["eps"])
+    ref.setMaximumIterations(C3_PARAMS["max_iter"])
+    ref.setStepSize(C3_PARAMS["step"])
+    ref.setResolution(C3_PARAMS["res"])
+    t0 = time.perf_counter()
+    n = 0
+    max_dT, same_counts = 0.0, True
+    for k in range(min(max_pairs, len(scans) - 1)):
+        ref.setInputTarget(scans[k])
+        ref.setInputSource(scans[k + 1])
+        ref.align(guesses[k])
+        n += 1
+        rr = ref.result()
+        if gpu_results[k] is not None:
+            max_dT = max(max_dT, float(np.abs(rr["final"] - gpu_results[k]["final"]).max()))
+            same_counts = same_counts and rr["iterations"] == gpu_results[k]["iterations"] and rr["n_evaluations"] == gpu_results[k]["n_evaluations"]
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return ({"value": n / dt, "unit": "aligns/s", "cores": oracle.max_threads(), "kind": "port",
+             "sample": "the first %d pairs of the same sequence, map build + align per pair, oracle C++/OpenMP port" % n},
+            {"pairs_checked": n, "max_abs_dT": max_dT, "iterations_and_evaluations_equal": bool(same_counts)})
+
+
+def run_c5(args):
+    """BASELINE configs[4]: target-map rebuild sweep.  A step = one VoxelGridCovariance build (ndtb200_set_target_device:
+    device-resident cloud in, voxel map out).  One JSON line per (points, resolution)."""
+    import torch
+    import toyslam_b200 as nb
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import build_bench
+    rank, world, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peak = 6454.9
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    for m_total in args.c5_points:
+        m = m_total // world                      # points by contiguous range: every rank builds the map of its slice
+        pts = build_bench.surface_points(m, 20260104 + rank, device=dev)
+        for res in args.c5_res:
+            ndt = nb.NormalDistributionsTransform(device=local)
+            ndt.setResolution(res)
+            ndt.set_target_device(pts.data_ptr(), m)
+            ndt.set_target_device(pts.data_ptr(), m)
+            st = ndt.stream_ptr()
+            stream = torch.cuda.ExternalStream(st, device=dev)
+            reps = max(3, min(args.steps, 10))
+            barrier(world)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                ndt.set_target_device(pts.data_ptr(), m)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = max_over_ranks(float(e0.elapsed_time(e1)) / reps, world, dev)
+            info = ndt.map_info()
+            alg = 16.0 * m + 72.0 * info["n_voxels"]
+            if rank == 0:
+                print(json.dumps({"metric": "map_build_points_per_s", "workload": "c5", "value": m * world / (ms * 1e-3), "unit": "points/s",
+                                  "n_gpus": world, "steps": reps, "ms_per_step": ms, "scaling": "strong", "dtype": "f64 moments / int32 keys",
+                                  "data": "synthetic", "config": {"workload": "c5: VoxelGridCovariance build, %d points (%d per GPU), resolution %.1f" % (m * world, m, res),
+                                                                  "voxels_per_gpu": info["n_voxels"], "valid_per_gpu": info["n_valid"]},
+                                  "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                                               "algorithmic_bytes": alg, "formula": "16*M + 72*V per GPU (SURVEY 8d)"}}), flush=True)
+            del ndt
+        del pts
+        torch.cuda.empty_cache()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -526,12 +749,20 @@ def main():
     ap.add_argument("--l2", default="inputs", choices=["inputs", "flush"],
                     help="how timed steps see a cold L2: inputs larger than L2 (default) or a 256 MiB flush write")
     ap.add_argument("--cache", default=None, help="directory for cached workload arrays")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--c3-distinct", type=int, default=128, help="distinct consecutive pairs generated per GPU (cycled)")
+    ap.add_argument("--c3-lanes", type=int, default=8, help="handles (+ host threads) per GPU for the c3 pipeline")
+    ap.add_argument("--c5-points", type=int, nargs="+", default=[10_000_000, 100_000_000])
+    ap.add_argument("--c5-res", type=float, nargs="+", default=[0.5, 1.0, 2.0])
     ap.add_argument("--c4-scans", type=int, default=16)
     ap.add_argument("--thin-leaf", type=float, default=0.1)
     args = ap.parse_args()
     if args.workload == "c4" and args.impl == "b200":
         return run_c4(args)
+    if args.workload == "c3" and args.impl == "b200":
+        return run_c3(args)
+    if args.workload == "c5" and args.impl == "b200":
+        return run_c5(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

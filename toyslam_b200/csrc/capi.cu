@@ -294,37 +294,24 @@ int build_map(ndtb200_handle* h) {
       h->prm.min_points_per_voxel, h->prm.eig_ratio, h->d_records.as<VoxelRecord>(), h->d_icov64.as<double>(),
       d_nvalid, nullptr, nullptr, nullptr, nullptr);
   LAUNCHED(h);
-  unsigned int n_valid = 0;
-  CK(cudaMemcpyAsync(&n_valid, d_nvalid, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  h->n_valid = n_valid;
-
-  // 6. hash over the valid voxels, load <= 0.25
-  uint32_t cap = 1024;
-  int log2cap = 10;
-  while (cap < 4ull * n_valid && log2cap < 31) { cap <<= 1; ++log2cap; }
-  h->hash_cap = cap;
-  h->hash_shift = 32 - log2cap;
-  CK(h->d_hash.ensure((size_t)cap * sizeof(HashSlot)));
-  CK(cudaMemsetAsync(h->d_hash.p, 0xFF, (size_t)cap * sizeof(HashSlot), h->stream));
-  hash_insert_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
-                                                               h->prm.min_points_per_voxel, h->d_hash.as<HashSlot>(),
-                                                               cap - 1, h->hash_shift);
-  LAUNCHED(h);
-
-  // 7. direct-mapped cell table (one 4-byte load per probe, no collisions) when dx*dy*dz int32 entries fit the budget:
-  //    <= 4 GiB and <= 1/4 of the free device memory; otherwise lookups go through the hash
+  // 6. the voxel index.  Direct-mapped cell table (one 4-byte load per probe, no collisions) when dx*dy*dz int32
+  //    entries fit the budget (<= 4 GiB and <= 1/4 of the free device memory); otherwise an open-addressing hash over
+  //    the valid voxels, load <= 0.25 (needs n_valid on the host: the only synchronisation left after the voxel count).
   h->use_dense = false;
+  h->n_valid = -1;  // fetched on demand (ndtb200_get_map_info) unless the hash needs it now
   {
     // cells actually addressed by keys: div_b product (the guard's dx*dy*dz, grid.ncell, is computed from the float
     // extents and can be smaller by one per axis)
     const unsigned long long ncell = static_cast<unsigned long long>(h->grid.div_b[0]) * static_cast<unsigned long long>(h->grid.div_b[1]) *
                                      static_cast<unsigned long long>(h->grid.div_b[2]);
     const unsigned long long bytes = ncell * sizeof(int32_t);
-    size_t free_b = 0, total_b = 0;
     const bool forced_hash = getenv("NDTB200_FORCE_HASH") != nullptr;
-    if (!forced_hash && ncell > 0 && bytes <= (4ull << 30) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
-        bytes <= (free_b + h->d_dense.cap) / 4) {
+    bool fits = !forced_hash && ncell > 0 && bytes <= (4ull << 30);
+    if (fits && bytes > h->d_dense.cap && bytes > (64ull << 20)) {  // cudaMemGetInfo is slow: only ask for large NEW tables
+      size_t free_b = 0, total_b = 0;
+      fits = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes <= (free_b + h->d_dense.cap) / 4;
+    }
+    if (fits) {
       CK(h->d_dense.ensure(bytes));
       CK(cudaMemsetAsync(h->d_dense.p, 0xFF, bytes, h->stream));
       dense_fill_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
@@ -332,6 +319,23 @@ int build_map(ndtb200_handle* h) {
       LAUNCHED(h);
       h->use_dense = true;
     }
+  }
+  if (!h->use_dense) {
+    unsigned int n_valid = 0;
+    CK(cudaMemcpyAsync(&n_valid, d_nvalid, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_valid = n_valid;
+    uint32_t cap = 1024;
+    int log2cap = 10;
+    while (cap < 4ull * n_valid && log2cap < 31) { cap <<= 1; ++log2cap; }
+    h->hash_cap = cap;
+    h->hash_shift = 32 - log2cap;
+    CK(h->d_hash.ensure((size_t)cap * sizeof(HashSlot)));
+    CK(cudaMemsetAsync(h->d_hash.p, 0xFF, (size_t)cap * sizeof(HashSlot), h->stream));
+    hash_insert_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
+                                                                 h->prm.min_points_per_voxel, h->d_hash.as<HashSlot>(),
+                                                                 cap - 1, h->hash_shift);
+    LAUNCHED(h);
   }
   h->map_status = NDTB200_OK;
   return NDTB200_OK;
@@ -845,7 +849,16 @@ int ndtb200_get_map_info(const ndtb200_handle* h, ndtb200_map_info* out) {
   }
   out->n_points = static_cast<int64_t>(h->n_target);
   out->n_voxels = h->n_voxels;
-  out->n_valid = h->n_valid;
+  if (h->n_valid < 0 && h->n_voxels > 0) {  // counted on the device during the build, fetched on first request
+    ndtb200_handle* hm = const_cast<ndtb200_handle*>(h);
+    cudaSetDevice(h->device);
+    unsigned int nv = 0;
+    if (cudaMemcpyAsync(&nv, hm->d_scalar.as<unsigned int>() + 4, sizeof(unsigned int), cudaMemcpyDeviceToHost, hm->stream) != cudaSuccess ||
+        cudaStreamSynchronize(hm->stream) != cudaSuccess)
+      return NDTB200_ERR_CUDA;
+    hm->n_valid = nv;
+  }
+  out->n_valid = h->n_valid < 0 ? 0 : h->n_valid;
   out->hash_capacity = h->hash_cap;
   return h->map_status;
 }

@@ -182,105 +182,179 @@ scan_add_kernel(uint32_t* __restrict__ out, size_t n, const uint32_t* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// stable LSD radix sort pass, 8-bit digit.  Tile = 256 threads x 8 keys; warp w owns 256
-// consecutive keys, lane = consecutive key, so global loads are fully coalesced.
-// Ranks come from __match_any_sync (stable inside a warp round) + per-warp digit counters.
+// stable LSD radix sort pass, 8-bit digit.  Tile = 8 warps x 16 rounds x 32 keys = 4096 keys; warp w owns 512
+// consecutive keys, lane = consecutive key, so global loads are fully coalesced and (warp, round, lane) order is the
+// input order (stability).
+//   * peers of a key (lanes of the round with the same digit) come from 8 ballots — __match_any_sync costs ~64 issue
+//     cycles per warp on this part, the ballots ~25;
+//   * count pass: per-warp private digit counters, the lowest peer adds popc(peers): no atomics, no ranks;
+//   * scatter pass: the tile is first sorted by digit INSIDE shared memory (stable local ranks), then written out:
+//     consecutive threads write consecutive addresses of a digit's run (>= 64 B runs on average) instead of 4-byte
+//     scattered stores.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSortItems = 8;
-constexpr int kSortTile = kBuildThreads * kSortItems;
+#ifndef NDTB200_SORT_ROUNDS
+#define NDTB200_SORT_ROUNDS 16
+#endif
+#ifndef NDTB200_SCATTER_MIN_BLOCKS
+#define NDTB200_SCATTER_MIN_BLOCKS 3
+#endif
+constexpr int kSortRounds = NDTB200_SORT_ROUNDS;
 constexpr int kSortWarps = kBuildThreads / 32;
+constexpr int kSortTile = kBuildThreads * kSortRounds;
 
-__device__ __forceinline__ void sort_tile_count(const uint32_t* __restrict__ keys, size_t n, int shift,
-                                                uint32_t (*warp_cnt)[256], uint32_t k[kSortItems],
-                                                unsigned int valid_bits[kSortItems]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int d = threadIdx.x; d < 256 * kSortWarps; d += blockDim.x) (&warp_cnt[0][0])[d] = 0u;
-  __syncthreads();
-  const size_t wbase = (size_t)blockIdx.x * kSortTile + (size_t)warp * (32 * kSortItems);
+__device__ __forceinline__ unsigned int digit_peers(uint32_t d, bool valid) {
+  unsigned int m = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-  for (int r = 0; r < kSortItems; ++r) {
-    const size_t i = wbase + r * 32 + lane;
-    const bool valid = i < n;
-    k[r] = valid ? keys[i] : 0u;
-    const uint32_t d = valid ? ((k[r] >> shift) & 255u) : (256u + lane);
-    const unsigned int m = __match_any_sync(0xffffffffu, d);
-    valid_bits[r] = m;
-    if (valid && lane == (__ffs(m) - 1)) warp_cnt[warp][d] += __popc(m);
-    __syncwarp();
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned int bal = __ballot_sync(0xffffffffu, bit);
+    m &= bit ? bal : ~bal;
   }
+  return m;
 }
 
+// Count pass: only the per-tile digit totals are needed (no ranks), so shared-memory atomics do: a round whose 32 keys
+// share one digit (clouds in scan order) is added by one lane, otherwise every lane adds 1 to its warp's private bin.
 __global__ void __launch_bounds__(kBuildThreads)
 radix_count_kernel(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t* __restrict__ hist, int ntiles) {
   __shared__ uint32_t warp_cnt[kSortWarps][256];
-  uint32_t k[kSortItems];
-  unsigned int m[kSortItems];
-  sort_tile_count(keys, n, shift, warp_cnt, k, m);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = threadIdx.x; d < 256 * kSortWarps; d += kBuildThreads) (&warp_cnt[0][0])[d] = 0u;
+  __syncthreads();
+  const size_t wbase = (size_t)blockIdx.x * kSortTile + (size_t)warp * (32 * kSortRounds);
+  uint32_t k[kSortRounds];
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const size_t i = wbase + r * 32 + lane;
+    k[r] = (i < n) ? __ldg(keys + i) : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const size_t i = wbase + r * 32 + lane;
+    const bool valid = i < n;
+    const uint32_t d = (k[r] >> shift) & 255u;
+    const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+    if (__all_sync(0xffffffffu, valid && d == d0)) {
+      if (lane == 0) atomicAdd(&warp_cnt[warp][d0], 32u);
+    } else if (valid) {
+      atomicAdd(&warp_cnt[warp][d], 1u);
+    }
+  }
   __syncthreads();
   const int d = threadIdx.x;  // blockDim == 256
-  uint32_t s = 0;
+  uint32_t sum = 0;
 #pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) s += warp_cnt[w][d];
-  hist[(size_t)d * ntiles + blockIdx.x] = s;
+  for (int w = 0; w < kSortWarps; ++w) sum += warp_cnt[w][d];
+  hist[(size_t)d * ntiles + blockIdx.x] = sum;
 }
 
-__global__ void __launch_bounds__(kBuildThreads)
+__global__ void __launch_bounds__(kBuildThreads, NDTB200_SCATTER_MIN_BLOCKS)
 radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, size_t n, int shift,
                      const uint32_t* __restrict__ hist_scanned, int ntiles, uint32_t* __restrict__ keys_out,
                      uint32_t* __restrict__ vals_out) {
   __shared__ uint32_t warp_cnt[kSortWarps][256];
-  uint32_t k[kSortItems];
-  unsigned int m[kSortItems];
-  sort_tile_count(keys_in, n, shift, warp_cnt, k, m);
-  __syncthreads();
-  {
-    const int d = threadIdx.x;
-    uint32_t base = hist_scanned[(size_t)d * ntiles + blockIdx.x];
-#pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-      uint32_t c = warp_cnt[w][d];
-      warp_cnt[w][d] = base;
-      base += c;
-    }
-  }
-  __syncthreads();
+  __shared__ uint32_t s_dstart[256];
+  __shared__ uint32_t s_gbase[256];
+  __shared__ uint32_t s_scan[kBuildThreads / 32 + 1];
+  __shared__ uint32_t s_key[kSortTile];
+  __shared__ uint32_t s_val[kSortTile];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t wbase = (size_t)blockIdx.x * kSortTile + (size_t)warp * (32 * kSortItems);
+  for (int d = threadIdx.x; d < 256 * kSortWarps; d += kBuildThreads) (&warp_cnt[0][0])[d] = 0u;
+  __syncthreads();
+  const size_t tbase = (size_t)blockIdx.x * kSortTile;
+  const size_t wbase = tbase + (size_t)warp * (32 * kSortRounds);
+  uint32_t k[kSortRounds], v[kSortRounds];
+  uint16_t rank[kSortRounds];
 #pragma unroll
-  for (int r = 0; r < kSortItems; ++r) {
+  for (int r = 0; r < kSortRounds; ++r) {
+    const size_t i = wbase + r * 32 + lane;
+    k[r] = (i < n) ? __ldg(keys_in + i) : 0u;
+    v[r] = (i < n) ? (vals_in ? __ldg(vals_in + i) : static_cast<uint32_t>(i)) : 0u;
+  }
+  // stable rank of every key among the keys of ITS WARP with the same digit
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
     const size_t i = wbase + r * 32 + lane;
     const bool valid = i < n;
     const uint32_t d = (k[r] >> shift) & 255u;
-    const unsigned int mm = m[r];
+    const unsigned int m = digit_peers(d, valid);
     uint32_t pos = 0;
-    if (valid) pos = warp_cnt[warp][d] + __popc(mm & ((1u << lane) - 1u));
+    if (valid) pos = warp_cnt[warp][d] + __popc(m & ((1u << lane) - 1u));
     __syncwarp();
-    if (valid && lane == (__ffs(mm) - 1)) warp_cnt[warp][d] += __popc(mm);
+    if (valid && lane == (__ffs(m) - 1)) warp_cnt[warp][d] += __popc(m);
     __syncwarp();
-    if (valid) {
-      keys_out[pos] = k[r];
-      vals_out[pos] = vals_in ? vals_in[i] : static_cast<uint32_t>(i);
+    rank[r] = static_cast<uint16_t>(pos);
+  }
+  __syncthreads();
+  // per digit: exclusive prefix over the warps, then over the digits (tile-local sorted layout)
+  {
+    const int d = threadIdx.x;
+    uint32_t off = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = warp_cnt[w][d];
+      warp_cnt[w][d] = off;
+      off += c;
     }
+    uint32_t total;
+    const uint32_t dstart = block_exclusive_scan(off, s_scan, total);
+    s_dstart[d] = dstart;
+    s_gbase[d] = hist_scanned[(size_t)d * ntiles + blockIdx.x] - dstart;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const size_t i = wbase + r * 32 + lane;
+    if (i < n) {
+      const uint32_t d = (k[r] >> shift) & 255u;
+      const uint32_t p = s_dstart[d] + warp_cnt[warp][d] + rank[r];
+      s_key[p] = k[r];
+      s_val[p] = v[r];
+    }
+  }
+  __syncthreads();
+  const uint32_t count = static_cast<uint32_t>(n - tbase < (size_t)kSortTile ? n - tbase : (size_t)kSortTile);
+  for (uint32_t j = threadIdx.x; j < count; j += kBuildThreads) {
+    const uint32_t key = s_key[j];
+    const uint32_t pos = s_gbase[(key >> shift) & 255u] + j;
+    keys_out[pos] = key;
+    vals_out[pos] = s_val[j];
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // segment heads -> occupied voxel list
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBuildThreads)
-head_count_kernel(const uint32_t* __restrict__ skeys, size_t n, uint32_t sentinel, uint32_t* __restrict__ tile_counts) {
-  __shared__ uint32_t smem[kBuildThreads / 32 + 1];
-  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
-  uint32_t c = 0;
+// 8 consecutive sorted keys of this thread (two 16-byte loads) + the key before them; returns the head flags as bits
+__device__ __forceinline__ uint32_t load_heads(const uint32_t* __restrict__ skeys, size_t n, size_t base, uint32_t sentinel,
+                                               uint32_t (&key)[kScanItems]) {
+  uint32_t prev = sentinel;  // key[-1]: the first element is a head iff it is not the sentinel
+  if (base > 0 && base < n) prev = __ldg(skeys + base - 1);
+  if (base + kScanItems <= n) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(skeys + base));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(skeys + base) + 1);
+    key[0] = a.x; key[1] = a.y; key[2] = a.z; key[3] = a.w; key[4] = b.x; key[5] = b.y; key[6] = b.z; key[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) key[k] = (base + k < n) ? __ldg(skeys + base + k) : sentinel;
+  }
+  uint32_t flags = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    const size_t i = base + k;
-    if (i < n) {
-      uint32_t key = skeys[i];
-      bool head = (key != sentinel) && (i == 0 || skeys[i - 1] != key);
-      c += head ? 1u : 0u;
-    }
+    const bool head = (base + k < n) && (key[k] != sentinel) && (base + k == 0 || key[k] != prev);
+    flags |= head ? (1u << k) : 0u;
+    prev = key[k];
   }
+  return flags;
+}
+
+__global__ void __launch_bounds__(kBuildThreads)
+head_count_kernel(const uint32_t* __restrict__ skeys, size_t n, uint32_t sentinel, uint32_t* __restrict__ tile_counts) {
+  static_assert(kScanItems == 8, "load_heads reads two uint4");
+  __shared__ uint32_t smem[kBuildThreads / 32 + 1];
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+  uint32_t key[kScanItems];
+  const uint32_t c = __popc(load_heads(skeys, n, base, sentinel, key));
   uint32_t total;
   block_exclusive_scan(c, smem, total);
   if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
@@ -292,25 +366,13 @@ head_write_kernel(const uint32_t* __restrict__ skeys, size_t n, uint32_t sentine
                   uint32_t* __restrict__ voxel_start) {
   __shared__ uint32_t smem[kBuildThreads / 32 + 1];
   const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
-  uint32_t c = 0;
-  bool head[kScanItems];
   uint32_t key[kScanItems];
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const size_t i = base + k;
-    head[k] = false;
-    key[k] = 0;
-    if (i < n) {
-      key[k] = skeys[i];
-      head[k] = (key[k] != sentinel) && (i == 0 || skeys[i - 1] != key[k]);
-      c += head[k] ? 1u : 0u;
-    }
-  }
+  const uint32_t flags = load_heads(skeys, n, base, sentinel, key);
   uint32_t total;
-  uint32_t off = block_exclusive_scan(c, smem, total) + tile_offsets[blockIdx.x];
+  uint32_t off = block_exclusive_scan(__popc(flags), smem, total) + tile_offsets[blockIdx.x];
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    if (head[k]) {
+    if (flags & (1u << k)) {
       voxel_key[off] = static_cast<int32_t>(key[k]);
       voxel_start[off] = static_cast<uint32_t>(base + k);
       ++off;
@@ -323,6 +385,14 @@ head_write_kernel(const uint32_t* __restrict__ skeys, size_t n, uint32_t sentine
 // voxel's sorted point range (gather through the sorted index), then a fixed-order shuffle tree.
 // moments layout per voxel: [sx sy sz sxx sxy sxz syy syz szz] (9 doubles)
 // ---------------------------------------------------------------------------------------------
+// 16-byte gather load with the smallest L2 prefetch size: a random 16-byte read otherwise drags a 128-byte line out of
+// DRAM (measured: 126 B of DRAM traffic per gathered point).
+__device__ __forceinline__ float4 ldg_gather16(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::64B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 template <int GROUP>
 __global__ void __launch_bounds__(kBuildThreads)
 voxel_moments_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx,
@@ -335,12 +405,22 @@ voxel_moments_kernel(const float4* __restrict__ pts, const uint32_t* __restrict_
   if (active) {
     const uint32_t b = voxel_start[gid];
     const uint32_t e = (gid + 1 < n_voxels) ? voxel_start[gid + 1] : n_finite;
-    for (uint32_t i = b + gl; i < e; i += GROUP) {
-      const float4 p = __ldg(pts + __ldg(sorted_idx + i));
-      const double x = p.x, y = p.y, z = p.z;
-      s[0] += x; s[1] += y; s[2] += z;
-      s[3] += x * x; s[4] += x * y; s[5] += x * z;
-      s[6] += y * y; s[7] += y * z; s[8] += z * z;
+    // four gathers in flight per lane (index loads, then point loads), accumulated in index order
+    for (uint32_t i0 = b + gl; i0 < e; i0 += 4 * GROUP) {
+      uint32_t idx[4];
+      float4 p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) idx[u] = (i0 + u * GROUP < e) ? __ldg(sorted_idx + i0 + u * GROUP) : 0xffffffffu;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = (idx[u] != 0xffffffffu) ? ldg_gather16(pts + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (idx[u] == 0xffffffffu) continue;
+        const double x = p[u].x, y = p[u].y, z = p[u].z;
+        s[0] += x; s[1] += y; s[2] += z;
+        s[3] += x * x; s[4] += x * y; s[5] += x * z;
+        s[6] += y * y; s[7] += y * z; s[8] += z * z;
+      }
     }
   }
 #pragma unroll
@@ -444,13 +524,26 @@ finalize_voxels_kernel(const double* __restrict__ moments, const int32_t* __rest
     const double scale = (n - 1.0) / n;  // Q3, …_impl.hpp:330
     for (int a = 0; a < 3; ++a)
       for (int c = 0; c < 3; ++c) cov[a][c] *= scale;
-    double ev[3], evec[3][3];
-    sym_eig3_jacobi(cov, ev, evec);
+    // The eigen-decomposition only decides (a) rejection (a negative eigenvalue) and (b) inflation (ev0 < ratio * ev2,
+    // …_impl.hpp:337-356).  Invariants of the symmetric matrix bound the spectrum: with trace t > 0, sum of principal
+    // 2x2 minors c2 > 0 and det > 0 all eigenvalues are positive, ev2 < t and ev0 >= det / (ev1 ev2) >= det / c2.  So
+    // det / c2 >= ratio * t proves "no rejection, no inflation" with a >= 2 % margin, cov stays as it is and the
+    // Jacobi sweeps (the bulk of this kernel's fp64 work) are skipped for the well-conditioned voxels.
+    const double tr = cov[0][0] + cov[1][1] + cov[2][2];
+    const double c2 = (cov[0][0] * cov[1][1] - cov[0][1] * cov[1][0]) + (cov[0][0] * cov[2][2] - cov[0][2] * cov[2][0]) +
+                      (cov[1][1] * cov[2][2] - cov[1][2] * cov[2][1]);
+    const double det3 = cov[0][0] * (cov[1][1] * cov[2][2] - cov[1][2] * cov[2][1]) -
+                        cov[0][1] * (cov[1][0] * cov[2][2] - cov[1][2] * cov[2][0]) +
+                        cov[0][2] * (cov[1][0] * cov[2][1] - cov[1][1] * cov[2][0]);
+    const bool well_conditioned = (tr > 0.0) && (c2 > 0.0) && (det3 > 0.0) && (eig_ratio <= 0.5) && (det3 >= eig_ratio * tr * c2) &&
+                                  !isinf(tr) && !isinf(c2);
+    double ev[3] = {1.0, 1.0, 1.0}, evec[3][3];
+    if (!well_conditioned) sym_eig3_jacobi(cov, ev, evec);
     if (ev[0] < 0 || ev[1] < 0 || ev[2] <= 0) {
       count = -1;  // …_impl.hpp:337-341
     } else {
       const double min_ev = eig_ratio * ev[2];
-      if (ev[0] < min_ev) {  // …_impl.hpp:346-356
+      if (!well_conditioned && ev[0] < min_ev) {  // …_impl.hpp:346-356
         ev[0] = min_ev;
         if (ev[1] < min_ev) ev[1] = min_ev;
         double vinv[3][3], vd[3][3];

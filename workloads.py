@@ -190,3 +190,57 @@ def config2(map_points=1_000_000, n_map_scans=31, scan_seed=0, seed=SEED_C2, azi
     off = np.asarray(offset, dtype=np.float64)
     return {"target": (target.astype(np.float64) + off).astype(np.float32), "source": src.astype(np.float32),
             "truth": truth, "offset": off}
+
+
+def voxel_centroid_downsample(points, leaf):
+    """pcl::VoxelGrid-style centroid downsample (one fp32 centroid per occupied leaf-sized cell, cells in ascending
+    index order).  Input preparation only: the generator does not claim bit parity with PCL here."""
+    p = np.asarray(points, dtype=np.float32)
+    inv = np.float32(1.0) / np.float32(leaf)
+    q = np.floor(p * inv).astype(np.int64)
+    q -= q.min(axis=0)
+    dims = q.max(axis=0) + 1
+    key = (q[:, 2] * dims[1] + q[:, 1]) * dims[0] + q[:, 0]
+    uniq, inv_idx, cnt = np.unique(key, return_inverse=True, return_counts=True)
+    out = np.zeros((len(uniq), 3), dtype=np.float64)
+    for a in range(3):
+        out[:, a] = np.bincount(inv_idx, weights=p[:, a].astype(np.float64), minlength=len(uniq))
+    out /= cnt[:, None]
+    return np.ascontiguousarray(out, dtype=np.float32)
+
+
+def config3_sequence(n_scans, seed=SEED_C3, azimuth_steps=1875, leaf=0.3):
+    """BASELINE.json configs[2]: consecutive scans of a simulated drive through the c2 scene generator (seed 20260102):
+    10 Hz, 5-15 m/s, yaw rate <= 20 deg/s, each scan in the SENSOR frame, downsampled with a 0.3 m voxel grid (the
+    mapping node's default, ndt_rosbag_mapping_node.cpp:88).  Returns (scans, poses) with poses[k] = (x, y, yaw)."""
+    scene = Scene(seed)
+    rng = np.random.default_rng(seed + 17)
+    half = scene.tile / 2 - 40.0
+    x, y, yaw, v, direction = -half, 0.0, 0.0, 10.0, 1.0
+    scans, poses = [], []
+    for k in range(n_scans):
+        ps, _ = scene.scan((x, y, yaw), seed=seed + 9000 + k, azimuth_steps=azimuth_steps)
+        scans.append(voxel_centroid_downsample(ps, leaf))
+        poses.append((x, y, yaw))
+        v = float(np.clip(v + rng.uniform(-0.5, 0.5), 5.0, 15.0))
+        yaw_rate = float(np.deg2rad(rng.uniform(-20.0, 20.0)))
+        # keep the vehicle on the street corridor: steer back towards y = 0 and the street axis
+        heading = 0.0 if direction > 0 else math.pi
+        err = ((heading - yaw + math.pi) % (2 * math.pi)) - math.pi
+        yaw += 0.1 * float(np.clip(0.5 * yaw_rate + 2.0 * err - 0.3 * y * direction, -np.deg2rad(20.0), np.deg2rad(20.0)))
+        x += 0.1 * v * math.cos(yaw)
+        y += 0.1 * v * math.sin(yaw)
+        if abs(x) > half:
+            direction = -direction
+    return scans, poses
+
+
+def relative_pose_matrix(pose_a, pose_b):
+    """4x4 transform taking points of scan b's sensor frame into scan a's sensor frame (planar poses x, y, yaw)."""
+    def mat(p):
+        c, s = math.cos(p[2]), math.sin(p[2])
+        T = np.eye(4)
+        T[:2, :2] = [[c, -s], [s, c]]
+        T[0, 3], T[1, 3] = p[0], p[1]
+        return T
+    return np.linalg.inv(mat(pose_a)) @ mat(pose_b)
