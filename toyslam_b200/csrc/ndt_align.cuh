@@ -160,7 +160,11 @@ __device__ __forceinline__ int probe_cell(const MapView& m, int cx, int cy, int 
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifdef NDTB200_PREFETCH_L1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
 }
 
 // All K probes of a point (DIRECT1 / DIRECT7) with their loads in flight together.  In-bounds tests are unsigned
@@ -511,27 +515,35 @@ __device__ const TableTerm g_table_terms[69] = {
     TT(-1, 2, 6, 0, +1, 1, 4, 5), TT(-1, 1, 4, 6, -1, 2, 5, 0), TT(0, 0, 0, 0, 0, 0, 0, 0)};   // f3
 #undef TT
 
-// Called by all threads of warp 0 (others return immediately).  s_trig: 16 doubles of shared scratch.
-__device__ __forceinline__ void setup_pose_warp(const double* x_t, EvalCtx& ctx, float* final_T, double* s_trig,
-                                                const TableTerm* s_terms, bool build_matrix) {
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
-  // lanes 0..5 : fp64 cos/sin of the three angles with the small-angle snap (ndt_omp_impl.hpp:292-326)
-  // lanes 6..11: fp32 sin/cos of the fp32-cast angles for the matrix (Eigen::AngleAxis<float>)
+// pose -> evaluation context in three pieces so that two warps share the work:
+//   pose_trig   (warp 0, lanes 0..5)  one sincos per lane, a single code path: lanes 0..2 the fp64 angles with the
+//               small-angle snap (ndt_omp_impl.hpp:292-326), lanes 3..5 the fp32-cast angles (Eigen::AngleAxis<float>)
+//   pose_tables (warp 0)              the 69 table entries, two or three per lane
+//   pose_matrix (warp 1, lane 0)      Translation * Rx * Ry * Rz in fp32 (same arithmetic as pose_to_matrix)
+// s_trig: [0] = 1, [1..6] = cx sx cy sy cz sz (fp64, factor codes), [8..13] = the fp32 values of cx sx cy sy cz sz.
+__device__ __forceinline__ void pose_trig(const double* x_t, double* s_trig) {
+  const int lane = threadIdx.x & 31;
   if (lane < 6) {
-    const double a = x_t[3 + (lane >> 1)];
-    double v;
-    if (fabs(a) < 10e-5) v = (lane & 1) ? 0.0 : 1.0;
-    else v = (lane & 1) ? sin(a) : cos(a);
-    s_trig[1 + lane] = v;  // order cx sx cy sy cz sz = factor codes 1..6
-  } else if (lane < 12) {
-    const int l = lane - 6;
-    const double a = static_cast<double>(static_cast<float>(x_t[3 + (l >> 1)]));
-    s_trig[8 + l] = static_cast<double>(static_cast<float>((l & 1) ? sin(a) : cos(a)));  // cx sx cy sy cz sz (fp32 values)
+    const int ax = lane < 3 ? lane : lane - 3;
+    const double a64 = x_t[3 + ax];
+    const double a = lane < 3 ? a64 : static_cast<double>(static_cast<float>(a64));
+    double sv, cv;
+    sincos(a, &sv, &cv);
+    if (lane < 3) {
+      if (fabs(a64) < 10e-5) { cv = 1.0; sv = 0.0; }
+      s_trig[1 + 2 * ax] = cv;
+      s_trig[2 + 2 * ax] = sv;
+    } else {
+      s_trig[8 + 2 * ax] = static_cast<double>(static_cast<float>(cv));
+      s_trig[9 + 2 * ax] = static_cast<double>(static_cast<float>(sv));
+    }
   } else if (lane == 12) {
     s_trig[0] = 1.0;
   }
-  __syncwarp();
+}
+
+__device__ __forceinline__ void pose_tables(EvalCtx& ctx, const double* s_trig, const TableTerm* s_terms) {
+  const int lane = threadIdx.x & 31;
   for (int e = lane; e < 69; e += 32) {
     const TableTerm t = s_terms[e];
     double v = 0.0;
@@ -547,24 +559,27 @@ __device__ __forceinline__ void setup_pose_warp(const double* x_t, EvalCtx& ctx,
       reinterpret_cast<float*>(&ctx.tf[8 + r])[c] = (r == 6 && c == 2) ? static_cast<float>(s_trig[4]) : static_cast<float>(v);
     }
   }
-  if (build_matrix && lane == 0) {
-    // Translation * Rx * Ry * Rz in fp32 from the fp32 trig values (same arithmetic as pose_to_matrix)
-    const float cx = static_cast<float>(s_trig[8]), sx = static_cast<float>(s_trig[9]);
-    const float cy = static_cast<float>(s_trig[10]), sy = static_cast<float>(s_trig[11]);
-    const float cz = static_cast<float>(s_trig[12]), sz = static_cast<float>(s_trig[13]);
-    float Rx[3][3], Ry[3][3], Rz[3][3], Rxy[3][3], R[3][3];
-    angle_axis_from_sc(sx, cx, 0, Rx);
-    angle_axis_from_sc(sy, cy, 1, Ry);
-    angle_axis_from_sc(sz, cz, 2, Rz);
-    mul33f(Rx, Ry, Rxy);
-    mul33f(Rxy, Rz, R);
-    for (int i = 0; i < 3; ++i) {
-      for (int j = 0; j < 3; ++j) ctx.T[i * 4 + j] = R[i][j];
-      ctx.T[i * 4 + 3] = static_cast<float>(x_t[i]);
-    }
-    for (int i = 0; i < 12; ++i) final_T[i] = ctx.T[i];  // final_transformation_ = T(x_t) (ndt_omp_impl.hpp:827-830)
+}
+
+__device__ __forceinline__ void pose_matrix(const double* x_t, EvalCtx& ctx, float* final_T, const double* s_trig) {
+  const float cx = static_cast<float>(s_trig[8]), sx = static_cast<float>(s_trig[9]);
+  const float cy = static_cast<float>(s_trig[10]), sy = static_cast<float>(s_trig[11]);
+  const float cz = static_cast<float>(s_trig[12]), sz = static_cast<float>(s_trig[13]);
+  float Rx[3][3], Ry[3][3], Rz[3][3], Rxy[3][3], R[3][3];
+  angle_axis_from_sc(sx, cx, 0, Rx);
+  angle_axis_from_sc(sy, cy, 1, Ry);
+  angle_axis_from_sc(sz, cz, 2, Rz);
+  mul33f(Rx, Ry, Rxy);
+  mul33f(Rxy, Rz, R);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) ctx.T[i * 4 + j] = R[i][j];
+    ctx.T[i * 4 + 3] = static_cast<float>(x_t[i]);
   }
-  __syncwarp();
+  for (int i = 0; i < 12; ++i) final_T[i] = ctx.T[i];  // final_transformation_ = T(x_t) (ndt_omp_impl.hpp:827-830)
+}
+
+__device__ __forceinline__ void bar_sync_pair() {  // named barrier 1 shared by warps 0 and 1 (64 threads)
+  asm volatile("bar.sync 1, 64;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -718,8 +733,9 @@ __device__ __noinline__ int newton_post() {
       st.converged = (nrm == nrm) ? 1 : 0;
       return ACT_DONE;
     }
+    const double inv_nrm = 1.0 / nrm;  // one division instead of six (differs from x / nrm by at most one fp64 ulp)
 #pragma unroll
-    for (int i = 0; i < 6; ++i) st.dir[i] = delta[i] / nrm;
+    for (int i = 0; i < 6; ++i) st.dir[i] = delta[i] * inv_nrm;
     // computeStepLengthMT(p, dir, nrm, step_size, eps/2, ...)
     st.step_max = prm.step_size;
     st.step_min = prm.trans_eps / 2;
@@ -873,12 +889,20 @@ mt_finish: {
 // are formed once per point (~90 instructions).  J_E / H_E are only needed in that epilogue, which keeps the hit loop's
 // register footprint small.  Same validity test per hit (e2 > 1 || e2 < 0 || NaN contributes nothing, :506-507).
 // ---------------------------------------------------------------------------------------------
+struct RecordRegs { float4 a, b, c; };  // the 48 hot bytes of a voxel record
+
+__device__ __forceinline__ RecordRegs load_record(const VoxelRecord* R) {
+  RecordRegs r;
+  r.a = __ldg(reinterpret_cast<const float4*>(R));
+  r.b = __ldg(reinterpret_cast<const float4*>(R) + 1);
+  r.c = __ldg(reinterpret_cast<const float4*>(R) + 2);
+  return r;
+}
+
 template <bool HESS>
-__device__ __forceinline__ void hit_f32(const VoxelRecord* R, float tx, float ty, float tz, float d2f, float d1f,
+__device__ __forceinline__ void hit_f32(const RecordRegs& rr, float tx, float ty, float tz, float d2f, float d1f,
                                         float& S, float (&A)[3], float (&M)[6]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(R));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(R) + 1);
-  const float4 c = __ldg(reinterpret_cast<const float4*>(R) + 2);
+  const float4 a = rr.a, b = rr.b, c = rr.c;
   // x_trans = fl32(double(x') - mean) (ndt_omp_impl.hpp:259-262, 492) via the exact hi/lo split of the mean
   const float r0 = __fsub_rn(__fsub_rn(tx, a.x), a.w);
   const float r1 = __fsub_rn(__fsub_rn(ty, a.y), b.x);
@@ -924,11 +948,13 @@ __device__ __forceinline__ void point_f32(float px, float py, float pz, const Ev
   if constexpr (METHOD != 1) {
     int rec[K];
     probe_cells<K>(m, ix, iy, iz, rec);
+    // (a depth-1 software pipeline of the record loads was measured: the extra live registers spill at the 64-register
+    // cap and cost 12 % — the 32 resident warps already cover the L2 latency)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (rec[k] < 0) continue;
       ++nh;
-      hit_f32<HESS>(m.records + rec[k], tx, ty, tz, d2f, d1f, S, A, M);
+      hit_f32<HESS>(load_record(m.records + rec[k]), tx, ty, tz, d2f, d1f, S, A, M);
     }
   } else {
 #pragma unroll 1
@@ -938,7 +964,7 @@ __device__ __forceinline__ void point_f32(float px, float py, float pz, const Ev
       const int rec = probe_cell(m, ix + dx, iy + dy, iz + dz);
       if (rec < 0) continue;
       ++nh;
-      hit_f32<HESS>(m.records + rec, tx, ty, tz, d2f, d1f, S, A, M);
+      hit_f32<HESS>(load_record(m.records + rec), tx, ty, tz, d2f, d1f, S, A, M);
     }
   }
   if (nh == 0) return;
@@ -1169,13 +1195,18 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
         __syncwarp();
         if (timing) t_d2 = globaltimer_ns();
       }
-      if (st.need_pose) setup_pose_warp(st.x_t, ctx, st.final_T, s_trig, s_terms, /*build_matrix=*/true);
+      if (st.need_pose) pose_trig(st.x_t, s_trig);
+      bar_sync_pair();  // warp 1 builds the matrix while this warp fills the tables
+      if (st.need_pose) pose_tables(ctx, s_trig, s_terms);
       if (timing && slot < prm.trace_cap) {
         TraceRec& r = ws.trace[slot];
         r.t_start = t_start; r.t_local = t_local; r.t_reduced = t_reduced; r.t_advanced = globaltimer_ns();
         r.t_dbg[0] = t_d0; r.t_dbg[1] = t_d1; r.t_dbg[2] = t_d2; r.t_dbg[3] = t_last_arrive;
         r.t_phase[0] = s_dbg[0]; r.t_phase[1] = t_local;
       }
+    } else if (warp == 1) {
+      bar_sync_pair();
+      if (st.need_pose && lane == 0) pose_matrix(st.x_t, ctx, st.final_T, s_trig);
     }
     __syncthreads();
   }
