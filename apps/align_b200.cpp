@@ -103,5 +103,23 @@ int main(int argc, char** argv) {
   Cloud out;
   copy.align(out);
   std::cout << "copy converged: " << copy.hasConverged() << ", iterations " << copy.getFinalNumIteration() << std::endl;
+
+  // independent pairs aligned together (not in the reference): four copies of the pair, one batch call
+  typedef pclomp_b200::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ> Ndt;
+  std::vector<Ndt> objs(4, ndt);
+  std::vector<Ndt*> ptrs;
+  std::vector<Cloud> outs(objs.size());
+  std::vector<Cloud*> out_ptrs;
+  for (size_t i = 0; i < objs.size(); ++i) {
+    objs[i].setNeighborhoodSearchMethod(pclomp_b200::DIRECT7);
+    ptrs.push_back(&objs[i]);
+    out_ptrs.push_back(&outs[i]);
+  }
+  auto b0 = std::chrono::steady_clock::now();
+  Ndt::alignBatch(ptrs, out_ptrs);
+  auto b1 = std::chrono::steady_clock::now();
+  std::cout << "batch of " << objs.size() << ": " << std::chrono::duration<double, std::milli>(b1 - b0).count() << "[msec], iterations";
+  for (auto& o : objs) std::cout << " " << o.getFinalNumIteration();
+  std::cout << std::endl;
   return 0;
 }

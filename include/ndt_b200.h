@@ -144,6 +144,24 @@ int ndtb200_comm_export(ndtb200_handle* h, void* handle_out64);
 int ndtb200_comm_attach(ndtb200_handle* h, int rank, int world, const void* all_handles, int64_t n_source_total);
 int ndtb200_comm_detach(ndtb200_handle* h);
 
+/* ---- multi-GPU target-map build (not in the reference; SURVEY 8e "target-map build") ----------------------------
+ * The cloud is split by contiguous point ranges, one per rank.  (1) ndtb200_cloud_bounds: bounding box + finite count
+ * of this rank's slice (device pointer, float4 records); the caller all-reduces min / max / count over the ranks.
+ * (2) ndtb200_build_partials: keys with the COMMON grid, sort, per-voxel {key, count, sum x, sum x x^T} of the slice;
+ * (3) the caller all-gathers the partial arrays (ndtb200_copy_partials copies them into caller-owned device buffers:
+ * int32 keys, uint32 counts, 9 fp64 moments per voxel) and concatenates them in rank order;
+ * (4) ndtb200_build_from_partials merges them (stable sort by key, sums in rank order: identical bits on every
+ * rank), finalises every voxel and builds the index: every rank ends with the full map.  Keys and counts are exact;
+ * moments differ from a single-GPU build only by the fp64 summation order.  getFitnessScore is not available on a
+ * handle whose map was merged (it holds only its slice of the raw target). */
+int ndtb200_cloud_bounds(ndtb200_handle* h, const void* d_points_xyzw, size_t n, int is_dense, float out_min[3],
+                         float out_max[3], int64_t* n_finite);
+int ndtb200_build_partials(ndtb200_handle* h, const float global_min[3], const float global_max[3], int64_t* n_partials);
+int ndtb200_copy_partials(ndtb200_handle* h, void* d_keys, void* d_counts, void* d_moments);
+int ndtb200_build_from_partials(ndtb200_handle* h, const float global_min[3], const float global_max[3],
+                                int64_t n_finite_total, const void* d_keys, const void* d_counts, const void* d_moments,
+                                size_t n_total);
+
 /* ---- parity / inspection (stage dumps; used by tests, not by callers) ------------------------ */
 int ndtb200_get_map_info(const ndtb200_handle* h, ndtb200_map_info* out);
 /* voxel key of every target point, input order (-1 = skipped non-finite point). */

@@ -14,6 +14,7 @@
 #include <limits>
 #include <memory>
 #include <utility>
+#include <vector>
 
 #include "../ndt_b200.h"
 #include "pcl_compat.hpp"
@@ -141,6 +142,41 @@ class NormalDistributionsTransform {
   }
 
   ndtb200_handle* handle() { return h_; }
+
+  // ---- not in the reference: independent scan pairs aligned together (ndtb200_align_batch) ----
+  // Every object already holds its own target and source; outputs[i] receives the aligned cloud of objects[i] like
+  // align(output, guess) does.  guesses may be empty (identity) or hold one matrix per object.
+  static void alignBatch(const std::vector<NormalDistributionsTransform*>& objects, const std::vector<PointCloudSource*>& outputs,
+                         const std::vector<Eigen::Matrix4f>& guesses = std::vector<Eigen::Matrix4f>()) {
+    const int n = static_cast<int>(objects.size());
+    if (n == 0) return;
+    std::vector<ndtb200_handle*> hs(n, nullptr);
+    std::vector<void*> outs(n, nullptr);
+    std::vector<float> g;
+    if (!guesses.empty()) g.resize(16 * static_cast<size_t>(n));
+    for (int i = 0; i < n; ++i) {
+      NormalDistributionsTransform* o = objects[i];
+      if (!o || !o->h_ || !o->input_) { std::fprintf(stderr, "[pclomp_b200] alignBatch: object %d has no device handle / source\n", i); return; }
+      o->prm_.search_method = static_cast<int32_t>(o->search_method);
+      ndtb200_set_params(o->h_, &o->prm_);
+      hs[i] = o->h_;
+      if (i < static_cast<int>(outputs.size()) && outputs[i]) {
+        PointCloudSource& out = *outputs[i];
+        out.points.resize(o->input_->points.size());
+        out.width = static_cast<uint32_t>(out.points.size());
+        out.height = 1;
+        out.is_dense = o->input_->is_dense;
+        for (size_t k = 0; k < out.points.size(); ++k) out.points[k] = o->input_->points[k];
+        outs[i] = out.points.empty() ? nullptr : static_cast<void*>(out.points.data());
+      }
+      if (!guesses.empty()) {
+        const Eigen::Matrix4f& G = guesses[static_cast<size_t>(i) < guesses.size() ? i : guesses.size() - 1];
+        for (int k = 0; k < 16; ++k) g[16 * static_cast<size_t>(i) + k] = G.data()[k];
+      }
+    }
+    const int st = ndtb200_align_batch(hs.data(), n, guesses.empty() ? nullptr : g.data(), outs.data(), sizeof(PointSource), nullptr);
+    if (st != NDTB200_OK) std::fprintf(stderr, "[pclomp_b200] alignBatch failed (status %d): %s\n", st, ndtb200_last_error(hs[0]));
+  }
 
   NeighborSearchMethod search_method;  // public in the reference too (ndt_omp.h:499)
 

@@ -37,3 +37,10 @@ def test_sharded_align_matches_oracle(world):
         assert c["iterations"][0] == c["iterations"][1] and c["evaluations"][0] == c["evaluations"][1], c
         assert c["hessian_passes"][0] == c["hessian_passes"][1], c
         assert c["dt"] < 1e-4 and c["dr"] < 1e-4 and c["tp_rel"] < 1e-5, c
+    # sharded target-map build: keys / counts exact, every rank holds identical bits, moments within 1e-5
+    assert len(res["build"]) == 3
+    for c in res["build"]:
+        assert c["status"] == 0 and c["identical_across_ranks"], c
+        assert c["keys_equal"] and c["counts_equal"] and c["n_voxels"][0] == c["n_voxels"][1], c
+        assert c["mean_rel"] < 1e-5 and c["icov_rel_vs_single_gpu"] < 1e-5, c
+        assert c["hits_equal"] and c["grad_rel"] < 1e-5 and c["hess_rel"] < 1e-5, c

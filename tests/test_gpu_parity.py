@@ -44,12 +44,16 @@ def make_pair(nb, tgt, src, method=oracle.DIRECT7, res=1.0, **kw):
 
 
 def check_map(ref, gpu):
+    assert np.array_equal(ref.point_keys(), gpu.point_keys())  # bit-exact keys, input order
+    check_voxels(ref, gpu)
+
+
+def check_voxels(ref, gpu):
     ri, gi = ref.map_info(), gpu.map_info()
     for k in ("min_b", "max_b", "div_b"):
         assert np.array_equal(ri[k], gi[k]), k
     assert ri["n_voxels"] == gi["n_voxels"]
     assert ri["n_valid"] == gi["n_valid"]
-    assert np.array_equal(ref.point_keys(), gpu.point_keys())  # bit-exact keys, input order
     rl, gl = ref.dump_leaves(), gpu.dump_voxels()
     assert np.array_equal(rl["keys"], gl["keys"])
     assert np.array_equal(rl["counts"], gl["counts"])      # incl. -1 flags
@@ -125,6 +129,51 @@ def test_map_build_non_dense_and_faces(nb):
     assert ref.setInputTarget(tgt, is_dense=False) == gpu.setInputTarget(tgt, is_dense=False) == 0
     ref.setInputSource(tgt[:10]); gpu.setInputSource(tgt[:10])
     check_map(ref, gpu)
+
+
+@pytest.mark.parametrize("slices", [1, 3])
+def test_map_build_from_partials(nb, slices):
+    """The sharded build's pieces on one GPU: the cloud cut into contiguous slices, per-slice partials with the
+    common grid, merged in slice order — keys / counts exact, moments within the bar, same lookups and derivatives."""
+    import torch
+    from toyslam_b200.sharding import point_range
+    tgt, src = load_pair()
+    ref, single = make_pair(nb, tgt, src)
+    dev = torch.device("cuda", 0)
+    parts, boxes, nf_total = [], [], 0
+    workers = []
+    for r in range(slices):
+        lo, hi = point_range(len(tgt), r, slices)
+        loc = torch.ones((hi - lo, 4), dtype=torch.float32, device=dev)
+        loc[:, :3] = torch.as_tensor(tgt[lo:hi]).to(dev)
+        w = nb.NormalDistributionsTransform()
+        mn, mx, nf = w.cloud_bounds(loc.data_ptr(), hi - lo)
+        boxes.append((mn, mx)); nf_total += nf
+        workers.append((w, loc))
+    gmin = np.min([b[0] for b in boxes], axis=0)
+    gmax = np.max([b[1] for b in boxes], axis=0)
+    for w, loc in workers:
+        st, nv = w.build_partials(gmin, gmax)
+        assert st == 0 and nv > 0
+        k = torch.zeros(nv, dtype=torch.int32, device=dev)
+        c = torch.zeros(nv, dtype=torch.int32, device=dev)
+        m = torch.zeros((nv, 9), dtype=torch.float64, device=dev)
+        w.copy_partials(k.data_ptr(), c.data_ptr(), m.data_ptr())
+        parts.append((k, c, m))
+    keys = torch.cat([p[0] for p in parts]).contiguous()
+    cnts = torch.cat([p[1] for p in parts]).contiguous()
+    moms = torch.cat([p[2] for p in parts]).contiguous()
+    assert int(cnts.sum().item()) == len(tgt)
+    merged = nb.NormalDistributionsTransform()
+    assert merged.build_from_partials(gmin, gmax, nf_total, keys.data_ptr(), cnts.data_ptr(), moms.data_ptr(), len(keys)) == 0
+    check_voxels(ref, merged)
+    merged.setInputSource(src)
+    p = np.array([0.4, 0.1, -0.02, 0.005, -0.001, -0.01])
+    a, b = merged.eval_derivatives(p), ref.eval_derivatives(p)
+    assert a["hits"] == b["hits"]
+    assert rel_err(a["gradient"], b["gradient"]) < REL and rel_err(a["hessian"], b["hessian"]) < REL
+    with pytest.raises(nb.NdtError):
+        merged.getFitnessScore()       # the merged handle holds no raw target
 
 
 def test_grid_overflow_guard(nb):

@@ -69,7 +69,9 @@ struct ndtb200_handle {
   uint32_t hash_cap = 0;
   int hash_shift = 0;
   DevBuf d_grid, d_mm_partial, d_mm_finite, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_scan_tmp, d_scalar;
-  DevBuf d_voxel_key, d_voxel_start, d_moments, d_records, d_icov64, d_hash, d_dense;
+  DevBuf d_voxel_key, d_voxel_start, d_voxel_count, d_moments, d_records, d_icov64, d_hash, d_dense;
+  size_t n_partials = 0;       // voxels of the last partial-only build (sharded build, before the exchange)
+  bool map_is_merged = false;  // map built from all ranks' partials: d_target holds only this rank's slice
   bool use_dense = false;
 
   // source cloud
@@ -167,67 +169,41 @@ int ensure_empty_hash(ndtb200_handle* h) {
 }
 
 // ---- VoxelGridCovariance::applyFilter on the device -------------------------------------------
-int build_map(ndtb200_handle* h) {
-  clear_map(h);
-  std::memset(&h->grid, 0, sizeof(GridDesc));
-  for (int a = 0; a < 3; ++a) h->grid.leaf[a] = h->prm.resolution;
-  const size_t n = h->n_target;
-  if (!h->has_target || n == 0) {
-    h->map_status = NDTB200_ERR_NO_INPUT;
-    int st = ensure_empty_hash(h);
-    return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
-  }
-  if (n > 0xFFFFFFF0ull) { h->err = "target cloud too large (>= 2^32 points)"; return NDTB200_ERR_INVALID; }
-  const float4* pts = h->d_target.as<float4>();
-  const int dense = h->target_dense ? 1 : 0;
+struct BuildOpts {
+  // sharded build: the grid comes from the bounding box of the WHOLE cloud (all ranks), the handle
+  // processes only its slice and stops after the per-voxel moments ("partials")
+  const float* forced_min = nullptr;
+  const float* forced_max = nullptr;
+  bool partial_only = false;
+};
 
-  // 1. bounding box + grid description
+// bounding box of the handle's target slice + grid description -> h->grid (host copy); one synchronisation
+int compute_grid(ndtb200_handle* h, const float4* pts, size_t n, int dense, const BuildOpts& o) {
   const int mm_blocks = grid_for(n, kBuildThreads * 4, h->num_sms * 8);
-  CK(h->d_mm_partial.ensure(mm_blocks * 6 * sizeof(float)));
-  CK(h->d_mm_finite.ensure(mm_blocks * sizeof(unsigned int)));
+  CK(h->d_mm_partial.ensure((size_t)mm_blocks * 6 * sizeof(float)));
+  CK(h->d_mm_finite.ensure((size_t)mm_blocks * sizeof(unsigned int)));
   CK(h->d_grid.ensure(sizeof(GridDesc)));
   minmax3d_kernel<<<mm_blocks, kBuildThreads, 0, h->stream>>>(pts, n, dense, h->d_mm_partial.as<float>(),
                                                                h->d_mm_finite.as<unsigned int>());
   LAUNCHED(h);
+  ForcedBox fb;
+  fb.use = (o.forced_min && o.forced_max) ? 1 : 0;
+  for (int a = 0; a < 3; ++a) { fb.mn[a] = fb.use ? o.forced_min[a] : 0.f; fb.mx[a] = fb.use ? o.forced_max[a] : 0.f; }
   grid_setup_kernel<<<1, kBuildThreads, 0, h->stream>>>(h->d_mm_partial.as<float>(), h->d_mm_finite.as<unsigned int>(),
-                                              mm_blocks, h->prm.resolution, h->d_grid.as<GridDesc>());
+                                                        mm_blocks, h->prm.resolution, fb, h->d_grid.as<GridDesc>());
   LAUNCHED(h);
   CK(cudaMemcpyAsync(&h->grid, h->d_grid.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (h->grid.n_finite == 0) {
-    h->map_status = NDTB200_ERR_NO_INPUT;
-    int st = ensure_empty_hash(h);
-    return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
-  }
-  if (h->grid.overflow) {  // voxel_grid_covariance_omp_impl.hpp:79-84: warn, leave the map empty
-    h->map_status = NDTB200_ERR_GRID_OVERFLOW;
-    int st = ensure_empty_hash(h);
-    return st != NDTB200_OK ? st : NDTB200_ERR_GRID_OVERFLOW;
-  }
+  return NDTB200_OK;
+}
 
-  // 2. keys
-  unsigned long long key_space =
-      (unsigned long long)h->grid.div_b[0] * (unsigned long long)h->grid.div_b[1] * (unsigned long long)h->grid.div_b[2];
-  if (key_space > 0xFFFFFFFEull) key_space = 0xFFFFFFFEull;
-  const uint32_t sentinel = static_cast<uint32_t>(key_space);  // sorts after every real key
-  unsigned long long max_key = dense ? (key_space - 1) : key_space;
-  int bits = 1;
-  while (bits < 32 && (max_key >> bits) != 0) ++bits;
-  const int passes = (bits + 7) / 8;
-
-  CK(h->d_keys_a.ensure(n * sizeof(uint32_t)));
-  CK(h->d_keys_b.ensure(n * sizeof(uint32_t)));
-  CK(h->d_vals_a.ensure(n * sizeof(uint32_t)));
-  CK(h->d_vals_b.ensure(n * sizeof(uint32_t)));
-  const int key_blocks = grid_for(n, kBuildThreads * 4, h->num_sms * 16);
-  voxel_key_kernel<<<key_blocks, kBuildThreads, 0, h->stream>>>(pts, n, dense, h->d_grid.as<GridDesc>(), sentinel,
-                                                                 h->d_keys_a.as<uint32_t>(), nullptr);
-  LAUNCHED(h);
-
-  // 3. stable LSD radix sort of (key, point index)
+// stable LSD radix sort of the n (key, index) pairs whose keys sit in d_keys_a, then the segment heads:
+// -> d_voxel_key / d_voxel_start (n_vox entries), sorted indices in d_vals_a.  One synchronisation (the voxel count).
+int sort_and_segment(ndtb200_handle* h, size_t n, uint32_t sentinel, int passes, uint32_t* n_vox_out) {
   const int ntiles = static_cast<int>((n + kSortTile - 1) / kSortTile);
   const size_t hist_n = (size_t)256 * ntiles;
-  CK(h->d_hist.ensure(hist_n * sizeof(uint32_t)));
+  const int stiles = static_cast<int>((n + kScanTile - 1) / kScanTile);
+  CK(h->d_hist.ensure(std::max(hist_n, (size_t)stiles) * sizeof(uint32_t)));
   CK(h->d_scan_tmp.ensure(scan_tmp_elems(std::max(hist_n, n)) * sizeof(uint32_t)));
   uint32_t *ka = h->d_keys_a.as<uint32_t>(), *kb = h->d_keys_b.as<uint32_t>();
   uint32_t *va = h->d_vals_a.as<uint32_t>(), *vb = h->d_vals_b.as<uint32_t>();
@@ -243,12 +219,10 @@ int build_map(ndtb200_handle* h) {
     std::swap(ka, kb);
     std::swap(va, vb);
   }
-  // sorted keys in ka, sorted point indices in va.  Keep them addressable through fixed members.
+  // sorted keys in ka, sorted indices in va.  Keep them addressable through fixed members.
   if (ka != h->d_keys_a.as<uint32_t>()) { std::swap(h->d_keys_a, h->d_keys_b); std::swap(h->d_vals_a, h->d_vals_b); }
 
-  // 4. occupied voxels = segment heads
-  const int stiles = static_cast<int>((n + kScanTile - 1) / kScanTile);
-  uint32_t* tile_counts = h->d_hist.as<uint32_t>();  // reuse (hist_n >= stiles)
+  uint32_t* tile_counts = h->d_hist.as<uint32_t>();
   head_count_kernel<<<stiles, kBuildThreads, 0, h->stream>>>(ka, n, sentinel, tile_counts);
   LAUNCHED(h);
   uint32_t* d_total = h->d_scalar.as<uint32_t>();
@@ -259,44 +233,44 @@ int build_map(ndtb200_handle* h) {
   uint32_t n_vox = 0;
   CK(cudaMemcpyAsync(&n_vox, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  h->n_voxels = n_vox;
-  CK(h->d_voxel_key.ensure((size_t)n_vox * sizeof(int32_t)));
-  CK(h->d_voxel_start.ensure((size_t)n_vox * sizeof(uint32_t)));
-  CK(h->d_moments.ensure((size_t)n_vox * 9 * sizeof(double)));
-  CK(h->d_records.ensure((size_t)n_vox * sizeof(VoxelRecord)));
-  CK(h->d_icov64.ensure((size_t)n_vox * 6 * sizeof(double)));
+  CK(h->d_voxel_key.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(int32_t)));
+  CK(h->d_voxel_start.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(uint32_t)));
   head_write_kernel<<<stiles, kBuildThreads, 0, h->stream>>>(ka, n, sentinel, tile_counts, h->d_voxel_key.as<int32_t>(),
                                                               h->d_voxel_start.as<uint32_t>());
   LAUNCHED(h);
+  *n_vox_out = n_vox;
+  return NDTB200_OK;
+}
 
-  // 5. moments + finalize
-  const uint32_t n_finite = static_cast<uint32_t>(h->grid.n_finite);
-  const double avg = static_cast<double>(n_finite) / std::max<uint32_t>(1u, n_vox);
-  if (avg >= 48.0) {
-    const int blocks = static_cast<int>(((size_t)n_vox * 32 + kBuildThreads - 1) / kBuildThreads);
-    voxel_moments_kernel<32><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
-                                                                      n_finite, h->d_moments.as<double>());
-  } else if (avg >= 10.0) {
-    const int blocks = static_cast<int>(((size_t)n_vox * 8 + kBuildThreads - 1) / kBuildThreads);
-    voxel_moments_kernel<8><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
-                                                                     n_finite, h->d_moments.as<double>());
-  } else {
-    const int blocks = static_cast<int>(((size_t)n_vox * 4 + kBuildThreads - 1) / kBuildThreads);
-    voxel_moments_kernel<4><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
-                                                                     n_finite, h->d_moments.as<double>());
-  }
-  LAUNCHED(h);
+int passes_for(const GridDesc& g, bool with_sentinel, uint32_t* sentinel_out) {
+  unsigned long long key_space = (unsigned long long)g.div_b[0] * (unsigned long long)g.div_b[1] * (unsigned long long)g.div_b[2];
+  if (key_space > 0xFFFFFFFEull) key_space = 0xFFFFFFFEull;
+  *sentinel_out = static_cast<uint32_t>(key_space);  // sorts after every real key
+  const unsigned long long max_key = with_sentinel ? key_space : (key_space - 1);
+  int bits = 1;
+  while (bits < 32 && (max_key >> bits) != 0) ++bits;
+  return (bits + 7) / 8;
+}
+
+// second pass of applyFilter + the voxel index.  counts: per-voxel point counts (merged partials) or nullptr
+// (count = length of the voxel's sorted point range, n_finite closes the last one)
+int finalize_and_index(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite, const uint32_t* counts) {
+  CK(h->d_records.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(VoxelRecord)));
+  CK(h->d_icov64.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * 6 * sizeof(double)));
   unsigned int* d_nvalid = h->d_scalar.as<unsigned int>() + 4;
   CK(cudaMemsetAsync(d_nvalid, 0, sizeof(unsigned int), h->stream));
   const int vblocks = static_cast<int>(((size_t)n_vox + kBuildThreads - 1) / kBuildThreads);
-  finalize_voxels_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(
-      h->d_moments.as<double>(), h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), n_vox, n_finite,
-      h->prm.min_points_per_voxel, h->prm.eig_ratio, h->d_records.as<VoxelRecord>(), h->d_icov64.as<double>(),
-      d_nvalid, nullptr, nullptr, nullptr, nullptr);
-  LAUNCHED(h);
-  // 6. the voxel index.  Direct-mapped cell table (one 4-byte load per probe, no collisions) when dx*dy*dz int32
-  //    entries fit the budget (<= 4 GiB and <= 1/4 of the free device memory); otherwise an open-addressing hash over
-  //    the valid voxels, load <= 0.25 (needs n_valid on the host: the only synchronisation left after the voxel count).
+  if (n_vox > 0) {
+    finalize_voxels_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(
+        h->d_moments.as<double>(), h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), counts, n_vox, n_finite,
+        h->prm.min_points_per_voxel, h->prm.eig_ratio, h->d_records.as<VoxelRecord>(), h->d_icov64.as<double>(),
+        d_nvalid, nullptr, nullptr, nullptr, nullptr);
+    LAUNCHED(h);
+  }
+
+  // the voxel index.  Direct-mapped cell table (one 4-byte load per probe, no collisions) when dx*dy*dz int32
+  // entries fit the budget (<= 4 GiB and <= 1/4 of the free device memory); otherwise an open-addressing hash over
+  // the valid voxels, load <= 0.25 (needs n_valid on the host: the only synchronisation left after the voxel count).
   h->use_dense = false;
   h->n_valid = -1;  // fetched on demand (ndtb200_get_map_info) unless the hash needs it now
   {
@@ -314,9 +288,11 @@ int build_map(ndtb200_handle* h) {
     if (fits) {
       CK(h->d_dense.ensure(bytes));
       CK(cudaMemsetAsync(h->d_dense.p, 0xFF, bytes, h->stream));
-      dense_fill_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
-                                                                  h->prm.min_points_per_voxel, h->d_dense.as<int32_t>());
-      LAUNCHED(h);
+      if (n_vox > 0) {
+        dense_fill_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
+                                                                    h->prm.min_points_per_voxel, h->d_dense.as<int32_t>());
+        LAUNCHED(h);
+      }
       h->use_dense = true;
     }
   }
@@ -332,11 +308,168 @@ int build_map(ndtb200_handle* h) {
     h->hash_shift = 32 - log2cap;
     CK(h->d_hash.ensure((size_t)cap * sizeof(HashSlot)));
     CK(cudaMemsetAsync(h->d_hash.p, 0xFF, (size_t)cap * sizeof(HashSlot), h->stream));
-    hash_insert_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
-                                                                 h->prm.min_points_per_voxel, h->d_hash.as<HashSlot>(),
-                                                                 cap - 1, h->hash_shift);
-    LAUNCHED(h);
+    if (n_vox > 0) {
+      hash_insert_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
+                                                                   h->prm.min_points_per_voxel, h->d_hash.as<HashSlot>(),
+                                                                   cap - 1, h->hash_shift);
+      LAUNCHED(h);
+    }
   }
+  return NDTB200_OK;
+}
+
+int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
+  clear_map(h);
+  h->map_is_merged = false;
+  std::memset(&h->grid, 0, sizeof(GridDesc));
+  for (int a = 0; a < 3; ++a) h->grid.leaf[a] = h->prm.resolution;
+  const size_t n = h->n_target;
+  if (!h->has_target || (n == 0 && !o.partial_only)) {
+    h->map_status = NDTB200_ERR_NO_INPUT;
+    int st = ensure_empty_hash(h);
+    return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
+  }
+  if (n > 0xFFFFFFF0ull) { h->err = "target cloud too large (>= 2^32 points)"; return NDTB200_ERR_INVALID; }
+  const float4* pts = h->d_target.as<float4>();
+  const int dense = h->target_dense ? 1 : 0;
+
+  // 1. bounding box + grid description
+  {
+    int st = compute_grid(h, pts, n, dense, o);
+    if (st != NDTB200_OK) return st;
+  }
+  if (h->grid.n_finite == 0 && !o.partial_only) {
+    h->map_status = NDTB200_ERR_NO_INPUT;
+    int st = ensure_empty_hash(h);
+    return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
+  }
+  if (h->grid.overflow) {  // voxel_grid_covariance_omp_impl.hpp:79-84: warn, leave the map empty
+    h->map_status = NDTB200_ERR_GRID_OVERFLOW;
+    int st = ensure_empty_hash(h);
+    return st != NDTB200_OK ? st : NDTB200_ERR_GRID_OVERFLOW;
+  }
+  h->n_partials = 0;
+  if (h->grid.n_finite == 0) { h->map_status = NDTB200_OK; return NDTB200_OK; }  // empty slice of a sharded build
+
+  // 2. keys
+  uint32_t sentinel = 0;
+  const int passes = passes_for(h->grid, !dense, &sentinel);
+  CK(h->d_keys_a.ensure(n * sizeof(uint32_t)));
+  CK(h->d_keys_b.ensure(n * sizeof(uint32_t)));
+  CK(h->d_vals_a.ensure(n * sizeof(uint32_t)));
+  CK(h->d_vals_b.ensure(n * sizeof(uint32_t)));
+  const int key_blocks = grid_for(n, kBuildThreads * 4, h->num_sms * 16);
+  voxel_key_kernel<<<key_blocks, kBuildThreads, 0, h->stream>>>(pts, n, dense, h->d_grid.as<GridDesc>(), sentinel,
+                                                                 h->d_keys_a.as<uint32_t>(), nullptr);
+  LAUNCHED(h);
+
+  // 3. stable sort of (key, point index) + 4. occupied voxels = segment heads
+  uint32_t n_vox = 0;
+  {
+    int st = sort_and_segment(h, n, sentinel, passes, &n_vox);
+    if (st != NDTB200_OK) return st;
+  }
+  h->n_voxels = n_vox;
+  CK(h->d_moments.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * 9 * sizeof(double)));
+
+  // 5. moments
+  const uint32_t* va = h->d_vals_a.as<uint32_t>();
+  const uint32_t n_finite = static_cast<uint32_t>(h->grid.n_finite);
+  const double avg = static_cast<double>(n_finite) / std::max<uint32_t>(1u, n_vox);
+  if (avg >= 48.0) {
+    const int blocks = static_cast<int>(((size_t)n_vox * 32 + kBuildThreads - 1) / kBuildThreads);
+    voxel_moments_kernel<32><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
+                                                                      n_finite, h->d_moments.as<double>());
+  } else if (avg >= 10.0) {
+    const int blocks = static_cast<int>(((size_t)n_vox * 8 + kBuildThreads - 1) / kBuildThreads);
+    voxel_moments_kernel<8><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
+                                                                     n_finite, h->d_moments.as<double>());
+  } else {
+    const int blocks = static_cast<int>(((size_t)n_vox * 4 + kBuildThreads - 1) / kBuildThreads);
+    voxel_moments_kernel<4><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
+                                                                     n_finite, h->d_moments.as<double>());
+  }
+  LAUNCHED(h);
+  if (o.partial_only) {  // leave {voxel_key, count, moments} for the exchange
+    CK(h->d_voxel_count.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(uint32_t)));
+    const int vblocks = static_cast<int>(((size_t)n_vox + kBuildThreads - 1) / kBuildThreads);
+    segment_counts_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_voxel_start.as<uint32_t>(), n_vox, n_finite,
+                                                                     h->d_voxel_count.as<uint32_t>());
+    LAUNCHED(h);
+    h->n_partials = n_vox;
+    h->map_status = NDTB200_OK;
+    return NDTB200_OK;
+  }
+
+  // 6. finalize + index
+  {
+    int st = finalize_and_index(h, n_vox, n_finite, nullptr);
+    if (st != NDTB200_OK) return st;
+  }
+  h->map_status = NDTB200_OK;
+  return NDTB200_OK;
+}
+
+int build_map(ndtb200_handle* h) { return build_map_ex(h, BuildOpts()); }
+
+// Merge the per-voxel partials of all ranks (concatenated in rank order) into this handle's map: stable sort by key,
+// per-voxel sums in rank order (bit-identical on every rank), then the usual finalize + index.
+int build_from_partials(ndtb200_handle* h, const float* gmin, const float* gmax, long long n_finite_total,
+                        const uint32_t* d_keys, const uint32_t* d_counts, const double* d_moments, size_t total) {
+  clear_map(h);
+  std::memset(&h->grid, 0, sizeof(GridDesc));
+  // grid from the global box: one fake "partial" row
+  float box[6] = {gmin[0], gmin[1], gmin[2], gmax[0], gmax[1], gmax[2]};
+  CK(h->d_mm_partial.ensure(6 * sizeof(float)));
+  CK(h->d_mm_finite.ensure(sizeof(unsigned int)));
+  CK(h->d_grid.ensure(sizeof(GridDesc)));
+  const unsigned int nf_flag = n_finite_total > 0 ? 1u : 0u;
+  CK(cudaMemcpyAsync(h->d_mm_partial.p, box, sizeof(box), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_mm_finite.p, &nf_flag, sizeof(nf_flag), cudaMemcpyHostToDevice, h->stream));
+  ForcedBox fb;
+  fb.use = 0;
+  for (int a = 0; a < 3; ++a) fb.mn[a] = fb.mx[a] = 0.f;
+  grid_setup_kernel<<<1, kBuildThreads, 0, h->stream>>>(h->d_mm_partial.as<float>(), h->d_mm_finite.as<unsigned int>(), 1,
+                                                        h->prm.resolution, fb, h->d_grid.as<GridDesc>());
+  LAUNCHED(h);
+  CK(cudaMemcpyAsync(&h->grid, h->d_grid.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->grid.n_finite = static_cast<int32_t>(std::min<long long>(n_finite_total, 0x7fffffffll));
+  if (total == 0 || n_finite_total == 0) {
+    h->map_status = NDTB200_ERR_NO_INPUT;
+    int st = ensure_empty_hash(h);
+    return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
+  }
+  if (h->grid.overflow) {
+    h->map_status = NDTB200_ERR_GRID_OVERFLOW;
+    int st = ensure_empty_hash(h);
+    return st != NDTB200_OK ? st : NDTB200_ERR_GRID_OVERFLOW;
+  }
+  uint32_t sentinel = 0;
+  const int passes = passes_for(h->grid, false, &sentinel);
+  CK(h->d_keys_a.ensure(total * sizeof(uint32_t)));
+  CK(h->d_keys_b.ensure(total * sizeof(uint32_t)));
+  CK(h->d_vals_a.ensure(total * sizeof(uint32_t)));
+  CK(h->d_vals_b.ensure(total * sizeof(uint32_t)));
+  CK(cudaMemcpyAsync(h->d_keys_a.p, d_keys, total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+  uint32_t n_vox = 0;
+  {
+    int st = sort_and_segment(h, total, sentinel, passes, &n_vox);
+    if (st != NDTB200_OK) return st;
+  }
+  h->n_voxels = n_vox;
+  CK(h->d_moments.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * 9 * sizeof(double)));
+  CK(h->d_voxel_count.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(uint32_t)));
+  const int vblocks = static_cast<int>(((size_t)n_vox + kBuildThreads - 1) / kBuildThreads);
+  merge_partials_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_vals_a.as<uint32_t>(), h->d_voxel_start.as<uint32_t>(), n_vox,
+                                                                   static_cast<uint32_t>(total), d_counts, d_moments,
+                                                                   h->d_voxel_count.as<uint32_t>(), h->d_moments.as<double>());
+  LAUNCHED(h);
+  {
+    int st = finalize_and_index(h, n_vox, 0u, h->d_voxel_count.as<uint32_t>());
+    if (st != NDTB200_OK) return st;
+  }
+  h->map_is_merged = true;
   h->map_status = NDTB200_OK;
   return NDTB200_OK;
 }
@@ -614,7 +747,7 @@ int ndtb200_destroy(ndtb200_handle* h) {
   ndtb200_comm_detach(h);
   DevBuf* bufs[] = {&h->d_target, &h->d_grid, &h->d_mm_partial, &h->d_mm_finite, &h->d_keys_a, &h->d_keys_b,
                     &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_voxel_key,
-                    &h->d_voxel_start, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_dense, &h->d_source,
+                    &h->d_voxel_start, &h->d_voxel_count, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_dense, &h->d_source,
                     &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail};
   for (DevBuf* b : bufs) b->release();
   if (h->h_result) cudaFreeHost(h->h_result);
@@ -788,6 +921,10 @@ int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out) {
     h->err = "fitness needs a source and a target";
     return NDTB200_ERR_NO_INPUT;
   }
+  if (h->map_is_merged) {
+    h->err = "getFitnessScore is not available on a map merged from sharded partials (this rank holds only its slice of the raw target)";
+    return NDTB200_ERR_INVALID;
+  }
   cudaSetDevice(h->device);
   const int n = static_cast<int>(h->n_source);
   const int blocks = (n + 255) / 256;
@@ -895,7 +1032,8 @@ int ndtb200_dump_voxels(ndtb200_handle* h, int32_t* keys, int32_t* counts, doubl
   unsigned int* d_nvalid = h->d_scalar.as<unsigned int>() + 8;
   const int vblocks = static_cast<int>(((size_t)V + kBuildThreads - 1) / kBuildThreads);
   finalize_voxels_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(
-      h->d_moments.as<double>(), h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), V,
+      h->d_moments.as<double>(), h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(),
+      h->map_is_merged ? h->d_voxel_count.as<uint32_t>() : nullptr, V,
       static_cast<uint32_t>(h->grid.n_finite), h->prm.min_points_per_voxel, h->prm.eig_ratio, d_rec.as<VoxelRecord>(),
       d_ic64.as<double>(), d_nvalid, d_mean.as<double>(), d_cov.as<double>(), d_icov.as<double>(), d_infl.as<int>());
   LAUNCHED(h);
@@ -1138,6 +1276,64 @@ int ndtb200_clone(const ndtb200_handle* src, ndtb200_handle** out) {
   cudaStreamSynchronize(h->stream);
   *out = h;
   return NDTB200_OK;
+}
+
+// ---- sharded target-map build: points by contiguous range, one exchange of per-voxel partials -------
+int ndtb200_cloud_bounds(ndtb200_handle* h, const void* d_points, size_t n, int is_dense, float out_min[3], float out_max[3],
+                         int64_t* n_finite) {
+  if (!h || (!d_points && n) || !out_min || !out_max) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (n) {
+    CK(h->d_target.ensure(n * sizeof(float4)));
+    CK(cudaMemcpyAsync(h->d_target.p, d_points, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->n_target = n;
+  h->target_dense = is_dense != 0;
+  h->has_target = true;
+  std::memset(&h->grid, 0, sizeof(GridDesc));
+  for (int a = 0; a < 3; ++a) { out_min[a] = 3.402823466e+38f; out_max[a] = -3.402823466e+38f; }
+  if (n_finite) *n_finite = 0;
+  if (n == 0) return NDTB200_OK;
+  int st = compute_grid(h, h->d_target.as<float4>(), n, is_dense ? 1 : 0, BuildOpts());
+  if (st != NDTB200_OK) return st;
+  for (int a = 0; a < 3; ++a) { out_min[a] = h->grid.min_p[a]; out_max[a] = h->grid.max_p[a]; }
+  if (n_finite) *n_finite = h->grid.n_finite;
+  return NDTB200_OK;
+}
+
+int ndtb200_build_partials(ndtb200_handle* h, const float global_min[3], const float global_max[3], int64_t* n_partials) {
+  if (!h || !global_min || !global_max || !n_partials) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  BuildOpts o;
+  o.forced_min = global_min;
+  o.forced_max = global_max;
+  o.partial_only = true;
+  const int st = build_map_ex(h, o);
+  *n_partials = (st == NDTB200_OK) ? static_cast<int64_t>(h->n_partials) : 0;
+  return st;
+}
+
+int ndtb200_copy_partials(ndtb200_handle* h, void* d_keys, void* d_counts, void* d_moments) {
+  if (!h) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const size_t v = h->n_partials;
+  if (v == 0) return NDTB200_OK;
+  if (!d_keys || !d_counts || !d_moments) return NDTB200_ERR_INVALID;
+  CK(cudaMemcpyAsync(d_keys, h->d_voxel_key.p, v * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_counts, h->d_voxel_count.p, v * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_moments, h->d_moments.p, v * 9 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return NDTB200_OK;
+}
+
+int ndtb200_build_from_partials(ndtb200_handle* h, const float global_min[3], const float global_max[3], int64_t n_finite_total,
+                                const void* d_keys, const void* d_counts, const void* d_moments, size_t n_total) {
+  if (!h || !global_min || !global_max || (n_total && (!d_keys || !d_counts || !d_moments))) return NDTB200_ERR_INVALID;
+  if (n_total > 0xFFFFFFF0ull) { h->err = "too many partials"; return NDTB200_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  h->has_target = true;
+  return build_from_partials(h, global_min, global_max, n_finite_total, static_cast<const uint32_t*>(d_keys),
+                             static_cast<const uint32_t*>(d_counts), static_cast<const double*>(d_moments), n_total);
 }
 
 int ndtb200_set_throughput_mode(ndtb200_handle* h, int on) {

@@ -64,9 +64,14 @@ minmax3d_kernel(const float4* __restrict__ pts, size_t n, int is_dense, float* _
   }
 }
 
+struct ForcedBox {  // sharded build: every rank keys its slice with the bounding box of the WHOLE cloud
+  int use;
+  float mn[3], mx[3];
+};
+
 __global__ void __launch_bounds__(kBuildThreads)
 grid_setup_kernel(const float* __restrict__ partial, const unsigned int* __restrict__ finite_partial,
-                  int nblocks, float leaf, GridDesc* __restrict__ out) {
+                  int nblocks, float leaf, ForcedBox forced, GridDesc* __restrict__ out) {
   // one CTA: strided reduction of the per-CTA partials, then thread 0 derives the grid description
   __shared__ float s_mn[3][kBuildThreads / 32], s_mx[3][kBuildThreads / 32];
   __shared__ unsigned long long s_nf[kBuildThreads / 32];
@@ -96,6 +101,9 @@ grid_setup_kernel(const float* __restrict__ partial, const unsigned int* __restr
     for (int a = 0; a < 3; ++a) { mn[a] = fminf(mn[a], s_mn[a][w]); mx[a] = fmaxf(mx[a], s_mx[a][w]); }
     nf += s_nf[w];
   }
+  if (forced.use) {
+    for (int a = 0; a < 3; ++a) { mn[a] = forced.mn[a]; mx[a] = forced.mx[a]; }
+  }
   GridDesc g;
   const float inv = __fdiv_rn(1.0f, leaf);  // pcl::VoxelGrid::setLeafSize: inverse_leaf_size_ = 1.0f / leaf
   long long d[3];
@@ -112,7 +120,7 @@ grid_setup_kernel(const float* __restrict__ partial, const unsigned int* __restr
     g.div_b[a] = g.max_b[a] - g.min_b[a] + 1;
   }
   g.ncell = d[0] * d[1] * d[2];
-  g.overflow = (nf > 0 && g.ncell > 2147483647ll) ? 1 : 0;
+  g.overflow = ((nf > 0 || forced.use) && g.ncell > 2147483647ll) ? 1 : 0;
   g.mul[0] = 1;
   g.mul[1] = g.div_b[0];
   g.mul[2] = g.div_b[0] * g.div_b[1];
@@ -495,16 +503,22 @@ __device__ __forceinline__ void inv3_cofactor(const double a[3][3], double r[3][
 // dbg_cov / dbg_icov / dbg_inflated: optional full-precision dumps (parity API), NULL in production.
 __global__ void __launch_bounds__(kBuildThreads)
 finalize_voxels_kernel(const double* __restrict__ moments, const int32_t* __restrict__ voxel_key,
-                       const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
+                       const uint32_t* __restrict__ voxel_start, const uint32_t* __restrict__ voxel_count,
+                       uint32_t n_voxels, uint32_t n_finite,
                        int min_points, double eig_ratio, VoxelRecord* __restrict__ records,
                        double* __restrict__ icov64, unsigned int* __restrict__ n_valid,
                        double* __restrict__ dbg_mean, double* __restrict__ dbg_cov, double* __restrict__ dbg_icov,
                        int* __restrict__ dbg_inflated) {
   const uint32_t v = blockIdx.x * (uint32_t)blockDim.x + threadIdx.x;
   if (v >= n_voxels) return;
-  const uint32_t b = voxel_start[v];
-  const uint32_t e = (v + 1 < n_voxels) ? voxel_start[v + 1] : n_finite;
-  int count = static_cast<int>(e - b);
+  int count;
+  if (voxel_count) {  // merged partials: the count was summed with the moments
+    count = static_cast<int>(voxel_count[v]);
+  } else {
+    const uint32_t b = voxel_start[v];
+    const uint32_t e = (v + 1 < n_voxels) ? voxel_start[v + 1] : n_finite;
+    count = static_cast<int>(e - b);
+  }
   const double n = static_cast<double>(count);
   double m[9];
 #pragma unroll
@@ -604,6 +618,36 @@ hash_insert_kernel(const VoxelRecord* __restrict__ records, uint32_t n_voxels, i
     if (prev == NDTB200_HASH_EMPTY) return;
     h = (h + 1) & mask;
   }
+}
+
+// per-voxel point counts of a partial build (length of each sorted range)
+__global__ void __launch_bounds__(kBuildThreads)
+segment_counts_kernel(const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite, uint32_t* __restrict__ counts) {
+  const uint32_t v = blockIdx.x * (uint32_t)blockDim.x + threadIdx.x;
+  if (v >= n_voxels) return;
+  counts[v] = ((v + 1 < n_voxels) ? voxel_start[v + 1] : n_finite) - voxel_start[v];
+}
+
+// sharded build: sum the partials {count, 9 moments} of one voxel in the order of the (stable) sort = rank order
+__global__ void __launch_bounds__(kBuildThreads)
+merge_partials_kernel(const uint32_t* __restrict__ sorted_idx, const uint32_t* __restrict__ voxel_start, uint32_t n_voxels,
+                      uint32_t total, const uint32_t* __restrict__ part_counts, const double* __restrict__ part_moments,
+                      uint32_t* __restrict__ counts, double* __restrict__ moments) {
+  const uint32_t v = blockIdx.x * (uint32_t)blockDim.x + threadIdx.x;
+  if (v >= n_voxels) return;
+  const uint32_t b = voxel_start[v];
+  const uint32_t e = (v + 1 < n_voxels) ? voxel_start[v + 1] : total;
+  uint32_t c = 0;
+  double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (uint32_t i = b; i < e; ++i) {
+    const uint32_t j = sorted_idx[i];
+    c += part_counts[j];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] += part_moments[(size_t)j * 9 + k];
+  }
+  counts[v] = c;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) moments[(size_t)v * 9 + k] = s[k];
 }
 
 // direct-mapped cell table: table[key] = record index of every VALID voxel (the table is pre-filled with -1)

@@ -33,7 +33,10 @@ namespace ndtb200 {
 //                    streams) are co-resident on every SM, so one solve's barrier + Newton-step latency is covered by
 //                    the others' derivative passes (ndtb200_align_batch).
 constexpr int kThreadsLatency = 1024;
-constexpr int kThreadsThroughput = 256;
+#ifndef NDTB200_THROUGHPUT_THREADS
+#define NDTB200_THROUGHPUT_THREADS 256
+#endif
+constexpr int kThreadsThroughput = NDTB200_THROUGHPUT_THREADS;
 __host__ __device__ constexpr int min_blocks_for(int threads) { return 1024 / threads; }
 constexpr int kNV = 29;          // score, g[6], H upper triangle[21], hit count
 constexpr int kNVP = 32;         // padded row length of the partial / total buffers

@@ -81,6 +81,10 @@ def load_library():
     L.ndtb200_align_async.argtypes = [vp, f32p]
     L.ndtb200_sync.argtypes = [vp]
     L.ndtb200_set_throughput_mode.argtypes = [vp, C.c_int]
+    L.ndtb200_cloud_bounds.argtypes = [vp, vp, C.c_size_t, C.c_int, f32p, f32p, i64p]
+    L.ndtb200_build_partials.argtypes = [vp, f32p, f32p, i64p]
+    L.ndtb200_copy_partials.argtypes = [vp, vp, vp, vp]
+    L.ndtb200_build_from_partials.argtypes = [vp, f32p, f32p, C.c_int64, vp, vp, vp, C.c_size_t]
     L.ndtb200_align_batch.argtypes = [C.POINTER(vp), C.c_int, f32p, C.POINTER(vp), C.c_size_t, C.POINTER(Result)]
     L.ndtb200_align_batch_async.argtypes = [C.POINTER(vp), C.c_int, f32p, C.POINTER(vp), C.c_size_t]
     L.ndtb200_get_result.argtypes = [vp, C.POINTER(Result)]
@@ -311,6 +315,30 @@ class NormalDistributionsTransform:
     def align_async(self, guess=None):
         g = _colmajor(guess) if guess is not None else None
         self._check(self._L.ndtb200_align_async(self._h, _ptr(g, C.c_float) if g is not None else None))
+
+    # ---- sharded target-map build (ndtb200_cloud_bounds / build_partials / copy_partials / build_from_partials) ----
+    def cloud_bounds(self, dev_ptr, n, is_dense=True):
+        mn, mx = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        nf = C.c_int64(0)
+        self._n_target = int(n)
+        self._check(self._L.ndtb200_cloud_bounds(self._h, dev_ptr, n, 1 if is_dense else 0, _ptr(mn, C.c_float), _ptr(mx, C.c_float), C.byref(nf)))
+        return mn, mx, int(nf.value)
+
+    def build_partials(self, gmin, gmax):
+        gmin, gmax = np.ascontiguousarray(gmin, np.float32), np.ascontiguousarray(gmax, np.float32)
+        nv = C.c_int64(0)
+        st = self._L.ndtb200_build_partials(self._h, _ptr(gmin, C.c_float), _ptr(gmax, C.c_float), C.byref(nv))
+        self._check(st, allow=(ERR_GRID_OVERFLOW,))
+        return st, int(nv.value)
+
+    def copy_partials(self, keys_ptr, counts_ptr, moments_ptr):
+        self._check(self._L.ndtb200_copy_partials(self._h, keys_ptr, counts_ptr, moments_ptr))
+
+    def build_from_partials(self, gmin, gmax, n_finite_total, keys_ptr, counts_ptr, moments_ptr, n_total):
+        gmin, gmax = np.ascontiguousarray(gmin, np.float32), np.ascontiguousarray(gmax, np.float32)
+        return self._check(self._L.ndtb200_build_from_partials(self._h, _ptr(gmin, C.c_float), _ptr(gmax, C.c_float), int(n_finite_total),
+                                                               keys_ptr, counts_ptr, moments_ptr, int(n_total)),
+                           allow=(ERR_NO_INPUT, ERR_GRID_OVERFLOW))
 
     def set_throughput_mode(self, on=True):
         """Small-CTA solve kernel: several handles' solves share every SM (see ndtb200_set_throughput_mode)."""

@@ -14,6 +14,15 @@ def source_range(n_points, rank, world):
     return min(n_points, g_lo * 32), min(n_points, g_hi * 32)
 
 
+def point_range(n_points, rank, world):
+    """[lo, hi) of `rank`'s contiguous slice of an n_points target cloud (sizes differ by at most one point)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, extra = divmod(n_points, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
 class ShardedNdt:
     """One source cloud split over the GPUs of a node (one process per GPU, torch.distributed for the plumbing).
 
@@ -29,6 +38,65 @@ class ShardedNdt:
 
     def setInputTarget(self, points, is_dense=True):
         return self.ndt.setInputTarget(points, is_dense)
+
+    def setInputTargetSharded(self, points, is_dense=True):
+        """Target-map build split over the ranks: every rank sorts / reduces only its contiguous range
+        of `points`, one exchange of per-voxel partials {key, count, sum x, sum x x^T}, then every rank merges all
+        partials in rank order and ends with the full map (identical bits everywhere).  Collectives (NCCL, device
+        tensors): min/max/sum all-reduce of the bounding box, all-gather of the partials."""
+        import numpy as np
+        import torch
+        n = len(points)
+        lo, hi = point_range(n, self.rank, self.world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        local = torch.ones((hi - lo, 4), dtype=torch.float32, device=dev)
+        if hi > lo:
+            local[:, :3] = torch.as_tensor(np.ascontiguousarray(points[lo:hi, :3], dtype=np.float32)).to(dev)
+        return self.setInputTargetShardedDevice(local, is_dense)
+
+    def setInputTargetShardedDevice(self, local, is_dense=True):
+        """Same, for a slice that already lives on this rank's GPU: `local` is an (n_r, 4) float32 CUDA tensor."""
+        import torch
+        dist, ndt = self.dist, self.ndt
+        dev = local.device
+        mn, mx, nf = ndt.cloud_bounds(local.data_ptr(), local.shape[0], is_dense)
+        t_mn = torch.tensor(mn, dtype=torch.float32, device=dev)
+        t_mx = torch.tensor(mx, dtype=torch.float32, device=dev)
+        t_nf = torch.tensor([nf], dtype=torch.int64, device=dev)
+        if self.world > 1:
+            dist.all_reduce(t_mn, op=dist.ReduceOp.MIN)
+            dist.all_reduce(t_mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t_nf, op=dist.ReduceOp.SUM)
+        gmin, gmax, nf_total = t_mn.cpu().numpy(), t_mx.cpu().numpy(), int(t_nf.item())
+        st, nv = ndt.build_partials(gmin, gmax)
+        counts = torch.tensor([nv if st == 0 else 0], dtype=torch.int64, device=dev)
+        all_counts = [torch.zeros_like(counts) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(all_counts, counts)
+        else:
+            all_counts = [counts]
+        sizes = [int(c.item()) for c in all_counts]
+        cap = max(1, max(sizes))
+        keys = torch.zeros(cap, dtype=torch.int32, device=dev)
+        cnts = torch.zeros(cap, dtype=torch.int32, device=dev)
+        moms = torch.zeros((cap, 9), dtype=torch.float64, device=dev)
+        if sizes[self.rank] > 0:
+            ndt.copy_partials(keys.data_ptr(), cnts.data_ptr(), moms.data_ptr())
+        if self.world > 1:
+            g_keys = torch.empty(self.world * cap, dtype=torch.int32, device=dev)
+            g_cnts = torch.empty(self.world * cap, dtype=torch.int32, device=dev)
+            g_moms = torch.empty((self.world * cap, 9), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(g_keys, keys)
+            dist.all_gather_into_tensor(g_cnts, cnts)
+            dist.all_gather_into_tensor(g_moms, moms)
+            sel = torch.cat([torch.arange(r * cap, r * cap + sizes[r], device=dev) for r in range(self.world)])
+            keys, cnts, moms = g_keys[sel].contiguous(), g_cnts[sel].contiguous(), g_moms[sel].contiguous()
+        else:
+            keys, cnts, moms = keys[:sizes[0]].contiguous(), cnts[:sizes[0]].contiguous(), moms[:sizes[0]].contiguous()
+        total = int(sum(sizes))
+        torch.cuda.synchronize()
+        self._keep = (local, keys, cnts, moms)
+        return ndt.build_from_partials(gmin, gmax, nf_total, keys.data_ptr(), cnts.data_ptr(), moms.data_ptr(), total)
 
     def setInputSource(self, points):
         n = len(points)
