@@ -144,6 +144,18 @@ int ndtb200_comm_export(ndtb200_handle* h, void* handle_out64);
 int ndtb200_comm_attach(ndtb200_handle* h, int rank, int world, const void* all_handles, int64_t n_source_total);
 int ndtb200_comm_detach(ndtb200_handle* h);
 
+/* ---- scan pre-processing: pcl::VoxelGrid centroid downsample (callers: ndt_omp/apps/align.cpp:57-69,
+ * ndt_rosbag_mapping_node.cpp:108-118,153-160, ndt_omp_node.cpp:87-95) -------------------------------------------
+ * One fp32 centroid per occupied leaf-sized cell, cells in ascending index order, points of a cell added in input
+ * order: the same arithmetic as pcl::VoxelGrid, bit-identical output.  Non-finite points are skipped.
+ * out_points: host buffer of out_capacity records (NULL = count only); n_out receives the number of centroids.
+ * NDTB200_ERR_GRID_OVERFLOW = "Leaf size is too small for the input dataset" (PCL then passes the cloud through). */
+int ndtb200_voxelgrid_filter(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, float leaf,
+                             void* out_points, size_t out_capacity, size_t out_stride_bytes, int64_t* n_out);
+/* Same with device-resident float4 input / output (this device). */
+int ndtb200_voxelgrid_filter_device(ndtb200_handle* h, const void* d_points_xyzw, size_t n, float leaf, void* d_out_xyzw,
+                                    size_t out_capacity, int64_t* n_out);
+
 /* ---- multi-GPU target-map build (not in the reference; SURVEY 8e "target-map build") ----------------------------
  * The cloud is split by contiguous point ranges, one per rank.  (1) ndtb200_cloud_bounds: bounding box + finite count
  * of this rank's slice (device pointer, float4 records); the caller all-reduces min / max / count over the ranks.

@@ -176,6 +176,43 @@ def test_map_build_from_partials(nb, slices):
         merged.getFitnessScore()       # the merged handle holds no raw target
 
 
+@pytest.mark.parametrize("leaf", [0.1, 0.3, 0.5, 1.0])
+def test_voxelgrid_filter_bit_exact(nb, leaf):
+    """pcl::VoxelGrid centroid downsample on the device (apps/align.cpp:57-69): bit-identical to the oracle's
+    restatement (which is pinned bit-for-bit to the committed 0.1 m fixtures), same cell order."""
+    tgt, src = load_pair()
+    rng = np.random.default_rng(3)
+    dense = (np.repeat(src[:6000], 5, axis=0) + rng.normal(0, 0.04, size=(30000, 3))).astype(np.float32)
+    scene, _ = synthetic_scene(n_target=60000, seed=2, offset=(2000.0, -1500.0, 50.0))
+    gpu = nb.NormalDistributionsTransform()
+    for cloud in (dense, scene, tgt[:1], np.zeros((0, 3), np.float32)):
+        exp = oracle.voxelgrid_downsample(cloud, leaf) if len(cloud) else np.zeros((0, 3), np.float32)
+        got = gpu.voxelgrid_filter(cloud, leaf)
+        assert got.shape == exp[:, :3].shape
+        assert np.array_equal(got, exp[:, :3])
+    withnan = dense.copy()
+    withnan[::97, 1] = np.nan
+    assert np.array_equal(gpu.voxelgrid_filter(withnan, leaf), oracle.voxelgrid_downsample(withnan, leaf)[:, :3])
+    # the filter leaves the object's own map alone
+    gpu.setInputTarget(tgt); gpu.setInputSource(src)
+    before = gpu.dump_voxels()["keys"].copy()
+    gpu.voxelgrid_filter(dense, leaf)
+    assert np.array_equal(gpu.dump_voxels()["keys"], before)
+
+
+def test_voxelgrid_filter_reproduces_config1_fixture(nb):
+    """Config 1 end to end on the device: raw head of the bundled scan -> 0.1 m VoxelGrid equals the fixture pipeline."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "raw_head.npz")
+    d = np.load(path)
+    gpu = nb.NormalDistributionsTransform()
+    for k in ("target", "source"):
+        raw = np.ascontiguousarray(d[k][:, :3])
+        got = gpu.voxelgrid_filter(raw, 0.1)
+        assert np.array_equal(got, d[k + "_ds0p1"])      # committed fixture (independent numpy VoxelGrid)
+        assert np.array_equal(got, oracle.voxelgrid_downsample(raw, 0.1)[:, :3])
+
+
 def test_grid_overflow_guard(nb):
     tgt = np.array([[0, 0, 0], [3000, 3000, 3000], [1, 1, 1]], dtype=np.float32)
     ref = oracle.NormalDistributionsTransform()

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/t16_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/t16_pytest.log
-tail -25 gpurun_out/t16_pytest.log
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/t17_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/t17_pytest.log
+tail -25 gpurun_out/t17_pytest.log

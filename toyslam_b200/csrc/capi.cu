@@ -71,7 +71,8 @@ struct ndtb200_handle {
   DevBuf d_grid, d_mm_partial, d_mm_finite, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_scan_tmp, d_scalar;
   DevBuf d_voxel_key, d_voxel_start, d_voxel_count, d_moments, d_records, d_icov64, d_hash, d_dense;
   size_t n_partials = 0;       // voxels of the last partial-only build (sharded build, before the exchange)
-  bool map_is_merged = false;  // map built from all ranks' partials: d_target holds only this rank's slice
+  bool map_is_merged = false;
+  ndtb200_handle* aux = nullptr;  // scratch state of ndtb200_voxelgrid_filter (keeps the map's build buffers untouched)  // map built from all ranks' partials: d_target holds only this rank's slice
   bool use_dense = false;
 
   // source cloud
@@ -90,6 +91,15 @@ struct ndtb200_handle {
 };
 
 namespace {
+
+#define CK2(hh, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      (hh)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                             \
+      return NDTB200_ERR_CUDA;                                                                     \
+    }                                                                                              \
+  } while (0)
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -745,6 +755,7 @@ int ndtb200_destroy(ndtb200_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   ndtb200_comm_detach(h);
+  if (h->aux) { ndtb200_destroy(h->aux); h->aux = nullptr; }
   DevBuf* bufs[] = {&h->d_target, &h->d_grid, &h->d_mm_partial, &h->d_mm_finite, &h->d_keys_a, &h->d_keys_b,
                     &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_voxel_key,
                     &h->d_voxel_start, &h->d_voxel_count, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_dense, &h->d_source,
@@ -1334,6 +1345,102 @@ int ndtb200_build_from_partials(ndtb200_handle* h, const float global_min[3], co
   h->has_target = true;
   return build_from_partials(h, global_min, global_max, n_finite_total, static_cast<const uint32_t*>(d_keys),
                              static_cast<const uint32_t*>(d_counts), static_cast<const double*>(d_moments), n_total);
+}
+
+// ---- pcl::VoxelGrid centroid downsample on the device (the step before the path in every caller) ----
+static int voxelgrid_filter_impl(ndtb200_handle* h, float leaf, int64_t* n_out) {
+  // the cloud sits in a->d_target (n_target points); the result is left in a->d_out
+  ndtb200_handle* a = h;
+  *n_out = 0;
+  if (!(leaf > 0)) { a->err = "leaf size must be positive"; return NDTB200_ERR_INVALID; }
+  const size_t n = a->n_target;
+  if (n == 0) return NDTB200_OK;
+  a->prm.resolution = leaf;
+  const float4* pts = a->d_target.as<float4>();
+  std::memset(&a->grid, 0, sizeof(GridDesc));
+  int st = compute_grid(a, pts, n, /*dense=*/0, BuildOpts());
+  if (st != NDTB200_OK) return st;
+  if (a->grid.n_finite == 0) return NDTB200_OK;
+  if (a->grid.overflow) return NDTB200_ERR_GRID_OVERFLOW;  // pcl::VoxelGrid warns and passes the cloud through
+  uint32_t sentinel = 0;
+  const int passes = passes_for(a->grid, true, &sentinel);
+  CK2(a, a->d_keys_a.ensure(n * sizeof(uint32_t)));
+  CK2(a, a->d_keys_b.ensure(n * sizeof(uint32_t)));
+  CK2(a, a->d_vals_a.ensure(n * sizeof(uint32_t)));
+  CK2(a, a->d_vals_b.ensure(n * sizeof(uint32_t)));
+  const int key_blocks = grid_for(n, kBuildThreads * 4, a->num_sms * 16);
+  voxel_key_kernel<<<key_blocks, kBuildThreads, 0, a->stream>>>(pts, n, 0, a->d_grid.as<GridDesc>(), sentinel,
+                                                                 a->d_keys_a.as<uint32_t>(), nullptr);
+  LAUNCHED(a);
+  uint32_t n_vox = 0;
+  st = sort_and_segment(a, n, sentinel, passes, &n_vox);
+  if (st != NDTB200_OK) return st;
+  CK2(a, a->d_out.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(float4)));
+  if (n_vox > 0) {
+    const int vblocks = static_cast<int>(((size_t)n_vox + kBuildThreads - 1) / kBuildThreads);
+    voxel_centroid_kernel<<<vblocks, kBuildThreads, 0, a->stream>>>(pts, a->d_vals_a.as<uint32_t>(), a->d_voxel_start.as<uint32_t>(),
+                                                                     n_vox, static_cast<uint32_t>(a->grid.n_finite), a->d_out.as<float4>());
+    LAUNCHED(a);
+  }
+  *n_out = n_vox;
+  return NDTB200_OK;
+}
+
+static int ensure_aux(ndtb200_handle* h) {
+  if (h->aux) return NDTB200_OK;
+  const int st = ndtb200_create(&h->aux, h->device);
+  if (st != NDTB200_OK) h->err = "could not create the scratch state for ndtb200_voxelgrid_filter";
+  return st;
+}
+
+int ndtb200_voxelgrid_filter(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, float leaf, void* out_points,
+                             size_t out_capacity, size_t out_stride_bytes, int64_t* n_out) {
+  if (!h || !n_out || (!points && n)) return NDTB200_ERR_INVALID;
+  if (n > 0xFFFFFFF0ull) { h->err = "cloud too large"; return NDTB200_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  int st = ensure_aux(h);
+  if (st != NDTB200_OK) return st;
+  ndtb200_handle* a = h->aux;
+  st = upload_points(a, a->d_target, points, n, stride_bytes);
+  if (st != NDTB200_OK) { h->err = a->err; return st; }
+  a->n_target = n;
+  a->has_target = true;
+  st = voxelgrid_filter_impl(a, leaf, n_out);
+  if (st != NDTB200_OK) { h->err = a->err; return st; }
+  const size_t m = static_cast<size_t>(*n_out);
+  if (out_points && m > 0) {
+    if (out_stride_bytes < 16) { h->err = "out_stride_bytes must be >= 16"; return NDTB200_ERR_INVALID; }
+    if (m > out_capacity) { h->err = "output buffer too small"; return NDTB200_ERR_INVALID; }
+    if (out_stride_bytes == 16) CK(cudaMemcpyAsync(out_points, a->d_out.p, m * 16, cudaMemcpyDeviceToHost, a->stream));
+    else CK(cudaMemcpy2DAsync(out_points, out_stride_bytes, a->d_out.p, 16, 16, m, cudaMemcpyDeviceToHost, a->stream));
+  }
+  CK(cudaStreamSynchronize(a->stream));
+  return NDTB200_OK;
+}
+
+int ndtb200_voxelgrid_filter_device(ndtb200_handle* h, const void* d_points_xyzw, size_t n, float leaf, void* d_out_xyzw,
+                                    size_t out_capacity, int64_t* n_out) {
+  if (!h || !n_out || (!d_points_xyzw && n)) return NDTB200_ERR_INVALID;
+  if (n > 0xFFFFFFF0ull) { h->err = "cloud too large"; return NDTB200_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  int st = ensure_aux(h);
+  if (st != NDTB200_OK) return st;
+  ndtb200_handle* a = h->aux;
+  if (n) {
+    CK(a->d_target.ensure(n * sizeof(float4)));
+    CK(cudaMemcpyAsync(a->d_target.p, d_points_xyzw, n * sizeof(float4), cudaMemcpyDeviceToDevice, a->stream));
+  }
+  a->n_target = n;
+  a->has_target = true;
+  st = voxelgrid_filter_impl(a, leaf, n_out);
+  if (st != NDTB200_OK) { h->err = a->err; return st; }
+  const size_t m = static_cast<size_t>(*n_out);
+  if (d_out_xyzw && m > 0) {
+    if (m > out_capacity) { h->err = "output buffer too small"; return NDTB200_ERR_INVALID; }
+    CK(cudaMemcpyAsync(d_out_xyzw, a->d_out.p, m * 16, cudaMemcpyDeviceToDevice, a->stream));
+  }
+  CK(cudaStreamSynchronize(a->stream));
+  return NDTB200_OK;
 }
 
 int ndtb200_set_throughput_mode(ndtb200_handle* h, int on) {

@@ -620,6 +620,27 @@ hash_insert_kernel(const VoxelRecord* __restrict__ records, uint32_t n_voxels, i
   }
 }
 
+// pcl::VoxelGrid centroid downsample (callers: ndt_omp/apps/align.cpp:57-69, ndt_rosbag_mapping_node.cpp:108-118): one
+// thread per occupied cell adds its points in INPUT order in fp32 (the stable sort keeps it) and divides by the count
+// — the arithmetic of pcl::VoxelGrid::applyFilter's centroid, so the output is bit-identical; cells ascend by index.
+__global__ void __launch_bounds__(kBuildThreads)
+voxel_centroid_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx,
+                      const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite, float4* __restrict__ out) {
+  const uint32_t v = blockIdx.x * (uint32_t)blockDim.x + threadIdx.x;
+  if (v >= n_voxels) return;
+  const uint32_t b = voxel_start[v];
+  const uint32_t e = (v + 1 < n_voxels) ? voxel_start[v + 1] : n_finite;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (uint32_t i = b; i < e; ++i) {
+    const float4 p = __ldg(pts + __ldg(sorted_idx + i));
+    sx = __fadd_rn(sx, p.x);
+    sy = __fadd_rn(sy, p.y);
+    sz = __fadd_rn(sz, p.z);
+  }
+  const float cnt = static_cast<float>(e - b);
+  out[v] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 1.0f);
+}
+
 // per-voxel point counts of a partial build (length of each sorted range)
 __global__ void __launch_bounds__(kBuildThreads)
 segment_counts_kernel(const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite, uint32_t* __restrict__ counts) {

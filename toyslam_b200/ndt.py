@@ -81,6 +81,8 @@ def load_library():
     L.ndtb200_align_async.argtypes = [vp, f32p]
     L.ndtb200_sync.argtypes = [vp]
     L.ndtb200_set_throughput_mode.argtypes = [vp, C.c_int]
+    L.ndtb200_voxelgrid_filter.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_float, vp, C.c_size_t, C.c_size_t, i64p]
+    L.ndtb200_voxelgrid_filter_device.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.c_size_t, i64p]
     L.ndtb200_cloud_bounds.argtypes = [vp, vp, C.c_size_t, C.c_int, f32p, f32p, i64p]
     L.ndtb200_build_partials.argtypes = [vp, f32p, f32p, i64p]
     L.ndtb200_copy_partials.argtypes = [vp, vp, vp, vp]
@@ -315,6 +317,21 @@ class NormalDistributionsTransform:
     def align_async(self, guess=None):
         g = _colmajor(guess) if guess is not None else None
         self._check(self._L.ndtb200_align_async(self._h, _ptr(g, C.c_float) if g is not None else None))
+
+    # ---- pcl::VoxelGrid centroid downsample on the device ----
+    def voxelgrid_filter(self, points, leaf):
+        """(n,3|4) cloud -> (m,3) float32 centroids, bit-identical to pcl::VoxelGrid (ascending cell index)."""
+        p = as_xyzw(points)
+        out = np.empty((max(1, p.shape[0]), 4), dtype=np.float32)
+        m = C.c_int64(0)
+        st = self._L.ndtb200_voxelgrid_filter(self._h, p.ctypes.data, p.shape[0], 16, float(leaf), out.ctypes.data, out.shape[0], 16, C.byref(m))
+        self._check(st)
+        return np.ascontiguousarray(out[:m.value, :3])
+
+    def voxelgrid_filter_device(self, dev_ptr, n, leaf, out_dev_ptr, out_capacity):
+        m = C.c_int64(0)
+        self._check(self._L.ndtb200_voxelgrid_filter_device(self._h, dev_ptr, n, float(leaf), out_dev_ptr, out_capacity, C.byref(m)))
+        return int(m.value)
 
     # ---- sharded target-map build (ndtb200_cloud_bounds / build_partials / copy_partials / build_from_partials) ----
     def cloud_bounds(self, dev_ptr, n, is_dense=True):
