@@ -87,6 +87,23 @@ int main(int argc, char** argv) {
   if (!load_cloud(argv[2], *source_cloud)) { std::cerr << "failed to load " << argv[2] << std::endl; return 1; }
   std::cout << "target " << target_cloud->size() << " pts, source " << source_cloud->size() << " pts" << std::endl;
 
+  // downsampling (ndt_omp/apps/align.cpp:57-69): --leaf 0.1 reproduces the reference app on the raw PCD files
+  float leaf = 0.f;
+  for (int i = 3; i + 1 < argc; ++i)
+    if (std::string(argv[i]) == "--leaf") leaf = static_cast<float>(std::atof(argv[i + 1]));
+  if (leaf > 0.f) {
+    pclomp_b200::VoxelGrid<pcl::PointXYZ> voxelgrid;
+    voxelgrid.setLeafSize(leaf, leaf, leaf);
+    Cloud::Ptr downsampled(new Cloud());
+    voxelgrid.setInputCloud(target_cloud);
+    voxelgrid.filter(*downsampled);
+    *target_cloud = *downsampled;
+    voxelgrid.setInputCloud(source_cloud);
+    voxelgrid.filter(*downsampled);
+    source_cloud = downsampled;
+    std::cout << "downsampled (" << leaf << " m): target " << target_cloud->size() << " pts, source " << source_cloud->size() << " pts" << std::endl;
+  }
+
   pclomp_b200::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ> ndt;
   if (!ndt.handle()) return 2;
   ndt.setResolution(1.0);

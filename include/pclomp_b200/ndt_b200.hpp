@@ -205,4 +205,50 @@ class NormalDistributionsTransform {
   PointCloudSourceConstPtr input_;
 };
 
+// pcl::VoxelGrid<PointT> as the callers use it before the registration (ndt_omp/apps/align.cpp:57-69,
+// ndt_rosbag_mapping_node.cpp:108-118): setLeafSize / setInputCloud / filter, centroids computed on the device
+// (ndtb200_voxelgrid_filter) with pcl::VoxelGrid's own arithmetic.  Only x, y, z are produced (the reference's callers
+// run it on PointXYZ / use xyz only); the other fields of the output points are value-initialised.
+template <typename PointT>
+class VoxelGrid {
+ public:
+  typedef pcl::PointCloud<PointT> PointCloud;
+  typedef typename PointCloud::ConstPtr PointCloudConstPtr;
+  explicit VoxelGrid(int device = 0) : h_(nullptr), leaf_(0.f) { if (ndtb200_create(&h_, device) != NDTB200_OK) h_ = nullptr; }
+  ~VoxelGrid() { if (h_) ndtb200_destroy(h_); }
+  VoxelGrid(const VoxelGrid&) = delete;
+  VoxelGrid& operator=(const VoxelGrid&) = delete;
+  void setLeafSize(float lx, float, float) { leaf_ = lx; }  // the callers use cubic leaves
+  void setInputCloud(const PointCloudConstPtr& cloud) { input_ = cloud; }
+  void filter(PointCloud& output) {
+    output.points.clear();
+    if (!h_ || !input_ || input_->points.empty()) { output.width = 0; output.height = 1; return; }
+    struct Rec { float x, y, z, w; };
+    std::vector<Rec> out(input_->points.size());
+    int64_t m = 0;
+    const int st = ndtb200_voxelgrid_filter(h_, input_->points.data(), input_->points.size(), sizeof(PointT), leaf_, out.data(),
+                                            out.size(), sizeof(Rec), &m);
+    if (st == NDTB200_ERR_GRID_OVERFLOW) {  // pcl::VoxelGrid: warn and pass the cloud through
+      std::fprintf(stderr, "[pclomp_b200::VoxelGrid::applyFilter] Leaf size is too small for the input dataset. Integer indices would overflow.\n");
+      output = *input_;
+      return;
+    }
+    if (st != NDTB200_OK) { std::fprintf(stderr, "[pclomp_b200::VoxelGrid] filter failed: %s\n", ndtb200_last_error(h_)); return; }
+    output.points.resize(static_cast<size_t>(m));
+    for (int64_t i = 0; i < m; ++i) {
+      PointT p = PointT();
+      p.x = out[i].x; p.y = out[i].y; p.z = out[i].z;
+      output.points[static_cast<size_t>(i)] = p;
+    }
+    output.width = static_cast<uint32_t>(m);
+    output.height = 1;
+    output.is_dense = true;
+  }
+
+ private:
+  ndtb200_handle* h_;
+  float leaf_;
+  PointCloudConstPtr input_;
+};
+
 }  // namespace pclomp_b200

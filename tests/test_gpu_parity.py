@@ -408,6 +408,30 @@ def test_align_scan_to_map_offset(nb):
     check_align(ref, gpu, guess=pose_matrix([off[0], off[1], off[2], 0, 0, 0]))
 
 
+def test_fitness_grid_search_equals_brute_force(nb, monkeypatch):
+    """getFitnessScore's grid-accelerated nearest-neighbour search is exact: same value as the O(N*M) scan and as the
+    oracle, also when queries fall outside the target's grid (far guess) and at map-scale coordinates."""
+    cases = [load_pair(), synthetic_scene(offset=(2000.0, -1500.0, 50.0), seed=6)]
+    for ci, (tgt, src) in enumerate(cases):
+        ref, gpu = make_pair(nb, tgt, src)
+        guesses = [None, pose_matrix(np.array([3.0, -2.0, 0.5, 0.02, -0.01, 0.3])), pose_matrix(np.array([60.0, 0, 0, 0, 0, 0]))]
+        if ci == 1:
+            guesses = [pose_matrix(np.array([2000.0, -1500.0, 50.0, 0, 0, 0]))]
+        for g in guesses:
+            gpu.setMaximumIterations(1); ref.setMaximumIterations(1)
+            gpu.align(g); ref.align(g)
+            monkeypatch.delenv("NDTB200_FITNESS_BRUTE", raising=False)
+            fast = gpu.getFitnessScore()
+            fast_r = gpu.getFitnessScore(2.0)
+            monkeypatch.setenv("NDTB200_FITNESS_BRUTE", "1")
+            slow = gpu.getFitnessScore()
+            slow_r = gpu.getFitnessScore(2.0)
+            monkeypatch.delenv("NDTB200_FITNESS_BRUTE")
+            assert fast == slow and fast_r == slow_r          # identical fp32 minima, identical sums
+            assert abs(fast - ref.getFitnessScore()) <= 1e-6 * abs(fast)
+            assert abs(fast_r - ref.getFitnessScore(2.0)) <= 1e-6 * abs(fast_r)
+
+
 def test_calculate_score(nb):
     tgt, src = load_pair()
     ref, gpu = make_pair(nb, tgt, src)

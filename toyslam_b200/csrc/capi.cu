@@ -72,6 +72,8 @@ struct ndtb200_handle {
   DevBuf d_voxel_key, d_voxel_start, d_voxel_count, d_moments, d_records, d_icov64, d_hash, d_dense;
   size_t n_partials = 0;       // voxels of the last partial-only build (sharded build, before the exchange)
   bool map_is_merged = false;
+  DevBuf d_cell_all, d_best;      // getFitnessScore: cell table over all occupied voxels, per-query results
+  bool cell_all_valid = false;
   ndtb200_handle* aux = nullptr;  // scratch state of ndtb200_voxelgrid_filter (keeps the map's build buffers untouched)  // map built from all ranks' partials: d_target holds only this rank's slice
   bool use_dense = false;
 
@@ -163,6 +165,7 @@ size_t scan_tmp_elems(size_t n) {
 }
 
 void clear_map(ndtb200_handle* h) {
+  h->cell_all_valid = false;
   h->n_voxels = 0;
   h->n_valid = 0;
 }
@@ -759,7 +762,7 @@ int ndtb200_destroy(ndtb200_handle* h) {
   DevBuf* bufs[] = {&h->d_target, &h->d_grid, &h->d_mm_partial, &h->d_mm_finite, &h->d_keys_a, &h->d_keys_b,
                     &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_voxel_key,
                     &h->d_voxel_start, &h->d_voxel_count, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_dense, &h->d_source,
-                    &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail};
+                    &h->d_cell_all, &h->d_best, &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail};
   for (DevBuf* b : bufs) b->release();
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -944,9 +947,47 @@ int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out) {
   unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(d_sum + blocks);
   float* d_T = reinterpret_cast<float*>(h->d_scalar.as<char>() + 64);
   CK(cudaMemcpyAsync(d_T, h->last_final_T, 12 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  fitness_bruteforce_kernel<<<blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), n, h->d_target.as<float4>(),
-                                                           static_cast<int>(h->n_target), d_T, max_range, d_sum, d_cnt);
-  LAUNCHED(h);
+  // grid-accelerated exact search when the map's sorted point ranges are available and the cell table fits
+  const unsigned long long ncell = static_cast<unsigned long long>(h->grid.div_b[0]) * static_cast<unsigned long long>(h->grid.div_b[1]) *
+                                   static_cast<unsigned long long>(h->grid.div_b[2]);
+  const bool force_brute = getenv("NDTB200_FITNESS_BRUTE") != nullptr;  // tests: compare with the O(N*M) scan
+  const bool use_grid = !force_brute && h->map_status == NDTB200_OK && h->n_voxels > 0 && ncell > 0 && ncell * sizeof(int32_t) <= (2ull << 30) &&
+                        h->n_target <= 0x7fffffffull;
+  if (use_grid) {
+    if (!h->cell_all_valid) {
+      CK(h->d_cell_all.ensure(ncell * sizeof(int32_t)));
+      CK(cudaMemsetAsync(h->d_cell_all.p, 0xFF, ncell * sizeof(int32_t), h->stream));
+      const uint32_t nv = static_cast<uint32_t>(h->n_voxels);
+      cell_table_fill_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_voxel_key.as<int32_t>(), nv, h->d_cell_all.as<int32_t>());
+      LAUNCHED(h);
+      h->cell_all_valid = true;
+    }
+    CK(h->d_best.ensure((size_t)n * sizeof(float) + (size_t)n * sizeof(int) + 64));
+    float* d_best = h->d_best.as<float>();
+    int* d_list = reinterpret_cast<int*>(d_best + n);
+    int* d_count = reinterpret_cast<int*>(h->d_scalar.as<char>() + 128);
+    CK(cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
+    fitness_grid_kernel<<<blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), n, h->d_target.as<float4>(), h->d_vals_a.as<uint32_t>(),
+                                                        h->d_voxel_start.as<uint32_t>(), static_cast<uint32_t>(h->n_voxels),
+                                                        static_cast<uint32_t>(h->grid.n_finite), h->d_cell_all.as<int32_t>(),
+                                                        h->d_grid.as<GridDesc>(), d_T, d_best, d_list, d_count);
+    LAUNCHED(h);
+    fitness_fallback_kernel<<<blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), d_list, d_count, h->d_target.as<float4>(),
+                                                            static_cast<int>(h->n_target), d_T, d_best);
+    LAUNCHED(h);
+    fitness_reduce_kernel<<<blocks, 256, 0, h->stream>>>(d_best, n, max_range, d_sum, d_cnt);
+    LAUNCHED(h);
+    if (getenv("NDTB200_DEBUG_STEP")) {
+      int nf = 0;
+      CK(cudaMemcpyAsync(&nf, d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      std::fprintf(stderr, "  fitness: %d of %d queries went to the brute-force fallback\n", nf, n);
+    }
+  } else {
+    fitness_bruteforce_kernel<<<blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), n, h->d_target.as<float4>(),
+                                                             static_cast<int>(h->n_target), d_T, max_range, d_sum, d_cnt);
+    LAUNCHED(h);
+  }
   std::vector<double> hs(blocks);
   std::vector<unsigned long long> hc(blocks);
   CK(cudaMemcpyAsync(hs.data(), d_sum, blocks * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -77,6 +77,154 @@ fitness_bruteforce_kernel(const float4* __restrict__ src, int n_src, const float
   }
 }
 
+// ---- getFitnessScore, grid-accelerated (exact) ----------------------------------------------------------------
+// The build already sorted the raw target by NDT cell (sorted point indices + per-voxel ranges).  With a direct-mapped
+// table over ALL occupied cells, the nearest raw target point of a query is found by scanning the (2r+1)^3 cells
+// around it, r = 1, 2, ...: once the best squared distance is below the squared distance to the faces of the scanned
+// cube (minus a rounding margin) nothing outside can be closer, so the result is the brute-force minimum — the same
+// fp32 value whatever the scan order.  Queries outside the grid or unresolved after kMaxRing rings go to the
+// brute-force kernel below.  Distances: FLANN L2_Simple order, un-fused fp32.
+constexpr int kMaxRing = 6;
+
+__device__ __forceinline__ float l2_simple(float qx, float qy, float qz, const float4 t) {
+  const float dx = qx - t.x, dy = qy - t.y, dz = qz - t.z;
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// cell table over all occupied voxels (the lookup table of the derivative pass holds only the valid ones)
+__global__ void __launch_bounds__(256)
+cell_table_fill_kernel(const int32_t* __restrict__ voxel_key, uint32_t n_voxels, int32_t* __restrict__ table) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n_voxels) table[voxel_key[v]] = static_cast<int32_t>(v);
+}
+
+__global__ void __launch_bounds__(256)
+fitness_grid_kernel(const float4* __restrict__ src, int n_src, const float4* __restrict__ tgt, const uint32_t* __restrict__ sorted_idx,
+                    const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
+                    const int32_t* __restrict__ cell_table, const GridDesc* __restrict__ gd, const float* __restrict__ T_in,
+                    float* __restrict__ best_out, int* __restrict__ fallback_list, int* __restrict__ fallback_count) {
+  __shared__ float T[12];
+  __shared__ GridDesc g;
+  if (threadIdx.x < 12) T[threadIdx.x] = T_in[threadIdx.x];
+  if (threadIdx.x == 32) g = *gd;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_src) return;
+  const float4 p = __ldg(src + i);
+  float q[3];
+  transform_point(T, p.x, p.y, p.z, q[0], q[1], q[2]);
+  float cf[3];
+  int c[3];
+  bool inside = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    cf[a] = floorf(__fmul_rn(q[a], g.inv_leaf[a]));
+    const float rel = __fsub_rn(cf[a], static_cast<float>(g.min_b[a]));
+    inside = inside && (rel >= 0.0f) && (rel < static_cast<float>(g.div_b[a])) && (q[a] == q[a]);
+    c[a] = static_cast<int>(rel);
+  }
+  float best = __int_as_float(0x7f800000);
+  bool resolved = false;
+  if (inside) {
+    for (int r = 1; r <= kMaxRing && !resolved; ++r) {
+      for (int dz = -r; dz <= r; ++dz) {
+        const int cz = c[2] + dz;
+        if (cz < 0 || cz >= g.div_b[2]) continue;
+        for (int dy = -r; dy <= r; ++dy) {
+          const int cy = c[1] + dy;
+          if (cy < 0 || cy >= g.div_b[1]) continue;
+          for (int dx = -r; dx <= r; ++dx) {
+            const int cx = c[0] + dx;
+            if (cx < 0 || cx >= g.div_b[0]) continue;
+            if (r > 1 && abs(dx) < r && abs(dy) < r && abs(dz) < r) continue;  // inner cube was scanned by the previous ring
+            const int v = __ldg(cell_table + (cx * g.mul[0] + cy * g.mul[1] + cz * g.mul[2]));
+            if (v < 0) continue;
+            const uint32_t b = __ldg(voxel_start + v);
+            const uint32_t e = (static_cast<uint32_t>(v) + 1 < n_voxels) ? __ldg(voxel_start + v + 1) : n_finite;
+            for (uint32_t k = b; k < e; ++k) best = fminf(best, l2_simple(q[0], q[1], q[2], __ldg(tgt + __ldg(sorted_idx + k))));
+          }
+        }
+      }
+      // distance from the query to the faces of the scanned cube, minus a margin for the fp32 rounding of the cell
+      // boundaries (coordinates up to tens of km)
+      float margin = 3.402823466e+38f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float lo = (cf[a] - static_cast<float>(r)) * g.leaf[a], hi = (cf[a] + static_cast<float>(r) + 1.0f) * g.leaf[a];
+        const float eps = 1e-3f * g.leaf[a] + 4e-7f * (fabsf(q[a]) + g.leaf[a]);
+        margin = fminf(margin, fminf(q[a] - lo, hi - q[a]) - eps);
+      }
+      resolved = (margin > 0.0f) && (best <= margin * margin);
+    }
+  }
+  if (resolved) {
+    best_out[i] = best;
+  } else {
+    best_out[i] = -1.0f;
+    fallback_list[atomicAdd(fallback_count, 1)] = i;
+  }
+}
+
+// brute force over the whole raw target for the listed queries (outside the grid / no point within the scanned rings)
+__global__ void __launch_bounds__(256)
+fitness_fallback_kernel(const float4* __restrict__ src, const int* __restrict__ list, const int* __restrict__ count,
+                        const float4* __restrict__ tgt, int n_tgt, const float* __restrict__ T_in, float* __restrict__ best_out) {
+  __shared__ float4 tile[kNNTile];
+  __shared__ float T[12];
+  const int n = *count;
+  if (blockIdx.x * blockDim.x >= n) return;  // uniform per block
+  if (threadIdx.x < 12) T[threadIdx.x] = T_in[threadIdx.x];
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = j < n ? list[j] : -1;
+  float qx = 0, qy = 0, qz = 0;
+  if (i >= 0) {
+    const float4 p = __ldg(src + i);
+    transform_point(T, p.x, p.y, p.z, qx, qy, qz);
+  }
+  float best = __int_as_float(0x7f800000);
+  for (int base = 0; base < n_tgt; base += kNNTile) {
+    const int m = min(kNNTile, n_tgt - base);
+    __syncthreads();
+    for (int k = threadIdx.x; k < m; k += blockDim.x) tile[k] = __ldg(tgt + base + k);
+    __syncthreads();
+    if (i >= 0) {
+#pragma unroll 8
+      for (int k = 0; k < m; ++k) best = fminf(best, l2_simple(qx, qy, qz, tile[k]));
+    }
+  }
+  if (i >= 0) best_out[i] = best;
+}
+
+// mean of the accepted squared distances: one fp64 partial + count per CTA, the host adds them in CTA order
+__global__ void __launch_bounds__(256)
+fitness_reduce_kernel(const float* __restrict__ best, int n_src, double max_range, double* __restrict__ part_sum,
+                      unsigned long long* __restrict__ part_cnt) {
+  __shared__ double s_sum[8];
+  __shared__ unsigned int s_cnt[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0;
+  unsigned int c = 0;
+  if (i < n_src) {
+    const float b = best[i];
+    if (static_cast<double>(b) <= max_range) { v = b; c = 1; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_down_sync(0xffffffffu, v, o);
+    c += __shfl_down_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = v; s_cnt[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    unsigned long long cc = 0;
+    for (int w = 0; w < 8; ++w) { s += s_sum[w]; cc += s_cnt[w]; }
+    part_sum[blockIdx.x] = s;
+    part_cnt[blockIdx.x] = cc;
+  }
+}
+
 // calculateScore (ndt_omp_impl.hpp:935-983): fp64, mean over neighbours of (-d1*e - d3), mean over points.
 template <int METHOD>
 __global__ void __launch_bounds__(256)
