@@ -416,6 +416,7 @@ struct Leaf {  // vgc_h:98-193
   M3 evecs{{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}};
   double evals[3] = {0, 0, 0};
   bool inflated = false;
+  bool in_centroid_cloud = false;  // pushed to voxel_centroids_ (vgc_impl:311-317): what the KDTREE radius search sees
 };
 
 enum BuildStatus { BUILD_OK = 0, BUILD_NO_INPUT = 1, BUILD_GRID_OVERFLOW = 2 };
@@ -494,6 +495,7 @@ class VoxelGridCovariance {
 
       voxel_centroids.push_back(P4{leaf.centroid[0], leaf.centroid[1], leaf.centroid[2], 1.0f});
       voxel_centroids_leaf_indices.push_back(static_cast<int>(it->first));
+      leaf.in_centroid_cloud = true;  // stays there even if the leaf is rejected (nr_points = -1) further down
 
       const double n_pts = leaf.nr_points;
       for (int a = 0; a < 3; ++a)  // vgc_impl:329
@@ -554,6 +556,40 @@ class VoxelGridCovariance {
         if (out_keys) out_keys->push_back(key);
       }
     }
+    return static_cast<int>(out.size());
+  }
+
+  // radiusSearch (vgc_h:476-505): leaves whose fp32 centroid lies within `radius` of q.  [upstream] the search runs on
+  // a FLANN kd-tree over voxel_centroids_ (L2_Simple fp32 squared distances, strict "< radius^2", results sorted by
+  // distance).  A centroid within one leaf size of q sits in one of the 27 cells around q's cell, so scanning those
+  // is the same set; the reference does NOT re-check nr_points here, so a leaf rejected after it entered the
+  // centroid cloud (nr_points = -1, zero or infinite icov_) is returned too (quirk Q10).
+  int radiusSearch(const P4& q, double radius, std::vector<const Leaf*>& out) const {
+    out.clear();
+    const float r2 = static_cast<float>(radius * radius);
+    int ijk[3] = {static_cast<int>(std::floor(q.x / leaf_size[0])), static_cast<int>(std::floor(q.y / leaf_size[1])),
+                  static_cast<int>(std::floor(q.z / leaf_size[2]))};
+    std::vector<std::pair<float, const Leaf*>> found;
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int c[3] = {ijk[0] + dx, ijk[1] + dy, ijk[2] + dz};
+          bool inside = true;
+          for (int a = 0; a < 3; ++a) inside = inside && c[a] >= min_b[a] && c[a] <= max_b[a];
+          if (!inside) continue;
+          int key = 0;
+          for (int a = 0; a < 3; ++a) key += (c[a] - min_b[a]) * divb_mul[a];
+          auto it = leaves.find(static_cast<size_t>(key));
+          if (it == leaves.end() || !it->second.in_centroid_cloud) continue;
+          const Leaf& l = it->second;
+          const float d0 = q.x - l.centroid[0], d1 = q.y - l.centroid[1], d2 = q.z - l.centroid[2];
+          volatile float s = d0 * d0;
+          s = s + d1 * d1;
+          s = s + d2 * d2;
+          if (s < r2) found.emplace_back(s, &l);
+        }
+    std::stable_sort(found.begin(), found.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    for (const auto& f : found) out.push_back(f.second);
     return static_cast<int>(out.size());
   }
 };
@@ -813,6 +849,10 @@ class NormalDistributionsTransform {
   }
 
   void neighbours(const P4& q, std::vector<const Leaf*>& out) const {
+    if (search_method == KDTREE) {  // ndt_impl:234-236
+      target_cells_.radiusSearch(q, resolution_, out);
+      return;
+    }
     int rel[26][3];
     int K = neighbor_offsets(search_method, rel);
     target_cells_.getNeighborhoodAtPoint(rel, K, q, out);

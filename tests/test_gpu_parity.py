@@ -432,6 +432,36 @@ def test_fitness_grid_search_equals_brute_force(nb, monkeypatch):
             assert abs(fast_r - ref.getFitnessScore(2.0)) <= 1e-6 * abs(fast_r)
 
 
+def test_kdtree_mode(nb):
+    """The fourth search method (ndt_omp.h:52-57, radius search over the voxel centroids): derivatives, Hessian-only
+    pass, calculateScore and the whole align against the oracle, and the README's KDTREE fitness 0.213937."""
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src, method=oracle.KDTREE)
+    for p in POSES:
+        a, b = gpu.eval_derivatives(p, True), ref.eval_derivatives(p, True)
+        assert a["hits"] == b["hits"] and b["hits"] > 0
+        assert abs(a["score"] - b["score"]) <= REL * abs(b["score"])
+        assert rel_err(a["gradient"], b["gradient"]) < REL and rel_err(a["hessian"], b["hessian"]) < REL
+        assert rel_err(gpu.eval_hessian(p), ref.eval_hessian(p)) < REL
+    out, rr, rg = check_align(ref, gpu)
+    fit = gpu.getFitnessScore()
+    assert abs(fit - golden()["fitness"]["KDTREE"]) < 5e-7, fit
+    a, b = gpu.calculateScore(src), ref.calculateScore(src)
+    assert abs(a - b) <= 1e-9 * abs(b)
+    # node parameters + the throughput shape
+    tgt, src = load_pair("pair_ds0p3.npz")
+    ref, gpu = make_pair(nb, tgt, src, method=oracle.KDTREE, eps=0.01, max_iter=64)
+    gpu.set_throughput_mode(True)
+    check_align(ref, gpu)
+    # at map-scale coordinates
+    tgt, src = synthetic_scene(offset=(2000.0, -1500.0, 50.0), seed=9)
+    ref, gpu = make_pair(nb, tgt, src, method=oracle.KDTREE)
+    p = np.array([2000.2, -1500.1, 50.02, 0.003, -0.002, 0.01])
+    a, b = gpu.eval_derivatives(p), ref.eval_derivatives(p)
+    assert a["hits"] == b["hits"] and b["hits"] > 1000
+    assert rel_err(a["gradient"], b["gradient"]) < REL and rel_err(a["hessian"], b["hessian"]) < REL
+
+
 def test_calculate_score(nb):
     tgt, src = load_pair()
     ref, gpu = make_pair(nb, tgt, src)

@@ -49,6 +49,19 @@ def test_oracle_reproduces_readme_fitness(method, name, p_exp):
     assert "%.6f" % n.getFitnessScore() == "%.6f" % golden()["fitness"][name]
 
 
+def test_oracle_kdtree_mode_reproduces_readme_fitness():
+    """ndt_omp/README.md:21 (pclomp::NDT KDTREE, identical to pcl::NDT :16): fitness 0.213937 — pins the radius-search
+    neighbourhood (fp32 voxel centroids within one resolution of the transformed point)."""
+    tgt, src = load_pair()
+    n = oracle.NormalDistributionsTransform()
+    n.setNeighborhoodSearchMethod(oracle.KDTREE)
+    assert n.setInputTarget(tgt) == 0
+    n.setInputSource(src)
+    n.align()
+    assert n.result()["converged"]
+    assert "%.6f" % n.getFitnessScore() == "%.6f" % golden()["fitness"]["KDTREE"]
+
+
 def test_oracle_thread_count_invariance():
     """The reference's designed property (ndt_omp_impl.hpp:277): identical results for 1 and N threads."""
     tgt, src = load_pair("pair_ds0p3.npz")

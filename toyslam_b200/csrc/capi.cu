@@ -72,6 +72,8 @@ struct ndtb200_handle {
   DevBuf d_voxel_key, d_voxel_start, d_voxel_count, d_moments, d_records, d_icov64, d_hash, d_dense;
   size_t n_partials = 0;       // voxels of the last partial-only build (sharded build, before the exchange)
   bool map_is_merged = false;
+  DevBuf d_centroid;              // KDTREE mode: fp32 centroid of every voxel
+  bool centroids_valid = false;
   DevBuf d_cell_all, d_best;      // getFitnessScore: cell table over all occupied voxels, per-query results
   bool cell_all_valid = false;
   ndtb200_handle* aux = nullptr;  // scratch state of ndtb200_voxelgrid_filter (keeps the map's build buffers untouched)  // map built from all ranks' partials: d_target holds only this rank's slice
@@ -166,6 +168,7 @@ size_t scan_tmp_elems(size_t n) {
 
 void clear_map(ndtb200_handle* h) {
   h->cell_all_valid = false;
+  h->centroids_valid = false;
   h->n_voxels = 0;
   h->n_valid = 0;
 }
@@ -487,12 +490,51 @@ int build_from_partials(ndtb200_handle* h, const float* gmin, const float* gmax,
   return NDTB200_OK;
 }
 
+// cell table over ALL occupied voxels (shared by getFitnessScore and the KDTREE mode)
+int ensure_cell_table(ndtb200_handle* h) {
+  if (h->cell_all_valid) return NDTB200_OK;
+  const unsigned long long ncell = static_cast<unsigned long long>(h->grid.div_b[0]) * static_cast<unsigned long long>(h->grid.div_b[1]) *
+                                   static_cast<unsigned long long>(h->grid.div_b[2]);
+  if (ncell == 0 || ncell * sizeof(int32_t) > (2ull << 30)) { h->err = "cell table does not fit (grid too large)"; return NDTB200_ERR_INVALID; }
+  CK(h->d_cell_all.ensure(ncell * sizeof(int32_t)));
+  CK(cudaMemsetAsync(h->d_cell_all.p, 0xFF, ncell * sizeof(int32_t), h->stream));
+  const uint32_t nv = static_cast<uint32_t>(h->n_voxels);
+  if (nv > 0) {
+    cell_table_fill_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_voxel_key.as<int32_t>(), nv, h->d_cell_all.as<int32_t>());
+    LAUNCHED(h);
+  }
+  h->cell_all_valid = true;
+  return NDTB200_OK;
+}
+
+// KDTREE mode (voxel_grid_covariance_omp.h:476-505): the fp32 centroid of every voxel (Leaf::centroid: points added in
+// input order in fp32, then divided by the count, …_impl.hpp:228-262, 288) + the cell table over all occupied voxels
+int ensure_kdtree_index(ndtb200_handle* h) {
+  if (h->map_status != NDTB200_OK || h->n_voxels == 0) return NDTB200_OK;  // empty map: every probe misses
+  if (h->map_is_merged) { h->err = "KDTREE mode is not available on a map merged from sharded partials"; return NDTB200_ERR_INVALID; }
+  int st = ensure_cell_table(h);
+  if (st != NDTB200_OK) return st;
+  if (!h->centroids_valid) {
+    const uint32_t nv = static_cast<uint32_t>(h->n_voxels);
+    CK(h->d_centroid.ensure((size_t)nv * sizeof(float4)));
+    voxel_centroid_kernel<<<(nv + kBuildThreads - 1) / kBuildThreads, kBuildThreads, 0, h->stream>>>(
+        h->d_target.as<float4>(), h->d_vals_a.as<uint32_t>(), h->d_voxel_start.as<uint32_t>(), nv,
+        static_cast<uint32_t>(h->grid.n_finite), h->d_centroid.as<float4>());
+    LAUNCHED(h);
+    h->centroids_valid = true;
+  }
+  return NDTB200_OK;
+}
+
 MapView make_view(const ndtb200_handle* h) {
   MapView m;
   m.records = h->d_records.as<VoxelRecord>();
   m.icov64 = h->d_icov64.as<double>();
   m.hash = h->d_hash.as<HashSlot>();
   m.dense = (h->use_dense && h->n_voxels > 0) ? h->d_dense.as<int32_t>() : nullptr;
+  m.cell_all = (h->cell_all_valid && h->n_voxels > 0) ? h->d_cell_all.as<int32_t>() : nullptr;
+  m.centroids = h->centroids_valid ? h->d_centroid.as<float4>() : nullptr;
+  m.kd_r2 = static_cast<float>(static_cast<double>(h->prm.resolution) * static_cast<double>(h->prm.resolution));
   m.hash_mask = h->hash_cap - 1;
   m.hash_shift = h->hash_shift;
   for (int a = 0; a < 3; ++a) {
@@ -588,9 +630,13 @@ int query_coop_blocks(ndtb200_handle* h) {
 int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0[12], int has_guess, int eval_hessian) {
   if (!h->has_source || (h->n_source == 0 && h->comm_world == 1)) { h->err = "no input source"; return NDTB200_ERR_NO_INPUT; }
   const int method = h->prm.search_method;
-  if (method < NDTB200_DIRECT26 || method > NDTB200_DIRECT1) {
-    h->err = "search method not implemented (KDTREE)";
+  if (method < NDTB200_KDTREE || method > NDTB200_DIRECT1) {
+    h->err = "invalid search method";
     return NDTB200_ERR_INVALID;
+  }
+  if (method == NDTB200_KDTREE) {
+    const int st = ensure_kdtree_index(h);
+    if (st != NDTB200_OK) return st;
   }
   AlignParams prm;
   gauss_constants(h->prm, prm.d1, prm.d2, prm.d3);
@@ -642,11 +688,13 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   if (shape == 0)
     fn = method == NDTB200_DIRECT1 ? (const void*)ndt_align_kernel<3, kThreadsLatency>
        : method == NDTB200_DIRECT7 ? (const void*)ndt_align_kernel<2, kThreadsLatency>
-                                   : (const void*)ndt_align_kernel<1, kThreadsLatency>;
+       : method == NDTB200_DIRECT26 ? (const void*)ndt_align_kernel<1, kThreadsLatency>
+                                    : (const void*)ndt_align_kernel<0, kThreadsLatency>;
   else
     fn = method == NDTB200_DIRECT1 ? (const void*)ndt_align_kernel<3, kThreadsThroughput>
        : method == NDTB200_DIRECT7 ? (const void*)ndt_align_kernel<2, kThreadsThroughput>
-                                   : (const void*)ndt_align_kernel<1, kThreadsThroughput>;
+       : method == NDTB200_DIRECT26 ? (const void*)ndt_align_kernel<1, kThreadsThroughput>
+                                    : (const void*)ndt_align_kernel<0, kThreadsThroughput>;
   const int threads = shape == 0 ? kThreadsLatency : kThreadsThroughput;
   h->last_blocks = blocks;
   CK(cudaEventRecord(h->ev0, h->stream));
@@ -740,7 +788,8 @@ int ndtb200_create(ndtb200_handle** out, int device) {
   if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) return fail(NDTB200_ERR_CUDA);
   if (cudaMallocHost(&h->h_result, sizeof(AlignResultDev)) != cudaSuccess) return fail(NDTB200_ERR_CUDA);
   std::memset(h->h_result, 0, sizeof(AlignResultDev));
-  int st = query_coop_blocks<1>(h);
+  int st = query_coop_blocks<0>(h);
+  if (st == NDTB200_OK) st = query_coop_blocks<1>(h);
   if (st == NDTB200_OK) st = query_coop_blocks<2>(h);
   if (st == NDTB200_OK) st = query_coop_blocks<3>(h);
   if (st == NDTB200_OK) st = ensure_empty_hash(h);
@@ -762,7 +811,7 @@ int ndtb200_destroy(ndtb200_handle* h) {
   DevBuf* bufs[] = {&h->d_target, &h->d_grid, &h->d_mm_partial, &h->d_mm_finite, &h->d_keys_a, &h->d_keys_b,
                     &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_voxel_key,
                     &h->d_voxel_start, &h->d_voxel_count, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_dense, &h->d_source,
-                    &h->d_cell_all, &h->d_best, &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail};
+                    &h->d_cell_all, &h->d_best, &h->d_centroid, &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail};
   for (DevBuf* b : bufs) b->release();
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -954,13 +1003,9 @@ int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out) {
   const bool use_grid = !force_brute && h->map_status == NDTB200_OK && h->n_voxels > 0 && ncell > 0 && ncell * sizeof(int32_t) <= (2ull << 30) &&
                         h->n_target <= 0x7fffffffull;
   if (use_grid) {
-    if (!h->cell_all_valid) {
-      CK(h->d_cell_all.ensure(ncell * sizeof(int32_t)));
-      CK(cudaMemsetAsync(h->d_cell_all.p, 0xFF, ncell * sizeof(int32_t), h->stream));
-      const uint32_t nv = static_cast<uint32_t>(h->n_voxels);
-      cell_table_fill_kernel<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_voxel_key.as<int32_t>(), nv, h->d_cell_all.as<int32_t>());
-      LAUNCHED(h);
-      h->cell_all_valid = true;
+    {
+      const int st = ensure_cell_table(h);
+      if (st != NDTB200_OK) return st;
     }
     CK(h->d_best.ensure((size_t)n * sizeof(float) + (size_t)n * sizeof(int) + 64));
     float* d_best = h->d_best.as<float>();
@@ -1010,6 +1055,10 @@ int ndtb200_calculate_score(ndtb200_handle* h, const void* points, size_t n, siz
   CK(h->d_tmp.ensure((size_t)blocks * 8 + 64));
   double d1, d2, d3;
   gauss_constants(h->prm, d1, d2, d3);
+  if (h->prm.search_method == NDTB200_KDTREE) {
+    const int st2 = ensure_kdtree_index(h);
+    if (st2 != NDTB200_OK) return st2;
+  }
   MapView map = make_view(h);
   const float4* cloud = h->d_out.as<float4>();
   double* d_sum = h->d_tmp.as<double>();
@@ -1017,7 +1066,7 @@ int ndtb200_calculate_score(ndtb200_handle* h, const void* points, size_t n, siz
     case NDTB200_DIRECT1: calculate_score_kernel<3><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
     case NDTB200_DIRECT7: calculate_score_kernel<2><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
     case NDTB200_DIRECT26: calculate_score_kernel<1><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
-    default: h->err = "search method not implemented (KDTREE)"; return NDTB200_ERR_INVALID;
+    default: calculate_score_kernel<0><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
   }
   LAUNCHED(h);
   std::vector<double> hs(blocks);

@@ -53,6 +53,11 @@ struct MapView {  // what the kernels need to probe the map
   const double* icov64;  // [n_voxels][6] fp64 inverse covariance for the fp64 Hessian-only pass
   const HashSlot* hash;
   const int32_t* dense;  // direct-mapped cell table [dx*dy*dz] -> record index or -1 (nullptr: use the hash)
+  // KDTREE mode (radius search over the voxel centroids, voxel_grid_covariance_omp.h:476-505): cell table over ALL
+  // occupied voxels, the fp32 centroid of every voxel, squared radius
+  const int32_t* cell_all;
+  const float4* centroids;
+  float kd_r2;
   uint32_t hash_mask;
   int32_t hash_shift;
   int32_t min_b[3], max_b[3], mul[3];

@@ -135,9 +135,10 @@ __constant__ int8_t c_off26[26][3] = {
     {1, 1, 1}, {1, 0, 1}, {1, -1, 1}, {0, 1, 1}, {0, 0, 1}, {0, -1, 1}, {-1, 1, 1}, {-1, 0, 1}, {-1, -1, 1},
     {1, 1, 0}, {0, 1, 0}, {-1, 1, 0}, {1, 0, 0}};
 
+// METHOD: the reference's enum values (ndt_omp.h:52-57): 0 KDTREE, 1 DIRECT26, 2 DIRECT7, 3 DIRECT1
 template <int METHOD>
 __device__ __forceinline__ constexpr int num_offsets() {
-  return METHOD == 3 ? 1 : (METHOD == 2 ? 7 : 26);
+  return METHOD == 3 ? 1 : (METHOD == 2 ? 7 : (METHOD == 1 ? 26 : 27));
 }
 
 // DIRECT7 order (voxel_grid_covariance_omp_impl.hpp:423-430): centre, +x, -x, +y, -y, +z, -z
@@ -149,8 +150,10 @@ __device__ __forceinline__ void get_offset(int k, int& dx, int& dy, int& dz) {
     dx = (k == 1) - (k == 2);
     dy = (k == 3) - (k == 4);
     dz = (k == 5) - (k == 6);
-  } else {
+  } else if (METHOD == 1) {
     dx = c_off26[k][0]; dy = c_off26[k][1]; dz = c_off26[k][2];
+  } else {  // KDTREE: the 27 cells a centroid within one resolution of the point can sit in
+    dx = k % 3 - 1; dy = (k / 3) % 3 - 1; dz = k / 9 - 1;
   }
 }
 
@@ -160,6 +163,32 @@ __device__ __forceinline__ int probe_cell(const MapView& m, int cx, int cy, int 
     return -1;
   const int key = (cx - m.min_b[0]) * m.mul[0] + (cy - m.min_b[1]) * m.mul[1] + (cz - m.min_b[2]) * m.mul[2];
   return map_find(m, key);
+}
+
+// KDTREE mode: radiusSearch(x', resolution) over the voxel-centroid cloud (voxel_grid_covariance_omp.h:476-505,
+// ndt_omp_impl.hpp:234-236).  FLANN L2_Simple: fp32 squared distance, strict "< r^2".  The centroid cloud holds every
+// leaf that had >= min_points when it was pushed (…_impl.hpp:311-317) — also the ones rejected afterwards
+// (count == -1, zero / infinite icov): the reference does not re-check nr_points on this path (quirk Q10).
+__device__ __forceinline__ int probe_cell_kdtree(const MapView& m, int cx, int cy, int cz, float tx, float ty, float tz) {
+  if (cx < m.min_b[0] || cx > m.max_b[0] || cy < m.min_b[1] || cy > m.max_b[1] || cz < m.min_b[2] || cz > m.max_b[2])
+    return -1;
+  const int key = (cx - m.min_b[0]) * m.mul[0] + (cy - m.min_b[1]) * m.mul[1] + (cz - m.min_b[2]) * m.mul[2];
+  const int v = __ldg(m.cell_all + key);
+  if (v < 0) return -1;
+  const int count = __ldg(&m.records[v].count);
+  if (!(count >= m.min_points || count == -1)) return -1;
+  const float4 c = __ldg(m.centroids + v);
+  const float dx = tx - c.x, dy = ty - c.y, dz = tz - c.z;
+  const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  return (d < m.kd_r2) ? v : -1;
+}
+
+template <int METHOD>
+__device__ __forceinline__ int probe_neighbour(const MapView& m, int ix, int iy, int iz, int k, float tx, float ty, float tz) {
+  int dx, dy, dz;
+  get_offset<METHOD>(k, dx, dy, dz);
+  if constexpr (METHOD == 0) return probe_cell_kdtree(m, ix + dx, iy + dy, iz + dz, tx, ty, tz);
+  else return probe_cell(m, ix + dx, iy + dy, iz + dz);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -261,9 +290,7 @@ __device__ __forceinline__ void point_hessian_f64(const float4 pt, const EvalCtx
   int nh = 0;
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
-    int dx, dy, dz;
-    get_offset<METHOD>(k, dx, dy, dz);
-    const int rec = probe_cell(m, ix + dx, iy + dy, iz + dz);
+    const int rec = probe_neighbour<METHOD>(m, ix, iy, iz, k, tx, ty, tz);
     if (rec < 0) continue;
     ++nh;
     const VoxelRecord* R = m.records + rec;
@@ -948,7 +975,7 @@ __device__ __forceinline__ void point_f32(float px, float py, float pz, const Ev
   constexpr int K = num_offsets<METHOD>();
   float S = 0.f, A[3] = {0.f, 0.f, 0.f}, M[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int nh = 0;
-  if constexpr (METHOD != 1) {
+  if constexpr (METHOD == 2 || METHOD == 3) {
     int rec[K];
     probe_cells<K>(m, ix, iy, iz, rec);
     // (a depth-1 software pipeline of the record loads was measured: the extra live registers spill at the 64-register
@@ -962,9 +989,7 @@ __device__ __forceinline__ void point_f32(float px, float py, float pz, const Ev
   } else {
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
-      int dx, dy, dz;
-      get_offset<METHOD>(k, dx, dy, dz);
-      const int rec = probe_cell(m, ix + dx, iy + dy, iz + dz);
+      const int rec = probe_neighbour<METHOD>(m, ix, iy, iz, k, tx, ty, tz);
       if (rec < 0) continue;
       ++nh;
       hit_f32<HESS>(load_record(m.records + rec), tx, ty, tz, d2f, d1f, S, A, M);

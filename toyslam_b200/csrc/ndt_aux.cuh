@@ -242,9 +242,7 @@ calculate_score_kernel(const float4* __restrict__ cloud, int n, const MapView ma
     int recs[K];
     int cnt = 0;
     for (int k = 0; k < K; ++k) {
-      int dx, dy, dz;
-      get_offset<METHOD>(k, dx, dy, dz);
-      recs[k] = probe_cell(map, ix + dx, iy + dy, iz + dz);
+      recs[k] = probe_neighbour<METHOD>(map, ix, iy, iz, k, p.x, p.y, p.z);
       cnt += recs[k] >= 0;
     }
     for (int k = 0; k < K; ++k) {
