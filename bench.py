@@ -454,20 +454,39 @@ def run_c4(args):
     dev = torch.device("cuda", local)
     if world == 1:
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29655", rank=0, world_size=1, device_id=dev)
-    box = [None]
-    if rank == 0:
-        scene, target = workloads.config2_map(map_points=args.map_points, n_map_scans=args.map_scans, azimuth_steps=args.azimuth_steps,
-                                              thin_leaf=args.thin_leaf)
-        srcs = [workloads.config2_scan(scene, 100 + i, azimuth_steps=args.azimuth_steps, perturb_seed=100)[0] for i in range(args.c4_scans)]
-        box[0] = (target, np.concatenate(srcs))
-    dist.broadcast_object_list(box, src=0)
-    target, source = box[0]
     ndt = nb.NormalDistributionsTransform(device=local)
     ndt.setNeighborhoodSearchMethod(METHODS[args.method])
     sh = ShardedNdt(ndt, dist)
-    t0 = time.perf_counter()
-    sh.setInputTarget(target)
-    build_ms = (time.perf_counter() - t0) * 1e3
+    if args.c4_city_points > 0:
+        # BASELINE configs[3] at its stated size: a synthetic city map of --c4-city-points surface samples (ground, walls of
+        # a 40 m block grid, roofs; every rank generates the same cloud on its GPU) and a --c4-source-points source
+        # sampled from the same surfaces within 100 m of the origin, moved by a small pose
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import build_bench
+        tgt_dev = build_bench.surface_points(args.c4_city_points, 20260103, extent=args.c4_city_extent, device=dev)
+        src_dev = build_bench.surface_points(args.c4_source_points, 20260105, extent=200.0, device=dev)
+        T = torch.as_tensor(np.linalg.inv(workloads.pose_matrix([0.3, -0.2, 0.1, 0.004, -0.003, 0.015])), dtype=torch.float64, device=dev)
+        xyz = src_dev[:, :3].to(torch.float64) @ T[:3, :3].T + T[:3, 3]
+        source = np.ascontiguousarray(xyz.to(torch.float32).cpu().numpy())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ndt.set_target_device(tgt_dev.data_ptr(), args.c4_city_points)
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - t0) * 1e3
+        target = tgt_dev          # only len() is used below
+        del src_dev, xyz
+    else:
+        box = [None]
+        if rank == 0:
+            scene, target = workloads.config2_map(map_points=args.map_points, n_map_scans=args.map_scans, azimuth_steps=args.azimuth_steps,
+                                                  thin_leaf=args.thin_leaf)
+            srcs = [workloads.config2_scan(scene, 100 + i, azimuth_steps=args.azimuth_steps, perturb_seed=100)[0] for i in range(args.c4_scans)]
+            box[0] = (target, np.concatenate(srcs))
+        dist.broadcast_object_list(box, src=0)
+        target, source = box[0]
+        t0 = time.perf_counter()
+        sh.setInputTarget(target)
+        build_ms = (time.perf_counter() - t0) * 1e3
     sh.setInputSource(source)
     lo, hi = source_range(len(source), rank, world)
     for _ in range(max(3, args.warmup)):
@@ -498,9 +517,10 @@ def run_c4(args):
                 "steps": steps, "ms_per_step": total_ms / steps, "scaling": "strong", "dtype": "f32", "data": "synthetic",
                 "src_pt_iters_per_s": len(source) * evals * steps / (total_ms * 1e-3), "evaluations_per_align": evals,
                 "hessian_passes_per_align": hess, "hits_per_point_eval": res["n_hits"] / float((evals + hess) * len(source)),
-                "config": {"workload": "c4: %d-pt source (%d merged scans) sharded by contiguous ranges over %d GPU(s) vs %d-pt map "
+                "config": {"workload": "c4: %d-pt source (%s) sharded by contiguous ranges over %d GPU(s) vs %d-pt map "
                                        "(%d voxels, %d valid), res 1.0, %s; one in-kernel 29-value P2P exchange per evaluation" %
-                                       (len(source), args.c4_scans, world, len(target), info["n_voxels"], info["n_valid"], args.method),
+                                       (len(source), ("%d merged scans" % args.c4_scans) if args.c4_city_points == 0 else "synthetic city surfaces",
+                                        world, len(target), info["n_voxels"], info["n_valid"], args.method),
                            "map_build_ms_incl_h2d": build_ms, "points_this_rank": hi - lo},
                 "roofline": {"bound": "hbm", "achieved": alg_bytes / (total_ms / steps * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
                              "frac": alg_bytes / (total_ms / steps * 1e-3) / 1e9 / world / peak, "algorithmic_bytes_per_launch": alg_bytes},
@@ -763,6 +783,9 @@ def main():
     ap.add_argument("--c5-points", type=int, nargs="+", default=[10_000_000, 100_000_000])
     ap.add_argument("--c5-res", type=float, nargs="+", default=[0.5, 1.0, 2.0])
     ap.add_argument("--c4-scans", type=int, default=16)
+    ap.add_argument("--c4-city-points", type=int, default=0, help="c4 at full size: synthetic city map of this many points (e.g. 100000000)")
+    ap.add_argument("--c4-source-points", type=int, default=2_000_000)
+    ap.add_argument("--c4-city-extent", type=float, default=2000.0)
     ap.add_argument("--thin-leaf", type=float, default=0.1)
     args = ap.parse_args()
     if args.workload == "c4" and args.impl == "b200":

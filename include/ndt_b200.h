@@ -156,6 +156,29 @@ int ndtb200_voxelgrid_filter(ndtb200_handle* h, const void* points, size_t n, si
 int ndtb200_voxelgrid_filter_device(ndtb200_handle* h, const void* d_points_xyzw, size_t n, float leaf, void* d_out_xyzw,
                                     size_t out_capacity, int64_t* n_out);
 
+/* ---- the mapping-node loop as one device-resident pipeline (lidar_subscriber/src/ndt_rosbag_mapping_node.cpp:42-161) --
+ * push_scan(k) = downsample_cloud (VoxelGrid voxel_leaf) -> perform_registration(previous filtered scan, this one,
+ * guess = previous transform; Identity if not converged) -> pose = pose * transform -> update_global_map (transform by
+ * the pose, append, VoxelGrid map_voxel).  The first scan only initialises the map.  Clouds stay in HBM between
+ * steps; the map of scan k is built while scan k is still being aligned against the map of scan k-1.
+ * ndt_params NULL = the node's defaults (eps 0.01, 64 iterations, step 0.1, resolution 1.0, DIRECT7). */
+typedef struct ndtb200_mapper ndtb200_mapper;
+typedef struct ndtb200_mapper_step {
+  float transform[16];   /* column-major: this step's registration result (perform_registration's return value) */
+  float pose[16];        /* column-major: accumulated pose after this step */
+  double fitness;        /* getFitnessScore() of the registration (0 for the first scan or when disabled) */
+  int32_t converged, iterations, n_evaluations, pad;
+  int64_t n_filtered;    /* points of the downsampled scan */
+  int64_t n_map;         /* points of the global map after this step */
+} ndtb200_mapper_step;
+int ndtb200_mapper_create(ndtb200_mapper** out, int device, const ndtb200_params* ndt_params, float voxel_leaf, float map_voxel,
+                          int compute_fitness);
+int ndtb200_mapper_destroy(ndtb200_mapper* m);
+int ndtb200_mapper_push_scan(ndtb200_mapper* m, const void* points, size_t n, size_t stride_bytes, ndtb200_mapper_step* out);
+int ndtb200_mapper_get_map(ndtb200_mapper* m, void* out_points, size_t capacity, size_t out_stride_bytes, int64_t* n_out);
+const char* ndtb200_mapper_last_error(const ndtb200_mapper* m);
+int64_t ndtb200_mapper_launch_count(const ndtb200_mapper* m);
+
 /* ---- multi-GPU target-map build (not in the reference; SURVEY 8e "target-map build") ----------------------------
  * The cloud is split by contiguous point ranges, one per rank.  (1) ndtb200_cloud_bounds: bounding box + finite count
  * of this rank's slice (device pointer, float4 records); the caller all-reduces min / max / count over the ranks.

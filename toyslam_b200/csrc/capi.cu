@@ -1533,6 +1533,195 @@ int ndtb200_voxelgrid_filter_device(ndtb200_handle* h, const void* d_points_xyzw
   return NDTB200_OK;
 }
 
+// =================================================================================================
+// The mapping-node loop as a device-resident pipeline (lidar_subscriber/src/ndt_rosbag_mapping_node.cpp
+// :42-75 run loop, :108-118 downsample_cloud, :120-144 perform_registration, :146-161 update_global_map).
+// Only the raw scan goes up and one small step record comes down; the filtered scan, the voxel maps, the aligned
+// source and the global map never leave HBM.  Two NDT handles alternate: while handle A aligns scan k+1 against the
+// map of scan k, handle B already builds the map of scan k+1 on its own stream.
+// =================================================================================================
+struct ndtb200_mapper {
+  int device = 0;
+  ndtb200_handle* ndt[2] = {nullptr, nullptr};  // ndt[cur] holds the map of the previous scan
+  ndtb200_handle* vg = nullptr;                 // VoxelGrid filters (scan leaf, map leaf)
+  int cur = 0;
+  float voxel_leaf = 0.3f, map_voxel = 0.5f;
+  int compute_fitness = 1;
+  bool have_prev = false;
+  float pose[16];            // column-major, accumulated pose (Eigen::Matrix4f pose = pose * transform)
+  float pres_transform[16];  // column-major, guess of the next registration
+  DevBuf d_raw, d_filtered, d_transformed, d_map[2];
+  size_t n_map = 0;
+  int map_cur = 0;
+  long long scans = 0;
+  std::string err;
+};
+
+static void mat4_identity(float* m) { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0f : 0.0f; }
+static void mat4_mul_colmajor(const float* a, const float* b, float* c) {  // c = a * b, fp32
+  float r[16];
+  for (int col = 0; col < 4; ++col)
+    for (int row = 0; row < 4; ++row) {
+      float s = 0.f;
+      for (int k = 0; k < 4; ++k) s += a[k * 4 + row] * b[col * 4 + k];
+      r[col * 4 + row] = s;
+    }
+  std::memcpy(c, r, sizeof(r));
+}
+
+#define MCK(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      m->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                \
+      return NDTB200_ERR_CUDA;                                                                     \
+    }                                                                                              \
+  } while (0)
+
+int ndtb200_mapper_create(ndtb200_mapper** out, int device, const ndtb200_params* ndt_params, float voxel_leaf, float map_voxel,
+                          int compute_fitness) {
+  if (!out) return NDTB200_ERR_INVALID;
+  *out = nullptr;
+  ndtb200_mapper* m = new ndtb200_mapper();
+  m->device = device;
+  m->voxel_leaf = voxel_leaf;
+  m->map_voxel = map_voxel;
+  m->compute_fitness = compute_fitness;
+  mat4_identity(m->pose);
+  mat4_identity(m->pres_transform);
+  int st = ndtb200_create(&m->ndt[0], device);
+  if (st == NDTB200_OK) st = ndtb200_create(&m->ndt[1], device);
+  if (st == NDTB200_OK) st = ndtb200_create(&m->vg, device);
+  ndtb200_params p;
+  ndtb200_default_params(&p);
+  if (ndt_params) p = *ndt_params;
+  else { p.trans_eps = 0.01; p.max_iterations = 64; }  // the node's defaults (ndt_rosbag_mapping_node.cpp:83-88)
+  for (int i = 0; i < 2 && st == NDTB200_OK; ++i) st = ndtb200_set_params(m->ndt[i], &p);
+  if (st != NDTB200_OK) { ndtb200_mapper_destroy(m); return st; }
+  *out = m;
+  return NDTB200_OK;
+}
+
+int ndtb200_mapper_destroy(ndtb200_mapper* m) {
+  if (!m) return NDTB200_OK;
+  cudaSetDevice(m->device);
+  for (int i = 0; i < 2; ++i) if (m->ndt[i]) ndtb200_destroy(m->ndt[i]);
+  if (m->vg) ndtb200_destroy(m->vg);
+  m->d_raw.release(); m->d_filtered.release(); m->d_transformed.release(); m->d_map[0].release(); m->d_map[1].release();
+  delete m;
+  return NDTB200_OK;
+}
+
+const char* ndtb200_mapper_last_error(const ndtb200_mapper* m) { return m ? m->err.c_str() : "null mapper"; }
+
+// update_global_map (:146-161): transform the filtered scan by the pose, append, re-voxelise the whole map
+static int mapper_update_global_map(ndtb200_mapper* m, size_t n_f) {
+  ndtb200_handle* v = m->vg;
+  cudaStream_t s = v->stream;
+  const size_t total = m->n_map + n_f;
+  DevBuf& cat = m->d_map[1 - m->map_cur];
+  MCK(cat.ensure(std::max<size_t>(total, 1) * sizeof(float4)));
+  if (m->n_map) MCK(cudaMemcpyAsync(cat.p, m->d_map[m->map_cur].p, m->n_map * sizeof(float4), cudaMemcpyDeviceToDevice, s));
+  if (n_f) {
+    Mat34 T;
+    colmajor_to_T(m->pose, T.m);
+    transform_cloud_kernel<<<grid_for(n_f, 256, v->num_sms * 8), 256, 0, s>>>(m->d_filtered.as<float4>(), n_f, T,
+                                                                              cat.as<float4>() + m->n_map);
+    v->launches++;
+  }
+  MCK(cudaStreamSynchronize(s));
+  DevBuf& dst = m->d_map[m->map_cur];
+  MCK(dst.ensure(std::max<size_t>(total, 1) * sizeof(float4)));
+  int64_t n_out = 0;
+  const int st = ndtb200_voxelgrid_filter_device(v, cat.p, total, m->map_voxel, dst.p, total, &n_out);
+  if (st == NDTB200_ERR_GRID_OVERFLOW) {  // pcl::VoxelGrid passes the cloud through
+    MCK(cudaMemcpy(dst.p, cat.p, total * sizeof(float4), cudaMemcpyDeviceToDevice));
+    n_out = static_cast<int64_t>(total);
+  } else if (st != NDTB200_OK) {
+    m->err = ndtb200_last_error(v);
+    return st;
+  }
+  m->n_map = static_cast<size_t>(n_out);
+  return NDTB200_OK;
+}
+
+int ndtb200_mapper_push_scan(ndtb200_mapper* m, const void* points, size_t n, size_t stride_bytes, ndtb200_mapper_step* out) {
+  if (!m || !out || (!points && n)) return NDTB200_ERR_INVALID;
+  cudaSetDevice(m->device);
+  std::memset(out, 0, sizeof(*out));
+  mat4_identity(out->transform);
+  ndtb200_handle* v = m->vg;
+  // downsample_cloud (:108-118): raw scan up, centroids stay on the device
+  int st = upload_points(v, m->d_raw, points, n, stride_bytes);
+  if (st != NDTB200_OK) { m->err = v->err; return st; }
+  MCK(cudaStreamSynchronize(v->stream));
+  MCK(m->d_filtered.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+  int64_t n_f64 = 0;
+  st = ndtb200_voxelgrid_filter_device(v, m->d_raw.p, n, m->voxel_leaf, m->d_filtered.p, n, &n_f64);
+  if (st == NDTB200_ERR_GRID_OVERFLOW) {
+    MCK(cudaMemcpy(m->d_filtered.p, m->d_raw.p, n * sizeof(float4), cudaMemcpyDeviceToDevice));
+    n_f64 = static_cast<int64_t>(n);
+  } else if (st != NDTB200_OK) {
+    m->err = ndtb200_last_error(v);
+    return st;
+  }
+  const size_t n_f = static_cast<size_t>(n_f64);
+  out->n_filtered = n_f64;
+  ndtb200_handle* a = m->ndt[m->cur];       // holds the map of the previous scan
+  ndtb200_handle* b = m->ndt[1 - m->cur];   // builds the map of this scan meanwhile
+  if (m->have_prev) {
+    // perform_registration (:120-144): target = previous filtered scan (already built), source = this one
+    st = ndtb200_set_source_device(a, m->d_filtered.p, n_f);
+    if (st == NDTB200_OK) st = ndtb200_align_async(a, m->pres_transform);
+    if (st != NDTB200_OK) { m->err = ndtb200_last_error(a); return st; }
+  }
+  // the map of THIS scan (next step's target) is built on the other handle's stream while the solve runs
+  int st_b = ndtb200_set_target_device(b, m->d_filtered.p, n_f, 1);
+  if (st_b == NDTB200_ERR_CUDA || st_b == NDTB200_ERR_INVALID) { m->err = ndtb200_last_error(b); return st_b; }
+  if (m->have_prev) {
+    ndtb200_result r;
+    st = ndtb200_sync(a);
+    if (st == NDTB200_OK) st = ndtb200_get_result(a, &r);
+    if (st != NDTB200_OK) { m->err = ndtb200_last_error(a); return st; }
+    out->converged = r.converged;
+    out->iterations = r.iterations;
+    out->n_evaluations = r.n_evaluations;
+    if (m->compute_fitness) {
+      double f = 0;
+      if (ndtb200_fitness_score(a, 1.7976931348623157e308, &f) == NDTB200_OK) out->fitness = f;
+    }
+    if (r.converged) std::memcpy(out->transform, r.final_transformation, sizeof(out->transform));  // else Identity (:140-143)
+    std::memcpy(m->pres_transform, out->transform, sizeof(m->pres_transform));
+    mat4_mul_colmajor(m->pose, out->transform, m->pose);  // pose = pose * transform (:66)
+  }
+  std::memcpy(out->pose, m->pose, sizeof(out->pose));
+  st = mapper_update_global_map(m, n_f);
+  if (st != NDTB200_OK) return st;
+  out->n_map = static_cast<int64_t>(m->n_map);
+  m->cur = 1 - m->cur;
+  m->have_prev = true;
+  m->scans++;
+  return NDTB200_OK;
+}
+
+int ndtb200_mapper_get_map(ndtb200_mapper* m, void* out_points, size_t capacity, size_t out_stride_bytes, int64_t* n_out) {
+  if (!m || !n_out) return NDTB200_ERR_INVALID;
+  cudaSetDevice(m->device);
+  *n_out = static_cast<int64_t>(m->n_map);
+  if (!out_points || m->n_map == 0) return NDTB200_OK;
+  if (out_stride_bytes < 16 || capacity < m->n_map) { m->err = "output buffer too small / stride < 16"; return NDTB200_ERR_INVALID; }
+  if (out_stride_bytes == 16) MCK(cudaMemcpy(out_points, m->d_map[m->map_cur].p, m->n_map * 16, cudaMemcpyDeviceToHost));
+  else MCK(cudaMemcpy2D(out_points, out_stride_bytes, m->d_map[m->map_cur].p, 16, 16, m->n_map, cudaMemcpyDeviceToHost));
+  return NDTB200_OK;
+}
+
+int64_t ndtb200_mapper_launch_count(const ndtb200_mapper* m) {
+  if (!m) return 0;
+  long long c = m->ndt[0]->launches + m->ndt[1]->launches + m->vg->launches;
+  if (m->vg->aux) c += m->vg->aux->launches;
+  return c;
+}
+
 int ndtb200_set_throughput_mode(ndtb200_handle* h, int on) {
   if (!h) return NDTB200_ERR_INVALID;
   h->shape = on ? 1 : 0;

@@ -22,6 +22,19 @@ transform_output_kernel(const float4* __restrict__ src, int n, const AlignResult
   }
 }
 
+// pcl::transformPointCloud with a matrix given by value (the mapping pipeline's update_global_map)
+struct Mat34 { float m[12]; };
+__global__ void __launch_bounds__(256)
+transform_cloud_kernel(const float4* __restrict__ src, size_t n, Mat34 T, float4* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 p = __ldg(src + i);
+    float4 o;
+    transform_point(T.m, p.x, p.y, p.z, o.x, o.y, o.z);
+    o.w = 1.0f;
+    out[i] = o;
+  }
+}
+
 // getFitnessScore: exact 1-NN of T*source in the RAW target, squared distance in fp32 with FLANN's
 // L2_Simple order ((dx^2 + dy^2) + dz^2).  Brute force, target streamed through shared memory tiles.
 // One partial (sum of accepted d2 in fp64, count) per CTA; the host adds the partials in CTA order.
