@@ -462,6 +462,36 @@ def test_kdtree_mode(nb):
     assert rel_err(a["gradient"], b["gradient"]) < REL and rel_err(a["hessian"], b["hessian"]) < REL
 
 
+def test_mapping_pipeline_matches_reference_loop(nb):
+    """ndt_rosbag_mapping_node.cpp:42-161 as a device-resident pipeline (ndtb200_mapper_*): per-step downsample sizes
+    exact, registrations equal to the oracle's loop (same counts, transforms within the bar), accumulated pose and
+    global map consistent."""
+    import workloads
+    from util import oracle_mapping_loop
+    scans, poses = workloads.config3_sequence(6, azimuth_steps=600, leaf=0.05)   # dense-ish raw scans (sensor frame)
+    ref_steps, ref_map = oracle_mapping_loop(scans)
+    mapper = nb.Mapper()
+    for k, cloud in enumerate(scans):
+        s, r = mapper.push_scan(cloud), ref_steps[k]
+        assert s["n_filtered"] == r["n_filtered"]                       # VoxelGrid is bit-exact
+        assert s["converged"] == r["converged"] and s["iterations"] == r["iterations"] and s["n_evaluations"] == r["n_evaluations"]
+        dt, dr = transform_delta(s["transform"], r["transform"])
+        assert dt < TRANS_TOL and dr < ROT_TOL, (k, dt, dr)
+        dt, dr = transform_delta(s["pose"], r["pose"])
+        assert dt < 10 * TRANS_TOL and dr < 10 * ROT_TOL, (k, dt, dr)   # products of k step transforms
+        if k > 0:
+            assert abs(s["fitness"] - r["fitness"]) <= 1e-5 * abs(r["fitness"])
+        # poses differ by ~1e-7, so a few points may fall into the neighbouring map cell: sizes agree to 0.2 %
+        assert abs(s["n_map"] - r["n_map"]) <= max(2, 0.002 * r["n_map"]), (k, s["n_map"], r["n_map"])
+    gm = mapper.global_map()
+    assert len(gm) == s["n_map"]
+    # same map up to the cells touched by the ~1e-7 pose differences: compare the occupied 0.5 m cells
+    cells = lambda c: set(map(tuple, np.floor(c / 0.5).astype(np.int64)))
+    a, b = cells(gm), cells(ref_map)
+    assert len(a ^ b) <= max(4, 0.004 * len(b))
+    assert mapper.launch_count() > 0
+
+
 def test_calculate_score(nb):
     tgt, src = load_pair()
     ref, gpu = make_pair(nb, tgt, src)

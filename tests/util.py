@@ -85,3 +85,40 @@ def synthetic_scene(n_target=40000, n_source=8000, seed=0, offset=(0.0, 0.0, 0.0
     src = src @ inv[:3, :3].T + inv[:3, 3]
     off = np.asarray(offset, dtype=np.float64)
     return (tgt + off).astype(np.float32), src.astype(np.float32)
+
+
+def oracle_mapping_loop(scans, voxel_leaf=0.3, map_voxel=0.5, eps=0.01, max_iter=64, step=0.1, res=1.0):
+    """The reference's mapping loop (lidar_subscriber/src/ndt_rosbag_mapping_node.cpp:42-161) on the oracle:
+    downsample_cloud -> perform_registration(prev, cur, guess = previous transform) -> pose = pose * transform ->
+    update_global_map (transform, append, VoxelGrid map_voxel).  Returns the per-step records and the global map."""
+    import oracle
+    ndt = oracle.NormalDistributionsTransform()
+    ndt.setResolution(res); ndt.setStepSize(step); ndt.setTransformationEpsilon(eps); ndt.setMaximumIterations(max_iter)
+    ndt.setNeighborhoodSearchMethod(oracle.DIRECT7)
+    pose = np.eye(4, dtype=np.float32)
+    pres = np.eye(4, dtype=np.float32)
+    prev = None
+    gmap = np.zeros((0, 3), dtype=np.float32)
+    steps = []
+    for cloud in scans:
+        filtered = oracle.voxelgrid_downsample(cloud, voxel_leaf)
+        rec = {"n_filtered": len(filtered), "transform": np.eye(4, dtype=np.float32), "converged": False, "iterations": 0,
+               "n_evaluations": 0, "fitness": 0.0}
+        if prev is not None:
+            ndt.setInputTarget(prev)
+            ndt.setInputSource(filtered)
+            ndt.align(pres)
+            r = ndt.result()
+            rec.update(converged=bool(r["converged"]), iterations=r["iterations"], n_evaluations=r["n_evaluations"],
+                       fitness=ndt.getFitnessScore())
+            if r["converged"]:
+                rec["transform"] = r["final"].astype(np.float32)
+            pres = rec["transform"]
+            pose = (pose @ rec["transform"]).astype(np.float32)
+        rec["pose"] = pose.copy()
+        moved = oracle.transform_points(pose, filtered)[:, :3]
+        gmap = oracle.voxelgrid_downsample(np.concatenate([gmap, moved]).astype(np.float32), map_voxel)
+        rec["n_map"] = len(gmap)
+        steps.append(rec)
+        prev = filtered
+    return steps, gmap

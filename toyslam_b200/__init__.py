@@ -14,6 +14,7 @@ from .ndt import (  # noqa: F401
     KDTREE,
     NdtError,
     Batch,
+    Mapper,
     NormalDistributionsTransform,
     align_batch,
     device_count,
@@ -23,4 +24,4 @@ from .ndt import (  # noqa: F401
 )
 
 __all__ = ["NormalDistributionsTransform", "NdtError", "KDTREE", "DIRECT26", "DIRECT7", "DIRECT1",
-           "Batch", "align_batch", "device_count", "load_library", "library_path", "exported_symbols"]
+           "Batch", "Mapper", "align_batch", "device_count", "load_library", "library_path", "exported_symbols"]

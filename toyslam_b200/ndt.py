@@ -38,6 +38,12 @@ class MapInfo(C.Structure):
                 ("hash_capacity", C.c_int64)]
 
 
+class MapperStep(C.Structure):
+    _fields_ = [("transform", C.c_float * 16), ("pose", C.c_float * 16), ("fitness", C.c_double),
+                ("converged", C.c_int32), ("iterations", C.c_int32), ("n_evaluations", C.c_int32), ("pad", C.c_int32),
+                ("n_filtered", C.c_int64), ("n_map", C.c_int64)]
+
+
 _lib = None
 
 
@@ -83,6 +89,14 @@ def load_library():
     L.ndtb200_set_throughput_mode.argtypes = [vp, C.c_int]
     L.ndtb200_voxelgrid_filter.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_float, vp, C.c_size_t, C.c_size_t, i64p]
     L.ndtb200_voxelgrid_filter_device.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.c_size_t, i64p]
+    L.ndtb200_mapper_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Params), C.c_float, C.c_float, C.c_int]
+    L.ndtb200_mapper_destroy.argtypes = [vp]
+    L.ndtb200_mapper_push_scan.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.POINTER(MapperStep)]
+    L.ndtb200_mapper_get_map.argtypes = [vp, vp, C.c_size_t, C.c_size_t, i64p]
+    L.ndtb200_mapper_last_error.argtypes = [vp]
+    L.ndtb200_mapper_last_error.restype = C.c_char_p
+    L.ndtb200_mapper_launch_count.argtypes = [vp]
+    L.ndtb200_mapper_launch_count.restype = C.c_int64
     L.ndtb200_cloud_bounds.argtypes = [vp, vp, C.c_size_t, C.c_int, f32p, f32p, i64p]
     L.ndtb200_build_partials.argtypes = [vp, f32p, f32p, i64p]
     L.ndtb200_copy_partials.argtypes = [vp, vp, vp, vp]
@@ -153,6 +167,60 @@ class Batch:
             raise NdtError(st, "ndtb200_align_batch failed: " + "; ".join(
                 self._L.ndtb200_last_error(d._h).decode() for d in self.ndts[:4]))
         return [d.result() for d in self.ndts]
+
+
+class Mapper:
+    """The mapping-node loop (ndt_rosbag_mapping_node.cpp:42-161) as a device-resident pipeline: push raw scans, get
+    per-step transforms / poses; the global map stays on the device until asked for."""
+
+    def __init__(self, device=0, voxel_leaf=0.3, map_voxel=0.5, compute_fitness=True, **ndt_params):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        p = Params()
+        self._L.ndtb200_default_params(C.byref(p))
+        p.trans_eps, p.max_iterations = 0.01, 64     # the node's defaults
+        for k, v in ndt_params.items():
+            setattr(p, k, v)
+        st = self._L.ndtb200_mapper_create(C.byref(self._h), int(device), C.byref(p), float(voxel_leaf), float(map_voxel),
+                                           1 if compute_fitness else 0)
+        if st != OK:
+            self._h = C.c_void_p()
+            raise NdtError(st, "ndtb200_mapper_create failed")
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.ndtb200_mapper_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def push_scan_raw(self, ptr, n, stride=16):
+        s = MapperStep()
+        st = self._L.ndtb200_mapper_push_scan(self._h, ptr, n, stride, C.byref(s))
+        if st != OK:
+            raise NdtError(st, self._L.ndtb200_mapper_last_error(self._h).decode())
+        return {"transform": np.array(s.transform, dtype=np.float32).reshape(4, 4).T.copy(),
+                "pose": np.array(s.pose, dtype=np.float32).reshape(4, 4).T.copy(), "fitness": float(s.fitness),
+                "converged": bool(s.converged), "iterations": int(s.iterations), "n_evaluations": int(s.n_evaluations),
+                "n_filtered": int(s.n_filtered), "n_map": int(s.n_map)}
+
+    def push_scan(self, points):
+        p = as_xyzw(points)
+        self._keep = p
+        return self.push_scan_raw(p.ctypes.data, p.shape[0], 16)
+
+    def global_map(self):
+        n = C.c_int64(0)
+        self._L.ndtb200_mapper_get_map(self._h, None, 0, 16, C.byref(n))
+        out = np.empty((max(1, n.value), 4), dtype=np.float32)
+        st = self._L.ndtb200_mapper_get_map(self._h, out.ctypes.data, out.shape[0], 16, C.byref(n))
+        if st != OK:
+            raise NdtError(st, self._L.ndtb200_mapper_last_error(self._h).decode())
+        return np.ascontiguousarray(out[:n.value, :3])
+
+    def launch_count(self):
+        return int(self._L.ndtb200_mapper_launch_count(self._h))
 
 
 def align_batch(ndts, guesses=None):
