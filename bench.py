@@ -698,6 +698,94 @@ def c3_cpu(args, scans, guesses, gpu_results, max_pairs=24, max_seconds=25.0):
             {"pairs_checked": n, "max_abs_dT": max_dT, "iterations_and_evaluations_equal": bool(same_counts)})
 
 
+def run_mapper(args):
+    """the ndt_rosbag_mapping_node loop (downsample 0.3 m, scan-to-scan NDT with the node parameters, pose
+    chaining, global map re-voxelised at 0.5 m) as a device-resident pipeline.  A step = one raw scan pushed.  Ranks
+    run independent drives (replicas)."""
+    import torch
+    import toyslam_b200 as nb
+    import workloads
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n_scans = min(args.steps, args.mapper_scans)
+    path = None
+    scans = None
+    if args.cache:
+        os.makedirs(args.cache, exist_ok=True)
+        path = os.path.join(args.cache, "mapper_%d_%d_r%d.npz" % (n_scans, args.azimuth_steps, rank))
+        if os.path.exists(path):
+            d = np.load(path)
+            scans = [d["scan_%d" % i] for i in range(n_scans)]
+    if scans is None:
+        scans, _ = workloads.config3_sequence(n_scans, seed=workloads.SEED_C3 + 1000 * rank, azimuth_steps=args.azimuth_steps, leaf=0.02)
+        if path:
+            np.savez(path, **{"scan_%d" % i: s for i, s in enumerate(scans)})
+    hosts = []
+    for sc in scans:
+        hb = torch.ones((len(sc), 4), dtype=torch.float32).pin_memory()
+        hb[:, :3] = torch.from_numpy(sc)
+        hosts.append(hb)
+    warm = nb.Mapper(device=local)
+    for k in range(min(4, n_scans)):
+        warm.push_scan_raw(hosts[k].data_ptr(), len(scans[k]), 16)
+    del warm
+    mapper = nb.Mapper(device=local)
+    sampler = ClockSampler(local)
+    barrier(world)
+    torch.cuda.synchronize()
+    sampler.start()
+    t0 = time.perf_counter()
+    steps = []
+    step_ms = []
+    for k in range(n_scans):
+        tk = time.perf_counter()
+        steps.append(mapper.push_scan_raw(hosts[k].data_ptr(), len(scans[k]), 16))
+        step_ms.append((time.perf_counter() - tk) * 1e3)
+    torch.cuda.synchronize()
+    barrier(world)
+    wall = max_over_ranks(time.perf_counter() - t0, world, dev)
+    clocks = sampler.stop()
+    raw_pts = float(np.mean([len(s) for s in scans]))
+    line = {"metric": "mapper_scans_per_s", "workload": "mapper", "value": n_scans * world / wall, "unit": "scans/s", "n_gpus": world,
+            "steps": n_scans * world, "warmup": 4, "ms_per_step": wall / n_scans * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "mapping-node loop: %d raw scans (%.0f pts mean) of a simulated drive per GPU; per scan VoxelGrid 0.3 m (%.0f pts), "
+                                   "NDT vs the previous scan (eps 0.01, 64 iterations, DIRECT7, guess = previous transform), getFitnessScore, "
+                                   "global map += transformed scan, VoxelGrid 0.5 m (final map %d pts)" %
+                                   (n_scans, raw_pts, float(np.mean([s["n_filtered"] for s in steps])), steps[-1]["n_map"]),
+                       "timing": "host wall clock over the whole drive, pinned host scans in, step records out (this IS end to end)"},
+            "iterations_per_scan": float(np.mean([s["iterations"] for s in steps[1:]])),
+            "evaluations_per_scan": float(np.mean([s["n_evaluations"] for s in steps[1:]])),
+            "step_ms_percentiles": {"p10": float(np.percentile(step_ms, 10)), "p50": float(np.percentile(step_ms, 50)),
+                                    "p90": float(np.percentile(step_ms, 90)), "max": float(np.max(step_ms)), "first_half_mean": float(np.mean(step_ms[:len(step_ms) // 2])),
+                                    "second_half_mean": float(np.mean(step_ms[len(step_ms) // 2:]))},
+            "gpu_launches": mapper.launch_count(), "clocks": clocks,
+            "e2e": {"value": n_scans * world / wall, "unit": "scans/s", "h2d_bytes_per_step": int(raw_pts * 16), "d2h_bytes_per_step": 168}}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from util import oracle_mapping_loop
+            import oracle
+            n_cpu = min(n_scans, 12)
+            t0 = time.perf_counter()
+            ref_steps, _ = oracle_mapping_loop(scans[:n_cpu])
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "scans/s", "cores": oracle.max_threads(), "kind": "port",
+                                    "sample": "the first %d scans of the same drive through the oracle's restatement of the node loop" % n_cpu}
+            line["parity_vs_oracle"] = {"scans_checked": n_cpu,
+                                        "max_abs_dT": float(max(np.abs(a["transform"] - b["transform"]).max() for a, b in zip(steps[:n_cpu], ref_steps))),
+                                        "counts_equal": bool(all(a["iterations"] == b["iterations"] and a["n_filtered"] == b["n_filtered"]
+                                                                 for a, b in zip(steps[:n_cpu], ref_steps)))}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
 def run_c5(args):
     """BASELINE configs[4]: target-map rebuild sweep.  A step = one VoxelGridCovariance build (ndtb200_set_target_device:
     device-resident cloud in, voxel map out).  One JSON line per (points, resolution)."""
@@ -777,7 +865,8 @@ def main():
     ap.add_argument("--l2", default="inputs", choices=["inputs", "flush"],
                     help="how timed steps see a cold L2: inputs larger than L2 (default) or a 256 MiB flush write")
     ap.add_argument("--cache", default=None, help="directory for cached workload arrays")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "mapper"])
+    ap.add_argument("--mapper-scans", type=int, default=200)
     ap.add_argument("--c3-distinct", type=int, default=128, help="distinct consecutive pairs generated per GPU (cycled)")
     ap.add_argument("--c3-lanes", type=int, default=8, help="handles (+ host threads) per GPU for the c3 pipeline")
     ap.add_argument("--c5-points", type=int, nargs="+", default=[10_000_000, 100_000_000])
@@ -794,6 +883,8 @@ def main():
         return run_c3(args)
     if args.workload == "c5" and args.impl == "b200":
         return run_c5(args)
+    if args.workload == "mapper" and args.impl == "b200":
+        return run_mapper(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -22,10 +22,12 @@ struct DevBuf {
   size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    // first allocation: 12.5 % headroom; a buffer that has to grow again (the mapper's global map, a longer scan)
+    // grows by 50 % so that cudaFree + cudaMalloc (an implicit device synchronisation) stays rare
+    const size_t want = (cap == 0) ? bytes + bytes / 8 + 256 : bytes + bytes / 2 + 256;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -1012,12 +1014,13 @@ int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out) {
     int* d_list = reinterpret_cast<int*>(d_best + n);
     int* d_count = reinterpret_cast<int*>(h->d_scalar.as<char>() + 128);
     CK(cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
-    fitness_grid_kernel<<<blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), n, h->d_target.as<float4>(), h->d_vals_a.as<uint32_t>(),
+    const int warp_blocks = static_cast<int>(((size_t)n * 32 + 255) / 256);  // one warp per query
+    fitness_grid_kernel<<<warp_blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), n, h->d_target.as<float4>(), h->d_vals_a.as<uint32_t>(),
                                                         h->d_voxel_start.as<uint32_t>(), static_cast<uint32_t>(h->n_voxels),
                                                         static_cast<uint32_t>(h->grid.n_finite), h->d_cell_all.as<int32_t>(),
                                                         h->d_grid.as<GridDesc>(), d_T, d_best, d_list, d_count);
     LAUNCHED(h);
-    fitness_fallback_kernel<<<blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), d_list, d_count, h->d_target.as<float4>(),
+    fitness_fallback_kernel<<<std::min(n, h->num_sms * 8), 256, 0, h->stream>>>(h->d_source.as<float4>(), d_list, d_count, h->d_target.as<float4>(),
                                                             static_cast<int>(h->n_target), d_T, d_best);
     LAUNCHED(h);
     fitness_reduce_kernel<<<blocks, 256, 0, h->stream>>>(d_best, n, max_range, d_sum, d_cnt);

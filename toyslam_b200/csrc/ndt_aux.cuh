@@ -111,6 +111,9 @@ cell_table_fill_kernel(const int32_t* __restrict__ voxel_key, uint32_t n_voxels,
   if (v < n_voxels) table[voxel_key[v]] = static_cast<int32_t>(v);
 }
 
+// One WARP per query: the lanes share the cells of the current ring (27 cells of ring 1 = one cell per lane), each
+// lane scans the points of its cells, a shuffle tree takes the minimum.  A face of the scanned cube only limits the
+// search if the grid continues behind it; a query outside the grid starts from the nearest grid cell.
 __global__ void __launch_bounds__(256)
 fitness_grid_kernel(const float4* __restrict__ src, int n_src, const float4* __restrict__ tgt, const uint32_t* __restrict__ sorted_idx,
                     const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
@@ -121,92 +124,93 @@ fitness_grid_kernel(const float4* __restrict__ src, int n_src, const float4* __r
   if (threadIdx.x < 12) T[threadIdx.x] = T_in[threadIdx.x];
   if (threadIdx.x == 32) g = *gd;
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp-uniform query index
   if (i >= n_src) return;
   const float4 p = __ldg(src + i);
   float q[3];
   transform_point(T, p.x, p.y, p.z, q[0], q[1], q[2]);
   float cf[3];
   int c[3];
-  bool inside = true;
+  bool finite = true;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    cf[a] = floorf(__fmul_rn(q[a], g.inv_leaf[a]));
-    const float rel = __fsub_rn(cf[a], static_cast<float>(g.min_b[a]));
-    inside = inside && (rel >= 0.0f) && (rel < static_cast<float>(g.div_b[a])) && (q[a] == q[a]);
-    c[a] = static_cast<int>(rel);
+    finite = finite && (q[a] == q[a]) && (fabsf(q[a]) < 3.0e38f);
+    const float rel = __fsub_rn(floorf(__fmul_rn(q[a], g.inv_leaf[a])), static_cast<float>(g.min_b[a]));
+    const float relc = fminf(fmaxf(rel, 0.0f), static_cast<float>(g.div_b[a] - 1));  // nearest grid cell along this axis
+    c[a] = finite ? static_cast<int>(relc) : 0;
+    cf[a] = relc + static_cast<float>(g.min_b[a]);
   }
   float best = __int_as_float(0x7f800000);
   bool resolved = false;
-  if (inside) {
+  if (finite) {
     for (int r = 1; r <= kMaxRing && !resolved; ++r) {
-      for (int dz = -r; dz <= r; ++dz) {
-        const int cz = c[2] + dz;
-        if (cz < 0 || cz >= g.div_b[2]) continue;
-        for (int dy = -r; dy <= r; ++dy) {
-          const int cy = c[1] + dy;
-          if (cy < 0 || cy >= g.div_b[1]) continue;
-          for (int dx = -r; dx <= r; ++dx) {
-            const int cx = c[0] + dx;
-            if (cx < 0 || cx >= g.div_b[0]) continue;
-            if (r > 1 && abs(dx) < r && abs(dy) < r && abs(dz) < r) continue;  // inner cube was scanned by the previous ring
-            const int v = __ldg(cell_table + (cx * g.mul[0] + cy * g.mul[1] + cz * g.mul[2]));
-            if (v < 0) continue;
-            const uint32_t b = __ldg(voxel_start + v);
-            const uint32_t e = (static_cast<uint32_t>(v) + 1 < n_voxels) ? __ldg(voxel_start + v + 1) : n_finite;
-            for (uint32_t k = b; k < e; ++k) best = fminf(best, l2_simple(q[0], q[1], q[2], __ldg(tgt + __ldg(sorted_idx + k))));
-          }
-        }
+      const int side = 2 * r + 1, ncell = side * side * side;
+      for (int k = lane; k < ncell; k += 32) {
+        const int dx = k % side - r, dy = (k / side) % side - r, dz = k / (side * side) - r;
+        if (r > 1 && abs(dx) < r && abs(dy) < r && abs(dz) < r) continue;  // inner cube: scanned by the previous ring
+        const int cx = c[0] + dx, cy = c[1] + dy, cz = c[2] + dz;
+        if (cx < 0 || cx >= g.div_b[0] || cy < 0 || cy >= g.div_b[1] || cz < 0 || cz >= g.div_b[2]) continue;
+        const int v = __ldg(cell_table + (cx * g.mul[0] + cy * g.mul[1] + cz * g.mul[2]));
+        if (v < 0) continue;
+        const uint32_t b = __ldg(voxel_start + v);
+        const uint32_t e = (static_cast<uint32_t>(v) + 1 < n_voxels) ? __ldg(voxel_start + v + 1) : n_finite;
+        for (uint32_t j = b; j < e; ++j) best = fminf(best, l2_simple(q[0], q[1], q[2], __ldg(tgt + __ldg(sorted_idx + j))));
       }
-      // distance from the query to the faces of the scanned cube, minus a margin for the fp32 rounding of the cell
-      // boundaries (coordinates up to tens of km)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+      // distance from the query to those faces of the scanned cube that have grid cells behind them, minus a margin for
+      // the fp32 rounding of the cell boundaries (coordinates up to tens of km)
       float margin = 3.402823466e+38f;
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        const float lo = (cf[a] - static_cast<float>(r)) * g.leaf[a], hi = (cf[a] + static_cast<float>(r) + 1.0f) * g.leaf[a];
         const float eps = 1e-3f * g.leaf[a] + 4e-7f * (fabsf(q[a]) + g.leaf[a]);
-        margin = fminf(margin, fminf(q[a] - lo, hi - q[a]) - eps);
+        if (c[a] - r > 0) margin = fminf(margin, q[a] - (cf[a] - static_cast<float>(r)) * g.leaf[a] - eps);
+        if (c[a] + r < g.div_b[a] - 1) margin = fminf(margin, (cf[a] + static_cast<float>(r) + 1.0f) * g.leaf[a] - q[a] - eps);
       }
       resolved = (margin > 0.0f) && (best <= margin * margin);
     }
   }
-  if (resolved) {
-    best_out[i] = best;
-  } else {
-    best_out[i] = -1.0f;
-    fallback_list[atomicAdd(fallback_count, 1)] = i;
+  if (lane == 0) {
+    if (resolved) {
+      best_out[i] = best;
+    } else {
+      best_out[i] = -1.0f;
+      fallback_list[atomicAdd(fallback_count, 1)] = i;
+    }
   }
 }
 
-// brute force over the whole raw target for the listed queries (outside the grid / no point within the scanned rings)
+// brute force over the whole raw target for the listed queries (no point within the scanned rings): one CTA per query,
+// the 256 threads stride over the target and a block reduction takes the minimum — a handful of far-away queries must
+// not cost a serial scan of the target each
 __global__ void __launch_bounds__(256)
 fitness_fallback_kernel(const float4* __restrict__ src, const int* __restrict__ list, const int* __restrict__ count,
                         const float4* __restrict__ tgt, int n_tgt, const float* __restrict__ T_in, float* __restrict__ best_out) {
-  __shared__ float4 tile[kNNTile];
   __shared__ float T[12];
+  __shared__ float s_min[8];
   const int n = *count;
-  if (blockIdx.x * blockDim.x >= n) return;  // uniform per block
+  if (static_cast<int>(blockIdx.x) >= n) return;
   if (threadIdx.x < 12) T[threadIdx.x] = T_in[threadIdx.x];
   __syncthreads();
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = j < n ? list[j] : -1;
-  float qx = 0, qy = 0, qz = 0;
-  if (i >= 0) {
+  for (int j = blockIdx.x; j < n; j += gridDim.x) {
+    const int i = list[j];
     const float4 p = __ldg(src + i);
+    float qx, qy, qz;
     transform_point(T, p.x, p.y, p.z, qx, qy, qz);
-  }
-  float best = __int_as_float(0x7f800000);
-  for (int base = 0; base < n_tgt; base += kNNTile) {
-    const int m = min(kNNTile, n_tgt - base);
+    float best = __int_as_float(0x7f800000);
+    for (int k = threadIdx.x; k < n_tgt; k += blockDim.x) best = fminf(best, l2_simple(qx, qy, qz, __ldg(tgt + k)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = best;
     __syncthreads();
-    for (int k = threadIdx.x; k < m; k += blockDim.x) tile[k] = __ldg(tgt + base + k);
-    __syncthreads();
-    if (i >= 0) {
-#pragma unroll 8
-      for (int k = 0; k < m; ++k) best = fminf(best, l2_simple(qx, qy, qz, tile[k]));
+    if (threadIdx.x == 0) {
+      float m = s_min[0];
+      for (int w = 1; w < 8; ++w) m = fminf(m, s_min[w]);
+      best_out[i] = m;
     }
+    __syncthreads();
   }
-  if (i >= 0) best_out[i] = best;
 }
 
 // mean of the accepted squared distances: one fp64 partial + count per CTA, the host adds them in CTA order
