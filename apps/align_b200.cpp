@@ -19,39 +19,20 @@
 #include <vector>
 
 #include <pclomp_b200/ndt_b200.hpp>
+#include <pclomp_b200/pcd_io.hpp>
 
 typedef pcl::PointCloud<pcl::PointXYZ> Cloud;
 
 static bool load_cloud(const std::string& path, Cloud& cloud) {
-  std::ifstream f(path, std::ios::binary);
+  if (path.size() > 4 && path.substr(path.size() - 4) == ".pcd") return pclomp_b200::io::loadPCDFile(path, cloud) == 0;
+  std::ifstream f(path, std::ios::binary);  // .bin: raw float32 x,y,z triples
   if (!f) return false;
   std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-  size_t off = 0, stride = 12, npts = 0;
-  if (path.size() > 4 && path.substr(path.size() - 4) == ".pcd") {
-    const std::string marker = "DATA binary\n";
-    std::string head(raw.begin(), raw.begin() + std::min<size_t>(raw.size(), 4096));
-    const size_t pos = head.find(marker);
-    if (pos == std::string::npos) return false;
-    off = pos + marker.size();
-    std::istringstream hs(head.substr(0, pos));
-    std::string line;
-    size_t nfields = 0;
-    while (std::getline(hs, line)) {
-      std::istringstream ls(line);
-      std::string key;
-      ls >> key;
-      if (key == "FIELDS") { std::string t; while (ls >> t) ++nfields; }
-      if (key == "POINTS") ls >> npts;
-    }
-    stride = 4 * nfields;
-  } else {
-    npts = raw.size() / 12;
-  }
-  if (off + npts * stride > raw.size()) return false;
+  const size_t npts = raw.size() / 12;
   cloud.points.resize(npts);
   for (size_t i = 0; i < npts; ++i) {
     float xyz[3];
-    std::memcpy(xyz, raw.data() + off + i * stride, 12);
+    std::memcpy(xyz, raw.data() + i * 12, 12);
     cloud.points[i] = pcl::PointXYZ(xyz[0], xyz[1], xyz[2]);
   }
   cloud.width = static_cast<uint32_t>(npts);
@@ -138,5 +119,14 @@ int main(int argc, char** argv) {
   std::cout << "batch of " << objs.size() << ": " << std::chrono::duration<double, std::milli>(b1 - b0).count() << "[msec], iterations";
   for (auto& o : objs) std::cout << " " << o.getFinalNumIteration();
   std::cout << std::endl;
+
+  // --save-aligned out.pcd: the aligned source of the DIRECT7 copy as a binary PCD (pcl::io::savePCDFileBinary)
+  for (int i = 3; i + 1 < argc; ++i)
+    if (std::string(argv[i]) == "--save-aligned") {
+      if (pclomp_b200::io::savePCDFileBinary(argv[i + 1], out) != 0) { std::cerr << "failed to write " << argv[i + 1] << std::endl; return 1; }
+      Cloud back;
+      if (pclomp_b200::io::loadPCDFile(argv[i + 1], back) != 0 || back.size() != out.size()) { std::cerr << "PCD round trip failed" << std::endl; return 1; }
+      std::cout << "saved " << back.size() << " aligned points to " << argv[i + 1] << std::endl;
+    }
   return 0;
 }

@@ -18,6 +18,8 @@ N > 1: one process per GPU, each rank aligns its own independent scan against it
            memory, the solve, D2H of the transformed cloud and of the result block.
 """
 import argparse
+import os as _os
+_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # no lazy kernel-load stalls inside timed regions
 import json
 import os
 import subprocess

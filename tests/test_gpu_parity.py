@@ -548,3 +548,36 @@ def test_cpp_shim_app_reproduces_golden_fitness(nb, tmp_path):
     assert abs(float(fit[0]) - golden()["fitness"]["DIRECT7"]) < 1e-6
     assert abs(float(fit[1]) - golden()["fitness"]["DIRECT1"]) < 1e-6
     assert "copy converged: 1, iterations 5" in out.stdout
+    assert re.search(r"batch of 4: .*iterations 5 5 5 5", out.stdout), out.stdout      # alignBatch through the shim
+
+
+def test_cpp_shim_pcd_voxelgrid_pipeline(nb, tmp_path):
+    """The reference app's front end through the C++ shim: binary PCD files in (pcl::io::loadPCDFile), 0.1 m
+    pcl::VoxelGrid (apps/align.cpp:57-69) on the device, align, aligned cloud written back as a binary PCD."""
+    import os
+    import re
+    import subprocess
+    from toyslam_b200 import _build
+    app = _build.build_apps()
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "raw_head.npz"))
+
+    def write_pcd(path, xyz):   # the layout of ndt_omp/data/*.pcd: x y z intensity, float32, DATA binary
+        rec = np.zeros((len(xyz), 4), dtype=np.float32)
+        rec[:, :3] = xyz
+        with open(path, "wb") as f:
+            f.write(("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\n"
+                     "COUNT 1 1 1 1\nWIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (len(xyz), len(xyz))).encode())
+            f.write(rec.tobytes())
+
+    tp, sp, op = str(tmp_path / "t.pcd"), str(tmp_path / "s.pcd"), str(tmp_path / "aligned.pcd")
+    write_pcd(tp, d["target"]); write_pcd(sp, d["source"])
+    out = subprocess.run([os.path.abspath(app), tp, sp, "--leaf", "0.1", "--save-aligned", op], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "target 8192 pts, source 8192 pts" in out.stdout
+    assert "downsampled (0.1 m): target %d pts, source %d pts" % (len(d["target_ds0p1"]), len(d["source_ds0p1"])) in out.stdout
+    fit = [float(x) for x in re.findall(r"fitness: ([0-9.]+)", out.stdout)]
+    ref = oracle.NormalDistributionsTransform()
+    ref.setInputTarget(d["target_ds0p1"]); ref.setInputSource(d["source_ds0p1"]); ref.align()
+    assert abs(fit[0] - ref.getFitnessScore()) <= 2e-6 * max(1.0, fit[0])       # printed with 6 digits
+    assert ("saved %d aligned points" % len(d["source_ds0p1"])) in out.stdout
+    assert os.path.getsize(op) > 12 * len(d["source_ds0p1"])

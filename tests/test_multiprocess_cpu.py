@@ -45,7 +45,7 @@ def test_rank_reductions_gloo_world2(tmp_path):
         "bench.barrier(world)\n"
         "from toyslam_b200.sharding import source_range\n"
         "lo, hi = source_range(1000003, rank, world)\n"
-        "print(json.dumps({'rank': rank, 'world': world, 'max': mx, 'sum': sm, 'lo': lo, 'hi': hi}))\n"
+        "os.write(1, (json.dumps({'rank': rank, 'world': world, 'max': mx, 'sum': sm, 'lo': lo, 'hi': hi}) + '\\n').encode())  # one atomic write per rank\n"
         "dist.destroy_process_group()\n" % ROOT)
     out = _torchrun([str(script)], port=29612)
     assert out.returncode == 0, out.stderr[-2000:]
