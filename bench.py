@@ -11,11 +11,15 @@ pair (the `10times` loop of ndt_omp/apps/align.cpp:25-27: target map built once 
 N > 1: one process per GPU, each rank aligns its own independent scan against its own copy of the map
 (independent scan pairs are the unit that shards; no data-path collective) -> weak scaling.
 
-`value`  : aligns/s with inputs resident in HBM; every timed step is one launch of the persistent solve kernel,
-           timed with CUDA events on the handle's stream.  Steps cycle over 64 independent (scan, map) pairs whose
-           touched bytes exceed the L2 (inputs larger than L2); `--l2 flush` writes 256 MiB between steps instead.
-`e2e`    : the same align through the C ABI with HOST buffers: per step H2D of the source cloud from pinned
-           memory, the solve, D2H of the transformed cloud and of the result block.
+`value`  : aligns/s with inputs resident in HBM: 64 independent (scan, map) pairs per GPU (their touched bytes exceed the
+           L2: inputs larger than L2) aligned through ndtb200_align_batch_async — every step is one launch of the
+           persistent solve kernel, up to four of them co-resident per SM; CUDA events on a master stream bracket the
+           whole timed region.  `latency` is the same align with ONE solve in flight at a time.
+`e2e`    : the same through the C ABI with HOST buffers: per step H2D of the source cloud from pinned memory, the
+           solve, D2H of the transformed cloud and of the result block (batched; `e2e.single_call` = one blocking
+           ndtb200_align at a time).
+Other workloads: --workload c3 (batched odometry incl. map builds), c4 (source-sharded scan-to-map), c5 (map-build
+sweep), mapper (the mapping-node loop as a device-resident pipeline).
 """
 import argparse
 import os as _os

@@ -661,7 +661,7 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   const int max_blocks = h->coop_blocks[method][shape];
   // every SM takes part as soon as there is one 32-point group per CTA (the kernel deals groups to warps round-robin)
   int blocks = grid_for(h->n_source, 32, max_blocks);
-  CK(h->d_partials.ensure((size_t)max_blocks * kNVP * sizeof(double)));
+  CK(h->d_partials.ensure((size_t)2 * max_blocks * kNVP * sizeof(double)));  // double-buffered by evaluation parity
   if (h->d_totals.p == nullptr) {
     CK(h->d_totals.ensure(3 * kNVP * sizeof(double)));
     CK(cudaMemsetAsync(h->d_totals.p, 0, 3 * kNVP * sizeof(double), h->stream));
@@ -1232,7 +1232,8 @@ int ndtb200_get_timeline(ndtb200_handle* h, double* t4, int cap, int* n_out) {
   if (getenv("NDTB200_DEBUG_STEP")) {  // arrival-time spread of the CTAs at the LAST barrier
     const int G = static_cast<int>(h->last_blocks);
     std::vector<double> part((size_t)G * kNVP);
-    CK(cudaMemcpyAsync(part.data(), h->d_partials.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const size_t row_off = (h->comm_world == 1) ? (size_t)((h->h_result->n_trace - 1) & 1) * G * kNVP : 0;  // rows are double-buffered by evaluation parity
+    CK(cudaMemcpyAsync(part.data(), h->d_partials.as<double>() + row_off, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     std::vector<double> arr(G);
     const unsigned long long tl = tr[n - 1].t_start;
@@ -1266,7 +1267,7 @@ int ndtb200_get_timeline(ndtb200_handle* h, double* t4, int cap, int* n_out) {
       std::fprintf(stderr, "  eval %d CTA0: thread 0 points + warp sum %.2f us, (unused %.2f,) CTA fold %.2f us\n", i, (double)((long long)tr[i].t_phase[0] - (long long)tr[i].t_start) * 1e-3,
                    (double)((long long)tr[i].t_phase[1] - (long long)tr[i].t_phase[0]) * 1e-3, (double)((long long)tr[i].t_local - (long long)tr[i].t_phase[1]) * 1e-3);
     if (getenv("NDTB200_DEBUG_STEP"))
-      std::fprintf(stderr, "  step %d: last CTA arrived %.2f us after CTA 0 finished, totals %.2f us later; advance %.2f us, solve %.2f us, post %.2f us, pose setup %.2f us\n", i,
+      std::fprintf(stderr, "  step %d: grid complete %.2f us after CTA 0 finished, totals %.2f us later; advance %.2f us, solve %.2f us, post %.2f us, pose setup %.2f us\n", i,
                    (double)((long long)tr[i].t_dbg[3] - (long long)tr[i].t_local) * 1e-3, (double)((long long)tr[i].t_reduced - (long long)tr[i].t_dbg[3]) * 1e-3,
                    (tr[i].t_dbg[0] - tr[i].t_reduced) * 1e-3, (tr[i].t_dbg[1] - tr[i].t_dbg[0]) * 1e-3,
                    (tr[i].t_dbg[2] - tr[i].t_dbg[1]) * 1e-3, (tr[i].t_advanced - tr[i].t_dbg[2]) * 1e-3);

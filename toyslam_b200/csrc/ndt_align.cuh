@@ -288,23 +288,22 @@ __device__ __forceinline__ void point_hessian_f64(const float4 pt, const EvalCtx
   constexpr int K = num_offsets<METHOD>();
   double A[3] = {0, 0, 0}, M[6] = {0, 0, 0, 0, 0, 0};
   int nh = 0;
-#pragma unroll 1
-  for (int k = 0; k < K; ++k) {
-    const int rec = probe_neighbour<METHOD>(m, ix, iy, iz, k, tx, ty, tz);
-    if (rec < 0) continue;
+  auto hit = [&](int rec) {
     ++nh;
-    const VoxelRecord* R = m.records + rec;
-    const double* ic = m.icov64 + (size_t)rec * 6;
-    const double r0 = static_cast<double>(tx) - (static_cast<double>(__ldg(&R->mean_hi[0])) + static_cast<double>(__ldg(&R->mean_lo[0])));
-    const double r1 = static_cast<double>(ty) - (static_cast<double>(__ldg(&R->mean_hi[1])) + static_cast<double>(__ldg(&R->mean_lo[1])));
-    const double r2 = static_cast<double>(tz) - (static_cast<double>(__ldg(&R->mean_hi[2])) + static_cast<double>(__ldg(&R->mean_lo[2])));
-    const double c00 = __ldg(ic), c01 = __ldg(ic + 1), c02 = __ldg(ic + 2), c11 = __ldg(ic + 3), c12 = __ldg(ic + 4), c22 = __ldg(ic + 5);
+    const float4* R = reinterpret_cast<const float4*>(m.records + rec);
+    const float4 ra = __ldg(R), rb = __ldg(R + 1);  // mean_hi[3], mean_lo[3] (+ 2 icov words)
+    const double2* ic = reinterpret_cast<const double2*>(m.icov64 + (size_t)rec * 6);
+    const double2 i0 = __ldg(ic), i1 = __ldg(ic + 1), i2 = __ldg(ic + 2);
+    const double r0 = static_cast<double>(tx) - (static_cast<double>(ra.x) + static_cast<double>(ra.w));
+    const double r1 = static_cast<double>(ty) - (static_cast<double>(ra.y) + static_cast<double>(rb.x));
+    const double r2 = static_cast<double>(tz) - (static_cast<double>(ra.z) + static_cast<double>(rb.y));
+    const double c00 = i0.x, c01 = i0.y, c02 = i1.x, c11 = i1.y, c12 = i2.x, c22 = i2.y;
     const double u0 = c00 * r0 + c01 * r1 + c02 * r2;
     const double u1 = c01 * r0 + c11 * r1 + c12 * r2;
     const double u2 = c02 * r0 + c12 * r1 + c22 * r2;
     const double q = r0 * u0 + r1 * u1 + r2 * u2;
     const double e2 = d2 * exp(-d2 * q / 2);  // ndt_omp_impl.hpp:622-626
-    if (!(e2 <= 1.0 && e2 >= 0.0)) continue;
+    if (!(e2 <= 1.0 && e2 >= 0.0)) return;
     const double w = e2 * d1;
     A[0] += w * u0; A[1] += w * u1; A[2] += w * u2;
     const double kk = -d2 * w;
@@ -315,6 +314,19 @@ __device__ __forceinline__ void point_hessian_f64(const float4 pt, const EvalCtx
     M[3] += w * c11 + t1 * u1;
     M[4] += w * c12 + t1 * u2;
     M[5] += w * c22 + t2 * u2;
+  };
+  if constexpr (METHOD == 2 || METHOD == 3) {
+    int rec[K];
+    probe_cells<K>(m, ix, iy, iz, rec);  // all lookups of the point in flight together
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (rec[k] >= 0) hit(rec[k]);
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      const int rec = probe_neighbour<METHOD>(m, ix, iy, iz, k, tx, ty, tz);
+      if (rec >= 0) hit(rec);
+    }
   }
   if (nh == 0) return;
   acc[21] += static_cast<double>(nh);
@@ -427,6 +439,49 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
   const int W = ws.world;
   if (G == 1 && W == 1) {
     if (threadIdx.x < kNV) s_tot[threadIdx.x] = s_block[threadIdx.x];
+    __syncthreads();
+    ++epoch;
+    return;
+  }
+  if (W == 1) {
+    // Single GPU: EVERY CTA sums all partial rows itself (same fixed (slice, row) order -> identical bits everywhere)
+    // as soon as the arrival counter shows the grid complete: one round trip less than "the last CTA reduces and
+    // publishes".  Rows are double-buffered by evaluation parity: a CTA can only reach evaluation e+1's arrive after
+    // it finished reading evaluation e's rows, so a row is never overwritten while somebody still reads it.
+    double* rows = ws.partials + (size_t)(epoch & 1u) * G * kNVP;
+    if (threadIdx.x < kNV) rows[(size_t)blockIdx.x * kNVP + threadIdx.x] = s_block[threadIdx.x];
+    if (threadIdx.x == 31) rows[(size_t)blockIdx.x * kNVP + 31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: arrival time
+    if (threadIdx.x == 30) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); rows[(size_t)blockIdx.x * kNVP + 30] = static_cast<double>(smid); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atom_add_acq_rel_gpu(&ws.sync[0], 1u);  // release: this CTA's row
+      const unsigned int target = (epoch + 1u) * G;
+      while (ld_acquire_u32(&ws.sync[0]) < target) {}  // acquire: everyone's rows
+      s_tot[31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: grid complete
+      *s_flag = 1;
+    }
+    __syncthreads();
+    constexpr int kRedRows = red_rows_for(NW);
+    const int k = threadIdx.x & 31, slice = threadIdx.x >> 5;  // lane = value, warp = slice of the CTA rows
+    double sum = 0.0;
+    for (unsigned int b0 = 0; b0 < G; b0 += NW * kRedRows) {
+      double v[kRedRows];
+#pragma unroll
+      for (int i = 0; i < kRedRows; ++i) {
+        const unsigned int b = b0 + slice + NW * i;
+        v[i] = (b < G && k < kNV) ? __ldcg(rows + (size_t)b * kNVP + k) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < kRedRows; ++i) sum += v[i];
+    }
+    s_red8[slice][k] = sum;
+    __syncthreads();
+    if (threadIdx.x < kNV) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += s_red8[w][threadIdx.x];
+      s_tot[threadIdx.x] = t;
+    }
     __syncthreads();
     ++epoch;
     return;
@@ -1204,7 +1259,9 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     if (ws.world > 1 && *reinterpret_cast<volatile unsigned int*>(&ws.sync[3]) != 0u) break;  // a peer never answered (uniform: checked after a barrier)
     if (timing) t_reduced = globaltimer_ns();
     unsigned long long t_last_arrive = 0;
-    if (timing && gridDim.x > 1) t_last_arrive = static_cast<unsigned long long>(__double_as_longlong(__ldcg(ws.totals + 2 * kNVP + ((epoch - 1u) & 1u))));
+    if (timing && gridDim.x > 1)
+      t_last_arrive = (ws.world == 1) ? static_cast<unsigned long long>(__double_as_longlong(s_tot[31]))
+                                      : static_cast<unsigned long long>(__double_as_longlong(__ldcg(ws.totals + 2 * kNVP + ((epoch - 1u) & 1u))));
     int slot = 0;
     unsigned long long t_d0 = 0, t_d1 = 0, t_d2 = 0;
     // the step: warp 0 of every CTA runs the identical Newton / More-Thuente state machine on the identical totals
