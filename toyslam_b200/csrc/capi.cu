@@ -1362,6 +1362,7 @@ int ndtb200_clone(const ndtb200_handle* src, ndtb200_handle** out) {
   int st = ndtb200_create(&h, src->device);
   if (st != NDTB200_OK) return st;
   h->prm = src->prm;
+  h->shape = src->shape;
   if (src->has_target) {
     cudaStreamSynchronize(src->stream);
     // the copy keeps the source object's map: build it with the resolution the source map was built with
