@@ -1035,12 +1035,25 @@ __device__ __forceinline__ void point_f32(float px, float py, float pz, const Ev
     probe_cells<K>(m, ix, iy, iz, rec);
     // (a depth-1 software pipeline of the record loads was measured: the extra live registers spill at the 64-register
     // cap and cost 12 % — the 32 resident warps already cover the L2 latency)
+#ifdef NDTB200_ROLLED_HITS
+    // one copy of the hit body (instruction-cache footprint): the neighbour's record index is selected from the registers
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      int r = rec[0];
+#pragma unroll
+      for (int j = 1; j < K; ++j) r = (k == j) ? rec[j] : r;
+      if (r < 0) continue;
+      ++nh;
+      hit_f32<HESS>(load_record(m.records + r), tx, ty, tz, d2f, d1f, S, A, M);
+    }
+#else
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (rec[k] < 0) continue;
       ++nh;
       hit_f32<HESS>(load_record(m.records + rec[k]), tx, ty, tz, d2f, d1f, S, A, M);
     }
+#endif
   } else {
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
