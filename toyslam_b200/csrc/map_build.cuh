@@ -223,21 +223,22 @@ __device__ __forceinline__ unsigned int digit_peers(uint32_t d, bool valid) {
 
 // Count pass: only the per-tile digit totals are needed (no ranks), so shared-memory atomics do: a round whose 32 keys
 // share one digit (clouds in scan order) is added by one lane, otherwise every lane adds 1 to its warp's private bin.
-__global__ void __launch_bounds__(kBuildThreads)
-radix_count_kernel(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t* __restrict__ hist, int ntiles) {
-  __shared__ uint32_t warp_cnt[kSortWarps][256];
+// Tile `tile` of ROUNDS x 256 keys; called by all 256 threads of a CTA.  warp_cnt: [kSortWarps][256] shared words.
+template <int ROUNDS>
+__device__ __forceinline__ void radix_count_tile(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t* __restrict__ hist,
+                                                 int ntiles, int tile, uint32_t (*warp_cnt)[256]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = threadIdx.x; d < 256 * kSortWarps; d += kBuildThreads) (&warp_cnt[0][0])[d] = 0u;
   __syncthreads();
-  const size_t wbase = (size_t)blockIdx.x * kSortTile + (size_t)warp * (32 * kSortRounds);
-  uint32_t k[kSortRounds];
+  const size_t wbase = (size_t)tile * (kBuildThreads * ROUNDS) + (size_t)warp * (32 * ROUNDS);
+  uint32_t k[ROUNDS];
 #pragma unroll
-  for (int r = 0; r < kSortRounds; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const size_t i = wbase + r * 32 + lane;
-    k[r] = (i < n) ? __ldg(keys + i) : 0u;
+    k[r] = (i < n) ? __ldcg(keys + i) : 0u;  // L2-coherent: inside the fused small build the keys were written by other CTAs
   }
 #pragma unroll
-  for (int r = 0; r < kSortRounds; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const size_t i = wbase + r * 32 + lane;
     const bool valid = i < n;
     const uint32_t d = (k[r] >> shift) & 255u;
@@ -253,35 +254,41 @@ radix_count_kernel(const uint32_t* __restrict__ keys, size_t n, int shift, uint3
   uint32_t sum = 0;
 #pragma unroll
   for (int w = 0; w < kSortWarps; ++w) sum += warp_cnt[w][d];
-  hist[(size_t)d * ntiles + blockIdx.x] = sum;
+  hist[(size_t)d * ntiles + tile] = sum;
+  __syncthreads();
 }
 
-__global__ void __launch_bounds__(kBuildThreads, NDTB200_SCATTER_MIN_BLOCKS)
-radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, size_t n, int shift,
-                     const uint32_t* __restrict__ hist_scanned, int ntiles, uint32_t* __restrict__ keys_out,
-                     uint32_t* __restrict__ vals_out) {
+__global__ void __launch_bounds__(kBuildThreads)
+radix_count_kernel(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t* __restrict__ hist, int ntiles) {
   __shared__ uint32_t warp_cnt[kSortWarps][256];
-  __shared__ uint32_t s_dstart[256];
-  __shared__ uint32_t s_gbase[256];
-  __shared__ uint32_t s_scan[kBuildThreads / 32 + 1];
-  __shared__ uint32_t s_key[kSortTile];
-  __shared__ uint32_t s_val[kSortTile];
+  radix_count_tile<kSortRounds>(keys, n, shift, hist, ntiles, blockIdx.x, warp_cnt);
+}
+
+// Scatter pass of one tile (see the header comment).  Shared memory: warp_cnt [kSortWarps][256], s_dstart / s_gbase
+// [256], s_scan [9], s_key / s_val [ROUNDS * 256].
+template <int ROUNDS>
+__device__ __forceinline__ void radix_scatter_tile(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, size_t n,
+                                                   int shift, const uint32_t* __restrict__ hist_scanned, int ntiles, int tile,
+                                                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                   uint32_t (*warp_cnt)[256], uint32_t* s_dstart, uint32_t* s_gbase, uint32_t* s_scan,
+                                                   uint32_t* s_key, uint32_t* s_val) {
+  constexpr int kTile = kBuildThreads * ROUNDS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = threadIdx.x; d < 256 * kSortWarps; d += kBuildThreads) (&warp_cnt[0][0])[d] = 0u;
   __syncthreads();
-  const size_t tbase = (size_t)blockIdx.x * kSortTile;
-  const size_t wbase = tbase + (size_t)warp * (32 * kSortRounds);
-  uint32_t k[kSortRounds], v[kSortRounds];
-  uint16_t rank[kSortRounds];
+  const size_t tbase = (size_t)tile * kTile;
+  const size_t wbase = tbase + (size_t)warp * (32 * ROUNDS);
+  uint32_t k[ROUNDS], v[ROUNDS];
+  uint16_t rank[ROUNDS];
 #pragma unroll
-  for (int r = 0; r < kSortRounds; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const size_t i = wbase + r * 32 + lane;
-    k[r] = (i < n) ? __ldg(keys_in + i) : 0u;
-    v[r] = (i < n) ? (vals_in ? __ldg(vals_in + i) : static_cast<uint32_t>(i)) : 0u;
+    k[r] = (i < n) ? __ldcg(keys_in + i) : 0u;
+    v[r] = (i < n) ? (vals_in ? __ldcg(vals_in + i) : static_cast<uint32_t>(i)) : 0u;
   }
   // stable rank of every key among the keys of ITS WARP with the same digit
 #pragma unroll
-  for (int r = 0; r < kSortRounds; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const size_t i = wbase + r * 32 + lane;
     const bool valid = i < n;
     const uint32_t d = (k[r] >> shift) & 255u;
@@ -307,11 +314,11 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     uint32_t total;
     const uint32_t dstart = block_exclusive_scan(off, s_scan, total);
     s_dstart[d] = dstart;
-    s_gbase[d] = hist_scanned[(size_t)d * ntiles + blockIdx.x] - dstart;
+    s_gbase[d] = __ldcg(hist_scanned + (size_t)d * ntiles + tile) - dstart;
   }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < kSortRounds; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const size_t i = wbase + r * 32 + lane;
     if (i < n) {
       const uint32_t d = (k[r] >> shift) & 255u;
@@ -321,30 +328,42 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     }
   }
   __syncthreads();
-  const uint32_t count = static_cast<uint32_t>(n - tbase < (size_t)kSortTile ? n - tbase : (size_t)kSortTile);
+  const uint32_t count = static_cast<uint32_t>(n - tbase < (size_t)kTile ? n - tbase : (size_t)kTile);
   for (uint32_t j = threadIdx.x; j < count; j += kBuildThreads) {
     const uint32_t key = s_key[j];
     const uint32_t pos = s_gbase[(key >> shift) & 255u] + j;
     keys_out[pos] = key;
     vals_out[pos] = s_val[j];
   }
+  __syncthreads();
 }
 
-// ---------------------------------------------------------------------------------------------
-// segment heads -> occupied voxel list
-// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBuildThreads, NDTB200_SCATTER_MIN_BLOCKS)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, size_t n, int shift,
+                     const uint32_t* __restrict__ hist_scanned, int ntiles, uint32_t* __restrict__ keys_out,
+                     uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t warp_cnt[kSortWarps][256];
+  __shared__ uint32_t s_dstart[256];
+  __shared__ uint32_t s_gbase[256];
+  __shared__ uint32_t s_scan[kBuildThreads / 32 + 1];
+  __shared__ uint32_t s_key[kSortTile];
+  __shared__ uint32_t s_val[kSortTile];
+  radix_scatter_tile<kSortRounds>(keys_in, vals_in, n, shift, hist_scanned, ntiles, blockIdx.x, keys_out, vals_out, warp_cnt, s_dstart,
+                                  s_gbase, s_scan, s_key, s_val);
+}
+
 // 8 consecutive sorted keys of this thread (two 16-byte loads) + the key before them; returns the head flags as bits
 __device__ __forceinline__ uint32_t load_heads(const uint32_t* __restrict__ skeys, size_t n, size_t base, uint32_t sentinel,
                                                uint32_t (&key)[kScanItems]) {
   uint32_t prev = sentinel;  // key[-1]: the first element is a head iff it is not the sentinel
-  if (base > 0 && base < n) prev = __ldg(skeys + base - 1);
+  if (base > 0 && base < n) prev = __ldcg(skeys + base - 1);
   if (base + kScanItems <= n) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(skeys + base));
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(skeys + base) + 1);
+    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(skeys + base));
+    const uint4 b = __ldcg(reinterpret_cast<const uint4*>(skeys + base) + 1);
     key[0] = a.x; key[1] = a.y; key[2] = a.z; key[3] = a.w; key[4] = b.x; key[5] = b.y; key[6] = b.z; key[7] = b.w;
   } else {
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) key[k] = (base + k < n) ? __ldg(skeys + base + k) : sentinel;
+    for (int k = 0; k < kScanItems; ++k) key[k] = (base + k < n) ? __ldcg(skeys + base + k) : sentinel;
   }
   uint32_t flags = 0;
 #pragma unroll
@@ -500,6 +519,11 @@ __device__ __forceinline__ void inv3_cofactor(const double a[3][3], double r[3][
   r[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
 }
 
+__device__ __forceinline__ void finalize_one(uint32_t v, int count, const double (&m)[9], int32_t key, int min_points, double eig_ratio,
+                                             VoxelRecord* __restrict__ records, double* __restrict__ icov64,
+                                             unsigned int* __restrict__ n_valid, double* __restrict__ dbg_mean,
+                                             double* __restrict__ dbg_cov, double* __restrict__ dbg_icov, int* __restrict__ dbg_inflated);
+
 // dbg_cov / dbg_icov / dbg_inflated: optional full-precision dumps (parity API), NULL in production.
 __global__ void __launch_bounds__(kBuildThreads)
 finalize_voxels_kernel(const double* __restrict__ moments, const int32_t* __restrict__ voxel_key,
@@ -519,10 +543,18 @@ finalize_voxels_kernel(const double* __restrict__ moments, const int32_t* __rest
     const uint32_t e = (v + 1 < n_voxels) ? voxel_start[v + 1] : n_finite;
     count = static_cast<int>(e - b);
   }
-  const double n = static_cast<double>(count);
   double m[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) m[k] = moments[(size_t)v * 9 + k];
+  finalize_one(v, count, m, voxel_key[v], min_points, eig_ratio, records, icov64, n_valid, dbg_mean, dbg_cov, dbg_icov, dbg_inflated);
+}
+
+// second pass of applyFilter for ONE voxel (…_impl.hpp:282-367): count, moments {sum x (3), sum x x^T (6)} -> record
+__device__ __forceinline__ void finalize_one(uint32_t v, int count, const double (&m)[9], int32_t key, int min_points, double eig_ratio,
+                                             VoxelRecord* __restrict__ records, double* __restrict__ icov64,
+                                             unsigned int* __restrict__ n_valid, double* __restrict__ dbg_mean,
+                                             double* __restrict__ dbg_cov, double* __restrict__ dbg_icov, int* __restrict__ dbg_inflated) {
+  const double n = static_cast<double>(count);
   const double pt_sum[3] = {m[0], m[1], m[2]};
   const double mean[3] = {m[0] / n, m[1] / n, m[2] / n};
   // Q1: the reference accumulates x x^T on top of an Identity-initialised cov_ (vgc.h:107)
@@ -585,7 +617,7 @@ finalize_voxels_kernel(const double* __restrict__ moments, const int32_t* __rest
   r.icov[0] = static_cast<float>(icov[0][0]); r.icov[1] = static_cast<float>(icov[0][1]);
   r.icov[2] = static_cast<float>(icov[0][2]); r.icov[3] = static_cast<float>(icov[1][1]);
   r.icov[4] = static_cast<float>(icov[1][2]); r.icov[5] = static_cast<float>(icov[2][2]);
-  r.key = voxel_key[v];
+  r.key = key;
   r.count = count;
   r.pad[0] = r.pad[1] = 0;
   records[v] = r;
