@@ -213,6 +213,49 @@ def test_voxelgrid_filter_reproduces_config1_fixture(nb):
         assert np.array_equal(got, oracle.voxelgrid_downsample(raw, 0.1)[:, :3])
 
 
+def test_fused_and_staged_builds_identical(nb, monkeypatch):
+    """Scan-sized clouds are built by ONE cooperative kernel (small_build.cuh), large ones by the staged streaming
+    kernels: same arithmetic in the same order, so the two paths must agree bit for bit — map, downsample and what
+    the solver computes from them."""
+    rng = np.random.default_rng(12)
+    tgt, src = load_pair()
+    scene, _ = synthetic_scene(n_target=50000, seed=3, offset=(2000.0, -1500.0, 50.0))
+    nan_cloud = tgt.copy()
+    nan_cloud[::53, 2] = np.nan
+    tiny = (np.array([0.5, 0.5, 0.5]) + rng.uniform(-0.3, 0.3, size=(7, 3))).astype(np.float32)
+    cases = [(tgt, 1.0, True), (tgt, 0.5, True), (tgt, 2.0, True), (scene, 1.0, True), (nan_cloud, 1.0, False), (tiny, 1.0, True)]
+    for cloud, res, dense in cases:
+        out = {}
+        for path in ("staged", "fused"):
+            monkeypatch.setenv("NDTB200_BUILD_PATH", path)
+            g = nb.NormalDistributionsTransform()
+            g.setResolution(res)
+            st = g.setInputTarget(cloud, dense)
+            g.setInputSource(src)
+            d = g.dump_voxels()
+            e = g.eval_derivatives(np.array([0.3, 0.1, -0.02, 0.004, -0.002, -0.01]))
+            out[path] = (st, g.map_info(), g.point_keys(), d, e, g.voxelgrid_filter(cloud, 0.3), g.voxelgrid_filter(cloud, 1.7))
+        monkeypatch.delenv("NDTB200_BUILD_PATH")
+        a, b = out["staged"], out["fused"]
+        assert a[0] == b[0]
+        for k in ("min_b", "max_b", "div_b"):
+            assert np.array_equal(a[1][k], b[1][k])
+        assert a[1]["n_voxels"] == b[1]["n_voxels"] and a[1]["n_valid"] == b[1]["n_valid"]
+        assert np.array_equal(a[2], b[2])
+        for k in ("keys", "counts", "mean", "cov", "icov", "inflated"):
+            assert np.array_equal(a[3][k], b[3][k], equal_nan=True), k
+        assert a[4]["score"] == b[4]["score"] and np.array_equal(a[4]["gradient"], b[4]["gradient"]) and np.array_equal(a[4]["hessian"], b[4]["hessian"])
+        assert np.array_equal(a[5], b[5], equal_nan=True) and np.array_equal(a[6], b[6], equal_nan=True)
+    # the guard and the empty cloud behave the same on both paths
+    far = np.array([[0, 0, 0], [4000, 4000, 4000], [1, 1, 1], [2, 2, 2]], dtype=np.float32)
+    for path in ("staged", "fused"):
+        monkeypatch.setenv("NDTB200_BUILD_PATH", path)
+        g = nb.NormalDistributionsTransform()
+        g.setResolution(0.5)
+        assert g.setInputTarget(far) == 2 and g.map_info()["n_voxels"] == 0      # NDTB200_ERR_GRID_OVERFLOW
+    monkeypatch.delenv("NDTB200_BUILD_PATH")
+
+
 def test_grid_overflow_guard(nb):
     tgt = np.array([[0, 0, 0], [3000, 3000, 3000], [1, 1, 1]], dtype=np.float32)
     ref = oracle.NormalDistributionsTransform()

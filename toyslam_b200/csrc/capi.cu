@@ -12,6 +12,7 @@
 #include "map_build.cuh"
 #include "ndt_align.cuh"
 #include "ndt_aux.cuh"
+#include "small_build.cuh"
 
 using namespace ndtb200;
 
@@ -272,13 +273,15 @@ int passes_for(const GridDesc& g, bool with_sentinel, uint32_t* sentinel_out) {
 
 // second pass of applyFilter + the voxel index.  counts: per-voxel point counts (merged partials) or nullptr
 // (count = length of the voxel's sorted point range, n_finite closes the last one)
-int finalize_and_index(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite, const uint32_t* counts) {
-  CK(h->d_records.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(VoxelRecord)));
-  CK(h->d_icov64.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * 6 * sizeof(double)));
+int finalize_and_index(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite, const uint32_t* counts, bool records_done = false) {
   unsigned int* d_nvalid = h->d_scalar.as<unsigned int>() + 4;
-  CK(cudaMemsetAsync(d_nvalid, 0, sizeof(unsigned int), h->stream));
   const int vblocks = static_cast<int>(((size_t)n_vox + kBuildThreads - 1) / kBuildThreads);
-  if (n_vox > 0) {
+  if (!records_done) {
+    CK(h->d_records.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(VoxelRecord)));
+    CK(h->d_icov64.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * 6 * sizeof(double)));
+    CK(cudaMemsetAsync(d_nvalid, 0, sizeof(unsigned int), h->stream));
+  }
+  if (n_vox > 0 && !records_done) {
     finalize_voxels_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(
         h->d_moments.as<double>(), h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), counts, n_vox, n_finite,
         h->prm.min_points_per_voxel, h->prm.eig_ratio, h->d_records.as<VoxelRecord>(), h->d_icov64.as<double>(),
@@ -336,6 +339,67 @@ int finalize_and_index(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite, con
   return NDTB200_OK;
 }
 
+// ---- scan-sized clouds: the whole build (mode 0) or the VoxelGrid downsample (mode 1) in ONE cooperative launch ----
+bool use_fused_build(size_t n) {
+  const char* e = getenv("NDTB200_BUILD_PATH");  // tests: "staged" / "fused" force one path (bit-identical results)
+  if (e && std::strcmp(e, "staged") == 0) return false;
+  if (e && std::strcmp(e, "fused") == 0) return n > 0 && n <= (size_t)0x7fffffff / 64;
+  return n > 0 && n <= kSmallMaxPoints;
+}
+
+// Leaves: h->grid (host copy), *n_vox_out; mode 0: records / icov64 / moments / voxel lists / n_valid counter;
+// mode 1: centroids in h->d_out.  The sorted point indices end up in h->d_vals_a.  One host synchronisation.
+int run_fused_build(ndtb200_handle* h, const float4* pts, size_t n, int dense, int mode, float leaf, uint32_t* n_vox_out) {
+  const int G = std::min(h->num_sms, grid_for(n, kBuildThreads, h->num_sms));
+  const int ntiles = static_cast<int>((n + kSmallTile - 1) / kSmallTile);
+  const int stiles = static_cast<int>((n + kScanTile - 1) / kScanTile);
+  CK(h->d_mm_partial.ensure((size_t)G * 6 * sizeof(float)));
+  CK(h->d_mm_finite.ensure((size_t)G * sizeof(unsigned int)));
+  CK(h->d_grid.ensure(sizeof(GridDesc)));
+  CK(h->d_keys_a.ensure(n * sizeof(uint32_t)));
+  CK(h->d_keys_b.ensure(n * sizeof(uint32_t)));
+  CK(h->d_vals_a.ensure(n * sizeof(uint32_t)));
+  CK(h->d_vals_b.ensure(n * sizeof(uint32_t)));
+  CK(h->d_hist.ensure((size_t)256 * ntiles * sizeof(uint32_t)));
+  CK(h->d_scan_tmp.ensure((size_t)(stiles + 64) * sizeof(uint32_t)));
+  CK(h->d_voxel_key.ensure(n * sizeof(int32_t)));
+  CK(h->d_voxel_start.ensure(n * sizeof(uint32_t)));
+  if (mode == 0) {
+    CK(h->d_moments.ensure(n * 9 * sizeof(double)));
+    CK(h->d_records.ensure(n * sizeof(VoxelRecord)));
+    CK(h->d_icov64.ensure(n * 6 * sizeof(double)));
+  } else {
+    CK(h->d_out.ensure(n * sizeof(float4)));
+  }
+  char* sc = h->d_scalar.as<char>();
+  CK(cudaMemsetAsync(sc, 0, 256, h->stream));  // n_vox (0), n_valid (16), sorted-index pointer (160), barrier (192)
+  SmallBuildArgs a;
+  a.pts = pts; a.n = static_cast<uint32_t>(n); a.is_dense = dense; a.leaf = leaf;
+  a.min_points = h->prm.min_points_per_voxel; a.eig_ratio = h->prm.eig_ratio; a.mode = mode;
+  a.mm_partial = h->d_mm_partial.as<float>(); a.mm_finite = h->d_mm_finite.as<unsigned int>();
+  a.keys_a = h->d_keys_a.as<uint32_t>(); a.keys_b = h->d_keys_b.as<uint32_t>();
+  a.vals_a = h->d_vals_a.as<uint32_t>(); a.vals_b = h->d_vals_b.as<uint32_t>();
+  a.hist = h->d_hist.as<uint32_t>(); a.tile_heads = h->d_scan_tmp.as<uint32_t>();
+  a.barrier = reinterpret_cast<unsigned int*>(sc + 192);
+  a.grid = h->d_grid.as<GridDesc>(); a.n_vox = reinterpret_cast<uint32_t*>(sc); a.n_valid = reinterpret_cast<unsigned int*>(sc + 16);
+  a.voxel_key = h->d_voxel_key.as<int32_t>(); a.voxel_start = h->d_voxel_start.as<uint32_t>();
+  a.moments = h->d_moments.as<double>(); a.records = h->d_records.as<VoxelRecord>(); a.icov64 = h->d_icov64.as<double>();
+  a.centroids = h->d_out.as<float4>();
+  a.sorted_idx_out = reinterpret_cast<uint32_t**>(sc + 160);
+  void* args[] = {(void*)&a};
+  const void* fn = mode == 0 ? (const void*)small_build_kernel<0> : (const void*)small_build_kernel<1>;
+  CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kBuildThreads), args, 0, h->stream));
+  LAUNCHED(h);
+  struct { uint32_t n_vox; uint32_t pad[39]; uint32_t* sorted; } back;
+  static_assert(offsetof(decltype(back), sorted) == 160, "scalar block layout");
+  CK(cudaMemcpyAsync(&h->grid, h->d_grid.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&back, sc, sizeof(back), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (back.sorted == h->d_vals_b.as<uint32_t>()) { std::swap(h->d_vals_a, h->d_vals_b); std::swap(h->d_keys_a, h->d_keys_b); }
+  *n_vox_out = back.n_vox;
+  return NDTB200_OK;
+}
+
 int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
   clear_map(h);
   h->map_is_merged = false;
@@ -350,6 +414,27 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
   if (n > 0xFFFFFFF0ull) { h->err = "target cloud too large (>= 2^32 points)"; return NDTB200_ERR_INVALID; }
   const float4* pts = h->d_target.as<float4>();
   const int dense = h->target_dense ? 1 : 0;
+
+  if (!o.partial_only && !o.forced_min && use_fused_build(n)) {  // scan-sized cloud: one cooperative launch
+    uint32_t n_vox = 0;
+    int st = run_fused_build(h, pts, n, dense, 0, h->prm.resolution, &n_vox);
+    if (st != NDTB200_OK) return st;
+    if (h->grid.n_finite == 0) {
+      h->map_status = NDTB200_ERR_NO_INPUT;
+      st = ensure_empty_hash(h);
+      return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
+    }
+    if (h->grid.overflow) {
+      h->map_status = NDTB200_ERR_GRID_OVERFLOW;
+      st = ensure_empty_hash(h);
+      return st != NDTB200_OK ? st : NDTB200_ERR_GRID_OVERFLOW;
+    }
+    h->n_voxels = n_vox;
+    st = finalize_and_index(h, n_vox, static_cast<uint32_t>(h->grid.n_finite), nullptr, /*records_done=*/true);
+    if (st != NDTB200_OK) return st;
+    h->map_status = NDTB200_OK;
+    return NDTB200_OK;
+  }
 
   // 1. bounding box + grid description
   {
@@ -1453,6 +1538,15 @@ static int voxelgrid_filter_impl(ndtb200_handle* h, float leaf, int64_t* n_out) 
   a->prm.resolution = leaf;
   const float4* pts = a->d_target.as<float4>();
   std::memset(&a->grid, 0, sizeof(GridDesc));
+  if (use_fused_build(n)) {  // scan-sized cloud: one cooperative launch, centroids left in a->d_out
+    uint32_t n_vox = 0;
+    const int stf = run_fused_build(a, pts, n, /*dense=*/0, 1, leaf, &n_vox);
+    if (stf != NDTB200_OK) return stf;
+    if (a->grid.n_finite == 0) return NDTB200_OK;
+    if (a->grid.overflow) return NDTB200_ERR_GRID_OVERFLOW;
+    *n_out = n_vox;
+    return NDTB200_OK;
+  }
   int st = compute_grid(a, pts, n, /*dense=*/0, BuildOpts());
   if (st != NDTB200_OK) return st;
   if (a->grid.n_finite == 0) return NDTB200_OK;

@@ -64,6 +64,32 @@ minmax3d_kernel(const float4* __restrict__ pts, size_t n, int is_dense, float* _
   }
 }
 
+// VoxelGrid members from the bounding box (…_impl.hpp:75-103): inverse leaf, int64 overflow guard expression, min_b /
+// max_b / div_b / divb_mul — fp32 arithmetic exactly as the reference
+__device__ __forceinline__ void grid_from_box(const float (&mn)[3], const float (&mx)[3], unsigned long long nf, float leaf, bool forced,
+                                              GridDesc& g) {
+  const float inv = __fdiv_rn(1.0f, leaf);  // pcl::VoxelGrid::setLeafSize: inverse_leaf_size_ = 1.0f / leaf
+  long long d[3];
+  for (int a = 0; a < 3; ++a) {
+    g.leaf[a] = leaf;
+    g.inv_leaf[a] = inv;
+    g.min_p[a] = mn[a];
+    g.max_p[a] = mx[a];
+    // …_impl.hpp:75-77  int64((max - min) * inv_leaf) + 1, fp32 arithmetic
+    d[a] = static_cast<long long>(__fmul_rn(__fsub_rn(mx[a], mn[a]), inv)) + 1;
+    // …_impl.hpp:87-92
+    g.min_b[a] = static_cast<int>(floorf(__fmul_rn(mn[a], inv)));
+    g.max_b[a] = static_cast<int>(floorf(__fmul_rn(mx[a], inv)));
+    g.div_b[a] = g.max_b[a] - g.min_b[a] + 1;
+  }
+  g.ncell = d[0] * d[1] * d[2];
+  g.overflow = ((nf > 0 || forced) && g.ncell > 2147483647ll) ? 1 : 0;
+  g.mul[0] = 1;
+  g.mul[1] = g.div_b[0];
+  g.mul[2] = g.div_b[0] * g.div_b[1];
+  g.n_finite = static_cast<int>(nf);
+}
+
 struct ForcedBox {  // sharded build: every rank keys its slice with the bounding box of the WHOLE cloud
   int use;
   float mn[3], mx[3];
@@ -105,26 +131,7 @@ grid_setup_kernel(const float* __restrict__ partial, const unsigned int* __restr
     for (int a = 0; a < 3; ++a) { mn[a] = forced.mn[a]; mx[a] = forced.mx[a]; }
   }
   GridDesc g;
-  const float inv = __fdiv_rn(1.0f, leaf);  // pcl::VoxelGrid::setLeafSize: inverse_leaf_size_ = 1.0f / leaf
-  long long d[3];
-  for (int a = 0; a < 3; ++a) {
-    g.leaf[a] = leaf;
-    g.inv_leaf[a] = inv;
-    g.min_p[a] = mn[a];
-    g.max_p[a] = mx[a];
-    // …_impl.hpp:75-77  int64((max - min) * inv_leaf) + 1, fp32 arithmetic
-    d[a] = static_cast<long long>(__fmul_rn(__fsub_rn(mx[a], mn[a]), inv)) + 1;
-    // …_impl.hpp:87-92
-    g.min_b[a] = static_cast<int>(floorf(__fmul_rn(mn[a], inv)));
-    g.max_b[a] = static_cast<int>(floorf(__fmul_rn(mx[a], inv)));
-    g.div_b[a] = g.max_b[a] - g.min_b[a] + 1;
-  }
-  g.ncell = d[0] * d[1] * d[2];
-  g.overflow = ((nf > 0 || forced.use) && g.ncell > 2147483647ll) ? 1 : 0;
-  g.mul[0] = 1;
-  g.mul[1] = g.div_b[0];
-  g.mul[2] = g.div_b[0] * g.div_b[1];
-  g.n_finite = static_cast<int>(nf);
+  grid_from_box(mn, mx, nf, leaf, forced.use != 0, g);
   *out = g;
 }
 
