@@ -340,11 +340,14 @@ int finalize_and_index(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite, con
 }
 
 // ---- scan-sized clouds: the whole build (mode 0) or the VoxelGrid downsample (mode 1) in ONE cooperative launch ----
-bool use_fused_build(size_t n) {
+// Rule: a scan-sized cloud on a handle in latency mode (one pipeline owns the GPU: the mapping loop, a single caller) is
+// built by the fused kernel; handles in throughput mode (many pairs in flight) keep the staged kernels — their small
+// launches from different streams interleave freely, whereas cooperative launches must each be fully co-resident.
+bool use_fused_build(const ndtb200_handle* h, size_t n) {
   const char* e = getenv("NDTB200_BUILD_PATH");  // tests: "staged" / "fused" force one path (bit-identical results)
   if (e && std::strcmp(e, "staged") == 0) return false;
   if (e && std::strcmp(e, "fused") == 0) return n > 0 && n <= (size_t)0x7fffffff / 64;
-  return n > 0 && n <= kSmallMaxPoints;
+  return n > 0 && n <= kSmallMaxPoints && h->shape == 0;
 }
 
 // Leaves: h->grid (host copy), *n_vox_out; mode 0: records / icov64 / moments / voxel lists / n_valid counter;
@@ -361,7 +364,7 @@ int run_fused_build(ndtb200_handle* h, const float4* pts, size_t n, int dense, i
   CK(h->d_vals_a.ensure(n * sizeof(uint32_t)));
   CK(h->d_vals_b.ensure(n * sizeof(uint32_t)));
   CK(h->d_hist.ensure((size_t)256 * ntiles * sizeof(uint32_t)));
-  CK(h->d_scan_tmp.ensure((size_t)(stiles + 64) * sizeof(uint32_t)));
+  CK(h->d_scan_tmp.ensure((size_t)(stiles + 64 + 1024) * sizeof(uint32_t)));
   CK(h->d_voxel_key.ensure(n * sizeof(int32_t)));
   CK(h->d_voxel_start.ensure(n * sizeof(uint32_t)));
   if (mode == 0) {
@@ -380,6 +383,8 @@ int run_fused_build(ndtb200_handle* h, const float4* pts, size_t n, int dense, i
   a.keys_a = h->d_keys_a.as<uint32_t>(); a.keys_b = h->d_keys_b.as<uint32_t>();
   a.vals_a = h->d_vals_a.as<uint32_t>(); a.vals_b = h->d_vals_b.as<uint32_t>();
   a.hist = h->d_hist.as<uint32_t>(); a.tile_heads = h->d_scan_tmp.as<uint32_t>();
+  a.digit_totals = h->d_scan_tmp.as<uint32_t>() + ((stiles + 63) & ~63);
+  CK(cudaMemsetAsync(a.digit_totals, 0, 1024 * sizeof(uint32_t), h->stream));
   a.barrier = reinterpret_cast<unsigned int*>(sc + 192);
   a.grid = h->d_grid.as<GridDesc>(); a.n_vox = reinterpret_cast<uint32_t*>(sc); a.n_valid = reinterpret_cast<unsigned int*>(sc + 16);
   a.voxel_key = h->d_voxel_key.as<int32_t>(); a.voxel_start = h->d_voxel_start.as<uint32_t>();
@@ -415,7 +420,7 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
   const float4* pts = h->d_target.as<float4>();
   const int dense = h->target_dense ? 1 : 0;
 
-  if (!o.partial_only && !o.forced_min && use_fused_build(n)) {  // scan-sized cloud: one cooperative launch
+  if (!o.partial_only && !o.forced_min && use_fused_build(h, n)) {  // scan-sized cloud: one cooperative launch
     uint32_t n_vox = 0;
     int st = run_fused_build(h, pts, n, dense, 0, h->prm.resolution, &n_vox);
     if (st != NDTB200_OK) return st;
@@ -1538,7 +1543,7 @@ static int voxelgrid_filter_impl(ndtb200_handle* h, float leaf, int64_t* n_out) 
   a->prm.resolution = leaf;
   const float4* pts = a->d_target.as<float4>();
   std::memset(&a->grid, 0, sizeof(GridDesc));
-  if (use_fused_build(n)) {  // scan-sized cloud: one cooperative launch, centroids left in a->d_out
+  if (use_fused_build(a, n)) {  // scan-sized cloud: one cooperative launch, centroids left in a->d_out
     uint32_t n_vox = 0;
     const int stf = run_fused_build(a, pts, n, /*dense=*/0, 1, leaf, &n_vox);
     if (stf != NDTB200_OK) return stf;
@@ -1696,6 +1701,20 @@ int ndtb200_mapper_create(ndtb200_mapper** out, int device, const ndtb200_params
   if (ndt_params) p = *ndt_params;
   else { p.trans_eps = 0.01; p.max_iterations = 64; }  // the node's defaults (ndt_rosbag_mapping_node.cpp:83-88)
   for (int i = 0; i < 2 && st == NDTB200_OK; ++i) st = ndtb200_set_params(m->ndt[i], &p);
+  if (st == NDTB200_OK) st = ensure_aux(m->vg);
+  if (st == NDTB200_OK) {
+    // reserve the buffers that grow with the drive up front (a 2 M-point global map, 256 k-point scans): cudaMalloc /
+    // cudaFree in the middle of the loop are device-wide synchronisations worth tens of milliseconds
+    const size_t map_pts = 2u << 20, scan_pts = 256u << 10;
+    ndtb200_handle* a = m->vg->aux;
+    bool ok = m->d_map[0].ensure(map_pts * 16) == cudaSuccess && m->d_map[1].ensure(map_pts * 16) == cudaSuccess &&
+              m->d_raw.ensure(scan_pts * 16) == cudaSuccess && m->d_filtered.ensure(scan_pts * 16) == cudaSuccess &&
+              a->d_target.ensure(map_pts * 16) == cudaSuccess && a->d_out.ensure(map_pts * 16) == cudaSuccess &&
+              a->d_keys_a.ensure(map_pts * 4) == cudaSuccess && a->d_keys_b.ensure(map_pts * 4) == cudaSuccess &&
+              a->d_vals_a.ensure(map_pts * 4) == cudaSuccess && a->d_vals_b.ensure(map_pts * 4) == cudaSuccess &&
+              a->d_voxel_key.ensure(map_pts * 4) == cudaSuccess && a->d_voxel_start.ensure(map_pts * 4) == cudaSuccess;
+    if (!ok) st = NDTB200_ERR_CUDA;
+  }
   if (st != NDTB200_OK) { ndtb200_mapper_destroy(m); return st; }
   *out = m;
   return NDTB200_OK;

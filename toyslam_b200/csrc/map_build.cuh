@@ -231,9 +231,11 @@ __device__ __forceinline__ unsigned int digit_peers(uint32_t d, bool valid) {
 // Count pass: only the per-tile digit totals are needed (no ranks), so shared-memory atomics do: a round whose 32 keys
 // share one digit (clouds in scan order) is added by one lane, otherwise every lane adds 1 to its warp's private bin.
 // Tile `tile` of ROUNDS x 256 keys; called by all 256 threads of a CTA.  warp_cnt: [kSortWarps][256] shared words.
+// digit_totals != nullptr (fused small build): the tile's counts go to hist[tile][digit] (tile-major) and are added to
+// digit_totals[digit]; otherwise hist[digit][tile] for the staged path's global scan.
 template <int ROUNDS>
 __device__ __forceinline__ void radix_count_tile(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t* __restrict__ hist,
-                                                 int ntiles, int tile, uint32_t (*warp_cnt)[256]) {
+                                                 int ntiles, int tile, uint32_t (*warp_cnt)[256], uint32_t* digit_totals = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = threadIdx.x; d < 256 * kSortWarps; d += kBuildThreads) (&warp_cnt[0][0])[d] = 0u;
   __syncthreads();
@@ -261,7 +263,12 @@ __device__ __forceinline__ void radix_count_tile(const uint32_t* __restrict__ ke
   uint32_t sum = 0;
 #pragma unroll
   for (int w = 0; w < kSortWarps; ++w) sum += warp_cnt[w][d];
-  hist[(size_t)d * ntiles + tile] = sum;
+  if (digit_totals) {
+    hist[(size_t)tile * 256 + d] = sum;
+    if (sum) atomicAdd(digit_totals + d, sum);
+  } else {
+    hist[(size_t)d * ntiles + tile] = sum;
+  }
   __syncthreads();
 }
 
@@ -278,7 +285,7 @@ __device__ __forceinline__ void radix_scatter_tile(const uint32_t* __restrict__ 
                                                    int shift, const uint32_t* __restrict__ hist_scanned, int ntiles, int tile,
                                                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                    uint32_t (*warp_cnt)[256], uint32_t* s_dstart, uint32_t* s_gbase, uint32_t* s_scan,
-                                                   uint32_t* s_key, uint32_t* s_val) {
+                                                   uint32_t* s_key, uint32_t* s_val, const uint32_t* digit_totals = nullptr) {
   constexpr int kTile = kBuildThreads * ROUNDS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = threadIdx.x; d < 256 * kSortWarps; d += kBuildThreads) (&warp_cnt[0][0])[d] = 0u;
@@ -321,7 +328,26 @@ __device__ __forceinline__ void radix_scatter_tile(const uint32_t* __restrict__ 
     uint32_t total;
     const uint32_t dstart = block_exclusive_scan(off, s_scan, total);
     s_dstart[d] = dstart;
-    s_gbase[d] = __ldcg(hist_scanned + (size_t)d * ntiles + tile) - dstart;
+    uint32_t gpos;
+    if (digit_totals) {
+      // fused small build: no global scan — position of (digit d, this tile) = keys with a smaller digit (exclusive
+      // scan of the digit totals) + keys with digit d in earlier tiles (tile-major histogram: coalesced, 8 loads in flight)
+      uint32_t before = 0;
+      int t = 0;
+      for (; t + 8 <= tile; t += 8) {
+        uint32_t c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[u] = __ldcg(hist_scanned + (size_t)(t + u) * 256 + d);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) before += c[u];
+      }
+      for (; t < tile; ++t) before += __ldcg(hist_scanned + (size_t)t * 256 + d);
+      uint32_t tot_all;
+      gpos = block_exclusive_scan(__ldcg(digit_totals + d), s_scan, tot_all) + before;
+    } else {
+      gpos = __ldcg(hist_scanned + (size_t)d * ntiles + tile);
+    }
+    s_gbase[d] = gpos - dstart;
   }
   __syncthreads();
 #pragma unroll

@@ -8,7 +8,8 @@
 // grid description and the voxel count it needs for the index allocation:
 //
 //   bounding box -> grid description (every CTA derives the identical GridDesc from the CTA partials)
-//   keys -> [ count | scan (CTA 0) | scatter ] x passes      (the same tile code as the staged path, 512-key tiles)
+//   keys -> [ count | scatter ] x passes      (the same tile code as the staged path, 512-key tiles; the tile offsets
+//           come from a tile-major histogram + digit totals, so no global scan phase is needed)
 //   segment heads (count | scan (CTA 0) | write) -> voxel list
 //   MODE 0: per-voxel fp64 moments + finalize (mean, covariance, eigen-regularisation, inverse) -> records
 //   MODE 1: per-voxel fp32 centroid in input order (pcl::VoxelGrid)                              -> float4 cloud
@@ -21,7 +22,7 @@ namespace ndtb200 {
 
 constexpr int kSmallRounds = 2;                                 // 512-key sort tiles: a 30 k-point scan spreads over 59 CTAs
 constexpr int kSmallTile = kBuildThreads * kSmallRounds;
-constexpr size_t kSmallMaxPoints = 262144;                      // above this the staged streaming kernels win
+constexpr size_t kSmallMaxPoints = 65536;                       // above this the staged streaming kernels win
 
 struct SmallBuildArgs {
   const float4* pts;
@@ -35,7 +36,8 @@ struct SmallBuildArgs {
   float* mm_partial;            // [grid][6]
   unsigned int* mm_finite;      // [grid]
   uint32_t *keys_a, *keys_b, *vals_a, *vals_b;
-  uint32_t* hist;               // [256][ntiles]
+  uint32_t* hist;               // [ntiles][256] (tile-major)
+  uint32_t* digit_totals;       // [4 passes][256], zeroed before the launch
   uint32_t* tile_heads;         // [ceil(n / kScanTile)]
   unsigned int* barrier;        // zeroed before the launch
   // outputs
@@ -201,13 +203,12 @@ small_build_kernel(const SmallBuildArgs a) {
   uint32_t *ka = a.keys_a, *kb = a.keys_b, *va = a.vals_a, *vb = a.vals_b;
   for (int pass = 0; pass < passes; ++pass) {
     const int shift = pass * 8;
-    for (int t = blockIdx.x; t < ntiles; t += G) radix_count_tile<kSmallRounds>(ka, n, shift, a.hist, ntiles, t, warp_cnt);
-    small_grid_sync(a.barrier, phase);
-    if (blockIdx.x == 0) cta_exclusive_scan_inplace(a.hist, 256u * static_cast<uint32_t>(ntiles), s_scan);
+    uint32_t* totals = a.digit_totals + pass * 256;
+    for (int t = blockIdx.x; t < ntiles; t += G) radix_count_tile<kSmallRounds>(ka, n, shift, a.hist, ntiles, t, warp_cnt, totals);
     small_grid_sync(a.barrier, phase);
     for (int t = blockIdx.x; t < ntiles; t += G)
       radix_scatter_tile<kSmallRounds>(ka, pass == 0 ? nullptr : va, n, shift, a.hist, ntiles, t, kb, vb, warp_cnt, s_dstart, s_gbase,
-                                       s_scan, s_key, s_val);
+                                       s_scan, s_key, s_val, totals);
     small_grid_sync(a.barrier, phase);
     uint32_t* tk = ka; ka = kb; kb = tk;
     uint32_t* tv = va; va = vb; vb = tv;
