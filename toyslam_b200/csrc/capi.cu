@@ -75,6 +75,7 @@ struct ndtb200_handle {
   DevBuf d_voxel_key, d_voxel_start, d_voxel_count, d_moments, d_records, d_icov64, d_hash, d_dense;
   size_t n_partials = 0;       // voxels of the last partial-only build (sharded build, before the exchange)
   bool map_is_merged = false;
+  bool prefer_fused_build = false;  // set by the mapping pipeline: fused builds even with the small-CTA solve shape
   DevBuf d_centroid;              // KDTREE mode: fp32 centroid of every voxel
   bool centroids_valid = false;
   DevBuf d_cell_all, d_best;      // getFitnessScore: cell table over all occupied voxels, per-query results
@@ -347,7 +348,7 @@ bool use_fused_build(const ndtb200_handle* h, size_t n) {
   const char* e = getenv("NDTB200_BUILD_PATH");  // tests: "staged" / "fused" force one path (bit-identical results)
   if (e && std::strcmp(e, "staged") == 0) return false;
   if (e && std::strcmp(e, "fused") == 0) return n > 0 && n <= (size_t)0x7fffffff / 64;
-  return n > 0 && n <= kSmallMaxPoints && h->shape == 0;
+  return n > 0 && n <= kSmallMaxPoints && (h->shape == 0 || h->prefer_fused_build);
 }
 
 // Leaves: h->grid (host copy), *n_vox_out; mode 0: records / icov64 / moments / voxel lists / n_valid counter;
@@ -1701,6 +1702,12 @@ int ndtb200_mapper_create(ndtb200_mapper** out, int device, const ndtb200_params
   if (ndt_params) p = *ndt_params;
   else { p.trans_eps = 0.01; p.max_iterations = 64; }  // the node's defaults (ndt_rosbag_mapping_node.cpp:83-88)
   for (int i = 0; i < 2 && st == NDTB200_OK; ++i) st = ndtb200_set_params(m->ndt[i], &p);
+  for (int i = 0; i < 2 && st == NDTB200_OK; ++i) {
+    // small-CTA solve shape (16 k registers per SM) so that the other handle's fused build kernel (one 256-thread CTA per
+    // SM) can be co-resident: the map of scan k+1 is built while scan k+1 is still being aligned
+    m->ndt[i]->shape = 1;
+    m->ndt[i]->prefer_fused_build = true;
+  }
   if (st == NDTB200_OK) st = ensure_aux(m->vg);
   if (st == NDTB200_OK) {
     // reserve the buffers that grow with the drive up front (a 2 M-point global map, 256 k-point scans): cudaMalloc /
