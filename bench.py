@@ -587,7 +587,7 @@ def run_c3(args):
         hosts.append(hb)
     guesses = [np.eye(4)] + [workloads.relative_pose_matrix(poses[k - 1], poses[k]) for k in range(1, nd)]
     truths = [workloads.relative_pose_matrix(poses[k], poses[k + 1]) for k in range(nd)]
-    L = args.c3_lanes
+    L = args.c3_lanes if args.c3_lanes > 0 else max(2, min(8, (os.cpu_count() or 16) // (2 * max(1, world))))
     lanes = []
     for _ in range(L):
         ndt = nb.NormalDistributionsTransform(device=local)
@@ -878,7 +878,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "mapper"])
     ap.add_argument("--mapper-scans", type=int, default=200)
     ap.add_argument("--c3-distinct", type=int, default=128, help="distinct consecutive pairs generated per GPU (cycled)")
-    ap.add_argument("--c3-lanes", type=int, default=8, help="handles (+ host threads) per GPU for the c3 pipeline")
+    ap.add_argument("--c3-lanes", type=int, default=0,
+                    help="handles (+ host threads) per GPU for the c3 pipeline; 0 = auto: min(8, host cores / (2 * GPUs)), at least 2 "
+                         "(every lane is a host thread that spins in stream synchronisation: do not oversubscribe the host)")
     ap.add_argument("--c5-points", type=int, nargs="+", default=[10_000_000, 100_000_000])
     ap.add_argument("--c5-res", type=float, nargs="+", default=[0.5, 1.0, 2.0])
     ap.add_argument("--c4-scans", type=int, default=16)

@@ -341,20 +341,27 @@ int finalize_and_index(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite, con
 }
 
 // ---- scan-sized clouds: the whole build (mode 0) or the VoxelGrid downsample (mode 1) in ONE cooperative launch ----
-// Rule: a scan-sized cloud on a handle in latency mode (one pipeline owns the GPU: the mapping loop, a single caller) is
-// built by the fused kernel; handles in throughput mode (many pairs in flight) keep the staged kernels — their small
-// launches from different streams interleave freely, whereas cooperative launches must each be fully co-resident.
+// Rule: a scan-sized cloud is built by the fused kernel.  On a handle in latency mode (one pipeline owns the GPU: the
+// mapping loop, a single caller) it spreads over all SMs; on a handle in throughput mode (many pairs in flight on their
+// own streams) it takes 16 CTAs, because every cooperative launch must be fully co-resident: several builds and solves
+// then run side by side, and a pair costs ~4 launches instead of ~30 (measured on c3: 11.8 k pairs/s vs 9.8 k staged,
+// 8.2 k with 32 CTAs, 10.9 k with 8).
+constexpr int kFusedCtasThroughput = 16;
 bool use_fused_build(const ndtb200_handle* h, size_t n) {
   const char* e = getenv("NDTB200_BUILD_PATH");  // tests: "staged" / "fused" force one path (bit-identical results)
   if (e && std::strcmp(e, "staged") == 0) return false;
   if (e && std::strcmp(e, "fused") == 0) return n > 0 && n <= (size_t)0x7fffffff / 64;
-  return n > 0 && n <= kSmallMaxPoints && (h->shape == 0 || h->prefer_fused_build);
+  return n > 0 && n <= kSmallMaxPoints;
 }
 
 // Leaves: h->grid (host copy), *n_vox_out; mode 0: records / icov64 / moments / voxel lists / n_valid counter;
 // mode 1: centroids in h->d_out.  The sorted point indices end up in h->d_vals_a.  One host synchronisation.
 int run_fused_build(ndtb200_handle* h, const float4* pts, size_t n, int dense, int mode, float leaf, uint32_t* n_vox_out) {
-  const int G = std::min(h->num_sms, grid_for(n, kBuildThreads, h->num_sms));
+  int G = std::min(h->num_sms, grid_for(n, kBuildThreads, h->num_sms));
+  // throughput mode: many builds are in flight on different streams; a cooperative launch must be fully co-resident, so
+  // each one takes only a slice of the SMs and several of them run side by side
+  if (h->shape == 1 && !h->prefer_fused_build) G = std::min(G, kFusedCtasThroughput);
+  if (const char* e = getenv("NDTB200_FUSED_CTAS")) { const int c = atoi(e); if (c >= 1) G = std::min(G, c); }  // tuning
   const int ntiles = static_cast<int>((n + kSmallTile - 1) / kSmallTile);
   const int stiles = static_cast<int>((n + kScanTile - 1) / kScanTile);
   CK(h->d_mm_partial.ensure((size_t)G * 6 * sizeof(float)));
