@@ -120,6 +120,19 @@ int main(int argc, char** argv) {
   for (auto& o : objs) std::cout << " " << o.getFinalNumIteration();
   std::cout << std::endl;
 
+  // the mapping-node loop on the pipeline API: the two clouds as two consecutive scans
+  {
+    pclomp_b200::Mapper<pcl::PointXYZ> mapper(0.3f, 0.5f);
+    if (mapper.ok()) {
+      mapper.pushScan(*target_cloud);
+      const auto step = mapper.pushScan(*source_cloud);
+      Cloud gmap;
+      mapper.globalMap(gmap);
+      std::cout << "mapper: 2 scans, converged " << step.converged << ", iterations " << step.iterations << ", filtered " << step.n_filtered
+                << " pts, map " << gmap.size() << " pts" << std::endl;
+    }
+  }
+
   // --save-aligned out.pcd: the aligned source of the DIRECT7 copy as a binary PCD (pcl::io::savePCDFileBinary)
   for (int i = 3; i + 1 < argc; ++i)
     if (std::string(argv[i]) == "--save-aligned") {

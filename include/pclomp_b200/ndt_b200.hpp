@@ -251,4 +251,55 @@ class VoxelGrid {
   PointCloudConstPtr input_;
 };
 
+// The mapping-node loop (lidar_subscriber/src/ndt_rosbag_mapping_node.cpp:42-161) on the device-resident pipeline
+// (ndtb200_mapper_*): one pushScan() per raw scan replaces downsample_cloud + perform_registration + pose chaining +
+// update_global_map; globalMap() is what publish_global_map() sends.
+template <typename PointT>
+class Mapper {
+ public:
+  struct Step {
+    Eigen::Matrix4f transform, pose;
+    double fitness;
+    bool converged;
+    int iterations;
+    size_t n_filtered, n_map;
+  };
+  explicit Mapper(float voxel_leaf = 0.3f, float map_voxel = 0.5f, int device = 0, bool compute_fitness = true) : m_(nullptr) {
+    if (ndtb200_mapper_create(&m_, device, nullptr, voxel_leaf, map_voxel, compute_fitness ? 1 : 0) != NDTB200_OK) m_ = nullptr;
+  }
+  ~Mapper() { if (m_) ndtb200_mapper_destroy(m_); }
+  Mapper(const Mapper&) = delete;
+  Mapper& operator=(const Mapper&) = delete;
+  bool ok() const { return m_ != nullptr; }
+  Step pushScan(const pcl::PointCloud<PointT>& cloud) {
+    Step out;
+    out.transform = Eigen::Matrix4f::Identity();
+    out.pose = Eigen::Matrix4f::Identity();
+    out.fitness = 0; out.converged = false; out.iterations = 0; out.n_filtered = 0; out.n_map = 0;
+    if (!m_) return out;
+    ndtb200_mapper_step s;
+    const int st = ndtb200_mapper_push_scan(m_, cloud.points.empty() ? nullptr : cloud.points.data(), cloud.points.size(), sizeof(PointT), &s);
+    if (st != NDTB200_OK) { std::fprintf(stderr, "[pclomp_b200::Mapper] push_scan failed: %s\n", ndtb200_mapper_last_error(m_)); return out; }
+    for (int c = 0; c < 4; ++c)
+      for (int r = 0; r < 4; ++r) { out.transform(r, c) = s.transform[c * 4 + r]; out.pose(r, c) = s.pose[c * 4 + r]; }
+    out.fitness = s.fitness; out.converged = s.converged != 0; out.iterations = s.iterations;
+    out.n_filtered = static_cast<size_t>(s.n_filtered); out.n_map = static_cast<size_t>(s.n_map);
+    return out;
+  }
+  void globalMap(pcl::PointCloud<PointT>& out) {
+    out.points.clear();
+    int64_t n = 0;
+    if (!m_ || ndtb200_mapper_get_map(m_, nullptr, 0, sizeof(PointT), &n) != NDTB200_OK || n == 0) { out.width = 0; out.height = 1; return; }
+    struct Rec { float x, y, z, w; };
+    std::vector<Rec> tmp(static_cast<size_t>(n));
+    ndtb200_mapper_get_map(m_, tmp.data(), tmp.size(), sizeof(Rec), &n);
+    out.points.resize(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) { PointT p = PointT(); p.x = tmp[i].x; p.y = tmp[i].y; p.z = tmp[i].z; out.points[static_cast<size_t>(i)] = p; }
+    out.width = static_cast<uint32_t>(n); out.height = 1; out.is_dense = true;
+  }
+
+ private:
+  ndtb200_mapper* m_;
+};
+
 }  // namespace pclomp_b200

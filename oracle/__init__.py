@@ -256,6 +256,8 @@ class NormalDistributionsTransform:
 
     def eval_derivatives(self, p, T=None, compute_hessian=True):
         p = np.ascontiguousarray(p, dtype=np.float64)
+        if T is not None and np.ndim(T) != 2:
+            raise TypeError("T must be a 4x4 matrix or None (pass compute_hessian by keyword)")
         Tc = None if T is None else np.ascontiguousarray(np.asarray(T, dtype=np.float32).T).reshape(-1)
         out = np.empty(43, dtype=np.float64)
         hits = self._L.ndto_eval_derivatives(self._h, _f64(p), _f32(Tc) if Tc is not None else None,
@@ -264,6 +266,8 @@ class NormalDistributionsTransform:
 
     def eval_hessian(self, p, T=None):
         p = np.ascontiguousarray(p, dtype=np.float64)
+        if T is not None and np.ndim(T) != 2:
+            raise TypeError("T must be a 4x4 matrix or None (pass compute_hessian by keyword)")
         Tc = None if T is None else np.ascontiguousarray(np.asarray(T, dtype=np.float32).T).reshape(-1)
         out = np.empty(36, dtype=np.float64)
         self._L.ndto_eval_hessian(self._h, _f64(p), _f32(Tc) if Tc is not None else None, _f64(out))

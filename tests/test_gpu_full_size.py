@@ -76,7 +76,7 @@ def test_full_size_derivative_linearity_and_align(nb, c2):
     parts = []
     for part in (src, src[: len(src) // 2], src[len(src) // 2:]):
         g.setInputSource(part)
-        parts.append(g.eval_derivatives(p, True))
+        parts.append(g.eval_derivatives(p, compute_hessian=True))
     whole, a, b = parts
     assert whole["hits"] == a["hits"] + b["hits"]
     # (the point -> thread assignment changes with the split, so the fp32 partial sums round differently: 2e-6)
@@ -86,7 +86,7 @@ def test_full_size_derivative_linearity_and_align(nb, c2):
     # the oracle on the full-size pair
     ref = oracle.NormalDistributionsTransform()
     ref.setInputTarget(tgt); ref.setInputSource(src)
-    e = ref.eval_derivatives(p, True)
+    e = ref.eval_derivatives(p, compute_hessian=True)
     assert whole["hits"] == e["hits"]
     assert rel_err(whole["gradient"], e["gradient"]) < 1e-5 and rel_err(whole["hessian"], e["hessian"]) < 1e-5
     g.setInputSource(src)

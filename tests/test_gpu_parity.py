@@ -291,7 +291,7 @@ def test_hash_index_fallback(nb, method, monkeypatch):
     assert np.array_equal(gpu_hash.lookup(q, method), ref.lookup(q, method))
     assert np.array_equal(gpu_dense.lookup(q, method), ref.lookup(q, method))
     p = np.array([0.4, 0.1, -0.02, 0.005, -0.001, -0.01])
-    a, b = gpu_hash.eval_derivatives(p, True), gpu_dense.eval_derivatives(p, True)
+    a, b = gpu_hash.eval_derivatives(p, compute_hessian=True), gpu_dense.eval_derivatives(p, compute_hessian=True)
     assert a["score"] == b["score"] and np.array_equal(a["gradient"], b["gradient"]) and np.array_equal(a["hessian"], b["hessian"])
     gpu_hash.align()
     gpu_dense.align()
@@ -386,7 +386,7 @@ def test_align_throughput_shape(nb, method):
     gpu.set_throughput_mode(True)
     check_align(ref, gpu)
     for p in POSES[:3]:
-        a, b = gpu.eval_derivatives(p, True), ref.eval_derivatives(p, True)
+        a, b = gpu.eval_derivatives(p, compute_hessian=True), ref.eval_derivatives(p, compute_hessian=True)
         assert rel_err(a["gradient"], b["gradient"]) < REL and rel_err(a["hessian"], b["hessian"]) < REL
         assert rel_err(gpu.eval_hessian(p), ref.eval_hessian(p)) < REL
 
@@ -480,9 +480,10 @@ def test_kdtree_mode(nb):
     pass, calculateScore and the whole align against the oracle, and the README's KDTREE fitness 0.213937."""
     tgt, src = load_pair()
     ref, gpu = make_pair(nb, tgt, src, method=oracle.KDTREE)
-    for p in POSES:
-        a, b = gpu.eval_derivatives(p, True), ref.eval_derivatives(p, True)
-        assert a["hits"] == b["hits"] and b["hits"] > 0
+    for ip, p in enumerate(POSES):
+        a, b = gpu.eval_derivatives(p, compute_hessian=True), ref.eval_derivatives(p, compute_hessian=True)
+        assert a["hits"] == b["hits"] and b["hits"] > 0, (ip, p.tolist(), a["hits"], b["hits"], gpu.map_info(), ref.map_info(),
+                                                          float(np.nanmin(tgt)), float(np.nanmax(src)))
         assert abs(a["score"] - b["score"]) <= REL * abs(b["score"])
         assert rel_err(a["gradient"], b["gradient"]) < REL and rel_err(a["hessian"], b["hessian"]) < REL
         assert rel_err(gpu.eval_hessian(p), ref.eval_hessian(p)) < REL
@@ -592,6 +593,8 @@ def test_cpp_shim_app_reproduces_golden_fitness(nb, tmp_path):
     assert abs(float(fit[1]) - golden()["fitness"]["DIRECT1"]) < 1e-6
     assert "copy converged: 1, iterations 5" in out.stdout
     assert re.search(r"batch of 4: .*iterations 5 5 5 5", out.stdout), out.stdout      # alignBatch through the shim
+    mm = re.search(r"mapper: 2 scans, converged (\d), iterations (\d+), filtered (\d+) pts, map (\d+) pts", out.stdout)
+    assert mm and mm.group(1) == "1" and int(mm.group(3)) == len(oracle.voxelgrid_downsample(src, 0.3)) and int(mm.group(4)) > 0
 
 
 def test_cpp_shim_pcd_voxelgrid_pipeline(nb, tmp_path):

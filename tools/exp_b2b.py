@@ -34,5 +34,5 @@ print("blocking align_async+sync: %.1f us per align (wall)" % ((time.perf_counte
 p = np.zeros(6)
 t0 = time.perf_counter()
 for _ in range(100):
-    ndt.eval_derivatives(p, True)
+    ndt.eval_derivatives(p, compute_hessian=True)
 print("eval_derivatives (1 evaluation, blocking): %.1f us (wall); kernel ms (events) %.4f" % ((time.perf_counter() - t0) * 1e4, ndt.last_align_ms()))

@@ -14,7 +14,7 @@ for mode in (False, True):
     ndt.set_throughput_mode(mode)
     ndt.setInputTarget(w['target']); ndt.setInputSource(w['source'])
     p = np.array([0.1, 0.05, 0.0, 0.001, 0.0, 0.01])
-    for name, fn in (("eval+hessian", lambda: ndt.eval_derivatives(p, True)), ("eval no hessian", lambda: ndt.eval_derivatives(p, compute_hessian=False)),
+    for name, fn in (("eval+hessian", lambda: ndt.eval_derivatives(p, compute_hessian=True)), ("eval no hessian", lambda: ndt.eval_derivatives(p, compute_hessian=False)),
                      ("hessian-only fp64", lambda: ndt.eval_hessian(p))):
         fn(); ts = []
         for _ in range(20):

@@ -341,17 +341,18 @@ int finalize_and_index(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite, con
 }
 
 // ---- scan-sized clouds: the whole build (mode 0) or the VoxelGrid downsample (mode 1) in ONE cooperative launch ----
-// Rule: a scan-sized cloud is built by the fused kernel.  On a handle in latency mode (one pipeline owns the GPU: the
-// mapping loop, a single caller) it spreads over all SMs; on a handle in throughput mode (many pairs in flight on their
-// own streams) it takes 16 CTAs, because every cooperative launch must be fully co-resident: several builds and solves
-// then run side by side, and a pair costs ~4 launches instead of ~30 (measured on c3: 11.8 k pairs/s vs 9.8 k staged,
-// 8.2 k with 32 CTAs, 10.9 k with 8).
+// Rule: a scan-sized cloud on a handle in latency mode (one pipeline owns the GPU: a single caller, the mapping loop) is
+// built by the fused kernel.  Handles in throughput mode (many pairs in flight on their own streams) keep the staged
+// kernels by default: every cooperative launch must be fully co-resident, and although 16-CTA fused builds measured
+// 11.8-12.0 k pairs/s on c3 (staged: 9.7-9.8 k; 32-CTA builds 8.2 k, full-width 6.7 k) the same configuration also
+// produced 2.9 k and 6.4 k runs on other boxes — co-scheduling of many concurrent cooperative kernels is not
+// reproducible enough to be the default.  NDTB200_BUILD_PATH=fused selects it.
 constexpr int kFusedCtasThroughput = 16;
 bool use_fused_build(const ndtb200_handle* h, size_t n) {
   const char* e = getenv("NDTB200_BUILD_PATH");  // tests: "staged" / "fused" force one path (bit-identical results)
   if (e && std::strcmp(e, "staged") == 0) return false;
   if (e && std::strcmp(e, "fused") == 0) return n > 0 && n <= (size_t)0x7fffffff / 64;
-  return n > 0 && n <= kSmallMaxPoints;
+  return n > 0 && n <= kSmallMaxPoints && (h->shape == 0 || h->prefer_fused_build);
 }
 
 // Leaves: h->grid (host copy), *n_vox_out; mode 0: records / icov64 / moments / voxel lists / n_valid counter;

@@ -492,6 +492,8 @@ class NormalDistributionsTransform:
 
     def eval_derivatives(self, p, T=None, compute_hessian=True):
         p = np.ascontiguousarray(p, dtype=np.float64)
+        if T is not None and np.ndim(T) != 2:
+            raise TypeError("T must be a 4x4 matrix or None (pass compute_hessian by keyword)")
         Tc = None if T is None else _colmajor(T)
         out = np.empty(43, dtype=np.float64)
         hits = C.c_int64()
@@ -502,6 +504,8 @@ class NormalDistributionsTransform:
 
     def eval_hessian(self, p, T=None):
         p = np.ascontiguousarray(p, dtype=np.float64)
+        if T is not None and np.ndim(T) != 2:
+            raise TypeError("T must be a 4x4 matrix or None (pass compute_hessian by keyword)")
         Tc = None if T is None else _colmajor(T)
         out = np.empty(36, dtype=np.float64)
         self._check(self._L.ndtb200_eval_hessian(self._h, _ptr(p, C.c_double),
