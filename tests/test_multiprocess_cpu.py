@@ -67,3 +67,28 @@ def test_source_range_partition_properties():
             assert sizes.min() >= 0 and (sizes.max() - sizes[sizes > 0].min() <= 32 if (sizes > 0).any() else True)
             # boundaries fall on 32-point groups so every rank's warps stay fully coalesced
             assert all(lo % 32 == 0 for lo, hi in edges if hi > lo)
+
+
+def test_point_range_partition_properties():
+    """Contiguous target-point ranges of the sharded map build: cover [0, n) exactly, sizes differ by at most one."""
+    from toyslam_b200.sharding import point_range
+    for n in (0, 1, 7, 8, 9, 1_000_003, 500_000_000):
+        for world in (1, 2, 3, 4, 8):
+            edges = [point_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:]))
+            sizes = [hi - lo for lo, hi in edges]
+            assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1
+
+
+def test_c_abi_header_symbols_are_exported():
+    """Every function declared in include/ndt_b200.h is exported by libndt_b200.so (no compute call: no GPU needed)."""
+    import toyslam_b200 as nb
+    L = nb.load_library()
+    names = nb.exported_symbols()
+    assert len(names) >= 48
+    for name in names:
+        assert hasattr(L, name), name
+    for must in ("ndtb200_align", "ndtb200_align_batch", "ndtb200_set_target", "ndtb200_voxelgrid_filter", "ndtb200_mapper_push_scan",
+                 "ndtb200_build_from_partials", "ndtb200_fitness_score"):
+        assert must in names

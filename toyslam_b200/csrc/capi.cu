@@ -1301,7 +1301,7 @@ int ndtb200_lookup(ndtb200_handle* h, const void* points, size_t n, size_t strid
     case NDTB200_DIRECT1: lookup_kernel<3><<<blocks, 256, 0, h->stream>>>(q, (int)n, map, d_keys); break;
     case NDTB200_DIRECT7: lookup_kernel<2><<<blocks, 256, 0, h->stream>>>(q, (int)n, map, d_keys); break;
     case NDTB200_DIRECT26: lookup_kernel<1><<<blocks, 256, 0, h->stream>>>(q, (int)n, map, d_keys); break;
-    default: h->err = "search method not implemented (KDTREE)"; return NDTB200_ERR_INVALID;
+    default: h->err = "ndtb200_lookup dumps the DIRECT1/7/26 neighbourhoods (26 columns); KDTREE is checked through eval / align"; return NDTB200_ERR_INVALID;
   }
   LAUNCHED(h);
   CK(cudaMemcpyAsync(out_keys, d_keys, n * 26 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
