@@ -165,3 +165,52 @@ def test_cpp_shim_compiles_and_links():
     import subprocess
     out = subprocess.run([os.path.abspath(app)], capture_output=True, text=True, timeout=60)
     assert "usage: align_b200" in out.stdout
+
+
+def _f32_centroids(points, keys):
+    """pcl::VoxelGrid / Leaf::centroid arithmetic in numpy: per voxel, fp32 sum in input order, then / n."""
+    cent = {}
+    for p, k in zip(points.astype(np.float32), keys):
+        if k < 0:
+            continue
+        s, n = cent.get(k, (np.zeros(3, np.float32), 0))
+        cent[k] = (s + p, n + 1)
+    return {k: (s / np.float32(n), n) for k, (s, n) in cent.items()}
+
+
+def test_oracle_kdtree_neighbourhood_equals_brute_force_radius_search():
+    """KDTREE mode (vgc_h:476-505): the oracle scans the 27 cells around the query; a brute-force radius search over ALL
+    voxel centroids (what FLANN returns) must find the same number of leaves — checks the 27-cell argument."""
+    rng = np.random.default_rng(21)
+    tgt = np.concatenate([rng.uniform(-6, 6, size=(3000, 2)), rng.normal(0, 0.05, size=(3000, 1))], axis=1).astype(np.float32)
+    tgt = np.concatenate([tgt, (rng.uniform(-6, 6, size=(1500, 3)) * np.array([1, 0.02, 0.5]) + np.array([0, 3, 1.5])).astype(np.float32)])
+    src = (tgt[rng.choice(len(tgt), 600, replace=False)] + rng.normal(0, 0.4, size=(600, 3))).astype(np.float32)
+    n = oracle.NormalDistributionsTransform()
+    n.setNeighborhoodSearchMethod(oracle.KDTREE)
+    assert n.setInputTarget(tgt) == 0
+    n.setInputSource(src)
+    hits = n.eval_derivatives(np.zeros(6), compute_hessian=False)["hits"]
+    cent = _f32_centroids(tgt, n.point_keys())
+    c = np.array([v[0] for v in cent.values() if v[1] >= 6], dtype=np.float32)
+    d = src[:, None, :] - c[None, :, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]     # L2_Simple order, fp32
+    assert hits == int((d2 < np.float32(1.0)).sum()) and hits > 500
+
+
+def test_oracle_voxelgrid_matches_independent_numpy_centroids():
+    rng = np.random.default_rng(22)
+    for leaf in (0.1, 0.37, 1.0):
+        pts = (rng.uniform(-3, 3, size=(4000, 3)) * np.array([1.0, 0.5, 0.1])).astype(np.float32)
+        pts[::101] = np.nan
+        out = oracle.voxelgrid_downsample(pts, leaf)
+        fin = np.isfinite(pts).all(axis=1)
+        inv = np.float32(1.0) / np.float32(leaf)
+        mn = np.floor(pts[fin].min(axis=0) * inv).astype(np.int64)
+        mx = np.floor(pts[fin].max(axis=0) * inv).astype(np.int64)
+        div = mx - mn + 1
+        with np.errstate(invalid="ignore"):
+            ijk = (np.floor(np.nan_to_num(pts) * inv) - mn.astype(np.float32)).astype(np.int64)
+        keys = np.where(fin, ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1], -1)
+        cent = _f32_centroids(np.nan_to_num(pts), keys)
+        exp = np.array([cent[k][0] for k in sorted(cent)], dtype=np.float32)
+        assert out.shape == exp.shape and np.array_equal(out, exp)
