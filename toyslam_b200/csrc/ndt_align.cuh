@@ -812,6 +812,7 @@ __device__ __noinline__ int newton_post() {
   while (true) {
     const double* delta = st.delta;  // a zero-length step leaves H and g unchanged: same solution next round
     double nrm = 0;
+#pragma unroll
     for (int i = 0; i < 6; ++i) nrm += delta[i] * delta[i];
     nrm = sqrt(nrm);
     if (nrm == 0 || nrm != nrm) {  // ndt_omp_impl.hpp:134-139
@@ -826,6 +827,7 @@ __device__ __noinline__ int newton_post() {
     st.step_min = prm.trans_eps / 2;
     st.phi_0 = -st.score;
     double dphi = 0;
+#pragma unroll
     for (int i = 0; i < 6; ++i) dphi += st.g[i] * st.dir[i];
     st.d_phi_0 = -dphi;
     double a_ret = 0;
@@ -836,6 +838,7 @@ __device__ __noinline__ int newton_post() {
         evaluate = false;
       } else {
         st.d_phi_0 *= -1;
+#pragma unroll
         for (int i = 0; i < 6; ++i) st.dir[i] *= -1;
       }
     }
@@ -853,13 +856,16 @@ __device__ __noinline__ int newton_post() {
       a_t = std_min(a_t, st.step_max);
       a_t = std_max(a_t, st.step_min);
       st.a_t = a_t;
+#pragma unroll
       for (int i = 0; i < 6; ++i) st.x_t[i] = st.p[i] + st.dir[i] * a_t;
       st.need_pose = 1;
       st.state = ST_MT_FIRST;
       return ACT_EVAL_FULL;
     }
     // zero-length step: finish this Newton iteration without an evaluation
+#pragma unroll
     for (int i = 0; i < 6; ++i) st.last_dp[i] = st.dir[i] * a_ret;
+#pragma unroll
     for (int i = 0; i < 6; ++i) st.p[i] += st.last_dp[i];
     if (st.nr_iterations > prm.max_iterations || (st.nr_iterations && (fabs(a_ret) < prm.trans_eps))) st.converged = 1;
     st.nr_iterations++;
@@ -884,6 +890,7 @@ __device__ __noinline__ int advance(const double* tot, int kind, TraceRec* trace
     TraceRec& r = trace[st.n_trace];
     r.kind = kind - 1;
     r.pad = 0;
+#pragma unroll
     for (int i = 0; i < 6; ++i) r.x[i] = (st.state == ST_INITIAL || st.state == ST_SINGLE) ? st.p[i] : st.x_t[i];
     r.a_t = (st.state == ST_INITIAL || st.state == ST_SINGLE) ? 0.0 : st.a_t;
     r.score = st.score;
@@ -899,6 +906,7 @@ __device__ __noinline__ int advance(const double* tot, int kind, TraceRec* trace
     case ST_MT_FIRST: {
       st.phi_t = -st.score;
       double d = 0;
+#pragma unroll
       for (int i = 0; i < 6; ++i) d += st.g[i] * st.dir[i];
       st.d_phi_t = -d;
       st.psi_t = st.phi_t - st.phi_0 - mu * st.d_phi_0 * st.a_t;
@@ -908,6 +916,7 @@ __device__ __noinline__ int advance(const double* tot, int kind, TraceRec* trace
     case ST_MT_LOOP: {
       st.phi_t = -st.score;
       double d = 0;
+#pragma unroll
       for (int i = 0; i < 6; ++i) d += st.g[i] * st.dir[i];
       st.d_phi_t = -d;
       st.psi_t = st.phi_t - st.phi_0 - mu * st.d_phi_0 * st.a_t;
@@ -939,6 +948,7 @@ __device__ __noinline__ int advance(const double* tot, int kind, TraceRec* trace
     a_t = std_min(a_t, st.step_max);
     a_t = std_max(a_t, st.step_min);
     st.a_t = a_t;
+#pragma unroll
     for (int i = 0; i < 6; ++i) st.x_t[i] = st.p[i] + st.dir[i] * a_t;
     st.need_pose = 1;
     st.state = ST_MT_LOOP;
@@ -951,7 +961,9 @@ __device__ __noinline__ int advance(const double* tot, int kind, TraceRec* trace
 mt_finish: {
     // back in computeTransformation (ndt_omp_impl.hpp:143-164)
     const double a = st.a_t;
+#pragma unroll
     for (int i = 0; i < 6; ++i) st.last_dp[i] = st.dir[i] * a;
+#pragma unroll
     for (int i = 0; i < 6; ++i) st.p[i] = st.p[i] + st.last_dp[i];
     if (st.nr_iterations > prm.max_iterations || (st.nr_iterations && (fabs(a) < prm.trans_eps))) st.converged = 1;
     st.nr_iterations++;
