@@ -131,6 +131,9 @@ int ndtb200_align_batch_async(ndtb200_handle* const* hs, int n, const float* gue
 /* getFitnessScore(max_range) (pcl::Registration): mean squared distance of T*source to its exact
  * nearest raw target point. */
 int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out);
+/* The two sums behind it (sum of the accepted squared distances, their count): with the source sharded over several
+ * GPUs every rank calls this on its slice and the ranks all-reduce the pair (SURVEY 8e "getFitnessScore"). */
+int ndtb200_fitness_sums(ndtb200_handle* h, double max_range, double* sum_sq_dist, int64_t* n_accepted);
 /* calculateScore(cloud) (ndt_omp_impl.hpp:935-983). */
 int ndtb200_calculate_score(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, double* out);
 

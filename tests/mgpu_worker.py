@@ -38,6 +38,7 @@ def main():
         e = sh.eval_derivatives(np.array([0.3, 0.1, -0.02, 0.004, -0.002, -0.01]))
         sh.align()
         r = sh.result()
+        fit = sh.getFitnessScore()
         # every rank must hold identical bits (rank-ordered sum, redundant identical Newton step)
         blob = [None] * world
         dist.all_gather_object(blob, (r["final"].tobytes(), r["iterations"], r["n_evaluations"], float(e["score"])))
@@ -53,6 +54,7 @@ def main():
             ref.align()
             rr = ref.result()
             dt, dr = transform_delta(r["final"], rr["final"])
+            case.update({"fitness_rel": abs(fit - ref.getFitnessScore()) / ref.getFitnessScore()})
             case.update({"hits_equal": int(e["hits"]) == int(eo["hits"]), "score_rel": abs(e["score"] - eo["score"]) / abs(eo["score"]),
                          "grad_rel": rel_err(e["gradient"], eo["gradient"]), "hess_rel": rel_err(e["hessian"], eo["hessian"]),
                          "iterations": [r["iterations"], rr["iterations"]], "evaluations": [r["n_evaluations"], rr["n_evaluations"]],

@@ -37,6 +37,7 @@ def test_sharded_align_matches_oracle(world):
         assert c["iterations"][0] == c["iterations"][1] and c["evaluations"][0] == c["evaluations"][1], c
         assert c["hessian_passes"][0] == c["hessian_passes"][1], c
         assert c["dt"] < 1e-4 and c["dr"] < 1e-4 and c["tp_rel"] < 1e-5, c
+        assert c["fitness_rel"] < 1e-6, c            # sharded getFitnessScore: all-reduced sums
     # sharded target-map build: keys / counts exact, every rank holds identical bits, moments within 1e-5
     assert len(res["build"]) == 3
     for c in res["build"]:

@@ -536,6 +536,20 @@ def test_mapping_pipeline_matches_reference_loop(nb):
     assert mapper.launch_count() > 0
 
 
+def test_fitness_sums(nb):
+    """ndtb200_fitness_sums returns the two sums behind getFitnessScore (what the ranks of a sharded source all-reduce;
+    the 2-GPU test checks the all-reduced value against the oracle)."""
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src)
+    gpu.align(); ref.align()
+    s, c = gpu.fitness_sums()
+    assert c == len(src)
+    assert abs(gpu.getFitnessScore() - s / c) <= 1e-12 * s / c
+    assert abs(s / c - ref.getFitnessScore()) <= 1e-6 * s / c
+    s2, c2 = gpu.fitness_sums(0.05)                      # max_range is compared with the squared distance (pcl::Registration)
+    assert 0 < c2 < c and abs(s2 / c2 - ref.getFitnessScore(0.05)) <= 1e-6 * s2 / c2
+
+
 def test_calculate_score(nb):
     tgt, src = load_pair()
     ref, gpu = make_pair(nb, tgt, src)

@@ -1079,8 +1079,32 @@ int ndtb200_get_result(ndtb200_handle* h, ndtb200_result* out) {
   return NDTB200_OK;
 }
 
+static int fitness_sums(ndtb200_handle* h, double max_range, double* sum_out, unsigned long long* count_out);
+
 int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out) {
   if (!h || !out) return NDTB200_ERR_INVALID;
+  double s = 0;
+  unsigned long long c = 0;
+  const int st = fitness_sums(h, max_range, &s, &c);
+  if (st != NDTB200_OK) return st;
+  *out = c > 0 ? s / static_cast<double>(c) : 1.7976931348623157e308;
+  return NDTB200_OK;
+}
+
+// The two sums behind getFitnessScore: with the source sharded over several GPUs (every rank holds the full raw target
+// and its source range) the ranks all-reduce {sum of squared distances, accepted count} and divide.
+int ndtb200_fitness_sums(ndtb200_handle* h, double max_range, double* sum_sq_dist, int64_t* n_accepted) {
+  if (!h || !sum_sq_dist || !n_accepted) return NDTB200_ERR_INVALID;
+  *sum_sq_dist = 0;
+  *n_accepted = 0;
+  if (h->has_source && h->has_target && h->n_source == 0 && h->n_target > 0) return NDTB200_OK;  // an empty source slice
+  unsigned long long c = 0;
+  const int st = fitness_sums(h, max_range, sum_sq_dist, &c);
+  *n_accepted = static_cast<int64_t>(c);
+  return st;
+}
+
+static int fitness_sums(ndtb200_handle* h, double max_range, double* sum_out, unsigned long long* count_out) {
   if (!h->has_source || !h->has_target || h->n_source == 0 || h->n_target == 0) {
     h->err = "fitness needs a source and a target";
     return NDTB200_ERR_NO_INPUT;
@@ -1143,7 +1167,8 @@ int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out) {
   double s = 0;
   unsigned long long c = 0;
   for (int b = 0; b < blocks; ++b) { s += hs[b]; c += hc[b]; }
-  *out = c > 0 ? s / static_cast<double>(c) : 1.7976931348623157e308;
+  *sum_out = s;
+  *count_out = c;
   return NDTB200_OK;
 }
 

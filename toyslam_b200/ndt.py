@@ -105,6 +105,7 @@ def load_library():
     L.ndtb200_align_batch_async.argtypes = [C.POINTER(vp), C.c_int, f32p, C.POINTER(vp), C.c_size_t]
     L.ndtb200_get_result.argtypes = [vp, C.POINTER(Result)]
     L.ndtb200_fitness_score.argtypes = [vp, C.c_double, f64p]
+    L.ndtb200_fitness_sums.argtypes = [vp, C.c_double, f64p, i64p]
     L.ndtb200_calculate_score.argtypes = [vp, vp, C.c_size_t, C.c_size_t, f64p]
     L.ndtb200_get_map_info.argtypes = [vp, C.POINTER(MapInfo)]
     L.ndtb200_dump_point_keys.argtypes = [vp, i32p]
@@ -458,6 +459,12 @@ class NormalDistributionsTransform:
         v = C.c_double()
         self._check(self._L.ndtb200_fitness_score(self._h, float(max_range), C.byref(v)))
         return v.value
+
+    def fitness_sums(self, max_range=np.finfo(np.float64).max):
+        """(sum of accepted squared nearest-neighbour distances, count) of this handle's source: for sharded sources."""
+        s, c = C.c_double(0), C.c_int64(0)
+        self._check(self._L.ndtb200_fitness_sums(self._h, float(max_range), C.byref(s), C.byref(c)))
+        return float(s.value), int(c.value)
 
     def calculateScore(self, points):
         p = as_xyzw(points)

@@ -122,3 +122,17 @@ class ShardedNdt:
 
     def result(self):
         return self.ndt.result()
+
+    def getFitnessScore(self, max_range=float("inf")):
+        """pcl::Registration::getFitnessScore of the whole (sharded) source: every rank searches the nearest raw target
+        point of its slice, the ranks all-reduce {sum of squared distances, count}."""
+        import sys
+        import torch
+        mr = sys.float_info.max if max_range == float("inf") else float(max_range)
+        s, c = self.ndt.fitness_sums(mr)
+        if self.world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device()) if self.dist.get_backend() == "nccl" else torch.device("cpu")
+            t = torch.tensor([s, float(c)], dtype=torch.float64, device=dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            s, c = float(t[0].item()), int(round(float(t[1].item())))
+        return s / c if c > 0 else sys.float_info.max
