@@ -8,7 +8,9 @@
 // .bin: raw float32 x,y,z triples.  The reference app first downsamples both clouds with a 0.1 m pcl::VoxelGrid
 // (:57-69); pass clouds that are already downsampled (tests/golden/pair_ds0p1.npz exported as .bin), or see
 // INTEGRATION.md for the PCL build where pcl::VoxelGrid is available.
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,21 +43,23 @@ static bool load_cloud(const std::string& path, Cloud& cloud) {
   return true;
 }
 
-// align point clouds and measure processing time (ndt_omp/apps/align.cpp:15-33)
-template <typename Registration>
-static void align(Registration& registration, const Cloud::Ptr& target_cloud, const Cloud::Ptr& source_cloud) {
-  registration.setInputTarget(target_cloud);
-  registration.setInputSource(source_cloud);
-  Cloud aligned;
+// align point clouds and measure processing time — the helper of ndt_omp/apps/align.cpp:15-33 with its signature: it
+// takes a pcl::Registration pointer, which the shim class is (it derives from pcl::Registration like the reference class)
+static Cloud::Ptr align(pcl::Registration<pcl::PointXYZ, pcl::PointXYZ>::Ptr registration, const Cloud::Ptr& target_cloud,
+                        const Cloud::Ptr& source_cloud) {
+  registration->setInputTarget(target_cloud);
+  registration->setInputSource(source_cloud);
+  Cloud::Ptr aligned(new Cloud());
   auto t1 = std::chrono::steady_clock::now();
-  registration.align(aligned);
+  registration->align(*aligned);
   auto t2 = std::chrono::steady_clock::now();
   std::cout << "single : " << std::chrono::duration<double, std::milli>(t2 - t1).count() << "[msec]" << std::endl;
-  for (int i = 0; i < 10; i++) registration.align(aligned);
+  for (int i = 0; i < 10; i++) registration->align(*aligned);
   auto t3 = std::chrono::steady_clock::now();
   std::cout << "10times: " << std::chrono::duration<double, std::milli>(t3 - t2).count() << "[msec]" << std::endl;
   std::cout.precision(6);
-  std::cout << "fitness: " << registration.getFitnessScore() << std::endl << std::endl;
+  std::cout << "fitness: " << registration->getFitnessScore() << std::endl << std::endl;
+  return aligned;
 }
 
 int main(int argc, char** argv) {
@@ -85,21 +89,37 @@ int main(int argc, char** argv) {
     std::cout << "downsampled (" << leaf << " m): target " << target_cloud->size() << " pts, source " << source_cloud->size() << " pts" << std::endl;
   }
 
-  pclomp_b200::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ> ndt;
+  pclomp_b200::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ>::Ptr ndt_omp(
+      new pclomp_b200::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ>());
+  pclomp_b200::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ>& ndt = *ndt_omp;
   if (!ndt.handle()) return 2;
-  ndt.setResolution(1.0);
+  ndt_omp->setResolution(1.0);
   const std::pair<const char*, pclomp_b200::NeighborSearchMethod> methods[] = {
       {"DIRECT7", pclomp_b200::DIRECT7}, {"DIRECT1", pclomp_b200::DIRECT1}, {"DIRECT26", pclomp_b200::DIRECT26}};
   for (const auto& m : methods) {
     std::cout << "--- pclomp_b200::NDT (" << m.first << ") ---" << std::endl;
-    ndt.setNeighborhoodSearchMethod(m.second);
-    align(ndt, target_cloud, source_cloud);
+    ndt_omp->setNumThreads(1);
+    ndt_omp->setNeighborhoodSearchMethod(m.second);
+    align(ndt_omp, target_cloud, source_cloud);
   }
   // the mapping nodes copy the object (ndt_omp_mapping_node.cpp:151-169): a copy must give the same answer
   auto copy = ndt;
   copy.setNeighborhoodSearchMethod(pclomp_b200::DIRECT7);
   Cloud out;
   copy.align(out);
+  {  // static convertTransform (ndt_omp.h:216-233): the final pose vector re-composes to the final transformation
+    Eigen::Matrix<double, 6, 1> x;
+    ndtb200_result r;
+    ndtb200_get_result(copy.handle(), &r);
+    for (int i = 0; i < 6; ++i) x(i) = r.final_pose[i];
+    Eigen::Matrix4f M;
+    pclomp_b200::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ>::convertTransform(x, M);
+    const Eigen::Matrix4f F = copy.getFinalTransformation();
+    float d = 0.f;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) d = std::max(d, std::fabs(M(i, j) - F(i, j)));
+    std::cout << "convertTransform(final pose) == getFinalTransformation(): " << (d == 0.f ? "yes" : "no") << std::endl;
+  }
   std::cout << "copy converged: " << copy.hasConverged() << ", iterations " << copy.getFinalNumIteration() << std::endl;
 
   // independent pairs aligned together (not in the reference): four copies of the pair, one batch call

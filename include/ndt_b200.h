@@ -39,7 +39,7 @@ typedef enum ndtb200_status {
   NDTB200_ERR_NO_DEVICE = 5      /* no usable CUDA device (the library never falls back to the CPU) */
 } ndtb200_status;
 
-/* pclomp::NeighborSearchMethod (ndt_omp.h:52-57), same values. KDTREE is not implemented yet. */
+/* pclomp::NeighborSearchMethod (ndt_omp.h:52-57), same values. */
 enum { NDTB200_KDTREE = 0, NDTB200_DIRECT26 = 1, NDTB200_DIRECT7 = 2, NDTB200_DIRECT1 = 3 };
 
 /* Setters of the reference object, as one struct.  Defaults = ndt_omp_impl.hpp:46-76 and
@@ -146,6 +146,14 @@ int ndtb200_calculate_score(ndtb200_handle* h, const void* points, size_t n, siz
 int ndtb200_comm_export(ndtb200_handle* h, void* handle_out64);
 int ndtb200_comm_attach(ndtb200_handle* h, int rank, int world, const void* all_handles, int64_t n_source_total);
 int ndtb200_comm_detach(ndtb200_handle* h);
+/* The same source-sharded solve with `world` (2..8) ranks EMULATED inside one cooperative launch on this handle's GPU:
+ * the CTAs of the grid are divided evenly between the ranks, every rank works on the contiguous source range it would
+ * own on its own GPU (ranges start on 32-point group boundaries) with its own partial rows, barrier words, result
+ * block and mailbox, and the ranks exchange their 29 per-evaluation sums through the same tagged mailbox stores and
+ * polls as the multi-GPU path.  results[r] = rank r's own result block (all ranks must report identical bits).
+ * For boxes with fewer GPUs than ranks: separate launches that wait on one another are not guaranteed to be
+ * co-resident on one device, one cooperative launch is. */
+int ndtb200_align_emulated_ranks(ndtb200_handle* h, int world, const float* guess, ndtb200_result* results);
 
 /* ---- scan pre-processing: pcl::VoxelGrid centroid downsample (callers: ndt_omp/apps/align.cpp:57-69,
  * ndt_rosbag_mapping_node.cpp:108-118,153-160, ndt_omp_node.cpp:87-95) -------------------------------------------
@@ -155,6 +163,9 @@ int ndtb200_comm_detach(ndtb200_handle* h);
  * NDTB200_ERR_GRID_OVERFLOW = "Leaf size is too small for the input dataset" (PCL then passes the cloud through). */
 int ndtb200_voxelgrid_filter(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, float leaf,
                              void* out_points, size_t out_capacity, size_t out_stride_bytes, int64_t* n_out);
+/* pcl::VoxelGrid::setLeafSize(lx, ly, lz) with a non-cubic leaf. */
+int ndtb200_voxelgrid_filter3(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, const float leaf[3],
+                              void* out_points, size_t out_capacity, size_t out_stride_bytes, int64_t* n_out);
 /* Same with device-resident float4 input / output (this device). */
 int ndtb200_voxelgrid_filter_device(ndtb200_handle* h, const void* d_points_xyzw, size_t n, float leaf, void* d_out_xyzw,
                                     size_t out_capacity, int64_t* n_out);
@@ -219,6 +230,19 @@ int ndtb200_eval_hessian(ndtb200_handle* h, const double p[6], const float* T, d
  * out_keys[n][26], -1 padded, in the reference's offset order. */
 int ndtb200_lookup(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, int search_method,
                    int32_t* out_keys);
+
+/* static convertTransform (ndt_omp.h:216-233): x = [x, y, z, roll, pitch, yaw] -> Translation * AngleAxis(roll, X) *
+ * AngleAxis(pitch, Y) * AngleAxis(yaw, Z) as a column-major fp32 4x4.  Pure host arithmetic (no device, no handle). */
+int ndtb200_pose_to_matrix(const double x[6], float out16[16]);
+
+/* The pose vector computeTransformation starts from (ndt_omp_impl.hpp:103-111): translation and
+ * rotation().eulerAngles(0,1,2) (Eigen 3.3 conventions, polar factor of the linear part) of a column-major 4x4 guess.
+ * Pure host arithmetic: needs no device and no handle. */
+int ndtb200_debug_guess_to_pose(const float guess[16], double p_out[6]);
+/* The on-device Newton solve H * delta = -g (JacobiSVD(H).solve(-g), ndt_omp_impl.hpp:127-129) exactly as the persistent
+ * kernel runs it (one warp; definite elimination / pivoted elimination / SVD pseudo-inverse).  H row-major 6x6;
+ * path_out (may be NULL): 0 = definite fast path, 1 = pivoted / pseudo-inverse path. */
+int ndtb200_debug_newton_solve(ndtb200_handle* h, const double H[36], const double g[6], double delta_out[6], int* path_out);
 
 /* The on-device Newton / More-Thuente trace of the last align: one entry per evaluation
  * (kind 0 = derivatives+Hessian, 1 = derivatives only, 2 = Hessian only; pose; step length; score).

@@ -18,23 +18,54 @@
 
 #include "../ndt_b200.h"
 #include "pcl_compat.hpp"
+#if __has_include(<omp.h>)
+#include <omp.h>  // callers of the reference get omp_get_max_threads() through its headers (ndt_omp/apps/align.cpp:88)
+#endif
 
 namespace pclomp_b200 {
+
+namespace detail {
+template <typename P, typename T> struct rebind_ptr;
+template <template <typename...> class SP, typename U, typename T> struct rebind_ptr<SP<U>, T> { typedef SP<T> type; };
+}  // namespace detail
 
 enum NeighborSearchMethod { KDTREE = NDTB200_KDTREE, DIRECT26 = NDTB200_DIRECT26, DIRECT7 = NDTB200_DIRECT7, DIRECT1 = NDTB200_DIRECT1 };
 
 template <typename PointSource, typename PointTarget = PointSource>
-class NormalDistributionsTransform {
+class NormalDistributionsTransform : public pcl::Registration<PointSource, PointTarget> {
+  // Derived from pcl::Registration exactly like the reference class (ndt_omp.h:70-71): the real one when PCL is
+  // installed, the stand-in of pcl_compat.hpp otherwise.  A `pcl::Registration<P, P>::Ptr` can therefore hold this
+  // object (ndt_omp/apps/align.cpp:15, 95-103) and the base class's align() wrapper calls computeTransformation() below.
+  typedef pcl::Registration<PointSource, PointTarget> Base;
+
+ protected:
+  using Base::input_;
+  using Base::target_;
+  using Base::final_transformation_;
+  using Base::transformation_;
+  using Base::previous_transformation_;
+  using Base::converged_;
+  using Base::nr_iterations_;
+  using Base::max_iterations_;
+  using Base::transformation_epsilon_;
+  using Base::reg_name_;
+
  public:
   typedef pcl::PointCloud<PointSource> PointCloudSource;
   typedef typename PointCloudSource::Ptr PointCloudSourcePtr;
   typedef typename PointCloudSource::ConstPtr PointCloudSourceConstPtr;
   typedef pcl::PointCloud<PointTarget> PointCloudTarget;
   typedef typename PointCloudTarget::ConstPtr PointCloudTargetConstPtr;
-  typedef std::shared_ptr<NormalDistributionsTransform<PointSource, PointTarget>> Ptr;
-  typedef std::shared_ptr<const NormalDistributionsTransform<PointSource, PointTarget>> ConstPtr;
+  // the smart pointer template of the base class's Ptr (boost::shared_ptr up to PCL 1.10, std::shared_ptr from 1.11 and in
+  // the stand-in), so that a Ptr of this class converts to pcl::Registration<...>::Ptr as the reference's does
+  typedef typename detail::rebind_ptr<typename Base::Ptr, NormalDistributionsTransform<PointSource, PointTarget>>::type Ptr;
+  typedef typename detail::rebind_ptr<typename Base::Ptr, const NormalDistributionsTransform<PointSource, PointTarget>>::type ConstPtr;
+  static_assert(sizeof(PointSource) >= 16 && sizeof(PointTarget) >= 16,
+                "PCL point types start with float data[4] = {x, y, z, 1}: align() writes those 16 bytes of every output point");
 
-  explicit NormalDistributionsTransform(int device = 0) : search_method(DIRECT7), h_(nullptr), device_(device) {
+  // ndt_omp_impl.hpp:46-76: resolution 1.0, step 0.1, outlier ratio 0.55, epsilon 0.1, 35 iterations, DIRECT7
+  explicit NormalDistributionsTransform(int device = 0) : search_method(DIRECT7), h_(nullptr), device_(device), trans_probability_(0.0) {
+    reg_name_ = "NormalDistributionsTransform";
     const int st = ndtb200_create(&h_, device);
     if (st != NDTB200_OK) {
       std::fprintf(stderr, "[pclomp_b200::NormalDistributionsTransform] no usable CUDA device (status %d); "
@@ -42,47 +73,48 @@ class NormalDistributionsTransform {
       h_ = nullptr;
     }
     ndtb200_default_params(&prm_);
+    transformation_epsilon_ = prm_.trans_eps;
+    max_iterations_ = prm_.max_iterations;
   }
   ~NormalDistributionsTransform() { if (h_) ndtb200_destroy(h_); }
 
   // copy construction / assignment: the mapping node returns the object by value (ndt_omp_mapping_node.cpp:151-169)
   NormalDistributionsTransform(const NormalDistributionsTransform& o)
-      : search_method(o.search_method), h_(nullptr), device_(o.device_), prm_(o.prm_), target_(o.target_), input_(o.input_) {
+      : Base(o), search_method(o.search_method), h_(nullptr), device_(o.device_), prm_(o.prm_), trans_probability_(o.trans_probability_) {
     if (o.h_) ndtb200_clone(o.h_, &h_);
   }
   NormalDistributionsTransform& operator=(const NormalDistributionsTransform& o) {
     if (this != &o) {
+      Base::operator=(o);
       if (h_) ndtb200_destroy(h_);
       h_ = nullptr;
-      search_method = o.search_method; device_ = o.device_; prm_ = o.prm_; target_ = o.target_; input_ = o.input_;
+      search_method = o.search_method; device_ = o.device_; prm_ = o.prm_; trans_probability_ = o.trans_probability_;
       if (o.h_) ndtb200_clone(o.h_, &h_);
     }
     return *this;
   }
   NormalDistributionsTransform(NormalDistributionsTransform&& o) noexcept
-      : search_method(o.search_method), h_(o.h_), device_(o.device_), prm_(o.prm_), target_(std::move(o.target_)), input_(std::move(o.input_)) {
+      : Base(o), search_method(o.search_method), h_(o.h_), device_(o.device_), prm_(o.prm_), trans_probability_(o.trans_probability_) {
     o.h_ = nullptr;
   }
 
-  // ---- setters / getters (ndt_omp.h:115-209 + pcl::Registration) ----
+  // ---- setters / getters (ndt_omp.h:115-209); setMaximumIterations / setTransformationEpsilon / hasConverged /
+  //      getFinalTransformation / getLastIncrementalTransformation are pcl::Registration's own ----
   void setNumThreads(int) {}  // accepted, meaningless on the device path
   void setResolution(float resolution) { prm_.resolution = resolution; push(); }
   float getResolution() const { return prm_.resolution; }
   double getStepSize() const { return prm_.step_size; }
-  void setStepSize(double step_size) { prm_.step_size = step_size; push(); }
+  void setStepSize(double step_size) { prm_.step_size = step_size; }
   double getOutlierRatio() const { return prm_.outlier_ratio; }
-  void setOutlierRatio(double outlier_ratio) { prm_.outlier_ratio = outlier_ratio; push(); }
+  void setOutlierRatio(double outlier_ratio) { prm_.outlier_ratio = outlier_ratio; }
   void setNeighborhoodSearchMethod(NeighborSearchMethod method) { search_method = method; }
-  void setTransformationEpsilon(double epsilon) { prm_.trans_eps = epsilon; push(); }
-  double getTransformationEpsilon() const { return prm_.trans_eps; }
-  void setMaximumIterations(int nr_iterations) { prm_.max_iterations = nr_iterations; push(); }
-  int getMaximumIterations() const { return prm_.max_iterations; }
 
-  void setInputTarget(const PointCloudTargetConstPtr& cloud) {
-    target_ = cloud;
+  void setInputTarget(const PointCloudTargetConstPtr& cloud) override {
+    Base::setInputTarget(cloud);  // ndt_omp.h:122-127: pcl::Registration::setInputTarget(cloud); init();
     if (!h_) return;
     const void* p = (cloud && !cloud->points.empty()) ? static_cast<const void*>(cloud->points.data()) : nullptr;
     const size_t n = cloud ? cloud->points.size() : 0;
+    push();
     const int st = ndtb200_set_target(h_, p, n, sizeof(PointTarget), cloud ? (cloud->is_dense ? 1 : 0) : 1);
     if (st == NDTB200_ERR_NO_INPUT)
       std::fprintf(stderr, "[pclomp_b200::VoxelGridCovariance::applyFilter] No input dataset given!\n");
@@ -92,40 +124,24 @@ class NormalDistributionsTransform {
     else if (st != NDTB200_OK)
       std::fprintf(stderr, "[pclomp_b200] setInputTarget failed: %s\n", ndtb200_last_error(h_));
   }
-  void setInputSource(const PointCloudSourceConstPtr& cloud) {
-    input_ = cloud;
+  void setInputSource(const PointCloudSourceConstPtr& cloud) override {
+    Base::setInputSource(cloud);
     if (!h_) return;
     const void* p = (cloud && !cloud->points.empty()) ? static_cast<const void*>(cloud->points.data()) : nullptr;
     const int st = ndtb200_set_source(h_, p, cloud ? cloud->points.size() : 0, sizeof(PointSource));
     if (st != NDTB200_OK) std::fprintf(stderr, "[pclomp_b200] setInputSource failed: %s\n", ndtb200_last_error(h_));
   }
-  PointCloudTargetConstPtr getInputTarget() const { return target_; }
-  PointCloudSourceConstPtr getInputSource() const { return input_; }
 
-  // ---- registration (pcl::Registration::align -> computeTransformation, ndt_omp_impl.hpp:80-171) ----
-  void align(PointCloudSource& output) { align(output, Eigen::Matrix4f::Identity()); }
-  void align(PointCloudSource& output, const Eigen::Matrix4f& guess) {
-    if (!h_ || !input_) return;
-    prm_.search_method = static_cast<int32_t>(search_method);  // public field, read at align time like the reference
-    ndtb200_set_params(h_, &prm_);
-    output.points.resize(input_->points.size());
-    output.width = static_cast<uint32_t>(output.points.size());
-    output.height = 1;
-    output.is_dense = input_->is_dense;
-    for (size_t i = 0; i < output.points.size(); ++i) output.points[i] = input_->points[i];  // copies the non-xyz fields
-    const int st = ndtb200_align(h_, guess.data(), output.points.empty() ? nullptr : output.points.data(), sizeof(PointSource));
-    if (st != NDTB200_OK) std::fprintf(stderr, "[pclomp_b200] align failed: %s\n", ndtb200_last_error(h_));
-  }
-
-  Eigen::Matrix4f getFinalTransformation() { return matrix_of(true); }
-  Eigen::Matrix4f getLastIncrementalTransformation() { return matrix_of(false); }
-  bool hasConverged() { ndtb200_result r; return h_ && ndtb200_get_result(h_, &r) == NDTB200_OK && r.converged != 0; }
-  int getFinalNumIteration() { ndtb200_result r; return (h_ && ndtb200_get_result(h_, &r) == NDTB200_OK) ? r.iterations : 0; }
-  double getTransformationProbability() {
-    ndtb200_result r;
-    return (h_ && ndtb200_get_result(h_, &r) == NDTB200_OK) ? r.trans_probability : 0.0;
-  }
-  double getFitnessScore(double max_range = std::numeric_limits<double>::max()) {
+  int getFinalNumIteration() const { return nr_iterations_; }
+  double getTransformationProbability() const { return trans_probability_; }
+  // pcl::Registration::getFitnessScore — mean squared distance of every transformed source point to its nearest raw
+  // target point — on the device (exact nearest neighbours).  With the real PCL base class a call through a
+  // pcl::Registration pointer runs upstream's own kd-tree implementation on the same final_transformation_.
+  double getFitnessScore(double max_range = std::numeric_limits<double>::max())
+#if !PCLOMP_B200_HAVE_PCL_REGISTRATION
+      override
+#endif
+  {
     double v = std::numeric_limits<double>::max();
     if (h_) ndtb200_fitness_score(h_, max_range, &v);
     return v;
@@ -134,11 +150,29 @@ class NormalDistributionsTransform {
   double calculateScore(const PointCloudSource& cloud) {
     double v = 0.0;
     if (h_ && !cloud.points.empty()) {
-      prm_.search_method = static_cast<int32_t>(search_method);
-      ndtb200_set_params(h_, &prm_);
+      push();
       ndtb200_calculate_score(h_, cloud.points.data(), cloud.points.size(), sizeof(PointSource), &v);
     }
     return v;
+  }
+
+  // [x, y, z, roll, pitch, yaw] -> Translation * AngleAxis(roll, X) * AngleAxis(pitch, Y) * AngleAxis(yaw, Z), fp32
+  // (ndt_omp.h:216-233)
+  static void convertTransform(const Eigen::Matrix<double, 6, 1>& x, Eigen::Affine3f& trans) {
+#if PCLOMP_B200_HAVE_EIGEN
+    trans = Eigen::Translation<float, 3>(float(x(0)), float(x(1)), float(x(2))) *
+            Eigen::AngleAxis<float>(float(x(3)), Eigen::Vector3f::UnitX()) *
+            Eigen::AngleAxis<float>(float(x(4)), Eigen::Vector3f::UnitY()) *
+            Eigen::AngleAxis<float>(float(x(5)), Eigen::Vector3f::UnitZ());
+#else
+    const double p[6] = {x(0), x(1), x(2), x(3), x(4), x(5)};
+    ndtb200_pose_to_matrix(p, trans.matrix().data());  // the same fp32 arithmetic the solver uses for its trial poses
+#endif
+  }
+  static void convertTransform(const Eigen::Matrix<double, 6, 1>& x, Eigen::Matrix4f& trans) {
+    Eigen::Affine3f _affine;
+    convertTransform(x, _affine);
+    trans = _affine.matrix();
   }
 
   ndtb200_handle* handle() { return h_; }
@@ -157,8 +191,7 @@ class NormalDistributionsTransform {
     for (int i = 0; i < n; ++i) {
       NormalDistributionsTransform* o = objects[i];
       if (!o || !o->h_ || !o->input_) { std::fprintf(stderr, "[pclomp_b200] alignBatch: object %d has no device handle / source\n", i); return; }
-      o->prm_.search_method = static_cast<int32_t>(o->search_method);
-      ndtb200_set_params(o->h_, &o->prm_);
+      o->push();
       hs[i] = o->h_;
       if (i < static_cast<int>(outputs.size()) && outputs[i]) {
         PointCloudSource& out = *outputs[i];
@@ -176,33 +209,52 @@ class NormalDistributionsTransform {
     }
     const int st = ndtb200_align_batch(hs.data(), n, guesses.empty() ? nullptr : g.data(), outs.data(), sizeof(PointSource), nullptr);
     if (st != NDTB200_OK) std::fprintf(stderr, "[pclomp_b200] alignBatch failed (status %d): %s\n", st, ndtb200_last_error(hs[0]));
+    for (int i = 0; i < n; ++i) objects[i]->fetch_result();
   }
 
   NeighborSearchMethod search_method;  // public in the reference too (ndt_omp.h:499)
 
+ protected:
+  // pcl::Registration::align() has already copied the source into `output` (data[3] = 1) and reset the transforms
+  // (ndt_omp_impl.hpp:80-171 runs from here in the reference)
+  void computeTransformation(PointCloudSource& output, const Eigen::Matrix4f& guess) override {
+    nr_iterations_ = 0;
+    converged_ = false;
+    if (!h_ || !input_) return;
+    push();  // the public search_method field and the base class's epsilon / iteration cap are read at align time
+    const int st = ndtb200_align(h_, guess.data(), output.points.empty() ? nullptr : output.points.data(), sizeof(PointSource));
+    if (st != NDTB200_OK) { std::fprintf(stderr, "[pclomp_b200] align failed: %s\n", ndtb200_last_error(h_)); return; }
+    fetch_result();
+  }
+
  private:
+  // The C ABI keeps the reference's rule itself (ndtb200_set_params: a CHANGED resolution rebuilds the map only if a
+  // source is set, ndt_omp.h:132-142), so the whole parameter block can be pushed at any time.
   void push() {
     if (!h_) return;
     prm_.search_method = static_cast<int32_t>(search_method);
+    prm_.trans_eps = transformation_epsilon_;
+    prm_.max_iterations = max_iterations_;
     const int st = ndtb200_set_params(h_, &prm_);
     if (st == NDTB200_ERR_CUDA) std::fprintf(stderr, "[pclomp_b200] set_params failed: %s\n", ndtb200_last_error(h_));
   }
-  Eigen::Matrix4f matrix_of(bool final_not_increment) {
-    Eigen::Matrix4f M = Eigen::Matrix4f::Identity();
+  void fetch_result() {
     ndtb200_result r;
-    if (h_ && ndtb200_get_result(h_, &r) == NDTB200_OK) {
-      const float* src = final_not_increment ? r.final_transformation : r.last_increment;
-      for (int c = 0; c < 4; ++c)
-        for (int rr = 0; rr < 4; ++rr) M(rr, c) = src[c * 4 + rr];
-    }
-    return M;
+    if (!h_ || ndtb200_get_result(h_, &r) != NDTB200_OK) return;
+    for (int c = 0; c < 4; ++c)
+      for (int rr = 0; rr < 4; ++rr) {
+        final_transformation_(rr, c) = r.final_transformation[c * 4 + rr];
+        transformation_(rr, c) = r.last_increment[c * 4 + rr];
+      }
+    converged_ = r.converged != 0;
+    nr_iterations_ = r.iterations;
+    trans_probability_ = r.trans_probability;
   }
 
   ndtb200_handle* h_;
   int device_;
   ndtb200_params prm_;
-  PointCloudTargetConstPtr target_;
-  PointCloudSourceConstPtr input_;
+  double trans_probability_;
 };
 
 // pcl::VoxelGrid<PointT> as the callers use it before the registration (ndt_omp/apps/align.cpp:57-69,
@@ -214,11 +266,11 @@ class VoxelGrid {
  public:
   typedef pcl::PointCloud<PointT> PointCloud;
   typedef typename PointCloud::ConstPtr PointCloudConstPtr;
-  explicit VoxelGrid(int device = 0) : h_(nullptr), leaf_(0.f) { if (ndtb200_create(&h_, device) != NDTB200_OK) h_ = nullptr; }
+  explicit VoxelGrid(int device = 0) : h_(nullptr) { leaf_[0] = leaf_[1] = leaf_[2] = 0.f; if (ndtb200_create(&h_, device) != NDTB200_OK) h_ = nullptr; }
   ~VoxelGrid() { if (h_) ndtb200_destroy(h_); }
   VoxelGrid(const VoxelGrid&) = delete;
   VoxelGrid& operator=(const VoxelGrid&) = delete;
-  void setLeafSize(float lx, float, float) { leaf_ = lx; }  // the callers use cubic leaves
+  void setLeafSize(float lx, float ly, float lz) { leaf_[0] = lx; leaf_[1] = ly; leaf_[2] = lz; }
   void setInputCloud(const PointCloudConstPtr& cloud) { input_ = cloud; }
   void filter(PointCloud& output) {
     output.points.clear();
@@ -226,8 +278,8 @@ class VoxelGrid {
     struct Rec { float x, y, z, w; };
     std::vector<Rec> out(input_->points.size());
     int64_t m = 0;
-    const int st = ndtb200_voxelgrid_filter(h_, input_->points.data(), input_->points.size(), sizeof(PointT), leaf_, out.data(),
-                                            out.size(), sizeof(Rec), &m);
+    const int st = ndtb200_voxelgrid_filter3(h_, input_->points.data(), input_->points.size(), sizeof(PointT), leaf_, out.data(),
+                                             out.size(), sizeof(Rec), &m);
     if (st == NDTB200_ERR_GRID_OVERFLOW) {  // pcl::VoxelGrid: warn and pass the cloud through
       std::fprintf(stderr, "[pclomp_b200::VoxelGrid::applyFilter] Leaf size is too small for the input dataset. Integer indices would overflow.\n");
       output = *input_;
@@ -247,7 +299,7 @@ class VoxelGrid {
 
  private:
   ndtb200_handle* h_;
-  float leaf_;
+  float leaf_[3];
   PointCloudConstPtr input_;
 };
 

@@ -61,6 +61,8 @@ def lib():
     L.ndto_trace.restype = C.c_long
     L.ndto_voxelgrid.argtypes = [f32p, C.c_size_t, C.c_float, f32p, C.c_size_t]
     L.ndto_voxelgrid.restype = C.c_long
+    L.ndto_voxelgrid3.argtypes = [f32p, C.c_size_t, f32p, f32p, C.c_size_t]
+    L.ndto_voxelgrid3.restype = C.c_long
     L.ndto_pose_to_matrix.argtypes = [f64p, f32p]
     L.ndto_matrix_to_pose.argtypes = [f32p, f64p]
     L.ndto_transform.argtypes = [f32p, f32p, C.c_size_t, f32p]
@@ -96,9 +98,14 @@ def max_threads():
 
 
 def voxelgrid_downsample(points, leaf):
+    """pcl::VoxelGrid centroid downsample; `leaf` is a scalar or (lx, ly, lz)."""
     p = as_xyzw(points)
     out = np.empty_like(p)
-    n = lib().ndto_voxelgrid(_f32(p), p.shape[0], float(leaf), _f32(out), out.shape[0])
+    if np.ndim(leaf) == 0:
+        n = lib().ndto_voxelgrid(_f32(p), p.shape[0], float(leaf), _f32(out), out.shape[0])
+    else:
+        l3 = np.ascontiguousarray(leaf, dtype=np.float32)
+        n = lib().ndto_voxelgrid3(_f32(p), p.shape[0], _f32(l3), _f32(out), out.shape[0])
     if n < 0:
         raise OverflowError("leaf size too small (int32 voxel index overflow)")
     return out[:n, :3].copy()

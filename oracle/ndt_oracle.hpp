@@ -359,20 +359,21 @@ inline void min_max_3d(const P4* pts, size_t n, bool is_dense, float mn[3], floa
 // Same key arithmetic as vgc_impl:218-223; output ordered by voxel index; fp32
 // centroid (sum in sorted order / count).  Returns -1 on the int32 guard.
 // ---------------------------------------------------------------------------
-inline long voxelgrid_downsample(const P4* pts, size_t n, float leaf, std::vector<P4>& out) {
+// leaf3: pcl::VoxelGrid::setLeafSize(lx, ly, lz) — inverse_leaf_size_ = 1 / leaf per axis
+inline long voxelgrid_downsample(const P4* pts, size_t n, const float leaf3[3], std::vector<P4>& out) {
   out.clear();
   if (n == 0) return 0;
-  float inv = 1.0f / leaf;
+  const float inv3[3] = {1.0f / leaf3[0], 1.0f / leaf3[1], 1.0f / leaf3[2]};
   float mn[3], mx[3];
   min_max_3d(pts, n, false, mn, mx);
-  int64_t dx = static_cast<int64_t>((mx[0] - mn[0]) * inv) + 1;
-  int64_t dy = static_cast<int64_t>((mx[1] - mn[1]) * inv) + 1;
-  int64_t dz = static_cast<int64_t>((mx[2] - mn[2]) * inv) + 1;
+  int64_t dx = static_cast<int64_t>((mx[0] - mn[0]) * inv3[0]) + 1;
+  int64_t dy = static_cast<int64_t>((mx[1] - mn[1]) * inv3[1]) + 1;
+  int64_t dz = static_cast<int64_t>((mx[2] - mn[2]) * inv3[2]) + 1;
   if (dx * dy * dz > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) return -1;
   int min_b[3], max_b[3], div_b[3];
   for (int a = 0; a < 3; ++a) {
-    min_b[a] = static_cast<int>(std::floor(mn[a] * inv));
-    max_b[a] = static_cast<int>(std::floor(mx[a] * inv));
+    min_b[a] = static_cast<int>(std::floor(mn[a] * inv3[a]));
+    max_b[a] = static_cast<int>(std::floor(mx[a] * inv3[a]));
     div_b[a] = max_b[a] - min_b[a] + 1;
   }
   int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
@@ -381,9 +382,9 @@ inline long voxelgrid_downsample(const P4* pts, size_t n, float leaf, std::vecto
   for (size_t i = 0; i < n; ++i) {
     const P4& p = pts[i];
     if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
-    int i0 = static_cast<int>(std::floor(p.x * inv) - static_cast<float>(min_b[0]));
-    int i1 = static_cast<int>(std::floor(p.y * inv) - static_cast<float>(min_b[1]));
-    int i2 = static_cast<int>(std::floor(p.z * inv) - static_cast<float>(min_b[2]));
+    int i0 = static_cast<int>(std::floor(p.x * inv3[0]) - static_cast<float>(min_b[0]));
+    int i1 = static_cast<int>(std::floor(p.y * inv3[1]) - static_cast<float>(min_b[1]));
+    int i2 = static_cast<int>(std::floor(p.z * inv3[2]) - static_cast<float>(min_b[2]));
     order.emplace_back(i0 * mul[0] + i1 * mul[1] + i2 * mul[2], static_cast<uint32_t>(i));
   }
   std::stable_sort(order.begin(), order.end(),
@@ -402,6 +403,11 @@ inline long voxelgrid_downsample(const P4* pts, size_t n, float leaf, std::vecto
     i = j;
   }
   return static_cast<long>(out.size());
+}
+
+inline long voxelgrid_downsample(const P4* pts, size_t n, float leaf, std::vector<P4>& out) {
+  const float leaf3[3] = {leaf, leaf, leaf};
+  return voxelgrid_downsample(pts, n, leaf3, out);
 }
 
 // ---------------------------------------------------------------------------

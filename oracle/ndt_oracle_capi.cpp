@@ -194,6 +194,15 @@ long ndto_voxelgrid(const float* xyzw, size_t n, float leaf, float* out_xyzw, si
   return r;
 }
 
+long ndto_voxelgrid3(const float* xyzw, size_t n, const float* leaf3, float* out_xyzw, size_t cap) {
+  std::vector<P4> out;
+  long r = voxelgrid_downsample(as_p4(xyzw), n, leaf3, out);
+  if (r < 0) return r;
+  size_t m = std::min(cap, out.size());
+  if (out_xyzw) std::memcpy(out_xyzw, out.data(), m * sizeof(P4));
+  return r;
+}
+
 void ndto_pose_to_matrix(const double* p, float* T_colmajor) { to_colmajor(pose_to_matrix(p), T_colmajor); }
 
 void ndto_matrix_to_pose(const float* T_colmajor, double* p) {

@@ -10,7 +10,12 @@ Outputs : tests/golden/pair_ds0p1.npz   0.1 m pcl::VoxelGrid downsample of both 
                                         ndt_omp/apps/align.cpp:57-69 feeds to NDT (config 1)
           tests/golden/pair_ds0p3.npz   0.3 m downsample (ndt_rosbag_mapping_node.cpp:88 default;
                                         line-search fixture B of SURVEY Appendix A)
-          tests/golden/golden.json      the reference's published known answers (ndt_omp/README.md:13-46)
+          tests/golden/pair_raw.npz     the two RAW scans (no downsample): line-search fixture A of SURVEY Appendix A
+                                        (2 Newton iterations, 23 evaluations = 2 x 10 extra More-Thuente trials,
+                                        2 Hessian-only passes) — the heaviest exercise of trialValueSelectionMT /
+                                        updateIntervalMT / computeHessian the bundled data offers
+          tests/golden/golden.json      the reference's published known answers (ndt_omp/README.md:13-46) and the
+                                        counts / final poses of SURVEY Appendix A (independent numpy restatement)
 
 The downsample here is an independent numpy restatement of pcl::VoxelGrid<PointXYZ>::applyFilter
 (fp32 key arithmetic identical to voxel_grid_covariance_omp_impl.hpp:218-223, fp32 centroid summed
@@ -51,9 +56,9 @@ def read_pcd_xyz(path):
 
 
 def voxelgrid_downsample(xyz, leaf):
-    """pcl::VoxelGrid<PointXYZ> centroid downsample, fp32 throughout."""
+    """pcl::VoxelGrid<PointXYZ> centroid downsample, fp32 throughout.  leaf: scalar or (lx, ly, lz)."""
     xyz = np.asarray(xyz, dtype=np.float32)
-    leaf = np.float32(leaf)
+    leaf = np.asarray(leaf, dtype=np.float32)
     inv = np.float32(1.0) / leaf
     mn = xyz.min(axis=0)
     mx = xyz.max(axis=0)
@@ -83,6 +88,7 @@ def main():
         s = voxelgrid_downsample(src, leaf)
         print(leaf, t.shape, s.shape)
         np.savez_compressed(os.path.join(HERE, name), target=t, source=s)
+    np.savez_compressed(os.path.join(HERE, "pair_raw.npz"), target=tgt, source=src)
     # a small slice of the raw scans so the downsample itself can be checked where /root/reference is absent
     np.savez_compressed(os.path.join(HERE, "raw_head.npz"), target=tgt[:8192], source=src[:8192],
                         target_ds0p1=voxelgrid_downsample(tgt[:8192], 0.1),
@@ -91,6 +97,17 @@ def main():
         "source": "ndt_omp/README.md:13-46 (rosrun ndt_omp align 251370668.pcd 251371071.pcd, Core i7-6700K)",
         "fitness": {"DIRECT7": 0.214205, "DIRECT1": 0.208511, "KDTREE": 0.213937, "pcl_ndt": 0.213937},
         "raw_points": {"target": int(tgt.shape[0]), "source": int(src.shape[0])},
+        # SURVEY Appendix A (values of the survey's independent numpy restatement; class defaults, DIRECT7, identity guess)
+        "appendix_a": {
+            "config1_DIRECT7": {"iterations": 5, "evaluations": 6, "hessian_passes": 0,
+                                "p": [0.471692, 0.111211, -0.023818, 0.005899, -0.001002, -0.010327]},
+            "config1_DIRECT26": {"iterations": 2, "evaluations": 4, "hessian_passes": 1,
+                                 "p": [0.083691, 0.022196, 0.002907, 0.007005, -0.008102, -0.004304], "fitness": 0.265174},
+            "fixture_A_raw_pair": {"valid_voxels": 690, "iterations": 2, "evaluations": 23, "hessian_passes": 2,
+                                   "p": [-0.010123, -0.020243, -0.003812, 0.059494, 0.000758, -0.024049]},
+            "fixture_B_ds0p3_node_params": {"iterations": 7, "evaluations": 18, "hessian_passes": 1,
+                                            "p": [0.461994, 0.134161, -0.032969, 0.006620, -0.002877, -0.010950]},
+        },
         "published_ms": {
             "DIRECT7_1thr": {"single": 139.433, "10times": 1356.79},
             "DIRECT1_1thr": {"single": 34.6418, "10times": 317.03},

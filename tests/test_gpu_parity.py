@@ -641,3 +641,170 @@ def test_cpp_shim_pcd_voxelgrid_pipeline(nb, tmp_path):
     assert abs(fit[0] - ref.getFitnessScore()) <= 2e-6 * max(1.0, fit[0])       # printed with 6 digits
     assert ("saved %d aligned points" % len(d["source_ds0p1"])) in out.stdout
     assert os.path.getsize(op) > 12 * len(d["source_ds0p1"])
+
+
+# ---- round 2: independent checks, fixture A, non-finite sources, the setResolution rule, emulated ranks --------------
+
+def test_newton_solve_against_numpy_pinv(nb):
+    """The on-device Newton solve (definite elimination / pivoted elimination / SVD pseudo-inverse, ndt_omp_impl.hpp:127-129
+    = JacobiSVD(H).solve(-g)) against numpy.linalg.pinv — an independent implementation, not the oracle's twin."""
+    from test_independent_checks import _solve_cases, numpy_jacobisvd_solve
+    gpu = nb.NormalDistributionsTransform()
+    paths = set()
+    for H, g, kind in _solve_cases():
+        x, path = gpu.newton_solve(H, g)
+        paths.add((kind.split()[0][:4], path))
+        ref = numpy_jacobisvd_solve(H, -g)
+        cond = np.linalg.cond(H) if kind in ("definite", "indefinite") else 1.0
+        tol = max(1e-9, 50 * cond * np.finfo(np.float64).eps) if kind in ("definite", "indefinite") else 1e-8
+        assert np.abs(x - ref).max() <= tol * max(np.abs(ref).max(), 1e-12) + 1e-14, (kind, path, x, ref)
+    assert ("defi", 0) in paths and ("inde", 1) in paths and ("rank", 1) in paths   # every solver path was exercised
+
+
+@pytest.mark.parametrize("method,kind", [(oracle.DIRECT26, 26), (oracle.DIRECT7, 7), (oracle.DIRECT1, 1)])
+def test_neighbourhoods_against_enumeration(nb, method, kind):
+    """Q7: DIRECT26 = 3x3x3 minus the centre, DIRECT7 = centre + faces — as SETS against a brute enumeration built from
+    the dumped voxel list (independent of the offset tables the oracle and the kernel both carry)."""
+    from test_independent_checks import enumerated_neighbours, lookup_queries
+    tgt, q = lookup_queries()
+    gpu = nb.NormalDistributionsTransform()
+    gpu.setInputTarget(tgt)
+    info, vox = gpu.map_info(), gpu.dump_voxels()
+    valid = set(int(k) for k, c in zip(vox["keys"], vox["counts"]) if c >= 6)
+    got = gpu.lookup(q, method)
+    for i in range(len(q)):
+        exp = enumerated_neighbours(valid, (info["min_b"], info["max_b"], info["div_b"]), q[i], 1.0, kind)
+        row = [int(k) for k in got[i] if k >= 0]
+        assert len(row) == len(set(row)) and set(row) == exp, (i, q[i], sorted(row), sorted(exp))
+
+
+def test_align_line_search_fixture_a(nb):
+    """SURVEY Appendix A fixture A — the RAW bundled pair: 2 Newton iterations, 23 evaluations (2 x 10 extra More-Thuente
+    trials), 2 Hessian-only passes: the heaviest exercise of trialValueSelectionMT / updateIntervalMT / computeHessian."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "pair_raw.npz"))
+    ref, gpu = make_pair(nb, d["target"], d["source"])
+    assert gpu.map_info()["n_valid"] == golden()["appendix_a"]["fixture_A_raw_pair"]["valid_voxels"] == 690
+    _, rr, rg = check_align(ref, gpu)
+    ap = golden()["appendix_a"]["fixture_A_raw_pair"]
+    assert (rg["iterations"], rg["n_evaluations"], rg["n_hessian_passes"]) == (ap["iterations"], ap["evaluations"], ap["hessian_passes"])
+    tr = gpu.trace()
+    assert list(tr["kind"]) == [0] + ([0] + [1] * 10 + [2]) * 2
+    assert np.abs(tr["x"][-1] - np.array(ap["p"])).max() < 1e-6
+    gpu.set_throughput_mode(True)         # same bar for the small-CTA shape
+    check_align(ref, gpu)
+
+
+@pytest.mark.parametrize("method", [oracle.DIRECT7, oracle.DIRECT1, oracle.DIRECT26, oracle.KDTREE])
+def test_non_finite_source_points_contribute_nothing(nb, method):
+    """a NaN / inf source point has no neighbourhood in the reference (int(floor(NaN)) is far outside
+    every grid) and adds exactly 0.  CUDA converts NaN to cell 0 — which IS occupied in a sensor-centred map — so the
+    kernel must skip such points: score / gradient / Hessian / hit count equal the finite subset's, bit for bit, and
+    equal the oracle's on the polluted cloud."""
+    tgt, src = load_pair()
+    gpu0 = nb.NormalDistributionsTransform()
+    gpu0.setInputTarget(tgt)
+    vox = gpu0.dump_voxels()
+    info = gpu0.map_info()
+    # the map must have a valid voxel at or next to cell (0,0,0): that is where a NaN lands on the device
+    k0 = (0 - info["min_b"][0]) + (0 - info["min_b"][1]) * info["div_b"][0] + (0 - info["min_b"][2]) * info["div_b"][0] * info["div_b"][1]
+    near = {k0, k0 + 1, k0 - 1, k0 + info["div_b"][0], k0 - info["div_b"][0]}
+    assert any(int(k) in near and c >= 6 for k, c in zip(vox["keys"], vox["counts"]))
+    bad = src.copy()
+    bad[10] = [np.nan, 0.0, 0.0]
+    bad[500] = [0.0, np.inf, 0.0]
+    bad[501] = [np.nan, np.nan, np.nan]
+    bad[9000] = [1.0, 2.0, -np.inf]
+    bad[15000] = [3e38, 3e38, 3e38]       # finite, overflows in the transform
+    good_mask = np.isfinite(bad).all(axis=1) & (np.abs(bad).max(axis=1) < 1e30)
+    ref, gpu = make_pair(nb, tgt, bad, method=method)
+    _, gpu_clean = make_pair(nb, tgt, bad[good_mask], method=method)
+    for p in POSES[:3]:
+        a, b, c = gpu.eval_derivatives(p), ref.eval_derivatives(p), gpu_clean.eval_derivatives(p)
+        assert np.isfinite(a["score"]) and np.isfinite(a["gradient"]).all() and np.isfinite(a["hessian"]).all()
+        assert a["hits"] == b["hits"] == c["hits"]
+        assert abs(a["score"] - b["score"]) <= REL * abs(b["score"])
+        assert rel_err(a["gradient"], b["gradient"]) < REL and rel_err(a["hessian"], b["hessian"]) < REL
+        assert rel_err(a["gradient"], c["gradient"]) < 1e-9 and rel_err(a["hessian"], c["hessian"]) < 1e-9
+        ha, hb = gpu.eval_hessian(p), ref.eval_hessian(p)
+        assert np.isfinite(ha).all() and rel_err(ha, hb) < REL
+    check_align(ref, gpu)
+    sa, sb = gpu.calculateScore(bad[good_mask]), ref.calculateScore(bad[good_mask])
+    assert abs(sa - sb) <= 1e-9 * abs(sb)
+
+
+def test_set_resolution_rebuild_rule(nb):
+    """setResolution (ndt_omp.h:132-142) rebuilds the voxel map only if the value CHANGED and an input SOURCE is set
+    (`if (input_) init();`, sic): with a target but no source the old map stays until the next setInputTarget."""
+    tgt, src = load_pair()
+    gpu = nb.NormalDistributionsTransform()
+    gpu.setInputTarget(tgt)                       # built at 1.0
+    v1 = gpu.map_info()["n_voxels"]
+    gpu.setResolution(2.0)                        # no source yet: NOT rebuilt
+    assert gpu.map_info()["n_voxels"] == v1
+    gpu.setInputSource(src)
+    gpu.setResolution(2.0)                        # unchanged value: still not rebuilt
+    assert gpu.map_info()["n_voxels"] == v1
+    gpu.setResolution(0.5)                        # changed + source set: rebuilt
+    v05 = gpu.map_info()["n_voxels"]
+    ref = oracle.NormalDistributionsTransform()
+    ref.setResolution(0.5)
+    ref.setInputTarget(tgt)
+    assert v05 == ref.map_info()["n_voxels"] and v05 > v1
+    gpu.setInputTarget(tgt)                       # setInputTarget always rebuilds with the current value
+    assert gpu.map_info()["n_voxels"] == v05
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("pair,kw", [("pair_ds0p1.npz", {}), ("pair_ds0p3.npz", {"eps": 0.01, "max_iter": 64})])
+def test_sharded_align_emulated_ranks_one_gpu(nb, world, pair, kw):
+    """The source-sharded solve on ONE GPU: `world` ranks emulated inside one cooperative launch, each
+    on the contiguous source range it would own, exchanging the 29 sums through the same tagged mailbox stores / polls
+    as the multi-GPU path.  Same bar as tests/test_gpu_multi.py: every rank reports identical bits, counts equal the
+    oracle's, final transform within tolerance, and within 1e-9 of the single-rank solve (different summation grouping)."""
+    tgt, src = load_pair(pair)
+    ref, gpu = make_pair(nb, tgt, src, **kw)
+    ref.align()
+    rr = ref.result()
+    res = gpu.align_emulated_ranks(world)
+    assert len(res) == world
+    for r in res[1:]:
+        assert np.array_equal(r["final"], res[0]["final"]) and r["iterations"] == res[0]["iterations"]
+        assert r["n_evaluations"] == res[0]["n_evaluations"] and r["final_score"] == res[0]["final_score"]
+        assert r["trans_probability"] == res[0]["trans_probability"] and r["n_hits"] == res[0]["n_hits"]
+    rg = res[0]
+    assert (rg["iterations"], rg["n_evaluations"], rg["n_hessian_passes"], rg["converged"]) == \
+           (rr["iterations"], rr["n_evaluations"], rr["n_hessian_passes"], rr["converged"])
+    dt, dr = transform_delta(rg["final"], rr["final"])
+    assert dt < TRANS_TOL and dr < ROT_TOL, (dt, dr)
+    assert abs(rg["trans_probability"] - rr["trans_probability"]) <= 1e-5 * abs(rr["trans_probability"])
+    gpu.align()
+    single = gpu.result()
+    assert single["n_hits"] == rg["n_hits"]
+    assert abs(single["final_score"] - rg["final_score"]) <= 1e-9 * abs(single["final_score"])
+    assert np.abs(single["final_pose"] - rg["final_pose"]).max() < 1e-9
+    # run to run: identical bits
+    again = gpu.align_emulated_ranks(world)
+    assert np.array_equal(again[0]["final"], rg["final"]) and again[0]["final_score"] == rg["final_score"]
+    # with a guess (the tag sequence continues across launches)
+    g = pose_matrix([0.2, 0.05, -0.01, 0.01, -0.02, 0.03])
+    ref.align(g)
+    rg2 = gpu.align_emulated_ranks(world, g)[world - 1]
+    dt, dr = transform_delta(rg2["final"], ref.result()["final"])
+    assert dt < TRANS_TOL and dr < ROT_TOL and rg2["iterations"] == ref.result()["iterations"]
+
+
+def test_voxelgrid_filter_non_cubic_leaf(nb):
+    """pcl::VoxelGrid::setLeafSize(lx, ly, lz) (ADVICE r01: the shim used to drop ly, lz): per-axis leaves on the device,
+    bit-identical to the oracle (which is pinned to the independent numpy restatement on the CPU side)."""
+    tgt, src = load_pair()
+    gpu = nb.NormalDistributionsTransform()
+    big = np.concatenate([tgt + np.float32(0.013 * k) for k in range(6)]).astype(np.float32)   # > 64 k points: staged path
+    for cloud in (tgt, big):
+        for leaf in ((0.3, 0.5, 0.2), (1.0, 0.25, 2.0)):
+            assert np.array_equal(gpu.voxelgrid_filter(cloud, leaf), oracle.voxelgrid_downsample(cloud, leaf))
+    # the NDT grid of the same handle stays cubic after a non-cubic filter call
+    gpu.setInputTarget(tgt)
+    ref = oracle.NormalDistributionsTransform()
+    ref.setInputTarget(tgt)
+    assert gpu.map_info()["n_voxels"] == ref.map_info()["n_voxels"]

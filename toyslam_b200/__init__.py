@@ -19,9 +19,11 @@ from .ndt import (  # noqa: F401
     align_batch,
     device_count,
     exported_symbols,
+    guess_to_pose,
+    pose_to_matrix,
     library_path,
     load_library,
 )
 
 __all__ = ["NormalDistributionsTransform", "NdtError", "KDTREE", "DIRECT26", "DIRECT7", "DIRECT1",
-           "Batch", "Mapper", "align_batch", "device_count", "load_library", "library_path", "exported_symbols"]
+           "Batch", "Mapper", "align_batch", "device_count", "load_library", "library_path", "exported_symbols", "guess_to_pose", "pose_to_matrix"]

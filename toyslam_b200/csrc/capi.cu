@@ -80,6 +80,7 @@ struct ndtb200_handle {
   bool centroids_valid = false;
   DevBuf d_cell_all, d_best;      // getFitnessScore: cell table over all occupied voxels, per-query results
   bool cell_all_valid = false;
+  float vg_leaf[3] = {0.f, 0.f, 0.f};  // ndtb200_voxelgrid_filter*: per-axis leaf of the scratch handle (0 = use prm.resolution)
   ndtb200_handle* aux = nullptr;  // scratch state of ndtb200_voxelgrid_filter (keeps the map's build buffers untouched)  // map built from all ranks' partials: d_target holds only this rank's slice
   bool use_dense = false;
 
@@ -89,7 +90,9 @@ struct ndtb200_handle {
   bool has_source = false;
 
   // align workspace
-  DevBuf d_partials, d_totals, d_sync, d_result, d_trace, d_out, d_tmp;
+  DevBuf d_partials, d_totals, d_sync, d_result, d_trace, d_out, d_tmp, d_emu;
+  int emu_world = 0;
+  size_t emu_per_rank = 0, emu_result_off = 0;
   int coop_blocks[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // grid size per search method and CTA shape
   int shape = 0;  // 0 = latency shape (1024 threads, the whole GPU for one solve), 1 = throughput shape (256 threads, 1 CTA / SM)
   AlignResultDev* h_result = nullptr;  // pinned
@@ -198,6 +201,12 @@ struct BuildOpts {
 };
 
 // bounding box of the handle's target slice + grid description -> h->grid (host copy); one synchronisation
+Leaf3 leaf_of(const ndtb200_handle* h) {
+  Leaf3 l;
+  for (int a = 0; a < 3; ++a) l.v[a] = h->vg_leaf[a] > 0.f ? h->vg_leaf[a] : h->prm.resolution;
+  return l;
+}
+
 int compute_grid(ndtb200_handle* h, const float4* pts, size_t n, int dense, const BuildOpts& o) {
   const int mm_blocks = grid_for(n, kBuildThreads * 4, h->num_sms * 8);
   CK(h->d_mm_partial.ensure((size_t)mm_blocks * 6 * sizeof(float)));
@@ -210,7 +219,7 @@ int compute_grid(ndtb200_handle* h, const float4* pts, size_t n, int dense, cons
   fb.use = (o.forced_min && o.forced_max) ? 1 : 0;
   for (int a = 0; a < 3; ++a) { fb.mn[a] = fb.use ? o.forced_min[a] : 0.f; fb.mx[a] = fb.use ? o.forced_max[a] : 0.f; }
   grid_setup_kernel<<<1, kBuildThreads, 0, h->stream>>>(h->d_mm_partial.as<float>(), h->d_mm_finite.as<unsigned int>(),
-                                                        mm_blocks, h->prm.resolution, fb, h->d_grid.as<GridDesc>());
+                                                        mm_blocks, leaf_of(h), fb, h->d_grid.as<GridDesc>());
   LAUNCHED(h);
   CK(cudaMemcpyAsync(&h->grid, h->d_grid.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -357,7 +366,7 @@ bool use_fused_build(const ndtb200_handle* h, size_t n) {
 
 // Leaves: h->grid (host copy), *n_vox_out; mode 0: records / icov64 / moments / voxel lists / n_valid counter;
 // mode 1: centroids in h->d_out.  The sorted point indices end up in h->d_vals_a.  One host synchronisation.
-int run_fused_build(ndtb200_handle* h, const float4* pts, size_t n, int dense, int mode, float leaf, uint32_t* n_vox_out) {
+int run_fused_build(ndtb200_handle* h, const float4* pts, size_t n, int dense, int mode, uint32_t* n_vox_out) {
   int G = std::min(h->num_sms, grid_for(n, kBuildThreads, h->num_sms));
   // throughput mode: many builds are in flight on different streams; a cooperative launch must be fully co-resident, so
   // each one takes only a slice of the SMs and several of them run side by side
@@ -386,7 +395,7 @@ int run_fused_build(ndtb200_handle* h, const float4* pts, size_t n, int dense, i
   char* sc = h->d_scalar.as<char>();
   CK(cudaMemsetAsync(sc, 0, 256, h->stream));  // n_vox (0), n_valid (16), sorted-index pointer (160), barrier (192)
   SmallBuildArgs a;
-  a.pts = pts; a.n = static_cast<uint32_t>(n); a.is_dense = dense; a.leaf = leaf;
+  a.pts = pts; a.n = static_cast<uint32_t>(n); a.is_dense = dense; a.leaf = leaf_of(h);
   a.min_points = h->prm.min_points_per_voxel; a.eig_ratio = h->prm.eig_ratio; a.mode = mode;
   a.mm_partial = h->d_mm_partial.as<float>(); a.mm_finite = h->d_mm_finite.as<unsigned int>();
   a.keys_a = h->d_keys_a.as<uint32_t>(); a.keys_b = h->d_keys_b.as<uint32_t>();
@@ -431,7 +440,7 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
 
   if (!o.partial_only && !o.forced_min && use_fused_build(h, n)) {  // scan-sized cloud: one cooperative launch
     uint32_t n_vox = 0;
-    int st = run_fused_build(h, pts, n, dense, 0, h->prm.resolution, &n_vox);
+    int st = run_fused_build(h, pts, n, dense, 0, &n_vox);
     if (st != NDTB200_OK) return st;
     if (h->grid.n_finite == 0) {
       h->map_status = NDTB200_ERR_NO_INPUT;
@@ -547,7 +556,7 @@ int build_from_partials(ndtb200_handle* h, const float* gmin, const float* gmax,
   fb.use = 0;
   for (int a = 0; a < 3; ++a) fb.mn[a] = fb.mx[a] = 0.f;
   grid_setup_kernel<<<1, kBuildThreads, 0, h->stream>>>(h->d_mm_partial.as<float>(), h->d_mm_finite.as<unsigned int>(), 1,
-                                                        h->prm.resolution, fb, h->d_grid.as<GridDesc>());
+                                                        leaf_of(h), fb, h->d_grid.as<GridDesc>());
   LAUNCHED(h);
   CK(cudaMemcpyAsync(&h->grid, h->d_grid.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -728,7 +737,8 @@ int query_coop_blocks(ndtb200_handle* h) {
 }
 
 // Enqueue one launch of the persistent kernel (no host synchronisation).
-int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0[12], int has_guess, int eval_hessian) {
+int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0[12], int has_guess, int eval_hessian,
+                 int emulate_world = 0) {
   if (!h->has_source || (h->n_source == 0 && h->comm_world == 1)) { h->err = "no input source"; return NDTB200_ERR_NO_INPUT; }
   const int method = h->prm.search_method;
   if (method < NDTB200_KDTREE || method > NDTB200_DIRECT1) {
@@ -756,10 +766,11 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   prm.launch_tag = (++h->launch_seq) << 12;  // 4096 evaluations per launch before tags could repeat
   compute_angle_tables(p0, prm.tab0);
 
-  const int shape = (h->comm_world > 1) ? 0 : h->shape;  // the sharded exchange needs >= 8 warps per CTA
+  const int shape = (h->comm_world > 1 || emulate_world > 1) ? 0 : h->shape;  // the sharded exchange needs >= 8 warps per CTA
   const int max_blocks = h->coop_blocks[method][shape];
   // every SM takes part as soon as there is one 32-point group per CTA (the kernel deals groups to warps round-robin)
   int blocks = grid_for(h->n_source, 32, max_blocks);
+  if (const char* e = getenv("NDTB200_MAX_CTAS")) { const int c = atoi(e); if (c >= 1) blocks = std::min(blocks, c); }  // tests: small grids
   CK(h->d_partials.ensure((size_t)2 * max_blocks * kNVP * sizeof(double)));  // double-buffered by evaluation parity
   if (h->d_totals.p == nullptr) {
     CK(h->d_totals.ensure(3 * kNVP * sizeof(double)));
@@ -782,6 +793,49 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   ws.rank = h->comm_rank;
   ws.n_source_total = h->comm_world > 1 ? h->comm_n_total : static_cast<long long>(h->n_source);
   for (int r = 0; r < kMaxRanks; ++r) ws.mail[r] = h->mail_ptrs[r];
+  ws.vranks = 1;
+  ws.pad = 0;
+  ws.vr = nullptr;
+  if (emulate_world > 1) {
+    // `emulate_world` ranks of a source-sharded solve inside ONE cooperative launch on this GPU (see VirtualRank): the
+    // grid is divided evenly, every rank gets its own rows / barrier words / result block / mailbox and the contiguous
+    // source range a rank on its own GPU would get (slices start on a 32-point group boundary).
+    const int W = emulate_world;
+    const int cpr = std::max(1, std::min(blocks, max_blocks) / W);
+    blocks = cpr * W;
+    const size_t part_b = (size_t)cpr * kNVP * sizeof(double), tot_b = 3 * kNVP * sizeof(double), sync_b = 64;
+    const size_t res_b = (sizeof(AlignResultDev) + 63) & ~size_t(63), mail_b = (size_t)2 * kMaxRanks * kNVP * 2 * sizeof(unsigned long long);
+    const size_t per_rank = ((part_b + tot_b + sync_b + res_b + mail_b) + 255) & ~size_t(255);
+    const size_t vr_b = ((size_t)W * sizeof(VirtualRank) + 255) & ~size_t(255);
+    CK(h->d_emu.ensure(vr_b + per_rank * W));
+    CK(cudaMemsetAsync(h->d_emu.p, 0, vr_b + per_rank * W, h->stream));
+    std::vector<VirtualRank> vr(W);
+    const long long groups = (static_cast<long long>(h->n_source) + 31) / 32;
+    for (int r = 0; r < W; ++r) {
+      char* base = h->d_emu.as<char>() + vr_b + per_rank * r;
+      const long long g_lo = r * (groups / W) + std::min<long long>(r, groups % W);
+      const long long g_hi = g_lo + groups / W + (r < groups % W ? 1 : 0);
+      const long long lo = std::min<long long>(h->n_source, g_lo * 32), hi = std::min<long long>(h->n_source, g_hi * 32);
+      vr[r].src = h->d_source.as<float4>() + lo;
+      vr[r].n_source = static_cast<int32_t>(hi - lo);
+      vr[r].pad = 0;
+      vr[r].partials = reinterpret_cast<double*>(base);
+      vr[r].totals = reinterpret_cast<double*>(base + part_b);
+      vr[r].sync = reinterpret_cast<unsigned int*>(base + part_b + tot_b);
+      vr[r].result = reinterpret_cast<AlignResultDev*>(base + part_b + tot_b + sync_b);
+      ws.mail[r] = reinterpret_cast<unsigned long long*>(base + part_b + tot_b + sync_b + res_b);
+    }
+    CK(cudaMemcpyAsync(h->d_emu.p, vr.data(), W * sizeof(VirtualRank), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));  // vr is a stack-lifetime staging buffer
+    ws.world = W;
+    ws.rank = 0;
+    ws.vranks = W;
+    ws.vr = h->d_emu.as<VirtualRank>();
+    ws.n_source_total = static_cast<long long>(h->n_source);
+    h->emu_world = W;
+    h->emu_per_rank = per_rank;
+    h->emu_result_off = vr_b + part_b + tot_b + sync_b;
+  }
   MapView map = make_view(h);
   const float4* src = h->d_source.as<float4>();
   void* args[] = {(void*)&src, (void*)&map, (void*)&prm, (void*)&ws};
@@ -837,6 +891,30 @@ void T_to_colmajor(const float T[12], float* m) {
   m[3] = m[7] = m[11] = 0.0f;
   m[15] = 1.0f;
 }
+void fill_result(const AlignResultDev& r, ndtb200_result* out) {
+  T_to_colmajor(r.final_T, out->final_transformation);
+  float incr[12];
+  pose_to_matrix(r.last_dp, incr);  // transformation_ (ndt_omp_impl.hpp:146-149); Identity if no step was taken
+  T_to_colmajor(incr, out->last_increment);
+  out->converged = r.converged;
+  out->iterations = r.iterations;
+  out->trans_probability = r.trans_probability;
+  for (int i = 0; i < 6; ++i) out->final_pose[i] = r.final_pose[i];
+  out->final_score = r.final_score;
+  out->n_evaluations = r.n_evals;
+  out->n_hessian_passes = r.n_hess;
+  out->n_hits = r.n_hits;
+}
+
+// p = [translation, rotation().eulerAngles(0,1,2)] of the guess (ndt_omp_impl.hpp:103-111; Identity gives -0,0,-0)
+void guess_to_pose(const float T0[12], double p0[6]) {
+  float R[3][3], ang[3];
+  rotation_polar_host(T0, R);
+  euler_angles_012_host(R, ang);
+  p0[0] = T0[3]; p0[1] = T0[7]; p0[2] = T0[11];
+  p0[3] = ang[0]; p0[4] = ang[1]; p0[5] = ang[2];
+}
+
 bool is_identity_colmajor(const float* m) {
   for (int r = 0; r < 4; ++r)
     for (int c = 0; c < 4; ++c)
@@ -912,7 +990,7 @@ int ndtb200_destroy(ndtb200_handle* h) {
   DevBuf* bufs[] = {&h->d_target, &h->d_grid, &h->d_mm_partial, &h->d_mm_finite, &h->d_keys_a, &h->d_keys_b,
                     &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_voxel_key,
                     &h->d_voxel_start, &h->d_voxel_count, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_dense, &h->d_source,
-                    &h->d_cell_all, &h->d_best, &h->d_centroid, &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail};
+                    &h->d_cell_all, &h->d_best, &h->d_centroid, &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail, &h->d_emu};
   for (DevBuf* b : bufs) b->release();
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1006,12 +1084,7 @@ int ndtb200_align_async(ndtb200_handle* h, const float* guess) {
     has_guess = 1;
     colmajor_to_T(guess, T0);
   }
-  // p = [translation, rotation().eulerAngles(0,1,2)] of final_transformation_ (Identity gives -0,0,-0)
-  float R[3][3], ang[3];
-  rotation_polar_host(T0, R);
-  euler_angles_012_host(R, ang);
-  p0[0] = T0[3]; p0[1] = T0[7]; p0[2] = T0[11];
-  p0[3] = ang[0]; p0[4] = ang[1]; p0[5] = ang[2];
+  guess_to_pose(T0, p0);
   return launch_align(h, MODE_ALIGN, p0, T0, has_guess, 1);
 }
 
@@ -1063,20 +1136,39 @@ int ndtb200_get_result(ndtb200_handle* h, ndtb200_result* out) {
     int st = ndtb200_sync(h);
     if (st != NDTB200_OK) return st;
   }
-  const AlignResultDev& r = *h->h_result;
-  T_to_colmajor(r.final_T, out->final_transformation);
-  float incr[12];
-  pose_to_matrix(r.last_dp, incr);  // transformation_ (ndt_omp_impl.hpp:146-149); Identity if no step was taken
-  T_to_colmajor(incr, out->last_increment);
-  out->converged = r.converged;
-  out->iterations = r.iterations;
-  out->trans_probability = r.trans_probability;
-  for (int i = 0; i < 6; ++i) out->final_pose[i] = r.final_pose[i];
-  out->final_score = r.final_score;
-  out->n_evaluations = r.n_evals;
-  out->n_hessian_passes = r.n_hess;
-  out->n_hits = r.n_hits;
+  fill_result(*h->h_result, out);
   return NDTB200_OK;
+}
+
+// A source-sharded solve with `world` ranks emulated inside ONE cooperative launch on this handle's GPU: every rank
+// works on the contiguous source range it would own on its own GPU and the ranks exchange their 29 per-evaluation sums
+// through the same tagged mailbox stores / polls as the multi-GPU path (ndtb200_comm_*).  results[r] is rank r's own
+// result block: all ranks must report identical bits.  For boxes with fewer GPUs than ranks (tests, bring-up).
+int ndtb200_align_emulated_ranks(ndtb200_handle* h, int world, const float* guess, ndtb200_result* results) {
+  if (!h || !results || world < 2 || world > kMaxRanks) return NDTB200_ERR_INVALID;
+  if (h->comm_world > 1) { h->err = "handle is attached to a real communicator"; return NDTB200_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  float T0[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  double p0[6];
+  int has_guess = 0;
+  if (guess && !is_identity_colmajor(guess)) { has_guess = 1; colmajor_to_T(guess, T0); }
+  guess_to_pose(T0, p0);
+  int st = launch_align(h, MODE_ALIGN, p0, T0, has_guess, 1, world);
+  if (st != NDTB200_OK) return st;
+  std::vector<AlignResultDev> rr(world);
+  for (int r = 0; r < world; ++r)
+    CK(cudaMemcpyAsync(&rr[r], h->d_emu.as<char>() + h->emu_result_off + h->emu_per_rank * r, sizeof(AlignResultDev),
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  int rc = NDTB200_OK;
+  for (int r = 0; r < world; ++r) {
+    fill_result(rr[r], results + r);
+    if (rr[r].aborted) { h->err = "emulated sharded solve aborted"; rc = NDTB200_ERR_CUDA; }
+  }
+  std::memcpy(h->h_result, &rr[0], sizeof(AlignResultDev));
+  std::memcpy(h->last_final_T, rr[0].final_T, sizeof(h->last_final_T));
+  h->result_valid = true;
+  return rc;
 }
 
 static int fitness_sums(ndtb200_handle* h, double max_range, double* sum_out, unsigned long long* count_out);
@@ -1334,6 +1426,41 @@ int ndtb200_lookup(ndtb200_handle* h, const void* points, size_t n, size_t strid
   return NDTB200_OK;
 }
 
+// convertTransform (ndt_omp.h:216-233): [x, y, z, roll, pitch, yaw] -> Translation * Rx * Ry * Rz as a column-major fp32
+// 4x4, the same un-fused fp32 arithmetic the solver builds its trial poses with.  Host only.
+int ndtb200_pose_to_matrix(const double p[6], float out16[16]) {
+  if (!p || !out16) return NDTB200_ERR_INVALID;
+  float T[12];
+  pose_to_matrix(p, T);
+  T_to_colmajor(T, out16);
+  return NDTB200_OK;
+}
+
+int ndtb200_debug_guess_to_pose(const float guess[16], double p_out[6]) {
+  if (!guess || !p_out) return NDTB200_ERR_INVALID;
+  float T0[12];
+  colmajor_to_T(guess, T0);
+  guess_to_pose(T0, p_out);
+  return NDTB200_OK;
+}
+
+int ndtb200_debug_newton_solve(ndtb200_handle* h, const double H[36], const double g[6], double delta_out[6], int* path_out) {
+  if (!h || !H || !g || !delta_out) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CK(h->d_tmp.ensure(64 * sizeof(double)));
+  double* d = h->d_tmp.as<double>();
+  CK(cudaMemcpyAsync(d, H, 36 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d + 36, g, 6 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  newton_solve_debug_kernel<<<1, 32, 0, h->stream>>>(d, d + 36, d + 42, reinterpret_cast<int*>(d + 48));
+  LAUNCHED(h);
+  double back[7];
+  CK(cudaMemcpyAsync(back, d + 42, 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 6; ++i) delta_out[i] = back[i];
+  if (path_out) std::memcpy(path_out, &back[6], sizeof(int));
+  return NDTB200_OK;
+}
+
 // parity helper: the on-device line-search trace of the last align (kind, pose, a_t, score per evaluation)
 // profiling helper: CTA-0 timeline (ns since the first evaluation started) of the last solve, 4 stamps per evaluation
 int ndtb200_get_timeline(ndtb200_handle* h, double* t4, int cap, int* n_out) {
@@ -1567,19 +1694,20 @@ int ndtb200_build_from_partials(ndtb200_handle* h, const float global_min[3], co
 }
 
 // ---- pcl::VoxelGrid centroid downsample on the device (the step before the path in every caller) ----
-static int voxelgrid_filter_impl(ndtb200_handle* h, float leaf, int64_t* n_out) {
+static int voxelgrid_filter_impl(ndtb200_handle* h, const float leaf[3], int64_t* n_out) {
   // the cloud sits in a->d_target (n_target points); the result is left in a->d_out
   ndtb200_handle* a = h;
   *n_out = 0;
-  if (!(leaf > 0)) { a->err = "leaf size must be positive"; return NDTB200_ERR_INVALID; }
+  if (!(leaf[0] > 0 && leaf[1] > 0 && leaf[2] > 0)) { a->err = "leaf size must be positive"; return NDTB200_ERR_INVALID; }
   const size_t n = a->n_target;
   if (n == 0) return NDTB200_OK;
-  a->prm.resolution = leaf;
+  a->prm.resolution = leaf[0];
+  for (int k = 0; k < 3; ++k) a->vg_leaf[k] = leaf[k];
   const float4* pts = a->d_target.as<float4>();
   std::memset(&a->grid, 0, sizeof(GridDesc));
   if (use_fused_build(a, n)) {  // scan-sized cloud: one cooperative launch, centroids left in a->d_out
     uint32_t n_vox = 0;
-    const int stf = run_fused_build(a, pts, n, /*dense=*/0, 1, leaf, &n_vox);
+    const int stf = run_fused_build(a, pts, n, /*dense=*/0, 1, &n_vox);
     if (stf != NDTB200_OK) return stf;
     if (a->grid.n_finite == 0) return NDTB200_OK;
     if (a->grid.overflow) return NDTB200_ERR_GRID_OVERFLOW;
@@ -1623,7 +1751,13 @@ static int ensure_aux(ndtb200_handle* h) {
 
 int ndtb200_voxelgrid_filter(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, float leaf, void* out_points,
                              size_t out_capacity, size_t out_stride_bytes, int64_t* n_out) {
-  if (!h || !n_out || (!points && n)) return NDTB200_ERR_INVALID;
+  const float l3[3] = {leaf, leaf, leaf};
+  return ndtb200_voxelgrid_filter3(h, points, n, stride_bytes, l3, out_points, out_capacity, out_stride_bytes, n_out);
+}
+
+int ndtb200_voxelgrid_filter3(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, const float leaf[3], void* out_points,
+                              size_t out_capacity, size_t out_stride_bytes, int64_t* n_out) {
+  if (!h || !n_out || !leaf || (!points && n)) return NDTB200_ERR_INVALID;
   if (n > 0xFFFFFFF0ull) { h->err = "cloud too large"; return NDTB200_ERR_INVALID; }
   cudaSetDevice(h->device);
   int st = ensure_aux(h);
@@ -1660,7 +1794,8 @@ int ndtb200_voxelgrid_filter_device(ndtb200_handle* h, const void* d_points_xyzw
   }
   a->n_target = n;
   a->has_target = true;
-  st = voxelgrid_filter_impl(a, leaf, n_out);
+  const float l3[3] = {leaf, leaf, leaf};
+  st = voxelgrid_filter_impl(a, l3, n_out);
   if (st != NDTB200_OK) { h->err = a->err; return st; }
   const size_t m = static_cast<size_t>(*n_out);
   if (d_out_xyzw && m > 0) {

@@ -66,12 +66,14 @@ minmax3d_kernel(const float4* __restrict__ pts, size_t n, int is_dense, float* _
 
 // VoxelGrid members from the bounding box (…_impl.hpp:75-103): inverse leaf, int64 overflow guard expression, min_b /
 // max_b / div_b / divb_mul — fp32 arithmetic exactly as the reference
-__device__ __forceinline__ void grid_from_box(const float (&mn)[3], const float (&mx)[3], unsigned long long nf, float leaf, bool forced,
+struct Leaf3 { float v[3]; };  // pcl::VoxelGrid::setLeafSize(lx, ly, lz); the NDT grid is cubic (resolution)
+
+__device__ __forceinline__ void grid_from_box(const float (&mn)[3], const float (&mx)[3], unsigned long long nf, const Leaf3& leaf, bool forced,
                                               GridDesc& g) {
-  const float inv = __fdiv_rn(1.0f, leaf);  // pcl::VoxelGrid::setLeafSize: inverse_leaf_size_ = 1.0f / leaf
   long long d[3];
   for (int a = 0; a < 3; ++a) {
-    g.leaf[a] = leaf;
+    const float inv = __fdiv_rn(1.0f, leaf.v[a]);  // pcl::VoxelGrid::setLeafSize: inverse_leaf_size_ = 1.0f / leaf (per axis)
+    g.leaf[a] = leaf.v[a];
     g.inv_leaf[a] = inv;
     g.min_p[a] = mn[a];
     g.max_p[a] = mx[a];
@@ -97,7 +99,7 @@ struct ForcedBox {  // sharded build: every rank keys its slice with the boundin
 
 __global__ void __launch_bounds__(kBuildThreads)
 grid_setup_kernel(const float* __restrict__ partial, const unsigned int* __restrict__ finite_partial,
-                  int nblocks, float leaf, ForcedBox forced, GridDesc* __restrict__ out) {
+                  int nblocks, Leaf3 leaf, ForcedBox forced, GridDesc* __restrict__ out) {
   // one CTA: strided reduction of the per-CTA partials, then thread 0 derives the grid description
   __shared__ float s_mn[3][kBuildThreads / 32], s_mx[3][kBuildThreads / 32];
   __shared__ unsigned long long s_nf[kBuildThreads / 32];

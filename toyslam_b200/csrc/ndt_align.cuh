@@ -7,19 +7,24 @@
 //
 // Design (B200-first, not the reference's per-point-slot + serial-sum structure):
 //   * one thread per source point, float4 loads, in-register fp32 transform (never materialises
-//     trans_cloud), DIRECT1/7/26 probes into the HBM voxel hash (all probes of a point issued
-//     together), 64-byte Gaussian records prefetched, then consumed hit by hit;
+//     trans_cloud), DIRECT1/7/26 probes into the voxel index (direct-mapped cell table, or the open-addressing
+//     hash for grids whose table does not fit; all probes of a point issued together), 64-byte Gaussian
+//     records prefetched, then consumed hit by hit;
 //   * warps take 32-point groups interleaved over the whole grid, so every CTA sees the same mix of
 //     dense and empty regions of the scan (static, deterministic load balance);
 //   * accumulation: a thread adds the (fp32) contributions of at most kFlushPoints points in fp32,
-//     then the warp folds them into fp64 (shuffle tree) — fp64 everywhere a long sum is formed,
-//     without the fp32->fp64 conversion per hit that saturated the XU pipe in the first version;
-//     warp sums -> one fp64 partial per CTA -> the LAST-ARRIVING CTA sums the partials in CTA order
-//     (bit-reproducible) and publishes the 28 totals;
+//     then the warp folds them into fp64 (shuffle tree) — fp64 everywhere a long sum is formed;
+//     warp sums -> one fp64 partial row per CTA (rows double-buffered by evaluation parity);
+//   * grid reduction, single GPU: one acq_rel "arrive" per CTA on a counter whose target for evaluation e is
+//     (e + 1) * G; as soon as it is reached EVERY CTA sums the G rows itself in the same fixed (slice, row) order:
+//     identical bits everywhere, no broadcast.  The counter and the exit counter reset themselves at kernel exit;
+//   * grid reduction, source-sharded multi-GPU (world > 1): the last CTA of a rank to arrive sums the rank's rows
+//     and stores the 29 totals as tagged (flag-in-data) 64-bit words into every rank's mailbox (P2P stores over
+//     NVLink); all CTAs poll their own mailbox and add the W rows in rank order.  tag = launch_seq << 12 | (epoch+1);
 //   * every CTA then runs the identical Newton / More-Thuente step (scalar part in one thread, the
 //     trigonometry and the 69 table entries spread over a warp), so ONE grid barrier per evaluation
 //     is the only synchronisation and the whole align() never returns to the host;
-//   * launched cooperatively (all CTAs co-resident), gridDim = #SMs x occupancy.
+//   * launched cooperatively (all CTAs co-resident), gridDim = #SMs (x emulated ranks' share, see VirtualRank).
 #pragma once
 #include "common.cuh"
 #include "ndt_solve.cuh"
@@ -83,15 +88,30 @@ struct AlignParams {
   int32_t n_source;
   int32_t trace_cap;
   int32_t rot;          // profiling: rotate the CTA -> point-group assignment by this many CTAs
-  uint32_t launch_tag;  // launch sequence number << 10: makes the tags of the published totals unique per launch
+  uint32_t launch_tag;  // launch sequence number << 12 (kMaxEpochsSharded evaluations per launch): makes the mailbox tags unique per launch
   AngleTables tab0;     // angle tables of p0 (host-computed: the kernel prologue has no trigonometry)
 };
 
 constexpr int kMaxRanks = 8;  // GPUs of one NVSwitch node
+constexpr unsigned int kMaxEpochsSharded = 4095;  // mailbox tag = launch_seq << 12 | (epoch + 1): evaluations per sharded launch
+
+// One emulated rank of a source-sharded solve run as ONE cooperative launch on ONE GPU (the CTAs of the grid are
+// divided evenly between the ranks): every rank has its own source slice, partial rows, barrier words, result block
+// and mailbox, exactly as a rank on its own GPU, and the ranks exchange their 29 sums through the same tagged
+// mailbox stores and polls.  This is how a one-GPU box exercises the multi-GPU exchange code (separate launches that
+// wait on one another are not guaranteed to be co-resident on one device).
+struct VirtualRank {
+  const float4* src;
+  int32_t n_source, pad;
+  double* partials;
+  double* totals;
+  unsigned int* sync;
+  struct AlignResultDev* result;
+};
 
 struct AlignWorkspace {
-  double* partials;      // [gridDim][kNVP]
-  double* totals;        // [2][kNVP]
+  double* partials;      // [2][gridDim][kNVP] (single GPU: rows double-buffered by evaluation parity)
+  double* totals;        // [3][kNVP] (profiling stamps of the sharded path)
   unsigned int* sync;    // [0] arrive counter, [2] wrapping exit counter, [3] abort flag (zeroed once, self-resetting)
   AlignResultDev* result;
   TraceRec* trace;
@@ -99,7 +119,19 @@ struct AlignWorkspace {
   // 29 per-evaluation sums are exchanged by direct stores into every peer's mailbox over NVLink.
   int32_t world, rank;
   unsigned long long* mail[kMaxRanks];  // mail[r]: rank r's mailbox [2 parities][kMaxRanks][kNVP][2 words] (own or IPC-mapped peer memory)
-  long long n_source_total;              // points of the whole (unsharded) source cloud
+  long long n_source_total;              // points of the whole (unsigned) source cloud
+  int32_t vranks, pad;                   // > 1: `world` emulated ranks inside this one launch
+  const VirtualRank* vr;                 // [vranks] (device memory)
+};
+
+// What a CTA needs to know about the rank it works for (shared memory; filled once at kernel start).
+struct RankCtx {
+  double* partials;
+  double* totals;
+  unsigned int* sync;
+  AlignResultDev* result;
+  unsigned int G, bid;  // CTAs of this rank, index of this CTA inside the rank
+  int32_t rank, pad;
 };
 
 struct EvalCtx {
@@ -189,6 +221,15 @@ __device__ __forceinline__ int probe_neighbour(const MapView& m, int ix, int iy,
   get_offset<METHOD>(k, dx, dy, dz);
   if constexpr (METHOD == 0) return probe_cell_kdtree(m, ix + dx, iy + dy, iz + dz, tx, ty, tz);
   else return probe_cell(m, ix + dx, iy + dy, iz + dz);
+}
+
+// A non-finite transformed point (NaN / inf in the source, or 0 * inf in the transform) has no neighbourhood in the
+// reference: int(floor(NaN)) is INT_MIN on the reference's platform (x86 cvttss2si), far outside every grid, so
+// getNeighborhoodAtPoint returns nothing and the point adds exactly 0 (voxel_grid_covariance_omp_impl.hpp:379-391,
+// ndt_omp_impl.hpp:506-507 never runs).  CUDA's float->int conversion maps NaN to 0, i.e. to a real cell: skip the
+// point instead.  (A finite sum of three finite coordinates that overflows belongs to a point outside every grid too.)
+__device__ __forceinline__ bool point_is_finite(float tx, float ty, float tz) {
+  return fabsf(__fadd_rn(__fadd_rn(tx, ty), tz)) <= 3.402823466e+38f;
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -282,6 +323,7 @@ __device__ __forceinline__ void point_hessian_f64(const float4 pt, const EvalCtx
                                                   const double d1, double* acc /*[22]: H upper triangle, hits*/) {
   float tx, ty, tz;
   transform_point(c.T, pt.x, pt.y, pt.z, tx, ty, tz);
+  if (!point_is_finite(tx, ty, tz)) return;  // no neighbourhood, no contribution (see point_is_finite)
   const int ix = static_cast<int>(floorf(__fdiv_rn(tx, m.leaf[0])));
   const int iy = static_cast<int>(floorf(__fdiv_rn(ty, m.leaf[1])));
   const int iz = static_cast<int>(floorf(__fdiv_rn(tz, m.leaf[2])));
@@ -432,10 +474,10 @@ __device__ __forceinline__ double poll_tagged(const unsigned long long* slot, un
 }
 
 template <int NW>
-__device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_tot, const AlignWorkspace& ws,
+__device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_tot, const AlignWorkspace& ws, const RankCtx& rc,
                                                unsigned int& epoch, int* s_flag, double (*s_red8)[kNVP],
                                                unsigned int launch_tag) {
-  const unsigned int G = gridDim.x;
+  const unsigned int G = rc.G, bid = rc.bid;
   const int W = ws.world;
   if (G == 1 && W == 1) {
     if (threadIdx.x < kNV) s_tot[threadIdx.x] = s_block[threadIdx.x];
@@ -448,17 +490,16 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
     // as soon as the arrival counter shows the grid complete: one round trip less than "the last CTA reduces and
     // publishes".  Rows are double-buffered by evaluation parity: a CTA can only reach evaluation e+1's arrive after
     // it finished reading evaluation e's rows, so a row is never overwritten while somebody still reads it.
-    double* rows = ws.partials + (size_t)(epoch & 1u) * G * kNVP;
-    if (threadIdx.x < kNV) rows[(size_t)blockIdx.x * kNVP + threadIdx.x] = s_block[threadIdx.x];
-    if (threadIdx.x == 31) rows[(size_t)blockIdx.x * kNVP + 31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: arrival time
-    if (threadIdx.x == 30) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); rows[(size_t)blockIdx.x * kNVP + 30] = static_cast<double>(smid); }
+    double* rows = rc.partials + (size_t)(epoch & 1u) * G * kNVP;
+    if (threadIdx.x < kNV) rows[(size_t)bid * kNVP + threadIdx.x] = s_block[threadIdx.x];
+    if (threadIdx.x == 31) rows[(size_t)bid * kNVP + 31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: arrival time
+    if (threadIdx.x == 30) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); rows[(size_t)bid * kNVP + 30] = static_cast<double>(smid); }
     __syncthreads();
     if (threadIdx.x == 0) {
-      atom_add_acq_rel_gpu(&ws.sync[0], 1u);  // release: this CTA's row
+      atom_add_acq_rel_gpu(&rc.sync[0], 1u);  // release: this CTA's row
       const unsigned int target = (epoch + 1u) * G;
-      while (ld_acquire_u32(&ws.sync[0]) < target) {}  // acquire: everyone's rows
+      while (ld_acquire_u32(&rc.sync[0]) < target) {}  // acquire: everyone's rows
       s_tot[31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: grid complete
-      *s_flag = 1;
     }
     __syncthreads();
     constexpr int kRedRows = red_rows_for(NW);
@@ -486,26 +527,26 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
     ++epoch;
     return;
   }
+  // ---- source-sharded solve (W ranks, one per GPU or emulated inside this launch) ----
   const unsigned int tag = launch_tag + epoch + 1u;
   const int par = epoch & 1u;
   bool last = true;
   if (G > 1) {
-    if (threadIdx.x < kNV) ws.partials[(size_t)blockIdx.x * kNVP + threadIdx.x] = s_block[threadIdx.x];
-    if (threadIdx.x == 31) ws.partials[(size_t)blockIdx.x * kNVP + 31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: arrival time of this CTA
-    if (threadIdx.x == 30) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); ws.partials[(size_t)blockIdx.x * kNVP + 30] = static_cast<double>(smid); }
+    if (threadIdx.x < kNV) rc.partials[(size_t)bid * kNVP + threadIdx.x] = s_block[threadIdx.x];
+    if (threadIdx.x == 31) rc.partials[(size_t)bid * kNVP + 31] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling: arrival time of this CTA
+    if (threadIdx.x == 30) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); rc.partials[(size_t)bid * kNVP + 30] = static_cast<double>(smid); }
     __syncthreads();
     if (threadIdx.x == 0) {
-      const unsigned int ticket = atom_add_acq_rel_gpu(&ws.sync[0], 1u);  // release: the CTA's partials; acquire: everyone's
+      const unsigned int ticket = atom_add_acq_rel_gpu(&rc.sync[0], 1u);  // release: the CTA's partials; acquire: everyone's
       *s_flag = (ticket == (epoch + 1u) * G - 1u) ? 1 : 0;
     }
     __syncthreads();
     last = (*s_flag != 0);
   }
-  unsigned long long* slots = reinterpret_cast<unsigned long long*>(ws.totals);
-  if (last) {  // last CTA of this GPU to arrive: every partial is visible
+  if (last) {  // last CTA of this rank to arrive: every partial of the rank is visible
     double t = 0.0;
     if (G > 1) {
-      if (threadIdx.x == 0) ws.totals[2 * kNVP + (epoch & 1u)] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling stamp
+      if (threadIdx.x == 0) rc.totals[2 * kNVP + (epoch & 1u)] = __longlong_as_double(static_cast<long long>(globaltimer_ns()));  // profiling stamp
       const int k = threadIdx.x & 31, slice = threadIdx.x >> 5;  // lane = value, warp = slice of the CTA rows
       double s = 0.0;
       constexpr int kRedRows = red_rows_for(NW);
@@ -514,7 +555,7 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
 #pragma unroll
         for (int i = 0; i < kRedRows; ++i) {
           const unsigned int b = b0 + slice + NW * i;
-          v[i] = (b < G && k < kNV) ? __ldcg(ws.partials + (size_t)b * kNVP + k) : 0.0;
+          v[i] = (b < G && k < kNV) ? __ldcg(rc.partials + (size_t)b * kNVP + k) : 0.0;
         }
 #pragma unroll
         for (int i = 0; i < kRedRows; ++i) s += v[i];
@@ -525,33 +566,25 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
 #pragma unroll
         for (int w = 0; w < NW; ++w) t += s_red8[w][threadIdx.x];
       }
-      __syncthreads();
     } else if (threadIdx.x < kNV) {
       t = s_block[threadIdx.x];
     }
     if (threadIdx.x < kNV) {
+      // this rank's sums go straight into every rank's mailbox (P2P stores over NVLink; each 64-bit word is
+      // self-validating, so no ordering between them is needed)
       const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(t));
-      if (W == 1) {
-        st_volatile_u64(slots + 2 * threadIdx.x, pack_lo(tag, bits));
-        st_volatile_u64(slots + 2 * threadIdx.x + 1, pack_hi(tag, bits));
-      } else {
-        // this GPU's sums go straight into every rank's mailbox (P2P stores over NVLink; each 64-bit word is
-        // self-validating, so no ordering between them is needed)
-        const size_t off = (((size_t)par * kMaxRanks + ws.rank) * kNVP + threadIdx.x) * 2;
-        for (int r = 0; r < W; ++r) {
-          st_volatile_u64(ws.mail[r] + off, pack_lo(tag, bits));
-          st_volatile_u64(ws.mail[r] + off + 1, pack_hi(tag, bits));
-        }
+      const size_t off = (((size_t)par * kMaxRanks + rc.rank) * kNVP + threadIdx.x) * 2;
+      for (int r = 0; r < W; ++r) {
+        st_volatile_u64(ws.mail[r] + off, pack_lo(tag, bits));
+        st_volatile_u64(ws.mail[r] + off + 1, pack_hi(tag, bits));
       }
     }
   }
-  if (W == 1) {
-    if (threadIdx.x < kNV) s_tot[threadIdx.x] = poll_tagged(slots + 2 * threadIdx.x, tag, false, &ws.sync[3]);
-    __syncthreads();
-  } else {
+  __syncthreads();  // s_red8 (the rank-row buffer below) aliases the CTA-sum scratch read above
+  {
     const int r = threadIdx.x >> 5, k = threadIdx.x & 31;
     if (r < W && k < kNV)
-      s_red8[r][k] = poll_tagged(ws.mail[ws.rank] + (((size_t)par * kMaxRanks + r) * kNVP + k) * 2, tag, true, &ws.sync[3]);
+      s_red8[r][k] = poll_tagged(ws.mail[rc.rank] + (((size_t)par * kMaxRanks + r) * kNVP + k) * 2, tag, true, &rc.sync[3]);
     __syncthreads();
     if (threadIdx.x < kNV) {  // rank order: every GPU forms identical bits and takes the identical Newton step
       double t = 0.0;
@@ -804,6 +837,19 @@ __device__ __forceinline__ bool warp_solve_definite() {
   return true;
 }
 
+// parity hook (ndtb200_debug_newton_solve): the two warp solvers on a caller-supplied system, one warp
+__global__ void __launch_bounds__(32) newton_solve_debug_kernel(const double* __restrict__ H, const double* __restrict__ g,
+                                                                double* __restrict__ delta, int* __restrict__ path) {
+  for (int i = threadIdx.x; i < 36; i += 32) g_st.H[i] = H[i];
+  if (threadIdx.x < 6) { g_st.g[threadIdx.x] = g[threadIdx.x]; g_st.delta[threadIdx.x] = 0.0; }
+  __syncwarp();
+  const bool fast = warp_solve_definite();
+  if (!fast) warp_newton_solve(g_st);
+  __syncwarp();
+  if (threadIdx.x < 6) delta[threadIdx.x] = g_st.delta[threadIdx.x];
+  if (threadIdx.x == 0) *path = fast ? 0 : 1;
+}
+
 // After the Newton solve: step-length bookkeeping and start of the line search
 // (ndt_omp_impl.hpp:131-142, 772-837).  Returns the next action.
 __device__ __noinline__ int newton_post() {
@@ -1035,6 +1081,7 @@ __device__ __forceinline__ void point_f32(float px, float py, float pz, const Ev
                                           float d1f, float (&acc)[32]) {
   float tx, ty, tz;
   transform_point(ctx.T, px, py, pz, tx, ty, tz);
+  if (!point_is_finite(tx, ty, tz)) return;  // no neighbourhood, no contribution (see point_is_finite)
   // getNeighborhoodAtPoint (…_impl.hpp:379-381): cell = floor(x' / leaf), fp32 DIVISION (Q8)
   const int ix = static_cast<int>(floorf(__fdiv_rn(tx, m.leaf[0])));
   const int iy = static_cast<int>(floorf(__fdiv_rn(ty, m.leaf[1])));
@@ -1175,7 +1222,7 @@ __device__ __forceinline__ double eval_warp_f32(const float4* __restrict__ src, 
 // ---------------------------------------------------------------------------------------------
 template <int METHOD, int THREADS>
 __global__ void __launch_bounds__(THREADS, min_blocks_for(THREADS))
-ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignParams prm, const AlignWorkspace ws) {
+ndt_align_kernel(const float4* __restrict__ src_in, const MapView map, const AlignParams prm, const AlignWorkspace ws) {
   constexpr int kAlignWarps = THREADS / 32;
   SolverState& st = g_st;
   EvalCtx& ctx = g_ctx;
@@ -1187,15 +1234,40 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
   __shared__ TableTerm s_terms[69];
   __shared__ int s_action;
   __shared__ int s_flag;
+  __shared__ int s_abort;
+  __shared__ RankCtx s_rc;
   __shared__ MapView s_map;  // for the out-of-line fp64 pass (taking the parameter's address would copy it to local memory)
 
   const unsigned long long t_kernel_begin = globaltimer_ns();
-  const int n = prm.n_source;
+  // the rank this CTA works for: the whole grid (one rank per GPU), or one of `vranks` emulated ranks sharing the launch
+  const float4* __restrict__ src = src_in;
+  int n = prm.n_source;
+  unsigned int G = gridDim.x, bid = blockIdx.x;
+  int my_rank = ws.rank;
+  if (ws.vranks > 1) {  // uniform
+    G = gridDim.x / static_cast<unsigned int>(ws.vranks);
+    my_rank = static_cast<int>(blockIdx.x / G);
+    bid = blockIdx.x - static_cast<unsigned int>(my_rank) * G;
+    src = ws.vr[my_rank].src;
+    n = ws.vr[my_rank].n_source;
+  }
+  if (threadIdx.x == 64 % THREADS) {
+    RankCtx rc;
+    if (ws.vranks > 1) {
+      const VirtualRank v = ws.vr[my_rank];
+      rc.partials = v.partials; rc.totals = v.totals; rc.sync = v.sync; rc.result = v.result;
+    } else {
+      rc.partials = ws.partials; rc.totals = ws.totals; rc.sync = ws.sync; rc.result = ws.result;
+    }
+    rc.G = G; rc.bid = bid; rc.rank = my_rank; rc.pad = 0;
+    s_rc = rc;
+    s_abort = 0;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // 32-point groups interleaved over all warps of the grid (deterministic static balance)
+  // 32-point groups interleaved over all warps of the rank's CTAs (deterministic static balance)
   const int n_groups = (n + 31) >> 5;
-  const int warp_global = warp * gridDim.x + (blockIdx.x + prm.rot) % gridDim.x;  // consecutive groups go to different SMs
-  const int warps_total = gridDim.x * kAlignWarps;
+  const int warp_global = warp * G + (bid + prm.rot) % G;  // consecutive groups go to different SMs
+  const int warps_total = G * kAlignWarps;
   unsigned int epoch = 0;
 
   // this thread's first two source points stay in registers for the whole solve
@@ -1251,6 +1323,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     for (int r = 0; r < 15; ++r) ctx.tf[8 + r] = make_float4(prm.tab0.hf[r][0], prm.tab0.hf[r][1], prm.tab0.hf[r][2], 0.f);
   }
   __syncthreads();
+  const bool trace_cta = (blockIdx.x == 0);  // the CTA that records the optimiser trace / timeline
 
   const float d2f = static_cast<float>(prm.d2);
   const float d1f = static_cast<float>(prm.d1);
@@ -1258,7 +1331,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     const int action = s_action;
     if (action == ACT_DONE) break;
     unsigned long long t_start = 0, t_local = 0, t_reduced = 0;
-    const bool timing = (blockIdx.x == 0 && threadIdx.x == 0 && ws.trace != nullptr);
+    const bool timing = (trace_cta && threadIdx.x == 0 && ws.trace != nullptr);
     if (timing) t_start = globaltimer_ns();
 
     if (action == ACT_HESS_ONLY) {
@@ -1280,13 +1353,23 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
       s_block[threadIdx.x] = s;
     }
     if (timing) t_local = globaltimer_ns();
-    grid_allreduce<kAlignWarps>(s_block, s_tot, ws, epoch, &s_flag, s_warp, prm.launch_tag);
-    if (ws.world > 1 && *reinterpret_cast<volatile unsigned int*>(&ws.sync[3]) != 0u) break;  // a peer never answered (uniform: checked after a barrier)
+    grid_allreduce<kAlignWarps>(s_block, s_tot, ws, s_rc, epoch, &s_flag, s_warp, prm.launch_tag);
+    if (ws.world > 1) {
+      // a peer that never answered (bounded poll) or a launch that ran out of mailbox tags: every thread of the CTA must
+      // take the same decision, so ONE thread reads the flag and the CTA breaks on the shared copy
+      if (threadIdx.x == 0) {
+        unsigned int ab = *reinterpret_cast<volatile unsigned int*>(&s_rc.sync[3]);
+        if (epoch >= kMaxEpochsSharded) ab = 1u;
+        s_abort = static_cast<int>(ab);
+      }
+      __syncthreads();
+      if (s_abort) break;
+    }
     if (timing) t_reduced = globaltimer_ns();
     unsigned long long t_last_arrive = 0;
-    if (timing && gridDim.x > 1)
+    if (timing && G > 1)
       t_last_arrive = (ws.world == 1) ? static_cast<unsigned long long>(__double_as_longlong(s_tot[31]))
-                                      : static_cast<unsigned long long>(__double_as_longlong(__ldcg(ws.totals + 2 * kNVP + ((epoch - 1u) & 1u))));
+                                      : static_cast<unsigned long long>(__double_as_longlong(__ldcg(s_rc.totals + 2 * kNVP + ((epoch - 1u) & 1u))));
     int slot = 0;
     unsigned long long t_d0 = 0, t_d1 = 0, t_d2 = 0;
     // the step: warp 0 of every CTA runs the identical Newton / More-Thuente state machine on the identical totals
@@ -1294,7 +1377,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
       unpack_hessian_warp(s_tot, action);
       if (lane == 0) {
         slot = st.n_trace;
-        s_action = advance(s_tot, action, blockIdx.x == 0 ? ws.trace : nullptr);
+        s_action = advance(s_tot, action, trace_cta ? ws.trace : nullptr);
       }
       __syncwarp();
       if (timing) t_d0 = t_d1 = t_d2 = globaltimer_ns();
@@ -1321,8 +1404,8 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     __syncthreads();
   }
 
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    AlignResultDev& r = *ws.result;
+  if (bid == 0 && threadIdx.x == 0) {
+    AlignResultDev& r = *s_rc.result;
     for (int i = 0; i < 12; ++i) r.final_T[i] = st.final_T[i];
     for (int i = 0; i < 6; ++i) r.last_dp[i] = st.last_dp[i];  // transformation_ = T(last_dp) is formed on the host
     r.converged = st.converged;
@@ -1330,7 +1413,7 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     r.n_evals = st.n_evals;
     r.n_hess = st.n_hess;
     r.trans_probability = st.score / static_cast<double>(ws.world > 1 ? ws.n_source_total : (long long)n);  // ndt_omp_impl.hpp:136, 170
-    r.aborted = (ws.world > 1) ? static_cast<int32_t>(*reinterpret_cast<volatile unsigned int*>(&ws.sync[3])) : 0;
+    r.aborted = (ws.world > 1) ? s_abort : 0;
     const bool trial = (st.n_evals > 1) || prm.mode != MODE_ALIGN;
     for (int i = 0; i < 6; ++i) r.final_pose[i] = trial ? st.x_t[i] : prm.p0[i];
     r.final_score = st.score;
@@ -1342,14 +1425,18 @@ ndt_align_kernel(const float4* __restrict__ src, const MapView map, const AlignP
     r.t_kernel_begin = t_kernel_begin;
     r.t_kernel_end = globaltimer_ns();
   }
-  // Leave the barrier words zeroed for the next launch: the LAST CTA to get here resets them (every other
+  // Leave the barrier words zeroed for the next launch: the LAST CTA of the rank to get here resets them (every other
   // CTA has finished its last barrier by then); sync[2] is a wrapping exit counter that resets itself.
-  if (threadIdx.x == 0 && gridDim.x > 1) {
-    const unsigned int old = atomicInc(&ws.sync[2], gridDim.x - 1);
-    if (old == gridDim.x - 1) {
-      ws.sync[0] = 0u;
-      ws.sync[3] = 0u;
-      __threadfence();
+  if (threadIdx.x == 0) {
+    if (G > 1) {
+      const unsigned int old = atomicInc(&s_rc.sync[2], G - 1);
+      if (old == G - 1) {
+        s_rc.sync[0] = 0u;
+        s_rc.sync[3] = 0u;
+        __threadfence();
+      }
+    } else {
+      s_rc.sync[3] = 0u;  // a one-CTA rank of a sharded solve: nobody else reads the flag of this launch any more
     }
   }
 }

@@ -250,8 +250,9 @@ calculate_score_kernel(const float4* __restrict__ cloud, int n, const MapView ma
   __shared__ double s_sum[8];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double score = 0;
-  if (i < n) {
-    const float4 p = __ldg(cloud + i);
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n) p = __ldg(cloud + i);
+  if (i < n && point_is_finite(p.x, p.y, p.z)) {  // a non-finite point has no neighbourhood (see point_is_finite)
     const int ix = static_cast<int>(floorf(__fdiv_rn(p.x, map.leaf[0])));
     const int iy = static_cast<int>(floorf(__fdiv_rn(p.y, map.leaf[1])));
     const int iz = static_cast<int>(floorf(__fdiv_rn(p.z, map.leaf[2])));
@@ -297,7 +298,7 @@ lookup_kernel(const float4* __restrict__ q, int n, const MapView map, int32_t* _
   const int iz = static_cast<int>(floorf(__fdiv_rn(p.z, map.leaf[2])));
   constexpr int K = num_offsets<METHOD>();
   int w = 0;
-  for (int k = 0; k < K; ++k) {
+  for (int k = 0; k < K && point_is_finite(p.x, p.y, p.z); ++k) {
     int dx, dy, dz;
     get_offset<METHOD>(k, dx, dy, dz);
     const int rec = probe_cell(map, ix + dx, iy + dy, iz + dz);

@@ -28,7 +28,7 @@ struct SmallBuildArgs {
   const float4* pts;
   uint32_t n;
   int is_dense;
-  float leaf;
+  Leaf3 leaf;
   int min_points;
   double eig_ratio;
   int mode;  // 0: NDT voxel map, 1: VoxelGrid centroids

@@ -88,6 +88,8 @@ def load_library():
     L.ndtb200_sync.argtypes = [vp]
     L.ndtb200_set_throughput_mode.argtypes = [vp, C.c_int]
     L.ndtb200_voxelgrid_filter.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_float, vp, C.c_size_t, C.c_size_t, i64p]
+    L.ndtb200_voxelgrid_filter3.argtypes = [vp, vp, C.c_size_t, C.c_size_t, f32p, vp, C.c_size_t, C.c_size_t, i64p]
+    L.ndtb200_pose_to_matrix.argtypes = [f64p, f32p]
     L.ndtb200_voxelgrid_filter_device.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.c_size_t, i64p]
     L.ndtb200_mapper_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Params), C.c_float, C.c_float, C.c_int]
     L.ndtb200_mapper_destroy.argtypes = [vp]
@@ -118,6 +120,9 @@ def load_library():
     L.ndtb200_comm_export.argtypes = [vp, vp]
     L.ndtb200_comm_attach.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64]
     L.ndtb200_comm_detach.argtypes = [vp]
+    L.ndtb200_align_emulated_ranks.argtypes = [vp, C.c_int, f32p, C.POINTER(Result)]
+    L.ndtb200_debug_guess_to_pose.argtypes = [f32p, f64p]
+    L.ndtb200_debug_newton_solve.argtypes = [vp, f64p, f64p, f64p, C.POINTER(C.c_int)]
     L.ndtb200_stream.argtypes = [vp]
     L.ndtb200_stream.restype = vp
     L.ndtb200_launch_count.argtypes = [vp]
@@ -234,6 +239,27 @@ def align_batch(ndts, guesses=None):
 
 def device_count():
     return int(load_library().ndtb200_device_count())
+
+
+def pose_to_matrix(p):
+    """ndtb200_pose_to_matrix = static convertTransform (ndt_omp.h:216-233).  Needs no device."""
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    out = np.zeros(16, dtype=np.float32)
+    st = load_library().ndtb200_pose_to_matrix(_ptr(p, C.c_double), _ptr(out, C.c_float))
+    if st != OK:
+        raise NdtError(st, "ndtb200_pose_to_matrix failed")
+    return out.reshape(4, 4).T.copy()
+
+
+def guess_to_pose(guess):
+    """ndtb200_debug_guess_to_pose: [translation, rotation().eulerAngles(0,1,2)] of a 4x4 guess as the align entry point
+    computes it on the host (ndt_omp_impl.hpp:103-111).  Needs no device."""
+    g = _colmajor(guess)
+    p = np.zeros(6, dtype=np.float64)
+    st = load_library().ndtb200_debug_guess_to_pose(_ptr(g, C.c_float), _ptr(p, C.c_double))
+    if st != OK:
+        raise NdtError(st, "ndtb200_debug_guess_to_pose failed")
+    return p
 
 
 def _ptr(a, t):
@@ -389,11 +415,16 @@ class NormalDistributionsTransform:
 
     # ---- pcl::VoxelGrid centroid downsample on the device ----
     def voxelgrid_filter(self, points, leaf):
-        """(n,3|4) cloud -> (m,3) float32 centroids, bit-identical to pcl::VoxelGrid (ascending cell index)."""
+        """(n,3|4) cloud -> (m,3) float32 centroids, bit-identical to pcl::VoxelGrid (ascending cell index).
+        `leaf`: scalar or (lx, ly, lz)."""
         p = as_xyzw(points)
         out = np.empty((max(1, p.shape[0]), 4), dtype=np.float32)
         m = C.c_int64(0)
-        st = self._L.ndtb200_voxelgrid_filter(self._h, p.ctypes.data, p.shape[0], 16, float(leaf), out.ctypes.data, out.shape[0], 16, C.byref(m))
+        if np.ndim(leaf) == 0:
+            st = self._L.ndtb200_voxelgrid_filter(self._h, p.ctypes.data, p.shape[0], 16, float(leaf), out.ctypes.data, out.shape[0], 16, C.byref(m))
+        else:
+            l3 = np.ascontiguousarray(leaf, dtype=np.float32)
+            st = self._L.ndtb200_voxelgrid_filter3(self._h, p.ctypes.data, p.shape[0], 16, _ptr(l3, C.c_float), out.ctypes.data, out.shape[0], 16, C.byref(m))
         self._check(st)
         return np.ascontiguousarray(out[:m.value, :3])
 
@@ -433,15 +464,36 @@ class NormalDistributionsTransform:
     def sync(self):
         self._check(self._L.ndtb200_sync(self._h))
 
-    def result(self):
-        r = Result()
-        self._check(self._L.ndtb200_get_result(self._h, C.byref(r)))
+    @staticmethod
+    def _result_dict(r):
         return {"final": np.array(r.final_transformation, dtype=np.float32).reshape(4, 4).T.copy(),
                 "last_increment": np.array(r.last_increment, dtype=np.float32).reshape(4, 4).T.copy(),
                 "converged": bool(r.converged), "iterations": int(r.iterations),
                 "trans_probability": float(r.trans_probability), "final_pose": np.array(r.final_pose),
                 "final_score": float(r.final_score), "n_evaluations": int(r.n_evaluations),
                 "n_hessian_passes": int(r.n_hessian_passes), "n_hits": int(r.n_hits)}
+
+    def result(self):
+        r = Result()
+        self._check(self._L.ndtb200_get_result(self._h, C.byref(r)))
+        return self._result_dict(r)
+
+    def align_emulated_ranks(self, world, guess=None):
+        """ndtb200_align_emulated_ranks: the source-sharded solve with `world` ranks inside one cooperative launch on this
+        GPU.  Returns one result dict per rank."""
+        g = _colmajor(guess) if guess is not None else None
+        res = (Result * int(world))()
+        self._check(self._L.ndtb200_align_emulated_ranks(self._h, int(world), _ptr(g, C.c_float) if g is not None else None, res))
+        return [self._result_dict(r) for r in res]
+
+    def newton_solve(self, H, g):
+        """ndtb200_debug_newton_solve: delta = solve(H, -g) by the kernel's warp solvers.  Returns (delta, path)."""
+        H = np.ascontiguousarray(H, dtype=np.float64).reshape(36)
+        g = np.ascontiguousarray(g, dtype=np.float64).reshape(6)
+        d = np.zeros(6, dtype=np.float64)
+        path = C.c_int(-1)
+        self._check(self._L.ndtb200_debug_newton_solve(self._h, _ptr(H, C.c_double), _ptr(g, C.c_double), _ptr(d, C.c_double), C.byref(path)))
+        return d, int(path.value)
 
     def getFinalTransformation(self):
         return self.result()["final"]
