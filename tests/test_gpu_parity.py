@@ -725,7 +725,7 @@ def test_non_finite_source_points_contribute_nothing(nb, method):
         assert a["hits"] == b["hits"] == c["hits"]
         assert abs(a["score"] - b["score"]) <= REL * abs(b["score"])
         assert rel_err(a["gradient"], b["gradient"]) < REL and rel_err(a["hessian"], b["hessian"]) < REL
-        assert rel_err(a["gradient"], c["gradient"]) < 1e-9 and rel_err(a["hessian"], c["hessian"]) < 1e-9
+        assert rel_err(a["gradient"], c["gradient"]) < 1e-6 and rel_err(a["hessian"], c["hessian"]) < 1e-6   # other point-to-lane grouping: fp32 sum order
         ha, hb = gpu.eval_hessian(p), ref.eval_hessian(p)
         assert np.isfinite(ha).all() and rel_err(ha, hb) < REL
     check_align(ref, gpu)
