@@ -808,3 +808,68 @@ def test_voxelgrid_filter_non_cubic_leaf(nb):
     ref = oracle.NormalDistributionsTransform()
     ref.setInputTarget(tgt)
     assert gpu.map_info()["n_voxels"] == ref.map_info()["n_voxels"]
+
+
+def test_large_source_sorted_by_voxel_key(nb, monkeypatch):
+    """Sources of >= 262 144 points are aligned from a copy sorted by voxel key (coalesced probes, shared Gaussian
+    records): only the summation order changes.  Oracle parity on a 300 k-point source in random order, equality
+    (to summation-order noise) with the unsorted path, the caller's point order in the output cloud, emulated ranks."""
+    tgt, src = synthetic_scene(n_target=120000, n_source=300000, seed=31)
+    ref, gpu = make_pair(nb, tgt, src)
+    monkeypatch.setenv("NDTB200_SORT_SOURCE_MIN", "0")
+    _, plain = make_pair(nb, tgt, src)
+    p = np.array([0.3, -0.2, 0.04, 0.004, -0.005, 0.012])
+    b = ref.eval_derivatives(p)
+    c = plain.eval_derivatives(p)
+    monkeypatch.delenv("NDTB200_SORT_SOURCE_MIN")
+    a = gpu.eval_derivatives(p)
+    assert a["hits"] == b["hits"] == c["hits"] and b["hits"] > 500000
+    assert abs(a["score"] - b["score"]) <= REL * abs(b["score"])
+    assert rel_err(a["gradient"], b["gradient"]) < REL and rel_err(a["hessian"], b["hessian"]) < REL
+    assert rel_err(a["gradient"], c["gradient"]) < 1e-6 and rel_err(a["hessian"], c["hessian"]) < 1e-6
+    assert rel_err(gpu.eval_hessian(p), ref.eval_hessian(p)) < REL
+    out, rr, rg = check_align(ref, gpu)
+    assert np.array_equal(out[:, :3], oracle.transform_points(rg["final"], src)[:, :3])      # output keeps the caller's order
+    again = gpu.align()
+    assert np.array_equal(again, out)                                                        # reproducible
+    res = gpu.align_emulated_ranks(4)
+    assert all(np.array_equal(r["final"], res[0]["final"]) for r in res)
+    dt, dr = transform_delta(res[0]["final"], rr["final"])
+    assert dt < TRANS_TOL and dr < ROT_TOL and res[0]["n_evaluations"] == rr["n_evaluations"]
+
+
+@pytest.mark.parametrize("leaf", [0.3, 0.7, 1.0, 2.5])
+def test_lookup_cells_near_faces_are_bit_exact(nb, leaf):
+    """The lookup's cell index is int(floor(x / leaf)) with an fp32 DIVISION (Q8); the kernel decides most points from
+    x * fl(1/leaf) and falls back to the exact division near cell faces (lookup_cell).  Queries ON and within a few ulps
+    of the faces (both the fp32 product k * leaf and the fp32 nearest to the real face), for leaves whose reciprocal is
+    inexact, must land in the oracle's cells — checked through the returned neighbour keys and through the hit count
+    of a derivative evaluation over a source made of such points."""
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src, res=leaf)
+    info = gpu.map_info()
+    rng = np.random.default_rng(17)
+    n = 4000
+    clouds = []
+    for axis in range(3):
+        k = rng.integers(info["min_b"][axis] - 2, info["max_b"][axis] + 3, size=n)
+        f1 = (k.astype(np.float32) * np.float32(leaf)).astype(np.float32)          # fp32 product
+        f2 = (k.astype(np.float64) * leaf).astype(np.float32)                      # nearest fp32 to the real face
+        variants = []
+        for f in (f1, f2):
+            up = dn = f
+            variants.append(f)
+            for _ in range(3):
+                up = np.nextafter(up, np.float32(np.inf)); dn = np.nextafter(dn, np.float32(-np.inf))
+                variants += [up, dn]
+        for v in variants:
+            pts = src[rng.integers(0, len(src), size=n)].copy()
+            pts[:, axis] = v
+            clouds.append(pts)
+    q = np.concatenate(clouds).astype(np.float32)
+    assert np.array_equal(gpu.lookup(q, oracle.DIRECT7), ref.lookup(q, oracle.DIRECT7))
+    assert np.array_equal(gpu.lookup(q, oracle.DIRECT26), ref.lookup(q, oracle.DIRECT26))
+    ref.setInputSource(q); gpu.setInputSource(q)
+    a, b = gpu.eval_derivatives(np.zeros(6)), ref.eval_derivatives(np.zeros(6))
+    assert a["hits"] == b["hits"] and b["hits"] > 10000
+    assert rel_err(a["gradient"], b["gradient"]) < REL

@@ -71,7 +71,7 @@ struct ndtb200_handle {
   long long n_voxels = 0, n_valid = 0;
   uint32_t hash_cap = 0;
   int hash_shift = 0;
-  DevBuf d_grid, d_mm_partial, d_mm_finite, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_scan_tmp, d_scalar;
+  DevBuf d_grid, d_mm_partial, d_mm_finite, d_keys_a, d_keys_b, d_vals_a, d_vals_b, d_hist, d_scan_tmp, d_scalar, d_sortmeta, d_status;
   DevBuf d_voxel_key, d_voxel_start, d_voxel_count, d_moments, d_records, d_icov64, d_hash, d_dense;
   size_t n_partials = 0;       // voxels of the last partial-only build (sharded build, before the exchange)
   bool map_is_merged = false;
@@ -88,6 +88,10 @@ struct ndtb200_handle {
   DevBuf d_source;
   size_t n_source = 0;
   bool has_source = false;
+  // large sources: a copy ordered by voxel key (cells of the source's own grid at the map resolution), so that the 32
+  // points of a warp fall into one or two voxels — coalesced probes, shared Gaussian records (SURVEY 7.1 last bullet)
+  DevBuf d_source_sorted;
+  bool source_sorted_valid = false, source_sort_failed = false;
 
   // align workspace
   DevBuf d_partials, d_totals, d_sync, d_result, d_trace, d_out, d_tmp, d_emu;
@@ -226,31 +230,66 @@ int compute_grid(ndtb200_handle* h, const float4* pts, size_t n, int dense, cons
   return NDTB200_OK;
 }
 
-// stable LSD radix sort of the n (key, index) pairs whose keys sit in d_keys_a, then the segment heads:
-// -> d_voxel_key / d_voxel_start (n_vox entries), sorted indices in d_vals_a.  One synchronisation (the voxel count).
-int sort_and_segment(ndtb200_handle* h, size_t n, uint32_t sentinel, int passes, uint32_t* n_vox_out) {
+// One-sweep sort bookkeeping (map_build.cuh): [digit_hist 4 x 256 u64 | digit_base 4 x 256 u64 | tickets 4 x u32 (+ pad)]
+constexpr size_t kSortMetaHistOff = 0, kSortMetaBaseOff = kMaxSortPasses * 256 * sizeof(unsigned long long),
+                 kSortMetaTicketOff = 2 * kSortMetaBaseOff, kSortMetaBytes = kSortMetaTicketOff + 64;
+
+// zero the histograms / tickets before the keys are produced (the key kernel accumulates the digit histograms)
+int sort_meta_reset(ndtb200_handle* h) {
+  CK(h->d_sortmeta.ensure(kSortMetaBytes));
+  CK(cudaMemsetAsync(h->d_sortmeta.p, 0, kSortMetaBytes, h->stream));
+  return NDTB200_OK;
+}
+unsigned long long* sort_meta_hist(ndtb200_handle* h) { return reinterpret_cast<unsigned long long*>(h->d_sortmeta.as<char>() + kSortMetaHistOff); }
+
+// stable LSD radix sort (one-sweep passes) of the n (key, index) pairs whose keys sit in d_keys_a:
+// sorted keys -> d_keys_a, sorted indices -> d_vals_a.  hist_ready: the digit histograms were accumulated by the key
+// kernel (sort_meta_reset was called before it); otherwise they are computed from the keys here.  No synchronisation.
+int sort_pairs(ndtb200_handle* h, size_t n, int passes, bool hist_ready) {
   const int ntiles = static_cast<int>((n + kSortTile - 1) / kSortTile);
-  const size_t hist_n = (size_t)256 * ntiles;
-  const int stiles = static_cast<int>((n + kScanTile - 1) / kScanTile);
-  CK(h->d_hist.ensure(std::max(hist_n, (size_t)stiles) * sizeof(uint32_t)));
-  CK(h->d_scan_tmp.ensure(scan_tmp_elems(std::max(hist_n, n)) * sizeof(uint32_t)));
+  unsigned long long* hist = sort_meta_hist(h);
+  unsigned long long* base = reinterpret_cast<unsigned long long*>(h->d_sortmeta.as<char>() + kSortMetaBaseOff);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(h->d_sortmeta.as<char>() + kSortMetaTicketOff);
   uint32_t *ka = h->d_keys_a.as<uint32_t>(), *kb = h->d_keys_b.as<uint32_t>();
   uint32_t *va = h->d_vals_a.as<uint32_t>(), *vb = h->d_vals_b.as<uint32_t>();
-  for (int pass = 0; pass < passes; ++pass) {
-    const int shift = pass * 8;
-    radix_count_kernel<<<ntiles, kBuildThreads, 0, h->stream>>>(ka, n, shift, h->d_hist.as<uint32_t>(), ntiles);
-    LAUNCHED(h);
-    int st = exclusive_scan(h, h->d_hist.as<uint32_t>(), hist_n, h->d_scan_tmp.as<uint32_t>(), nullptr);
+  if (!hist_ready) {
+    int st = sort_meta_reset(h);
     if (st != NDTB200_OK) return st;
-    radix_scatter_kernel<<<ntiles, kBuildThreads, 0, h->stream>>>(ka, pass == 0 ? nullptr : va, n, shift,
-                                                                   h->d_hist.as<uint32_t>(), ntiles, kb, vb);
+    hist = sort_meta_hist(h);
+    base = reinterpret_cast<unsigned long long*>(h->d_sortmeta.as<char>() + kSortMetaBaseOff);
+    tickets = reinterpret_cast<unsigned int*>(h->d_sortmeta.as<char>() + kSortMetaTicketOff);
+    digit_hist_kernel<<<grid_for(n, kBuildThreads * 8, h->num_sms * 8), kBuildThreads, 0, h->stream>>>(ka, n, hist, passes);
+    LAUNCHED(h);
+  }
+  digit_base_kernel<<<1, 256, 0, h->stream>>>(hist, passes, base);
+  LAUNCHED(h);
+  const size_t status_bytes = (size_t)passes * ntiles * 256 * sizeof(unsigned long long);
+  CK(h->d_status.ensure(status_bytes));
+  CK(cudaMemsetAsync(h->d_status.p, 0, status_bytes, h->stream));
+  for (int pass = 0; pass < passes; ++pass) {
+    onesweep_kernel<<<ntiles, kBuildThreads, 0, h->stream>>>(ka, pass == 0 ? nullptr : va, n, pass * 8, base + pass * 256,
+                                                              h->d_status.as<unsigned long long>() + (size_t)pass * ntiles * 256,
+                                                              tickets + pass, kb, vb);
     LAUNCHED(h);
     std::swap(ka, kb);
     std::swap(va, vb);
   }
   // sorted keys in ka, sorted indices in va.  Keep them addressable through fixed members.
   if (ka != h->d_keys_a.as<uint32_t>()) { std::swap(h->d_keys_a, h->d_keys_b); std::swap(h->d_vals_a, h->d_vals_b); }
+  return NDTB200_OK;
+}
 
+// sort + the segment heads: -> d_voxel_key / d_voxel_start (n_vox entries), sorted indices in d_vals_a.  One
+// synchronisation (the voxel count, needed to size the voxel arrays).
+int sort_and_segment(ndtb200_handle* h, size_t n, uint32_t sentinel, int passes, uint32_t* n_vox_out, bool hist_ready = false) {
+  {
+    int st = sort_pairs(h, n, passes, hist_ready);
+    if (st != NDTB200_OK) return st;
+  }
+  const int stiles = static_cast<int>((n + kScanTile - 1) / kScanTile);
+  CK(h->d_hist.ensure((size_t)stiles * sizeof(uint32_t)));
+  CK(h->d_scan_tmp.ensure(scan_tmp_elems(std::max<size_t>(stiles, 1)) * sizeof(uint32_t)));
+  uint32_t* ka = h->d_keys_a.as<uint32_t>();
   uint32_t* tile_counts = h->d_hist.as<uint32_t>();
   head_count_kernel<<<stiles, kBuildThreads, 0, h->stream>>>(ka, n, sentinel, tile_counts);
   LAUNCHED(h);
@@ -484,15 +523,19 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
   CK(h->d_keys_b.ensure(n * sizeof(uint32_t)));
   CK(h->d_vals_a.ensure(n * sizeof(uint32_t)));
   CK(h->d_vals_b.ensure(n * sizeof(uint32_t)));
-  const int key_blocks = grid_for(n, kBuildThreads * 4, h->num_sms * 16);
+  {
+    int st = sort_meta_reset(h);
+    if (st != NDTB200_OK) return st;
+  }
+  const int key_blocks = grid_for(n, kBuildThreads * 4, h->num_sms * 8);
   voxel_key_kernel<<<key_blocks, kBuildThreads, 0, h->stream>>>(pts, n, dense, h->d_grid.as<GridDesc>(), sentinel,
-                                                                 h->d_keys_a.as<uint32_t>(), nullptr);
+                                                                 h->d_keys_a.as<uint32_t>(), nullptr, sort_meta_hist(h), passes);
   LAUNCHED(h);
 
-  // 3. stable sort of (key, point index) + 4. occupied voxels = segment heads
+  // 3. stable sort of (key, point index), one-sweep passes + 4. occupied voxels = segment heads
   uint32_t n_vox = 0;
   {
-    int st = sort_and_segment(h, n, sentinel, passes, &n_vox);
+    int st = sort_and_segment(h, n, sentinel, passes, &n_vox, /*hist_ready=*/true);
     if (st != NDTB200_OK) return st;
   }
   h->n_voxels = n_vox;
@@ -652,6 +695,7 @@ MapView make_view(const ndtb200_handle* h) {
     m.max_b[a] = h->grid.max_b[a];
     m.mul[a] = h->grid.mul[a];
     m.leaf[a] = h->grid.leaf[a];
+    m.inv_leaf[a] = 1.0f / h->grid.leaf[a];
   }
   if (h->n_voxels == 0) {  // empty map: every bounds test fails
     for (int a = 0; a < 3; ++a) { m.min_b[a] = 1; m.max_b[a] = 0; m.mul[a] = 0; }
@@ -736,6 +780,60 @@ int query_coop_blocks(ndtb200_handle* h) {
   return NDTB200_OK;
 }
 
+int ensure_aux(ndtb200_handle* h) {  // scratch handle: VoxelGrid filters and the source sort keep the map's build buffers untouched
+  if (h->aux) return NDTB200_OK;
+  const int st = ndtb200_create(&h->aux, h->device);
+  if (st != NDTB200_OK) h->err = "could not create the scratch state (ndtb200_voxelgrid_filter / source sort)";
+  return st;
+}
+
+// Sources of at least this many points are aligned from a copy sorted by voxel key (NDTB200_SORT_SOURCE_MIN overrides;
+// 0 = never).  A LiDAR scan in ring order is already coherent and small enough to live in L1 / L2; a merged or
+// map-sized source in arbitrary order is not: its warps would touch 32 different voxels per probe.
+size_t sort_source_min() {
+  const char* e = getenv("NDTB200_SORT_SOURCE_MIN");  // read per call: tests switch it inside one process
+  const long long v = e ? atoll(e) : 262144;
+  return v <= 0 ? ~size_t(0) : static_cast<size_t>(v);
+}
+
+// The sort changes only the ORDER in which the per-point contributions are summed (fixed and reproducible for a given
+// cloud): keys are the cells of the source's own bounding-box grid at the map resolution, untransformed — a rigid
+// guess keeps neighbours neighbours.  Once per set_source; the output cloud of align() keeps the caller's order.
+int ensure_sorted_source(ndtb200_handle* h) {
+  if (h->source_sorted_valid || h->source_sort_failed) return NDTB200_OK;
+  const size_t n = h->n_source;
+  if (n < sort_source_min() || n > 0xFFFFFFF0ull) { h->source_sort_failed = true; return NDTB200_OK; }
+  int st = ensure_aux(h);
+  if (st != NDTB200_OK) return st;
+  ndtb200_handle* a = h->aux;
+  CK(cudaStreamSynchronize(h->stream));  // the source copy was enqueued on h's stream; the sort runs on the scratch handle's
+  for (int k = 0; k < 3; ++k) a->vg_leaf[k] = h->prm.resolution;
+  const float4* pts = h->d_source.as<float4>();
+  st = compute_grid(a, pts, n, /*dense=*/0, BuildOpts());
+  if (st != NDTB200_OK) { h->err = a->err; return st; }
+  if (a->grid.overflow || a->grid.n_finite == 0) { h->source_sort_failed = true; return NDTB200_OK; }  // keep the caller's order
+  uint32_t sentinel = 0;
+  const int passes = passes_for(a->grid, true, &sentinel);
+  CK2(a, a->d_keys_a.ensure(n * sizeof(uint32_t)));
+  CK2(a, a->d_keys_b.ensure(n * sizeof(uint32_t)));
+  CK2(a, a->d_vals_a.ensure(n * sizeof(uint32_t)));
+  CK2(a, a->d_vals_b.ensure(n * sizeof(uint32_t)));
+  st = sort_meta_reset(a);
+  if (st != NDTB200_OK) return st;
+  voxel_key_kernel<<<grid_for(n, kBuildThreads * 4, a->num_sms * 8), kBuildThreads, 0, a->stream>>>(
+      pts, n, 0, a->d_grid.as<GridDesc>(), sentinel, a->d_keys_a.as<uint32_t>(), nullptr, sort_meta_hist(a), passes);
+  LAUNCHED(a);
+  st = sort_pairs(a, n, passes, /*hist_ready=*/true);
+  if (st != NDTB200_OK) { h->err = a->err; return st; }
+  CK(h->d_source_sorted.ensure(n * sizeof(float4)));
+  gather_points_kernel<<<grid_for(n, kBuildThreads * 4, a->num_sms * 16), kBuildThreads, 0, a->stream>>>(
+      pts, a->d_vals_a.as<uint32_t>(), n, h->d_source_sorted.as<float4>());
+  LAUNCHED(a);
+  CK(cudaStreamSynchronize(a->stream));
+  h->source_sorted_valid = true;
+  return NDTB200_OK;
+}
+
 // Enqueue one launch of the persistent kernel (no host synchronisation).
 int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0[12], int has_guess, int eval_hessian,
                  int emulate_world = 0) {
@@ -749,6 +847,11 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
     const int st = ensure_kdtree_index(h);
     if (st != NDTB200_OK) return st;
   }
+  {
+    const int st = ensure_sorted_source(h);
+    if (st != NDTB200_OK) return st;
+  }
+  const float4* d_src = h->source_sorted_valid ? h->d_source_sorted.as<float4>() : h->d_source.as<float4>();
   AlignParams prm;
   gauss_constants(h->prm, prm.d1, prm.d2, prm.d3);
   prm.step_size = h->prm.step_size;
@@ -816,7 +919,7 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
       const long long g_lo = r * (groups / W) + std::min<long long>(r, groups % W);
       const long long g_hi = g_lo + groups / W + (r < groups % W ? 1 : 0);
       const long long lo = std::min<long long>(h->n_source, g_lo * 32), hi = std::min<long long>(h->n_source, g_hi * 32);
-      vr[r].src = h->d_source.as<float4>() + lo;
+      vr[r].src = d_src + lo;
       vr[r].n_source = static_cast<int32_t>(hi - lo);
       vr[r].pad = 0;
       vr[r].partials = reinterpret_cast<double*>(base);
@@ -837,7 +940,7 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
     h->emu_result_off = vr_b + part_b + tot_b + sync_b;
   }
   MapView map = make_view(h);
-  const float4* src = h->d_source.as<float4>();
+  const float4* src = d_src;
   void* args[] = {(void*)&src, (void*)&map, (void*)&prm, (void*)&ws};
   const void* fn;
   if (shape == 0)
@@ -988,9 +1091,9 @@ int ndtb200_destroy(ndtb200_handle* h) {
   ndtb200_comm_detach(h);
   if (h->aux) { ndtb200_destroy(h->aux); h->aux = nullptr; }
   DevBuf* bufs[] = {&h->d_target, &h->d_grid, &h->d_mm_partial, &h->d_mm_finite, &h->d_keys_a, &h->d_keys_b,
-                    &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_voxel_key,
+                    &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_sortmeta, &h->d_status, &h->d_voxel_key,
                     &h->d_voxel_start, &h->d_voxel_count, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_dense, &h->d_source,
-                    &h->d_cell_all, &h->d_best, &h->d_centroid, &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail, &h->d_emu};
+                    &h->d_cell_all, &h->d_best, &h->d_centroid, &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail, &h->d_emu, &h->d_source_sorted};
   for (DevBuf* b : bufs) b->release();
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1058,6 +1161,7 @@ int ndtb200_set_source(ndtb200_handle* h, const void* points, size_t n, size_t s
   if (st != NDTB200_OK) return st;
   h->n_source = n;
   h->has_source = true;
+  h->source_sorted_valid = h->source_sort_failed = false;
   return NDTB200_OK;
 }
 
@@ -1071,6 +1175,7 @@ int ndtb200_set_source_device(ndtb200_handle* h, const void* d_points, size_t n)
   }
   h->n_source = n;
   h->has_source = true;
+  h->source_sorted_valid = h->source_sort_failed = false;
   return NDTB200_OK;
 }
 
@@ -1328,7 +1433,7 @@ int ndtb200_dump_point_keys(ndtb200_handle* h, int32_t* keys) {
   CK(h->d_tmp.ensure(n * sizeof(uint32_t)));
   voxel_key_kernel<<<grid_for(n, kBuildThreads * 4, h->num_sms * 16), kBuildThreads, 0, h->stream>>>(
       h->d_target.as<float4>(), n, h->target_dense ? 1 : 0, h->d_grid.as<GridDesc>(), 0xFFFFFFFFu,
-      h->d_tmp.as<uint32_t>(), nullptr);
+      h->d_tmp.as<uint32_t>(), nullptr, nullptr, 0);
   LAUNCHED(h);
   CK(cudaMemcpyAsync(keys, h->d_tmp.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1724,12 +1829,14 @@ static int voxelgrid_filter_impl(ndtb200_handle* h, const float leaf[3], int64_t
   CK2(a, a->d_keys_b.ensure(n * sizeof(uint32_t)));
   CK2(a, a->d_vals_a.ensure(n * sizeof(uint32_t)));
   CK2(a, a->d_vals_b.ensure(n * sizeof(uint32_t)));
-  const int key_blocks = grid_for(n, kBuildThreads * 4, a->num_sms * 16);
+  st = sort_meta_reset(a);
+  if (st != NDTB200_OK) return st;
+  const int key_blocks = grid_for(n, kBuildThreads * 4, a->num_sms * 8);
   voxel_key_kernel<<<key_blocks, kBuildThreads, 0, a->stream>>>(pts, n, 0, a->d_grid.as<GridDesc>(), sentinel,
-                                                                 a->d_keys_a.as<uint32_t>(), nullptr);
+                                                                 a->d_keys_a.as<uint32_t>(), nullptr, sort_meta_hist(a), passes);
   LAUNCHED(a);
   uint32_t n_vox = 0;
-  st = sort_and_segment(a, n, sentinel, passes, &n_vox);
+  st = sort_and_segment(a, n, sentinel, passes, &n_vox, /*hist_ready=*/true);
   if (st != NDTB200_OK) return st;
   CK2(a, a->d_out.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(float4)));
   if (n_vox > 0) {
@@ -1742,12 +1849,6 @@ static int voxelgrid_filter_impl(ndtb200_handle* h, const float leaf[3], int64_t
   return NDTB200_OK;
 }
 
-static int ensure_aux(ndtb200_handle* h) {
-  if (h->aux) return NDTB200_OK;
-  const int st = ndtb200_create(&h->aux, h->device);
-  if (st != NDTB200_OK) h->err = "could not create the scratch state for ndtb200_voxelgrid_filter";
-  return st;
-}
 
 int ndtb200_voxelgrid_filter(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, float leaf, void* out_points,
                              size_t out_capacity, size_t out_stride_bytes, int64_t* n_out) {

@@ -62,6 +62,7 @@ struct MapView {  // what the kernels need to probe the map
   int32_t hash_shift;
   int32_t min_b[3], max_b[3], mul[3];
   float leaf[3];
+  float inv_leaf[3];  // fl32(1 / leaf): fast path of lookup_cell only (the reference's lookup DIVIDES, Q8)
   int32_t min_points;
 };
 
@@ -88,6 +89,21 @@ __device__ __forceinline__ void transform_point(const float* T, float x, float y
   ox = __fadd_rn(__fmul_rn(T[0], x), __fadd_rn(__fmul_rn(T[1], y), __fadd_rn(__fmul_rn(T[2], z), T[3])));
   oy = __fadd_rn(__fmul_rn(T[4], x), __fadd_rn(__fmul_rn(T[5], y), __fadd_rn(__fmul_rn(T[6], z), T[7])));
   oz = __fadd_rn(__fmul_rn(T[8], x), __fadd_rn(__fmul_rn(T[9], y), __fadd_rn(__fmul_rn(T[10], z), T[11])));
+}
+
+// getNeighborhoodAtPoint's cell index (voxel_grid_covariance_omp_impl.hpp:379-381): int(floor(x / leaf)), an fp32
+// DIVISION (quirk Q8 — the build multiplies by the inverse instead).  A correctly rounded division costs ~35
+// instructions; here the product q = x * fl(1/leaf) decides whenever it can:
+//     |q - x/leaf| <= 2^-23 |x/leaf| (two roundings) and |fl(x/leaf) - x/leaf| <= 2^-24 |x/leaf|,
+// so if q is further than 2^-20 |q| from every integer, fl(x/leaf) lies strictly inside the same unit interval and has
+// the same floor.  Otherwise (q within ~1e-6 |q| of a cell face, q == 0, huge or NaN) the exact division decides —
+// bit-identical cells, ~0.1 % of the points take the slow path at scan-scale coordinates.
+__device__ __forceinline__ int lookup_cell(float x, float leaf, float inv_leaf) {
+  const float q = __fmul_rn(x, inv_leaf);
+  const float f = floorf(q);
+  const float d = fminf(__fsub_rn(q, f), __fsub_rn(__fadd_rn(f, 1.0f), q));  // distance to the nearest integer
+  if (d > __fmul_rn(fabsf(q), 9.5367431640625e-07f)) return static_cast<int>(f);
+  return static_cast<int>(floorf(__fdiv_rn(x, leaf)));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -147,17 +147,95 @@ __device__ __forceinline__ int32_t voxel_key_of(const float4& p, const GridDesc&
   return ijk0 * g.mul[0] + ijk1 * g.mul[1] + ijk2 * g.mul[2];
 }
 
+// Digit histograms of ALL radix passes at once (one-sweep sort: the per-pass count kernels and their scans go away).
+// s_hist: [kMaxSortPasses][256] shared counters; a warp whose 32 keys share the digit (clouds in scan order, and always
+// the high digits of coherent clouds) adds once.
+constexpr int kMaxSortPasses = 4;
+
+__device__ __forceinline__ void digit_hist_add(uint32_t (*s_hist)[256], uint32_t key, bool valid, int passes) {
+  for (int p = 0; p < passes; ++p) {
+    const uint32_t d = (key >> (8 * p)) & 255u;
+    const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+    const unsigned int act = __ballot_sync(0xffffffffu, valid);
+    if (__all_sync(0xffffffffu, !valid || d == d0)) {
+      if ((threadIdx.x & 31) == 0 && act) atomicAdd(&s_hist[p][d0], static_cast<uint32_t>(__popc(act)));
+    } else if (valid) {
+      atomicAdd(&s_hist[p][d], 1u);
+    }
+  }
+}
+
+// keys[i] = voxel key of point i (sentinel for a skipped non-finite point); digit_hist != nullptr: also accumulate the
+// 8-bit digit histograms of the `passes` radix passes into digit_hist[pass][256] (zeroed by the caller)
 __global__ void __launch_bounds__(kBuildThreads)
 voxel_key_kernel(const float4* __restrict__ pts, size_t n, int is_dense, const GridDesc* __restrict__ gd,
-                 uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+                 uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
+                 unsigned long long* __restrict__ digit_hist, int passes) {
   __shared__ GridDesc g;
+  __shared__ uint32_t s_hist[kMaxSortPasses][256];
   if (threadIdx.x == 0) g = *gd;
+  if (digit_hist)
+    for (int i = threadIdx.x; i < kMaxSortPasses * 256; i += kBuildThreads) (&s_hist[0][0])[i] = 0u;
   __syncthreads();
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float4 p = __ldg(pts + i);
-    bool ok = is_dense || (isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
-    keys[i] = ok ? static_cast<uint32_t>(voxel_key_of(p, g)) : sentinel;
-    if (idx) idx[i] = static_cast<uint32_t>(i);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n_round = ((n + 31) / 32) * 32;  // whole warps stay in the loop (the histogram uses warp votes)
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool in = i < n;
+    uint32_t key = sentinel;
+    if (in) {
+      float4 p = __ldg(pts + i);
+      bool ok = is_dense || (isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
+      if (ok) key = static_cast<uint32_t>(voxel_key_of(p, g));
+      keys[i] = key;
+      if (idx) idx[i] = static_cast<uint32_t>(i);
+    }
+    if (digit_hist) digit_hist_add(s_hist, key, in, passes);
+  }
+  if (digit_hist) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * 256; i += kBuildThreads) {
+      const uint32_t c = (&s_hist[0][0])[i];
+      if (c) atomicAdd(digit_hist + i, static_cast<unsigned long long>(c));
+    }
+  }
+}
+
+// the same histograms for keys that already exist (merged partials, VoxelGrid filter)
+__global__ void __launch_bounds__(kBuildThreads)
+digit_hist_kernel(const uint32_t* __restrict__ keys, size_t n, unsigned long long* __restrict__ digit_hist, int passes) {
+  __shared__ uint32_t s_hist[kMaxSortPasses][256];
+  for (int i = threadIdx.x; i < kMaxSortPasses * 256; i += kBuildThreads) (&s_hist[0][0])[i] = 0u;
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n_round = ((n + 31) / 32) * 32;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool in = i < n;
+    const uint32_t key = in ? __ldg(keys + i) : 0u;
+    digit_hist_add(s_hist, key, in, passes);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * 256; i += kBuildThreads) {
+    const uint32_t c = (&s_hist[0][0])[i];
+    if (c) atomicAdd(digit_hist + i, static_cast<unsigned long long>(c));
+  }
+}
+
+// exclusive scan of every pass's 256 digit totals -> first output position of each digit; one CTA of 256 threads
+__global__ void __launch_bounds__(256)
+digit_base_kernel(const unsigned long long* __restrict__ digit_hist, int passes, unsigned long long* __restrict__ digit_base) {
+  __shared__ unsigned long long s[256];
+  for (int p = 0; p < passes; ++p) {
+    const unsigned long long c = digit_hist[p * 256 + threadIdx.x];
+    s[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+      const unsigned long long t = (threadIdx.x >= o) ? s[threadIdx.x - o] : 0ull;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    digit_base[p * 256 + threadIdx.x] = s[threadIdx.x] - c;
+    __syncthreads();
   }
 }
 
@@ -385,6 +463,120 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
   __shared__ uint32_t s_val[kSortTile];
   radix_scatter_tile<kSortRounds>(keys_in, vals_in, n, shift, hist_scanned, ntiles, blockIdx.x, keys_out, vals_out, warp_cnt, s_dstart,
                                   s_gbase, s_scan, s_key, s_val);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ONE-SWEEP pass: the scatter kernel finds its own global offsets.  Every tile publishes its 256 digit counts in a
+// status row and obtains, per digit, the number of equal digits in all earlier tiles by decoupled look-back (walk the
+// earlier tiles' rows backwards, adding "aggregate" words until an "inclusive prefix" word is found); the first output
+// position of every digit comes from the up-front histograms (digit_base).  Per pass the keys are read ONCE and no
+// count / scan kernels run.  Tiles are numbered in the order CTAs START (atomic ticket), so a tile only ever waits for
+// tiles that are already running.  status word: bits 63..62 = 0 not ready / 1 aggregate / 2 inclusive prefix.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kBuildThreads, NDTB200_SCATTER_MIN_BLOCKS)
+onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, size_t n, int shift,
+                const unsigned long long* __restrict__ digit_base, unsigned long long* __restrict__ status,
+                unsigned int* __restrict__ ticket, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  constexpr int ROUNDS = kSortRounds;
+  constexpr int kTile = kBuildThreads * ROUNDS;
+  __shared__ uint32_t warp_cnt[kSortWarps][256];
+  __shared__ uint32_t s_dstart[256];
+  __shared__ unsigned long long s_gbase[256];
+  __shared__ uint32_t s_scan[kBuildThreads / 32 + 1];
+  __shared__ uint32_t s_key[kTile];
+  __shared__ uint32_t s_val[kTile];
+  __shared__ unsigned int s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int d = threadIdx.x; d < 256 * kSortWarps; d += kBuildThreads) (&warp_cnt[0][0])[d] = 0u;
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  const size_t tbase = (size_t)tile * kTile;
+  const size_t wbase = tbase + (size_t)warp * (32 * ROUNDS);
+  uint32_t k[ROUNDS], v[ROUNDS];
+  uint16_t rank[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const size_t i = wbase + r * 32 + lane;
+    k[r] = (i < n) ? __ldcs(keys_in + i) : 0u;   // streaming: every element is touched exactly once per pass
+    v[r] = (i < n) ? (vals_in ? __ldcs(vals_in + i) : static_cast<uint32_t>(i)) : 0u;
+  }
+  // stable rank of every key among the keys of ITS WARP with the same digit
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const size_t i = wbase + r * 32 + lane;
+    const bool valid = i < n;
+    const uint32_t d = (k[r] >> shift) & 255u;
+    const unsigned int m = digit_peers(d, valid);
+    uint32_t pos = 0;
+    if (valid) pos = warp_cnt[warp][d] + __popc(m & ((1u << lane) - 1u));
+    __syncwarp();
+    if (valid && lane == (__ffs(m) - 1)) warp_cnt[warp][d] += __popc(m);
+    __syncwarp();
+    rank[r] = static_cast<uint16_t>(pos);
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;  // one digit per thread (blockDim == 256)
+    uint32_t off = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = warp_cnt[w][d];
+      warp_cnt[w][d] = off;
+      off += c;
+    }
+    // publish this tile's count, then look back
+    unsigned long long* row = status + (size_t)tile * 256;
+    const unsigned long long kMask = (1ull << 62) - 1ull;
+    unsigned long long excl = 0;
+    if (tile == 0) {
+      st_relaxed_u64(row + d, (2ull << 62) | off);
+    } else {
+      st_relaxed_u64(row + d, (1ull << 62) | off);
+      long long t = static_cast<long long>(tile) - 1;
+      while (true) {
+        const unsigned long long w = ld_relaxed_u64(status + (size_t)t * 256 + d);
+        const unsigned int flag = static_cast<unsigned int>(w >> 62);
+        if (flag == 0u) continue;
+        excl += w & kMask;
+        if (flag == 2u) break;
+        --t;
+      }
+      st_relaxed_u64(row + d, (2ull << 62) | (excl + off));
+    }
+    uint32_t total;
+    const uint32_t dstart = block_exclusive_scan(off, s_scan, total);
+    s_dstart[d] = dstart;
+    s_gbase[d] = digit_base[d] + excl - dstart;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const size_t i = wbase + r * 32 + lane;
+    if (i < n) {
+      const uint32_t d = (k[r] >> shift) & 255u;
+      const uint32_t p = s_dstart[d] + warp_cnt[warp][d] + rank[r];
+      s_key[p] = k[r];
+      s_val[p] = v[r];
+    }
+  }
+  __syncthreads();
+  const uint32_t count = static_cast<uint32_t>(n - tbase < (size_t)kTile ? n - tbase : (size_t)kTile);
+  for (uint32_t j = threadIdx.x; j < count; j += kBuildThreads) {
+    const uint32_t key = s_key[j];
+    const unsigned long long pos = s_gbase[(key >> shift) & 255u] + j;
+    keys_out[pos] = key;
+    vals_out[pos] = s_val[j];
+  }
 }
 
 // 8 consecutive sorted keys of this thread (two 16-byte loads) + the key before them; returns the head flags as bits
@@ -706,6 +898,13 @@ voxel_centroid_kernel(const float4* __restrict__ pts, const uint32_t* __restrict
   }
   const float cnt = static_cast<float>(e - b);
   out[v] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 1.0f);
+}
+
+// out[j] = pts[idx[j]]: the source cloud in voxel-key order (large sources: see ensure_sorted_source in capi.cu)
+__global__ void __launch_bounds__(kBuildThreads)
+gather_points_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ idx, size_t n, float4* __restrict__ out) {
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x)
+    out[j] = ldg_gather16(pts + __ldg(idx + j));
 }
 
 // per-voxel point counts of a partial build (length of each sorted range)

@@ -253,9 +253,9 @@ calculate_score_kernel(const float4* __restrict__ cloud, int n, const MapView ma
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < n) p = __ldg(cloud + i);
   if (i < n && point_is_finite(p.x, p.y, p.z)) {  // a non-finite point has no neighbourhood (see point_is_finite)
-    const int ix = static_cast<int>(floorf(__fdiv_rn(p.x, map.leaf[0])));
-    const int iy = static_cast<int>(floorf(__fdiv_rn(p.y, map.leaf[1])));
-    const int iz = static_cast<int>(floorf(__fdiv_rn(p.z, map.leaf[2])));
+    const int ix = lookup_cell(p.x, map.leaf[0], map.inv_leaf[0]);
+    const int iy = lookup_cell(p.y, map.leaf[1], map.inv_leaf[1]);
+    const int iz = lookup_cell(p.z, map.leaf[2], map.inv_leaf[2]);
     constexpr int K = num_offsets<METHOD>();
     int recs[K];
     int cnt = 0;
@@ -293,9 +293,9 @@ lookup_kernel(const float4* __restrict__ q, int n, const MapView map, int32_t* _
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = __ldg(q + i);
-  const int ix = static_cast<int>(floorf(__fdiv_rn(p.x, map.leaf[0])));
-  const int iy = static_cast<int>(floorf(__fdiv_rn(p.y, map.leaf[1])));
-  const int iz = static_cast<int>(floorf(__fdiv_rn(p.z, map.leaf[2])));
+  const int ix = lookup_cell(p.x, map.leaf[0], map.inv_leaf[0]);
+  const int iy = lookup_cell(p.y, map.leaf[1], map.inv_leaf[1]);
+  const int iz = lookup_cell(p.z, map.leaf[2], map.inv_leaf[2]);
   constexpr int K = num_offsets<METHOD>();
   int w = 0;
   for (int k = 0; k < K && point_is_finite(p.x, p.y, p.z); ++k) {
