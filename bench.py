@@ -342,8 +342,10 @@ def run_b200(args):
 
     # roofline of the dominant (only) kernel in the timed region: ndt_align_kernel
     kprobe = KPROBE[args.method]
-    alg_bytes = float(np.mean([(per_pair[i % R]["n_evaluations"] + per_pair[i % R]["n_hessian_passes"]) * n_srcs[i % R] * (16 + 4 * kprobe)
-                               + 64 * per_pair[i % R]["n_hits"] for i in range(args.steps)]))  # SURVEY §8d, per launch
+    # SURVEY §8d, per launch.  The reference's Hessian-only passes are fused into the preceding line-search trial on the
+    # device (no pass over the source of their own), so only the derivative evaluations count
+    alg_bytes = float(np.mean([per_pair[i % R]["n_evaluations"] * n_srcs[i % R] * (16 + 4 * kprobe)
+                               + 64 * per_pair[i % R]["n_hits"] for i in range(args.steps)]))
     hits_total = float(np.mean([u["n_hits"] for u in used]))
     # up to four launches of the kernel are co-resident on every SM, so the GPU-level rate is what the roofline is
     # compared with: algorithmic bytes of all launches / device time of the timed region (= bytes per launch / the
@@ -373,7 +375,7 @@ def run_b200(args):
                 "launch_duration_ms_while_sharing": co_resident_ms,
                 "single_launch": {"kernel_ms": lat_ms, "achieved": achieved_latency, "frac": achieved_latency / peak,
                                   "note": "one align in flight, 148 x 1024-thread CTAs (the latency arm)"},
-                "formula": "(evals+hessian passes)*N*(16+4K) + 64*hits"}
+                "formula": "evals*N*(16+4K) + 64*hits"}
 
     # end-to-end through the C ABI with host buffers: per pair H2D of the source (pinned), solve, D2H of the aligned
     # cloud and of the result block; pairs of a batch in flight together (ndtb200_set_source + ndtb200_align_batch)
@@ -428,7 +430,7 @@ def run_b200(args):
                        "arith": "fp32 per-hit math, fp64 accumulation of the sums",
                        "map": {"voxels": info["n_voxels"], "valid": info["n_valid"], "build_ms_incl_h2d": map_build_ms}},
             "src_pt_iters_per_s": pt_iters, "evaluations_per_align": evals, "hessian_passes_per_align": hess,
-            "hits_per_point_eval": hits_total / float(max(1.0, (evals + hess) * n_src)),
+            "hits_per_point_eval": hits_total / float(max(1.0, evals * n_src)),
             "latency": {"ms_per_align": lat_ms, "aligns_per_s": 1e3 / lat_ms,
                         "ms_max": float(np.max(lat_all)), "ms_mean": float(np.mean(lat_all)), "steps": len(lat_all),
                         "note": "one align in flight at a time, default CTA shape, inputs resident, CUDA events per launch (median)"},
@@ -515,7 +517,7 @@ def run_c4(args):
     total_ms = float(t.item())
     evals, hess = res["n_evaluations"], res["n_hessian_passes"]
     kprobe = KPROBE[args.method]
-    alg_bytes = (evals + hess) * len(source) * (16 + 4 * kprobe) + 64 * res["n_hits"]
+    alg_bytes = evals * len(source) * (16 + 4 * kprobe) + 64 * res["n_hits"]
     peak = 6454.9
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -526,7 +528,7 @@ def run_c4(args):
         line = {"metric": "ndt_aligns_per_s", "workload": "c4", "value": steps / (total_ms * 1e-3), "unit": "aligns/s", "n_gpus": world,
                 "steps": steps, "ms_per_step": total_ms / steps, "scaling": "strong", "dtype": "f32", "data": "synthetic",
                 "src_pt_iters_per_s": len(source) * evals * steps / (total_ms * 1e-3), "evaluations_per_align": evals,
-                "hessian_passes_per_align": hess, "hits_per_point_eval": res["n_hits"] / float((evals + hess) * len(source)),
+                "hessian_passes_per_align": hess, "hits_per_point_eval": res["n_hits"] / float(evals * len(source)),
                 "config": {"workload": "c4: %d-pt source (%s) sharded by contiguous ranges over %d GPU(s) vs %d-pt map "
                                        "(%d voxels, %d valid), res 1.0, %s; one in-kernel 29-value P2P exchange per evaluation" %
                                        (len(source), ("%d merged scans" % args.c4_scans) if args.c4_city_points == 0 else "synthetic city surfaces",

@@ -1615,6 +1615,11 @@ int ndtb200_get_timeline(ndtb200_handle* h, double* t4, int cap, int* n_out) {
     std::fprintf(stderr, "  max arrival first half of CTAs %.2f, second half %.2f\n", mx_lo, mx_hi);
   }
   for (int i = 0; i < n; ++i) {
+    if (tr[i].t_start == 0) {  // a Hessian pass fused into the preceding line-search trial: no device time of its own
+      const double t_prev = i > 0 ? t4[(i - 1) * 4 + 3] : 0.0;
+      t4[i * 4 + 0] = t4[i * 4 + 1] = t4[i * 4 + 2] = t4[i * 4 + 3] = t_prev;
+      continue;
+    }
     t4[i * 4 + 0] = static_cast<double>(tr[i].t_start - t0);
     t4[i * 4 + 1] = static_cast<double>(tr[i].t_local - t0);
     t4[i * 4 + 2] = static_cast<double>(tr[i].t_reduced - t0);

@@ -153,6 +153,7 @@ struct SolverState {
   int32_t need_pose;  // 1 => ctx (matrix + tables) must be rebuilt from x_t before the next evaluation
   double last_dp[6];  // last Newton increment (transformation_ is built from it once, at the end)
   double delta[6];    // Newton step H^-1 (-g), written by the warp solver
+  double H_ls[36];    // Hessian of the LAST line-search trial, computeHessian's table variant (see unpack_hessian_warp)
   float final_T[12];
   // copies of the launch parameters the step functions need (the parameter struct itself is never address-taken, so it
   // stays in the constant bank instead of being copied to every thread's local memory)
@@ -651,7 +652,7 @@ __device__ __forceinline__ void pose_trig(const double* x_t, double* s_trig) {
   }
 }
 
-__device__ __forceinline__ void pose_tables(EvalCtx& ctx, const double* s_trig, const TableTerm* s_terms) {
+__device__ __forceinline__ void pose_tables(EvalCtx& ctx, const double* s_trig, const TableTerm* s_terms, bool line_search_trial) {
   const int lane = threadIdx.x & 31;
   for (int e = lane; e < 69; e += 32) {
     const TableTerm t = s_terms[e];
@@ -664,8 +665,12 @@ __device__ __forceinline__ void pose_tables(EvalCtx& ctx, const double* s_trig, 
     } else {
       const int r = (e - 24) / 3, c = (e - 24) % 3;
       ctx.tab.hd[r][c] = v;
-      // Q2: the fp32 table carries +sy in row d1 (ndt_omp_impl.hpp:383), the fp64 table -sy (:361)
-      reinterpret_cast<float*>(&ctx.tf[8 + r])[c] = (r == 6 && c == 2) ? static_cast<float>(s_trig[4]) : static_cast<float>(v);
+      // Q2: the fp32 table carries +sy in row d1 (ndt_omp_impl.hpp:383), the fp64 table -sy (:361).  computeDerivatives
+      // with compute_hessian = true (the first trial of a line search) reads the fp32 table: +sy.  A later trial runs
+      // without a Hessian in the reference and is followed — if it was the last — by computeHessian, which reads the
+      // fp64 table: its Hessian sums are formed during the trial itself, so those evaluations take -sy (= v).
+      reinterpret_cast<float*>(&ctx.tf[8 + r])[c] =
+          (r == 6 && c == 2 && !line_search_trial) ? static_cast<float>(s_trig[4]) : static_cast<float>(v);
     }
   }
 }
@@ -766,7 +771,10 @@ __device__ __forceinline__ void warp_newton_solve(SolverState& st) {
 }
 
 // H (6x6, both triangles) from the 21 reduced upper-triangle totals, one or two entries per lane.
-// computeDerivatives(..., false) leaves H zeroed (ndt_omp_impl.hpp:186, 218).
+// computeDerivatives(..., false) leaves H zeroed (ndt_omp_impl.hpp:186, 218): the solver sees H = 0 after a line-search
+// trial.  The trial's own Hessian sums are kept aside in H_ls: they were formed with computeHessian's angle table (the
+// fp64 table's -sy in row d1, quirk Q2 — see pose_tables) at the pose computeHessian would be called with, so when the
+// line search ends after extra trials (ndt_omp_impl.hpp:928-929) the "Hessian-only pass" is already done.
 __device__ __forceinline__ void unpack_hessian_warp(const double* tot, int kind) {
   const int lane = threadIdx.x & 31;
   for (int idx = lane; idx < 36; idx += 32) {
@@ -774,6 +782,7 @@ __device__ __forceinline__ void unpack_hessian_warp(const double* tot, int kind)
     const int a = i < j ? i : j, b = i < j ? j : i;
     const int k = 7 + a * 6 - (a * (a - 1)) / 2 + (b - a);
     g_st.H[idx] = (kind == ACT_EVAL_NOHESS) ? 0.0 : tot[k];
+    if (kind == ACT_EVAL_NOHESS) g_st.H_ls[idx] = tot[k];
   }
   __syncwarp();
 }
@@ -991,9 +1000,23 @@ __device__ __noinline__ int advance(const double* tot, int kind, TraceRec* trace
     st.state = ST_MT_LOOP;
     return ACT_EVAL_NOHESS;
   }
-  if (st.step_iterations) {  // ndt_omp_impl.hpp:928-929: same pose, same tables
-    st.state = ST_MT_HESS;
-    return ACT_HESS_ONLY;
+  if (st.step_iterations) {
+    // ndt_omp_impl.hpp:928-929: computeHessian(hessian, trans_cloud, x_t) — same pose as the last trial, whose
+    // evaluation already summed this Hessian (H_ls).  Recorded in the trace like the pass it replaces.
+#pragma unroll
+    for (int i = 0; i < 36; ++i) st.H[i] = st.H_ls[i];
+    st.n_hess++;
+    if (trace && st.n_trace < prm.trace_cap) {
+      TraceRec& r = trace[st.n_trace];
+      r.kind = 2;
+      r.pad = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) r.x[i] = st.x_t[i];
+      r.a_t = st.a_t;
+      r.score = st.score;
+      r.t_start = r.t_local = r.t_reduced = r.t_advanced = 0;
+    }
+    st.n_trace++;
   }
 mt_finish: {
     // back in computeTransformation (ndt_omp_impl.hpp:143-164)
@@ -1329,7 +1352,10 @@ ndt_align_kernel(const float4* __restrict__ src_in, const MapView map, const Ali
       eval_hessian_f64<METHOD>(src, n, n_groups, warp_global, warps_total, &ctx, &s_map, prm.d2, prm.d1, s_warp[warp]);
     } else {
       double wsum;
-      if (action == ACT_EVAL_FULL)
+      // a line-search trial (ACT_EVAL_NOHESS) sums its Hessian as well — with computeHessian's table variant, see
+      // pose_tables — so that no separate Hessian-only pass is needed when the line search ends on it.  A
+      // derivatives-only evaluation requested through the parity API (MODE_EVAL, no pose update) skips the Hessian.
+      if (action == ACT_EVAL_FULL || prm.mode == MODE_ALIGN)
         wsum = eval_warp_f32<METHOD, true>(src, n, n_groups, warp_global, warps_total, cached, ctx, map, d2f, d1f);
       else
         wsum = eval_warp_f32<METHOD, false>(src, n, n_groups, warp_global, warps_total, cached, ctx, map, d2f, d1f);
@@ -1381,7 +1407,7 @@ ndt_align_kernel(const float4* __restrict__ src_in, const MapView map, const Ali
       }
       if (st.need_pose) pose_trig(st.x_t, s_trig);
       bar_sync_pair();  // warp 1 builds the matrix while this warp fills the tables
-      if (st.need_pose) pose_tables(ctx, s_trig, s_terms);
+      if (st.need_pose) pose_tables(ctx, s_trig, s_terms, s_action == ACT_EVAL_NOHESS);
       if (timing && slot < prm.trace_cap) {
         TraceRec& r = ws.trace[slot];
         r.t_start = t_start; r.t_local = t_local; r.t_reduced = t_reduced; r.t_advanced = globaltimer_ns();
