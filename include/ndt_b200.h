@@ -101,6 +101,9 @@ int ndtb200_set_source(ndtb200_handle* h, const void* points, size_t n, size_t s
 /* Same, for clouds already resident in device memory (16-byte float4 records, this device). */
 int ndtb200_set_target_device(ndtb200_handle* h, const void* d_points_xyzw, size_t n, int is_dense);
 int ndtb200_set_source_device(ndtb200_handle* h, const void* d_points_xyzw, size_t n);
+/* setInputTarget WITHOUT a copy: the handle keeps the caller's device pointer (as the reference keeps the caller's cloud
+ * by shared pointer).  The buffer must stay alive and unchanged until the next set_target* call on this handle. */
+int ndtb200_set_target_device_view(ndtb200_handle* h, const void* d_points_xyzw, size_t n, int is_dense);
 
 /* ---- registration -------------------------------------------------------------------------- */
 /* align(output[, guess]) (pcl::Registration::align -> computeTransformation, ndt_omp_impl.hpp:80-171).
@@ -136,6 +139,13 @@ int ndtb200_fitness_score(ndtb200_handle* h, double max_range, double* out);
 int ndtb200_fitness_sums(ndtb200_handle* h, double max_range, double* sum_sq_dist, int64_t* n_accepted);
 /* calculateScore(cloud) (ndt_omp_impl.hpp:935-983). */
 int ndtb200_calculate_score(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, double* out);
+/* calculateScore of MANY already transformed clouds against the current map in one call (loop-closure screening:
+ * one upload, one launch).  Cloud c = points[cloud_offsets[c] .. cloud_offsets[c + 1]); out[c] = its score. */
+int ndtb200_calculate_score_batch(ndtb200_handle* h, const void* points, const size_t* cloud_offsets, int n_clouds,
+                                  size_t stride_bytes, double* out);
+/* The same screening for ONE cloud under MANY candidate poses: out[k] = calculateScore(transformPointCloud(source,
+ * poses[k])) for the handle's current source (nothing is uploaded but the poses; column-major 4x4 fp32 each). */
+int ndtb200_score_poses(ndtb200_handle* h, const float* poses16, int n_poses, double* out);
 
 /* ---- multi-GPU source sharding (one process + one handle per GPU of an NVSwitch node; not in the reference) ----
  * Every rank holds the full target map and a contiguous slice of the source; each derivative evaluation exchanges the
@@ -210,6 +220,20 @@ int ndtb200_copy_partials(ndtb200_handle* h, void* d_keys, void* d_counts, void*
 int ndtb200_build_from_partials(ndtb200_handle* h, const float global_min[3], const float global_max[3],
                                 int64_t n_finite_total, const void* d_keys, const void* d_counts, const void* d_moments,
                                 size_t n_total);
+
+/* Owner-partitioned variant of steps (3)-(4) (SURVEY 8e row 3 as designed): instead of gathering every partial on every
+ * rank, (3a) ndtb200_partials_split tells where this rank's (key-sorted) partials cross the owners' key boundaries
+ * (upper_keys[r] = first key NOT owned by rank r, world-1 ascending values; offsets_out[world+1]), (3b) the caller
+ * moves each range to its owner (all-to-all), (4a) ndtb200_merge_partials merges + finalises the received partials
+ * (rank order) into finished records without building an index, (4b) ndtb200_copy_records exports them (64-byte
+ * records + 6 fp64 inverse-covariance entries per voxel), the caller all-gathers them in rank (= key) order, and (4c)
+ * ndtb200_set_map_from_records installs the full map and builds the voxel index on every rank. */
+int ndtb200_partials_split(ndtb200_handle* h, const int32_t* upper_keys, int world, int64_t* offsets_out);
+int ndtb200_merge_partials(ndtb200_handle* h, const float global_min[3], const float global_max[3], int64_t n_finite_total,
+                           const void* d_keys, const void* d_counts, const void* d_moments, size_t n_total, int64_t* n_merged);
+int ndtb200_copy_records(ndtb200_handle* h, void* d_records_out, void* d_icov64_out);
+int ndtb200_set_map_from_records(ndtb200_handle* h, const float global_min[3], const float global_max[3],
+                                 int64_t n_finite_total, const void* d_records, const void* d_icov64, size_t n_total);
 
 /* ---- parity / inspection (stage dumps; used by tests, not by callers) ------------------------ */
 int ndtb200_get_map_info(const ndtb200_handle* h, ndtb200_map_info* out);

@@ -873,3 +873,125 @@ def test_lookup_cells_near_faces_are_bit_exact(nb, leaf):
     a, b = gpu.eval_derivatives(np.zeros(6)), ref.eval_derivatives(np.zeros(6))
     assert a["hits"] == b["hits"] and b["hits"] > 10000
     assert rel_err(a["gradient"], b["gradient"]) < REL
+
+
+@pytest.mark.parametrize("method", [oracle.DIRECT7, oracle.DIRECT1, oracle.DIRECT26, oracle.KDTREE])
+def test_calculate_score_batch_and_pose_screening(nb, method):
+    """calculateScore (ndt_omp_impl.hpp:935-983) for many clouds / many candidate poses in one call (loop-closure
+    screening): every entry equals the oracle's calculateScore of that cloud to 1e-9."""
+    tgt, src = load_pair()
+    ref, gpu = make_pair(nb, tgt, src, method=method)
+    rng = np.random.default_rng(23)
+    poses = [np.eye(4, dtype=np.float32)] + [pose_matrix(np.concatenate([rng.uniform(-1.0, 1.0, 3), rng.uniform(-0.1, 0.1, 3)])) for _ in range(9)]
+    poses.append(pose_matrix([500.0, 0, 0, 0, 0, 0]))                       # far away: no neighbourhood at all -> 0
+    clouds = [oracle.transform_points(T, src)[:, :3] for T in poses]
+    clouds.append(src[:7])                                                   # ragged sizes
+    clouds.append(np.zeros((0, 3), np.float32))                              # an empty cloud scores 0
+    exp = np.array([ref.calculateScore(c) if len(c) else 0.0 for c in clouds])
+    got = gpu.calculateScoreBatch(clouds)
+    assert got.shape == exp.shape
+    assert np.abs(got - exp).max() <= 1e-9 * np.abs(exp).max()
+    assert got[len(poses) - 1] == 0.0
+    got_p = gpu.scorePoses(poses)
+    assert np.abs(got_p - exp[:len(poses)]).max() <= 1e-9 * np.abs(exp).max()
+    assert abs(gpu.calculateScore(src) - exp[0]) <= 1e-12 * abs(exp[0])     # the single-cloud entry point: same kernel
+    assert int(np.argmin(got_p)) == int(np.argmin(exp[:len(poses)]))        # lower is better: the screening picks the same pose
+
+
+@pytest.mark.parametrize("slices,owners", [(3, 2), (4, 4), (2, 8)])
+def test_map_build_owner_partitioned(nb, slices, owners):
+    """The sharded build as designed with its pieces on one GPU: the cloud cut into contiguous slices,
+    per-slice partials with the common grid, every partial sent to the OWNER of its key range, owners merge (slice order)
+    and finalise, the finished records concatenated in owner (= key) order and installed: keys / counts exact, means /
+    inverse covariances within the bar, same lookups and derivatives as the single build."""
+    import torch
+    from toyslam_b200.sharding import point_range
+    tgt, src = load_pair()
+    ref, single = make_pair(nb, tgt, src)
+    dev = torch.device("cuda", 0)
+    workers, boxes, nf_total = [], [], 0
+    for r in range(slices):
+        lo, hi = point_range(len(tgt), r, slices)
+        loc = torch.ones((hi - lo, 4), dtype=torch.float32, device=dev)
+        loc[:, :3] = torch.as_tensor(tgt[lo:hi]).to(dev)
+        w = nb.NormalDistributionsTransform()
+        mn, mx, nf = w.cloud_bounds(loc.data_ptr(), hi - lo)
+        boxes.append((mn, mx)); nf_total += nf
+        workers.append((w, loc))
+    gmin = np.min([b[0] for b in boxes], axis=0)
+    gmax = np.max([b[1] for b in boxes], axis=0)
+    parts = []
+    for w, loc in workers:
+        st, nv = w.build_partials(gmin, gmax)
+        assert st == 0 and nv > 0
+        k = torch.zeros(nv, dtype=torch.int32, device=dev)
+        c = torch.zeros(nv, dtype=torch.int32, device=dev)
+        m = torch.zeros((nv, 9), dtype=torch.float64, device=dev)
+        w.copy_partials(k.data_ptr(), c.data_ptr(), m.data_ptr())
+        parts.append((k, c, m))
+    all_keys = torch.sort(torch.cat([p[0] for p in parts])).values
+    upper = [int(all_keys[(o + 1) * len(all_keys) // owners].item()) for o in range(owners - 1)]
+    offs = [w.partials_split(upper, owners) for w, _ in workers]
+    for o_, (k, _, _) in zip(offs, parts):
+        assert o_[0] == 0 and o_[-1] == len(k) and np.all(np.diff(o_) >= 0)
+    recs, ics, n_all = [], [], 0
+    for o in range(owners):
+        k = torch.cat([p[0][offs[i][o]:offs[i][o + 1]] for i, p in enumerate(parts)]).contiguous()
+        c = torch.cat([p[1][offs[i][o]:offs[i][o + 1]] for i, p in enumerate(parts)]).contiguous()
+        m = torch.cat([p[2][offs[i][o]:offs[i][o + 1]] for i, p in enumerate(parts)]).contiguous()
+        owner = nb.NormalDistributionsTransform()
+        st, n_own = owner.merge_partials(gmin, gmax, nf_total, k.data_ptr(), c.data_ptr(), m.data_ptr(), len(k))
+        assert st == 0
+        rec = torch.zeros((max(1, n_own), 16), dtype=torch.int32, device=dev)
+        ic = torch.zeros((max(1, n_own), 6), dtype=torch.float64, device=dev)
+        if n_own:
+            owner.copy_records(rec.data_ptr(), ic.data_ptr())
+        recs.append(rec[:n_own]); ics.append(ic[:n_own]); n_all += n_own
+    g_rec, g_ic = torch.cat(recs).contiguous(), torch.cat(ics).contiguous()
+    full = nb.NormalDistributionsTransform()
+    assert full.set_map_from_records(gmin, gmax, nf_total, g_rec.data_ptr(), g_ic.data_ptr(), n_all) == 0
+    ri, gi = ref.map_info(), full.map_info()
+    for key in ("min_b", "max_b", "div_b"):
+        assert np.array_equal(ri[key], gi[key])
+    assert ri["n_voxels"] == gi["n_voxels"] and ri["n_valid"] == gi["n_valid"]
+    rl, gl = ref.dump_leaves(), full.dump_voxels()
+    assert np.array_equal(rl["keys"], gl["keys"]) and np.array_equal(rl["counts"], gl["counts"])
+    valid = rl["counts"] >= 6
+    assert rel_err(gl["mean"], rl["mean"]) < REL
+    a, b = gl["icov"][valid], rl["icov"][valid]
+    assert (np.abs(a - b).reshape(len(b), -1).max(axis=1) / np.abs(b).reshape(len(b), -1).max(axis=1)).max() < REL
+    full.setInputSource(src)
+    p = np.array([0.4, 0.1, -0.02, 0.005, -0.001, -0.01])
+    x, y = full.eval_derivatives(p), ref.eval_derivatives(p)
+    assert x["hits"] == y["hits"]
+    assert rel_err(x["gradient"], y["gradient"]) < REL and rel_err(x["hessian"], y["hessian"]) < REL
+    q = np.concatenate([src[:2000], np.round(src[:200])]).astype(np.float32)
+    assert np.array_equal(full.lookup(q, oracle.DIRECT7), single.lookup(q, oracle.DIRECT7))
+    check_align(ref, full)
+    with pytest.raises(nb.NdtError):
+        full.getFitnessScore()       # a records-only map holds no raw target
+
+
+def test_set_target_device_view_builds_without_copy(nb):
+    """ndtb200_set_target_device_view: the map references the caller's device cloud (as the reference keeps the caller's
+    cloud by shared pointer): same map, same align, same fitness as the copying entry points."""
+    import torch
+    tgt, src = load_pair()
+    dev = torch.device("cuda", 0)
+    cloud = torch.ones((len(tgt), 4), dtype=torch.float32, device=dev)
+    cloud[:, :3] = torch.as_tensor(tgt).to(dev)
+    a, b = nb.NormalDistributionsTransform(), nb.NormalDistributionsTransform()
+    assert a.set_target_device_view(cloud.data_ptr(), len(tgt)) == 0
+    b.setInputTarget(tgt)
+    da, db = a.dump_voxels(), b.dump_voxels()
+    for k in ("keys", "counts", "mean", "cov", "icov"):
+        assert np.array_equal(da[k], db[k])
+    assert np.array_equal(a.point_keys(), b.point_keys())
+    a.setInputSource(src); b.setInputSource(src)
+    a.align(); b.align()
+    assert np.array_equal(a.result()["final"], b.result()["final"])
+    assert a.getFitnessScore() == b.getFitnessScore()
+    c = a.clone()                       # a copy owns its own cloud
+    del a
+    c.align()
+    assert np.array_equal(c.result()["final"], b.result()["final"]) and c.getFitnessScore() == b.getFitnessScore()

@@ -47,19 +47,27 @@ def build(force=False, verbose=False):
 
 APP_SRC = os.path.join(_HERE, "..", "apps", "align_b200.cpp")
 APP_BIN = os.path.join(_HERE, "..", "apps", "align_b200")
+REPLAY_SRC = os.path.join(_HERE, "..", "apps", "replay_b200.cpp")
+REPLAY_BIN = os.path.join(_HERE, "..", "apps", "replay_b200")
+
+
+def _build_app(src, out, force):
+    inc = os.path.join(_HERE, "..", "include")
+    hdrs = [os.path.join(inc, "ndt_b200.h")] + [os.path.join(inc, "pclomp_b200", h) for h in os.listdir(os.path.join(inc, "pclomp_b200"))]
+    deps = [src, LIB_PATH] + hdrs
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-I", inc, src, "-o", out, "-L", LIB_DIR, "-lndt_b200", "-Wl,-rpath,$ORIGIN/../toyslam_b200/lib"]
+    subprocess.check_call(cmd)
+    return out
 
 
 def build_apps(force=False):
-    """The C++ demo over the header-only shim (apps/align_b200.cpp): proves the reference-named API compiles and links."""
-    hdrs = [os.path.join(_HERE, "..", "include", "pclomp_b200", h) for h in ("ndt_b200.hpp", "pcl_compat.hpp")]
-    deps = [APP_SRC, LIB_PATH] + hdrs
-    if not force and os.path.exists(APP_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(APP_BIN) for d in deps):
-        return APP_BIN
-    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [cxx, "-O2", "-std=c++17", "-I", os.path.join(_HERE, "..", "include"), APP_SRC, "-o", APP_BIN,
-           "-L", LIB_DIR, "-lndt_b200", "-Wl,-rpath,$ORIGIN/../toyslam_b200/lib"]
-    subprocess.check_call(cmd)
-    return APP_BIN
+    """The C++ programs over the header-only shim: apps/align_b200 (the reference's benchmark app: proves the
+    reference-named API compiles and links) and apps/replay_b200 (PointCloud2 dump -> mapping loop).  Returns align_b200."""
+    _build_app(REPLAY_SRC, REPLAY_BIN, force)
+    return _build_app(APP_SRC, APP_BIN, force)
 
 
 if __name__ == "__main__":

@@ -64,6 +64,7 @@ struct ndtb200_handle {
 
   // target cloud + map
   DevBuf d_target;
+  const float4* target_view = nullptr;  // ndtb200_set_target_device_view: the caller's own device buffer, not copied
   size_t n_target = 0;
   bool target_dense = true, has_target = false;
   int map_status = NDTB200_ERR_NO_INPUT;
@@ -75,6 +76,8 @@ struct ndtb200_handle {
   DevBuf d_voxel_key, d_voxel_start, d_voxel_count, d_moments, d_records, d_icov64, d_hash, d_dense;
   size_t n_partials = 0;       // voxels of the last partial-only build (sharded build, before the exchange)
   bool map_is_merged = false;
+  bool records_only_map = false;  // map installed from finished records (sharded build): no moments, no raw target
+  bool moments_valid = false;  // d_moments holds the per-voxel moments of the current map (the staged build fuses them away)
   bool prefer_fused_build = false;  // set by the mapping pipeline: fused builds even with the small-CTA solve shape
   DevBuf d_centroid;              // KDTREE mode: fp32 centroid of every voxel
   bool centroids_valid = false;
@@ -106,6 +109,8 @@ struct ndtb200_handle {
 };
 
 namespace {
+
+inline const float4* target_pts(const ndtb200_handle* h) { return h->target_view ? h->target_view : h->d_target.as<float4>(); }
 
 #define CK2(hh, call)                                                                              \
   do {                                                                                             \
@@ -178,6 +183,7 @@ size_t scan_tmp_elems(size_t n) {
 }
 
 void clear_map(ndtb200_handle* h) {
+  h->records_only_map = false;
   h->cell_all_valid = false;
   h->centroids_valid = false;
   h->n_voxels = 0;
@@ -320,6 +326,33 @@ int passes_for(const GridDesc& g, bool with_sentinel, uint32_t* sentinel_out) {
   return (bits + 7) / 8;
 }
 
+// Which voxel index the map gets: the direct-mapped cell table (one 4-byte load per probe, no collisions) when dx*dy*dz
+// int32 entries fit the budget (<= 4 GiB and <= 1/4 of the free device memory) — allocated and filled with -1 here —
+// otherwise the open-addressing hash over the valid voxels (finish_hash_index).
+int prepare_index(ndtb200_handle* h) {
+  h->use_dense = false;
+  h->n_valid = -1;  // fetched on demand (ndtb200_get_map_info) unless the hash needs it
+  // cells actually addressed by keys: div_b product (the guard's dx*dy*dz, grid.ncell, is computed from the float
+  // extents and can be smaller by one per axis)
+  const unsigned long long ncell = static_cast<unsigned long long>(h->grid.div_b[0]) * static_cast<unsigned long long>(h->grid.div_b[1]) *
+                                   static_cast<unsigned long long>(h->grid.div_b[2]);
+  const unsigned long long bytes = ncell * sizeof(int32_t);
+  const bool forced_hash = getenv("NDTB200_FORCE_HASH") != nullptr;
+  bool fits = !forced_hash && ncell > 0 && bytes <= (4ull << 30);
+  if (fits && bytes > h->d_dense.cap && bytes > (64ull << 20)) {  // cudaMemGetInfo is slow: only ask for large NEW tables
+    size_t free_b = 0, total_b = 0;
+    fits = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes <= (free_b + h->d_dense.cap) / 4;
+  }
+  if (fits) {
+    CK(h->d_dense.ensure(bytes));
+    CK(cudaMemsetAsync(h->d_dense.p, 0xFF, bytes, h->stream));
+    h->use_dense = true;
+  }
+  return NDTB200_OK;
+}
+
+int finish_hash_index(ndtb200_handle* h, uint32_t n_vox);
+
 // second pass of applyFilter + the voxel index.  counts: per-voxel point counts (merged partials) or nullptr
 // (count = length of the voxel's sorted point range, n_finite closes the last one)
 int finalize_and_index(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite, const uint32_t* counts, bool records_done = false) {
@@ -338,34 +371,23 @@ int finalize_and_index(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite, con
     LAUNCHED(h);
   }
 
-  // the voxel index.  Direct-mapped cell table (one 4-byte load per probe, no collisions) when dx*dy*dz int32
-  // entries fit the budget (<= 4 GiB and <= 1/4 of the free device memory); otherwise an open-addressing hash over
-  // the valid voxels, load <= 0.25 (needs n_valid on the host: the only synchronisation left after the voxel count).
-  h->use_dense = false;
-  h->n_valid = -1;  // fetched on demand (ndtb200_get_map_info) unless the hash needs it now
   {
-    // cells actually addressed by keys: div_b product (the guard's dx*dy*dz, grid.ncell, is computed from the float
-    // extents and can be smaller by one per axis)
-    const unsigned long long ncell = static_cast<unsigned long long>(h->grid.div_b[0]) * static_cast<unsigned long long>(h->grid.div_b[1]) *
-                                     static_cast<unsigned long long>(h->grid.div_b[2]);
-    const unsigned long long bytes = ncell * sizeof(int32_t);
-    const bool forced_hash = getenv("NDTB200_FORCE_HASH") != nullptr;
-    bool fits = !forced_hash && ncell > 0 && bytes <= (4ull << 30);
-    if (fits && bytes > h->d_dense.cap && bytes > (64ull << 20)) {  // cudaMemGetInfo is slow: only ask for large NEW tables
-      size_t free_b = 0, total_b = 0;
-      fits = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes <= (free_b + h->d_dense.cap) / 4;
-    }
-    if (fits) {
-      CK(h->d_dense.ensure(bytes));
-      CK(cudaMemsetAsync(h->d_dense.p, 0xFF, bytes, h->stream));
-      if (n_vox > 0) {
-        dense_fill_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
-                                                                    h->prm.min_points_per_voxel, h->d_dense.as<int32_t>());
-        LAUNCHED(h);
-      }
-      h->use_dense = true;
-    }
+    int st = prepare_index(h);
+    if (st != NDTB200_OK) return st;
   }
+  if (h->use_dense && n_vox > 0) {
+    dense_fill_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox,
+                                                                h->prm.min_points_per_voxel, h->d_dense.as<int32_t>());
+    LAUNCHED(h);
+  }
+  return finish_hash_index(h, n_vox);
+}
+
+// The hash form of the voxel index (grids whose cell table does not fit): needs n_valid on the host, the only
+// synchronisation left after the voxel count.  No-op when the direct-mapped table is in use.
+int finish_hash_index(ndtb200_handle* h, uint32_t n_vox) {
+  unsigned int* d_nvalid = h->d_scalar.as<unsigned int>() + 4;
+  const int vblocks = static_cast<int>(((size_t)n_vox + kBuildThreads - 1) / kBuildThreads);
   if (!h->use_dense) {
     unsigned int n_valid = 0;
     CK(cudaMemcpyAsync(&n_valid, d_nvalid, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
@@ -462,6 +484,29 @@ int run_fused_build(ndtb200_handle* h, const float4* pts, size_t n, int dense, i
   return NDTB200_OK;
 }
 
+// per-voxel fp64 moments of the sorted target into h->d_moments (the partial builds of the sharded path, and the parity
+// dump of a map whose build fused the moments away)
+int compute_moments(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite) {
+  CK(h->d_moments.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * 9 * sizeof(double)));
+  h->moments_valid = true;
+  if (n_vox == 0) return NDTB200_OK;
+  const float4* pts = target_pts(h);
+  const uint32_t* va = h->d_vals_a.as<uint32_t>();
+  const double avg = static_cast<double>(n_finite) / std::max<uint32_t>(1u, n_vox);
+  if (avg >= 48.0) {
+    const int blocks = static_cast<int>(((size_t)n_vox * 32 + kBuildThreads - 1) / kBuildThreads);
+    voxel_moments_kernel<32><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox, n_finite, h->d_moments.as<double>());
+  } else if (avg >= 10.0) {
+    const int blocks = static_cast<int>(((size_t)n_vox * 8 + kBuildThreads - 1) / kBuildThreads);
+    voxel_moments_kernel<8><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox, n_finite, h->d_moments.as<double>());
+  } else {
+    const int blocks = static_cast<int>(((size_t)n_vox * 4 + kBuildThreads - 1) / kBuildThreads);
+    voxel_moments_kernel<4><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox, n_finite, h->d_moments.as<double>());
+  }
+  LAUNCHED(h);
+  return NDTB200_OK;
+}
+
 int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
   clear_map(h);
   h->map_is_merged = false;
@@ -474,7 +519,7 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
     return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
   }
   if (n > 0xFFFFFFF0ull) { h->err = "target cloud too large (>= 2^32 points)"; return NDTB200_ERR_INVALID; }
-  const float4* pts = h->d_target.as<float4>();
+  const float4* pts = target_pts(h);
   const int dense = h->target_dense ? 1 : 0;
 
   if (!o.partial_only && !o.forced_min && use_fused_build(h, n)) {  // scan-sized cloud: one cooperative launch
@@ -492,6 +537,7 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
       return st != NDTB200_OK ? st : NDTB200_ERR_GRID_OVERFLOW;
     }
     h->n_voxels = n_vox;
+    h->moments_valid = true;  // the fused kernel leaves the moment rows in d_moments
     st = finalize_and_index(h, n_vox, static_cast<uint32_t>(h->grid.n_finite), nullptr, /*records_done=*/true);
     if (st != NDTB200_OK) return st;
     h->map_status = NDTB200_OK;
@@ -539,27 +585,15 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
     if (st != NDTB200_OK) return st;
   }
   h->n_voxels = n_vox;
-  CK(h->d_moments.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * 9 * sizeof(double)));
-
-  // 5. moments
   const uint32_t* va = h->d_vals_a.as<uint32_t>();
   const uint32_t n_finite = static_cast<uint32_t>(h->grid.n_finite);
   const double avg = static_cast<double>(n_finite) / std::max<uint32_t>(1u, n_vox);
-  if (avg >= 48.0) {
-    const int blocks = static_cast<int>(((size_t)n_vox * 32 + kBuildThreads - 1) / kBuildThreads);
-    voxel_moments_kernel<32><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
-                                                                      n_finite, h->d_moments.as<double>());
-  } else if (avg >= 10.0) {
-    const int blocks = static_cast<int>(((size_t)n_vox * 8 + kBuildThreads - 1) / kBuildThreads);
-    voxel_moments_kernel<8><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
-                                                                     n_finite, h->d_moments.as<double>());
-  } else {
-    const int blocks = static_cast<int>(((size_t)n_vox * 4 + kBuildThreads - 1) / kBuildThreads);
-    voxel_moments_kernel<4><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox,
-                                                                     n_finite, h->d_moments.as<double>());
-  }
-  LAUNCHED(h);
-  if (o.partial_only) {  // leave {voxel_key, count, moments} for the exchange
+  const int group = avg >= 48.0 ? 32 : (avg >= 10.0 ? 8 : 4);  // lanes per voxel
+  const int blocks = static_cast<int>(((size_t)n_vox * group + kBuildThreads - 1) / kBuildThreads);
+
+  if (o.partial_only) {  // 5'. moments only: leave {voxel_key, count, moments} for the exchange
+    int st = compute_moments(h, n_vox, n_finite);
+    if (st != NDTB200_OK) return st;
     CK(h->d_voxel_count.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(uint32_t)));
     const int vblocks = static_cast<int>(((size_t)n_vox + kBuildThreads - 1) / kBuildThreads);
     segment_counts_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_voxel_start.as<uint32_t>(), n_vox, n_finite,
@@ -570,9 +604,29 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
     return NDTB200_OK;
   }
 
-  // 6. finalize + index
+  // 5. + 6. moments, finalize and the cell-table entries in one kernel (voxel_build_kernel)
   {
-    int st = finalize_and_index(h, n_vox, n_finite, nullptr);
+    int st = prepare_index(h);
+    if (st != NDTB200_OK) return st;
+  }
+  CK(h->d_records.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(VoxelRecord)));
+  CK(h->d_icov64.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * 6 * sizeof(double)));
+  unsigned int* d_nvalid = h->d_scalar.as<unsigned int>() + 4;
+  CK(cudaMemsetAsync(d_nvalid, 0, sizeof(unsigned int), h->stream));
+  h->moments_valid = false;
+  if (n_vox > 0) {
+    int32_t* table = h->use_dense ? h->d_dense.as<int32_t>() : nullptr;
+#define NDTB200_VOXEL_BUILD(G)                                                                                              \
+    voxel_build_kernel<G><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), \
+        n_vox, n_finite, h->prm.min_points_per_voxel, h->prm.eig_ratio, h->d_records.as<VoxelRecord>(), h->d_icov64.as<double>(), d_nvalid, table)
+    if (group == 32) NDTB200_VOXEL_BUILD(32);
+    else if (group == 8) NDTB200_VOXEL_BUILD(8);
+    else NDTB200_VOXEL_BUILD(4);
+#undef NDTB200_VOXEL_BUILD
+    LAUNCHED(h);
+  }
+  {
+    int st = finish_hash_index(h, n_vox);
     if (st != NDTB200_OK) return st;
   }
   h->map_status = NDTB200_OK;
@@ -583,11 +637,9 @@ int build_map(ndtb200_handle* h) { return build_map_ex(h, BuildOpts()); }
 
 // Merge the per-voxel partials of all ranks (concatenated in rank order) into this handle's map: stable sort by key,
 // per-voxel sums in rank order (bit-identical on every rank), then the usual finalize + index.
-int build_from_partials(ndtb200_handle* h, const float* gmin, const float* gmax, long long n_finite_total,
-                        const uint32_t* d_keys, const uint32_t* d_counts, const double* d_moments, size_t total) {
-  clear_map(h);
+// grid description of the COMMON bounding box (all ranks) -> h->grid; one synchronisation
+int grid_from_global_box(ndtb200_handle* h, const float* gmin, const float* gmax, long long n_finite_total) {
   std::memset(&h->grid, 0, sizeof(GridDesc));
-  // grid from the global box: one fake "partial" row
   float box[6] = {gmin[0], gmin[1], gmin[2], gmax[0], gmax[1], gmax[2]};
   CK(h->d_mm_partial.ensure(6 * sizeof(float)));
   CK(h->d_mm_finite.ensure(sizeof(unsigned int)));
@@ -604,7 +656,20 @@ int build_from_partials(ndtb200_handle* h, const float* gmin, const float* gmax,
   CK(cudaMemcpyAsync(&h->grid, h->d_grid.p, sizeof(GridDesc), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->grid.n_finite = static_cast<int32_t>(std::min<long long>(n_finite_total, 0x7fffffffll));
-  if (total == 0 || n_finite_total == 0) {
+  return NDTB200_OK;
+}
+
+// records_only: merge + finalize the given partials (this rank's share of the key space) and stop before the index —
+// the records are then all-gathered and installed everywhere by set_map_from_records.
+int build_from_partials(ndtb200_handle* h, const float* gmin, const float* gmax, long long n_finite_total,
+                        const uint32_t* d_keys, const uint32_t* d_counts, const double* d_moments, size_t total,
+                        bool records_only = false) {
+  clear_map(h);
+  {
+    int st = grid_from_global_box(h, gmin, gmax, n_finite_total);
+    if (st != NDTB200_OK) return st;
+  }
+  if (n_finite_total == 0 || (total == 0 && !records_only)) {
     h->map_status = NDTB200_ERR_NO_INPUT;
     int st = ensure_empty_hash(h);
     return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
@@ -614,6 +679,7 @@ int build_from_partials(ndtb200_handle* h, const float* gmin, const float* gmax,
     int st = ensure_empty_hash(h);
     return st != NDTB200_OK ? st : NDTB200_ERR_GRID_OVERFLOW;
   }
+  if (total == 0) { h->n_voxels = 0; h->map_status = NDTB200_OK; return NDTB200_OK; }  // an owner without voxels
   uint32_t sentinel = 0;
   const int passes = passes_for(h->grid, false, &sentinel);
   CK(h->d_keys_a.ensure(total * sizeof(uint32_t)));
@@ -634,6 +700,23 @@ int build_from_partials(ndtb200_handle* h, const float* gmin, const float* gmax,
                                                                    static_cast<uint32_t>(total), d_counts, d_moments,
                                                                    h->d_voxel_count.as<uint32_t>(), h->d_moments.as<double>());
   LAUNCHED(h);
+  h->moments_valid = true;
+  if (records_only) {  // finalize only: the index is built from the all-gathered records
+    unsigned int* d_nvalid = h->d_scalar.as<unsigned int>() + 4;
+    CK(h->d_records.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * sizeof(VoxelRecord)));
+    CK(h->d_icov64.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * 6 * sizeof(double)));
+    CK(cudaMemsetAsync(d_nvalid, 0, sizeof(unsigned int), h->stream));
+    if (n_vox > 0) {
+      finalize_voxels_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(
+          h->d_moments.as<double>(), h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), h->d_voxel_count.as<uint32_t>(), n_vox, 0u,
+          h->prm.min_points_per_voxel, h->prm.eig_ratio, h->d_records.as<VoxelRecord>(), h->d_icov64.as<double>(), d_nvalid, nullptr, nullptr,
+          nullptr, nullptr);
+      LAUNCHED(h);
+    }
+    h->map_is_merged = true;
+    h->map_status = NDTB200_OK;
+    return NDTB200_OK;
+  }
   {
     int st = finalize_and_index(h, n_vox, 0u, h->d_voxel_count.as<uint32_t>());
     if (st != NDTB200_OK) return st;
@@ -671,7 +754,7 @@ int ensure_kdtree_index(ndtb200_handle* h) {
     const uint32_t nv = static_cast<uint32_t>(h->n_voxels);
     CK(h->d_centroid.ensure((size_t)nv * sizeof(float4)));
     voxel_centroid_kernel<<<(nv + kBuildThreads - 1) / kBuildThreads, kBuildThreads, 0, h->stream>>>(
-        h->d_target.as<float4>(), h->d_vals_a.as<uint32_t>(), h->d_voxel_start.as<uint32_t>(), nv,
+        target_pts(h), h->d_vals_a.as<uint32_t>(), h->d_voxel_start.as<uint32_t>(), nv,
         static_cast<uint32_t>(h->grid.n_finite), h->d_centroid.as<float4>());
     LAUNCHED(h);
     h->centroids_valid = true;
@@ -984,6 +1067,30 @@ int fetch_result(ndtb200_handle* h) {
   return NDTB200_OK;
 }
 
+// parity dump of a map that was installed from finished records (the owner-partitioned sharded build): keys, counts,
+// means and fp64 inverse covariances come from the records; covariances / inflation flags are not part of a record
+int dump_records_only(ndtb200_handle* h, int32_t* keys, int32_t* counts, double* mean, double* cov, double* icov, int32_t* inflated) {
+  const size_t V = static_cast<size_t>(h->n_voxels);
+  std::vector<VoxelRecord> recs(V);
+  std::vector<double> ic(V * 6);
+  CK(cudaMemcpyAsync(recs.data(), h->d_records.p, V * sizeof(VoxelRecord), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(ic.data(), h->d_icov64.p, V * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (size_t v = 0; v < V; ++v) {
+    if (keys) keys[v] = recs[v].key;
+    if (counts) counts[v] = recs[v].count;
+    if (mean) for (int a = 0; a < 3; ++a) mean[v * 3 + a] = record_mean(recs[v], a);
+    if (icov) {
+      const double* c = &ic[v * 6];
+      const double full[9] = {c[0], c[1], c[2], c[1], c[3], c[4], c[2], c[4], c[5]};
+      for (int k = 0; k < 9; ++k) icov[v * 9 + k] = full[k];
+    }
+    if (cov) for (int k = 0; k < 9; ++k) cov[v * 9 + k] = std::nan("");
+    if (inflated) inflated[v] = -1;
+  }
+  return NDTB200_OK;
+}
+
 void colmajor_to_T(const float* m, float T[12]) {
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 4; ++c) T[r * 4 + c] = m[c * 4 + r];
@@ -1132,8 +1239,23 @@ int ndtb200_get_params(const ndtb200_handle* h, ndtb200_params* p) {
 int ndtb200_set_target(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, int is_dense) {
   if (!h || (!points && n)) return NDTB200_ERR_INVALID;
   cudaSetDevice(h->device);
+  h->target_view = nullptr;
   int st = upload_points(h, h->d_target, points, n, stride_bytes);
   if (st != NDTB200_OK) return st;
+  h->n_target = n;
+  h->target_dense = is_dense != 0;
+  h->has_target = true;
+  return build_map(h);
+}
+
+// setInputTarget for a cloud that already lives on this device and STAYS there: the reference keeps the caller's cloud by
+// shared pointer (pcl::Registration::target_) and never copies it; here the handle keeps the caller's device pointer.
+// The buffer must stay alive and unchanged until the next set_target call or the handle's destruction (getFitnessScore and
+// the KDTREE centroids read the raw target later).
+int ndtb200_set_target_device_view(ndtb200_handle* h, const void* d_points, size_t n, int is_dense) {
+  if (!h || (!d_points && n)) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  h->target_view = n ? static_cast<const float4*>(d_points) : nullptr;
   h->n_target = n;
   h->target_dense = is_dense != 0;
   h->has_target = true;
@@ -1143,6 +1265,7 @@ int ndtb200_set_target(ndtb200_handle* h, const void* points, size_t n, size_t s
 int ndtb200_set_target_device(ndtb200_handle* h, const void* d_points, size_t n, int is_dense) {
   if (!h || (!d_points && n)) return NDTB200_ERR_INVALID;
   cudaSetDevice(h->device);
+  h->target_view = nullptr;
   if (n) {
     CK(h->d_target.ensure(n * sizeof(float4)));
     CK(cudaMemcpyAsync(h->d_target.p, d_points, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
@@ -1335,12 +1458,12 @@ static int fitness_sums(ndtb200_handle* h, double max_range, double* sum_out, un
     int* d_count = reinterpret_cast<int*>(h->d_scalar.as<char>() + 128);
     CK(cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
     const int warp_blocks = static_cast<int>(((size_t)n * 32 + 255) / 256);  // one warp per query
-    fitness_grid_kernel<<<warp_blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), n, h->d_target.as<float4>(), h->d_vals_a.as<uint32_t>(),
+    fitness_grid_kernel<<<warp_blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), n, target_pts(h), h->d_vals_a.as<uint32_t>(),
                                                         h->d_voxel_start.as<uint32_t>(), static_cast<uint32_t>(h->n_voxels),
                                                         static_cast<uint32_t>(h->grid.n_finite), h->d_cell_all.as<int32_t>(),
                                                         h->d_grid.as<GridDesc>(), d_T, d_best, d_list, d_count);
     LAUNCHED(h);
-    fitness_fallback_kernel<<<std::min(n, h->num_sms * 8), 256, 0, h->stream>>>(h->d_source.as<float4>(), d_list, d_count, h->d_target.as<float4>(),
+    fitness_fallback_kernel<<<std::min(n, h->num_sms * 8), 256, 0, h->stream>>>(h->d_source.as<float4>(), d_list, d_count, target_pts(h),
                                                             static_cast<int>(h->n_target), d_T, d_best);
     LAUNCHED(h);
     fitness_reduce_kernel<<<blocks, 256, 0, h->stream>>>(d_best, n, max_range, d_sum, d_cnt);
@@ -1352,7 +1475,7 @@ static int fitness_sums(ndtb200_handle* h, double max_range, double* sum_out, un
       std::fprintf(stderr, "  fitness: %d of %d queries went to the brute-force fallback\n", nf, n);
     }
   } else {
-    fitness_bruteforce_kernel<<<blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), n, h->d_target.as<float4>(),
+    fitness_bruteforce_kernel<<<blocks, 256, 0, h->stream>>>(h->d_source.as<float4>(), n, target_pts(h),
                                                              static_cast<int>(h->n_target), d_T, max_range, d_sum, d_cnt);
     LAUNCHED(h);
   }
@@ -1369,37 +1492,83 @@ static int fitness_sums(ndtb200_handle* h, double max_range, double* sum_out, un
   return NDTB200_OK;
 }
 
+// shared by the three calculateScore entry points: cloud (float4, device) + segments or poses -> out[n_seg] (means)
+static int calculate_scores(ndtb200_handle* h, const float4* d_cloud, const unsigned long long* h_seg_start, const float* h_poses12,
+                            int n_seg, size_t n_points_per_pose, double* out) {
+  if (h->prm.search_method == NDTB200_KDTREE) {
+    const int st2 = ensure_kdtree_index(h);
+    if (st2 != NDTB200_OK) return st2;
+  }
+  size_t longest = n_points_per_pose;
+  if (h_seg_start)
+    for (int s = 0; s < n_seg; ++s) longest = std::max<size_t>(longest, h_seg_start[s + 1] - h_seg_start[s]);
+  const int chunks = static_cast<int>(std::max<size_t>(1, std::min<size_t>((longest + 255) / 256, std::max(1, 8 * h->num_sms / std::max(1, n_seg)))));
+  CK(h->d_tmp.ensure((size_t)n_seg * chunks * sizeof(double) + (size_t)(n_seg + 1) * sizeof(unsigned long long) + (size_t)n_seg * 12 * sizeof(float) + 256));
+  double* d_sum = h->d_tmp.as<double>();
+  unsigned long long* d_seg = reinterpret_cast<unsigned long long*>(d_sum + (size_t)n_seg * chunks);
+  float* d_pose = reinterpret_cast<float*>(d_seg + n_seg + 1);
+  if (h_seg_start) CK(cudaMemcpyAsync(d_seg, h_seg_start, (size_t)(n_seg + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+  if (h_poses12) CK(cudaMemcpyAsync(d_pose, h_poses12, (size_t)n_seg * 12 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  double d1, d2, d3;
+  gauss_constants(h->prm, d1, d2, d3);
+  MapView map = make_view(h);
+  const dim3 grid(chunks, n_seg);
+  const float* poses = h_poses12 ? d_pose : nullptr;
+  const int npp = static_cast<int>(n_points_per_pose);
+  switch (h->prm.search_method) {
+    case NDTB200_DIRECT1: calculate_score_kernel<3><<<grid, 256, 0, h->stream>>>(d_cloud, d_seg, poses, npp, map, d1, d2, d3, chunks, d_sum); break;
+    case NDTB200_DIRECT7: calculate_score_kernel<2><<<grid, 256, 0, h->stream>>>(d_cloud, d_seg, poses, npp, map, d1, d2, d3, chunks, d_sum); break;
+    case NDTB200_DIRECT26: calculate_score_kernel<1><<<grid, 256, 0, h->stream>>>(d_cloud, d_seg, poses, npp, map, d1, d2, d3, chunks, d_sum); break;
+    default: calculate_score_kernel<0><<<grid, 256, 0, h->stream>>>(d_cloud, d_seg, poses, npp, map, d1, d2, d3, chunks, d_sum); break;
+  }
+  LAUNCHED(h);
+  std::vector<double> hs((size_t)n_seg * chunks);
+  CK(cudaMemcpyAsync(hs.data(), d_sum, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int s = 0; s < n_seg; ++s) {
+    double acc = 0;
+    for (int c = 0; c < chunks; ++c) acc += hs[(size_t)s * chunks + c];
+    const size_t cnt = h_seg_start ? static_cast<size_t>(h_seg_start[s + 1] - h_seg_start[s]) : n_points_per_pose;
+    out[s] = cnt ? acc / static_cast<double>(cnt) : 0.0;
+  }
+  return NDTB200_OK;
+}
+
 int ndtb200_calculate_score(ndtb200_handle* h, const void* points, size_t n, size_t stride_bytes, double* out) {
   if (!h || !out || (!points && n)) return NDTB200_ERR_INVALID;
   if (n == 0) { *out = 0; return NDTB200_ERR_NO_INPUT; }
   cudaSetDevice(h->device);
   int st = upload_points(h, h->d_out, points, n, stride_bytes);
   if (st != NDTB200_OK) return st;
-  const int blocks = static_cast<int>((n + 255) / 256);
-  CK(h->d_tmp.ensure((size_t)blocks * 8 + 64));
-  double d1, d2, d3;
-  gauss_constants(h->prm, d1, d2, d3);
-  if (h->prm.search_method == NDTB200_KDTREE) {
-    const int st2 = ensure_kdtree_index(h);
-    if (st2 != NDTB200_OK) return st2;
+  const unsigned long long seg[2] = {0ull, static_cast<unsigned long long>(n)};
+  return calculate_scores(h, h->d_out.as<float4>(), seg, nullptr, 1, 0, out);
+}
+
+int ndtb200_calculate_score_batch(ndtb200_handle* h, const void* points, const size_t* cloud_offsets, int n_clouds, size_t stride_bytes,
+                                  double* out) {
+  if (!h || !out || !cloud_offsets || n_clouds < 0 || (!points && n_clouds && cloud_offsets[n_clouds])) return NDTB200_ERR_INVALID;
+  if (n_clouds == 0) return NDTB200_OK;
+  const size_t n = cloud_offsets[n_clouds];
+  std::vector<unsigned long long> seg(n_clouds + 1);
+  for (int s = 0; s <= n_clouds; ++s) {
+    if (s && cloud_offsets[s] < cloud_offsets[s - 1]) { h->err = "cloud_offsets must be non-decreasing"; return NDTB200_ERR_INVALID; }
+    seg[s] = cloud_offsets[s];
   }
-  MapView map = make_view(h);
-  const float4* cloud = h->d_out.as<float4>();
-  double* d_sum = h->d_tmp.as<double>();
-  switch (h->prm.search_method) {
-    case NDTB200_DIRECT1: calculate_score_kernel<3><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
-    case NDTB200_DIRECT7: calculate_score_kernel<2><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
-    case NDTB200_DIRECT26: calculate_score_kernel<1><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
-    default: calculate_score_kernel<0><<<blocks, 256, 0, h->stream>>>(cloud, (int)n, map, d1, d2, d3, d_sum); break;
-  }
-  LAUNCHED(h);
-  std::vector<double> hs(blocks);
-  CK(cudaMemcpyAsync(hs.data(), d_sum, blocks * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  double s = 0;
-  for (int b = 0; b < blocks; ++b) s += hs[b];
-  *out = s / static_cast<double>(n);
-  return NDTB200_OK;
+  cudaSetDevice(h->device);
+  if (n == 0) { for (int s = 0; s < n_clouds; ++s) out[s] = 0.0; return NDTB200_OK; }
+  int st = upload_points(h, h->d_out, points, n, stride_bytes);
+  if (st != NDTB200_OK) return st;
+  return calculate_scores(h, h->d_out.as<float4>(), seg.data(), nullptr, n_clouds, 0, out);
+}
+
+int ndtb200_score_poses(ndtb200_handle* h, const float* poses16, int n_poses, double* out) {
+  if (!h || !out || (!poses16 && n_poses) || n_poses < 0) return NDTB200_ERR_INVALID;
+  if (n_poses == 0) return NDTB200_OK;
+  if (!h->has_source || h->n_source == 0) { h->err = "no input source"; return NDTB200_ERR_NO_INPUT; }
+  cudaSetDevice(h->device);
+  std::vector<float> T((size_t)n_poses * 12);
+  for (int s = 0; s < n_poses; ++s) colmajor_to_T(poses16 + (size_t)s * 16, T.data() + (size_t)s * 12);
+  return calculate_scores(h, h->d_source.as<float4>(), nullptr, T.data(), n_poses, h->n_source, out);
 }
 
 int ndtb200_get_map_info(const ndtb200_handle* h, ndtb200_map_info* out) {
@@ -1432,7 +1601,7 @@ int ndtb200_dump_point_keys(ndtb200_handle* h, int32_t* keys) {
   const size_t n = h->n_target;
   CK(h->d_tmp.ensure(n * sizeof(uint32_t)));
   voxel_key_kernel<<<grid_for(n, kBuildThreads * 4, h->num_sms * 16), kBuildThreads, 0, h->stream>>>(
-      h->d_target.as<float4>(), n, h->target_dense ? 1 : 0, h->d_grid.as<GridDesc>(), 0xFFFFFFFFu,
+      target_pts(h), n, h->target_dense ? 1 : 0, h->d_grid.as<GridDesc>(), 0xFFFFFFFFu,
       h->d_tmp.as<uint32_t>(), nullptr, nullptr, 0);
   LAUNCHED(h);
   CK(cudaMemcpyAsync(keys, h->d_tmp.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -1447,6 +1616,11 @@ int ndtb200_dump_voxels(ndtb200_handle* h, int32_t* keys, int32_t* counts, doubl
   cudaSetDevice(h->device);
   const uint32_t V = static_cast<uint32_t>(h->n_voxels);
   if (V == 0) return NDTB200_OK;
+  if (h->records_only_map) return dump_records_only(h, keys, counts, mean, cov, icov, inflated);
+  if (!h->moments_valid) {
+    const int st = compute_moments(h, V, static_cast<uint32_t>(h->grid.n_finite));
+    if (st != NDTB200_OK) return st;
+  }
   DevBuf d_mean, d_cov, d_icov, d_infl, d_rec, d_ic64;
   CK(d_mean.ensure((size_t)V * 3 * sizeof(double)));
   CK(d_cov.ensure((size_t)V * 9 * sizeof(double)));
@@ -1729,7 +1903,7 @@ int ndtb200_clone(const ndtb200_handle* src, ndtb200_handle** out) {
     // the copy keeps the source object's map: build it with the resolution the source map was built with
     ndtb200_params p = src->prm;
     if (src->grid.leaf[0] > 0) h->prm.resolution = src->grid.leaf[0];
-    st = ndtb200_set_target_device(h, src->d_target.p, src->n_target, src->target_dense ? 1 : 0);
+    st = ndtb200_set_target_device(h, target_pts(src), src->n_target, src->target_dense ? 1 : 0);
     h->prm = p;
     if (st == NDTB200_ERR_CUDA) { ndtb200_destroy(h); return st; }
   }
@@ -1750,6 +1924,7 @@ int ndtb200_cloud_bounds(ndtb200_handle* h, const void* d_points, size_t n, int 
                          int64_t* n_finite) {
   if (!h || (!d_points && n) || !out_min || !out_max) return NDTB200_ERR_INVALID;
   cudaSetDevice(h->device);
+  h->target_view = nullptr;
   if (n) {
     CK(h->d_target.ensure(n * sizeof(float4)));
     CK(cudaMemcpyAsync(h->d_target.p, d_points, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
@@ -1801,6 +1976,114 @@ int ndtb200_build_from_partials(ndtb200_handle* h, const float global_min[3], co
   h->has_target = true;
   return build_from_partials(h, global_min, global_max, n_finite_total, static_cast<const uint32_t*>(d_keys),
                              static_cast<const uint32_t*>(d_counts), static_cast<const double*>(d_moments), n_total);
+}
+
+// ---- sharded build, owner-partitioned: partials travel to the rank that OWNS their key range (all-to-all),
+// the owner merges / finalises its voxels, the finished 64-byte records are all-gathered and installed everywhere ----
+__global__ void lower_bound_kernel(const int32_t* __restrict__ keys, uint32_t n, const int32_t* __restrict__ bounds, int nb,
+                                   long long* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const int32_t b = bounds[i];
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if (keys[mid] < b) lo = mid + 1; else hi = mid;
+  }
+  out[i] = lo;
+}
+
+int ndtb200_partials_split(ndtb200_handle* h, const int32_t* upper_keys, int world, int64_t* offsets_out) {
+  if (!h || !offsets_out || world < 1 || (world > 1 && !upper_keys)) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const uint32_t n = static_cast<uint32_t>(h->n_partials);
+  offsets_out[0] = 0;
+  offsets_out[world] = n;
+  if (world == 1) return NDTB200_OK;
+  CK(h->d_tmp.ensure((size_t)world * (sizeof(int32_t) + sizeof(long long)) + 64));
+  long long* d_out = h->d_tmp.as<long long>();
+  int32_t* d_b = reinterpret_cast<int32_t*>(d_out + world);
+  CK(cudaMemcpyAsync(d_b, upper_keys, (size_t)(world - 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  lower_bound_kernel<<<1, 32 * ((world + 30) / 32), 0, h->stream>>>(h->d_voxel_key.as<int32_t>(), n, d_b, world - 1, d_out);
+  LAUNCHED(h);
+  std::vector<long long> back(world - 1);
+  CK(cudaMemcpyAsync(back.data(), d_out, (size_t)(world - 1) * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int r = 1; r < world; ++r) offsets_out[r] = back[r - 1];
+  return NDTB200_OK;
+}
+
+int ndtb200_merge_partials(ndtb200_handle* h, const float global_min[3], const float global_max[3], int64_t n_finite_total,
+                           const void* d_keys, const void* d_counts, const void* d_moments, size_t n_total, int64_t* n_merged) {
+  if (!h || !global_min || !global_max || !n_merged || (n_total && (!d_keys || !d_counts || !d_moments))) return NDTB200_ERR_INVALID;
+  if (n_total > 0xFFFFFFF0ull) { h->err = "too many partials"; return NDTB200_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  h->has_target = true;
+  const int st = build_from_partials(h, global_min, global_max, n_finite_total, static_cast<const uint32_t*>(d_keys),
+                                     static_cast<const uint32_t*>(d_counts), static_cast<const double*>(d_moments), n_total, /*records_only=*/true);
+  *n_merged = (st == NDTB200_OK) ? h->n_voxels : 0;
+  return st;
+}
+
+int ndtb200_copy_records(ndtb200_handle* h, void* d_records_out, void* d_icov64_out) {
+  if (!h) return NDTB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const size_t v = static_cast<size_t>(h->n_voxels);
+  if (v == 0) return NDTB200_OK;
+  if (!d_records_out || !d_icov64_out) return NDTB200_ERR_INVALID;
+  CK(cudaMemcpyAsync(d_records_out, h->d_records.p, v * sizeof(VoxelRecord), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_icov64_out, h->d_icov64.p, v * 6 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return NDTB200_OK;
+}
+
+__global__ void record_keys_kernel(const VoxelRecord* __restrict__ records, uint32_t n, int32_t* __restrict__ keys, int min_points,
+                                   unsigned int* __restrict__ n_valid) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  keys[v] = records[v].key;
+  if (records[v].count >= min_points) atomicAdd(n_valid, 1u);
+}
+
+int ndtb200_set_map_from_records(ndtb200_handle* h, const float global_min[3], const float global_max[3], int64_t n_finite_total,
+                                 const void* d_records, const void* d_icov64, size_t n_total) {
+  if (!h || !global_min || !global_max || (n_total && (!d_records || !d_icov64))) return NDTB200_ERR_INVALID;
+  if (n_total > 0x7FFFFFF0ull) { h->err = "too many voxels"; return NDTB200_ERR_INVALID; }
+  cudaSetDevice(h->device);
+  h->has_target = true;
+  clear_map(h);
+  int st = grid_from_global_box(h, global_min, global_max, n_finite_total);
+  if (st != NDTB200_OK) return st;
+  if (n_finite_total == 0 || n_total == 0) {
+    h->map_status = NDTB200_ERR_NO_INPUT;
+    st = ensure_empty_hash(h);
+    return st != NDTB200_OK ? st : NDTB200_ERR_NO_INPUT;
+  }
+  if (h->grid.overflow) {
+    h->map_status = NDTB200_ERR_GRID_OVERFLOW;
+    st = ensure_empty_hash(h);
+    return st != NDTB200_OK ? st : NDTB200_ERR_GRID_OVERFLOW;
+  }
+  const uint32_t n_vox = static_cast<uint32_t>(n_total);
+  CK(h->d_records.ensure(n_total * sizeof(VoxelRecord)));
+  CK(h->d_icov64.ensure(n_total * 6 * sizeof(double)));
+  CK(h->d_voxel_key.ensure(n_total * sizeof(int32_t)));
+  CK(cudaMemcpyAsync(h->d_records.p, d_records, n_total * sizeof(VoxelRecord), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_icov64.p, d_icov64, n_total * 6 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  unsigned int* d_nvalid = h->d_scalar.as<unsigned int>() + 4;
+  CK(cudaMemsetAsync(d_nvalid, 0, sizeof(unsigned int), h->stream));
+  const int vblocks = static_cast<int>(((size_t)n_vox + kBuildThreads - 1) / kBuildThreads);
+  record_keys_kernel<<<vblocks, kBuildThreads, 0, h->stream>>>(h->d_records.as<VoxelRecord>(), n_vox, h->d_voxel_key.as<int32_t>(),
+                                                                h->prm.min_points_per_voxel, d_nvalid);
+  LAUNCHED(h);
+  h->n_voxels = n_vox;
+  h->moments_valid = false;
+  h->map_is_merged = true;
+  h->records_only_map = true;
+  st = finalize_and_index(h, n_vox, 0u, nullptr, /*records_done=*/true);
+  if (st != NDTB200_OK) return st;
+  h->map_status = NDTB200_OK;
+  return NDTB200_OK;
 }
 
 // ---- pcl::VoxelGrid centroid downsample on the device (the step before the path in every caller) ----

@@ -647,18 +647,19 @@ __device__ __forceinline__ float4 ldg_gather16(const float4* p) {
   return v;
 }
 
+// the GROUP lanes of voxel `gid` sum its points (4 gathers in flight per lane, index order) and fold by a fixed shuffle
+// tree: lane gl == 0 ends with the 9 sums.  Every lane of the warp must call this (shuffles).
 template <int GROUP>
-__global__ void __launch_bounds__(kBuildThreads)
-voxel_moments_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx,
-                     const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
-                     double* __restrict__ moments) {
-  const uint32_t gid = (blockIdx.x * (uint32_t)blockDim.x + threadIdx.x) / GROUP;
-  const int gl = threadIdx.x % GROUP;
-  const bool active = gid < n_voxels;
-  double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+__device__ __forceinline__ void voxel_moments_group(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx,
+                                                    const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
+                                                    uint32_t gid, int gl, bool active, double (&s)[9], uint32_t& count) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) s[k] = 0.0;
+  count = 0;
   if (active) {
     const uint32_t b = voxel_start[gid];
     const uint32_t e = (gid + 1 < n_voxels) ? voxel_start[gid + 1] : n_finite;
+    count = e - b;
     // four gathers in flight per lane (index loads, then point loads), accumulated in index order
     for (uint32_t i0 = b + gl; i0 < e; i0 += 4 * GROUP) {
       uint32_t idx[4];
@@ -682,9 +683,51 @@ voxel_moments_kernel(const float4* __restrict__ pts, const uint32_t* __restrict_
 #pragma unroll
     for (int k = 0; k < 9; ++k) s[k] += __shfl_down_sync(0xffffffffu, s[k], o, GROUP);
   }
+}
+
+template <int GROUP>
+__global__ void __launch_bounds__(kBuildThreads)
+voxel_moments_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx,
+                     const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
+                     double* __restrict__ moments) {
+  const uint32_t gid = (blockIdx.x * (uint32_t)blockDim.x + threadIdx.x) / GROUP;
+  const int gl = threadIdx.x % GROUP;
+  const bool active = gid < n_voxels;
+  double s[9];
+  uint32_t count;
+  voxel_moments_group<GROUP>(pts, sorted_idx, voxel_start, n_voxels, n_finite, gid, gl, active, s, count);
   if (active && gl == 0) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) moments[(size_t)gid * 9 + k] = s[k];
+  }
+}
+
+__device__ __forceinline__ void finalize_one(uint32_t v, int count, const double (&m)[9], int32_t key, int min_points, double eig_ratio,
+                                             VoxelRecord* __restrict__ records, double* __restrict__ icov64,
+                                             unsigned int* __restrict__ n_valid, double* __restrict__ dbg_mean,
+                                             double* __restrict__ dbg_cov, double* __restrict__ dbg_icov, int* __restrict__ dbg_inflated);
+
+// Both passes of applyFilter for the occupied voxels in ONE kernel (the map build of clouds above scan size): the
+// GROUP lanes of a voxel sum its moments, lane 0 finalises the leaf (mean, covariance, eigen-regularisation, inverse:
+// finalize_one) straight from registers — the 72-byte moment row never goes to memory and back — and enters a valid
+// voxel into the direct-mapped cell table (nullptr: the hash index is filled afterwards).  Same arithmetic in the same
+// order as voxel_moments_kernel + finalize_voxels_kernel + dense_fill_kernel.
+template <int GROUP>
+__global__ void __launch_bounds__(kBuildThreads, 4)  // <= 64 registers: the gather phase lives on resident warps; the finalize part may spill
+voxel_build_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx, const int32_t* __restrict__ voxel_key,
+                   const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite, int min_points, double eig_ratio,
+                   VoxelRecord* __restrict__ records, double* __restrict__ icov64, unsigned int* __restrict__ n_valid,
+                   int32_t* __restrict__ dense_table) {
+  const uint32_t gid = (blockIdx.x * (uint32_t)blockDim.x + threadIdx.x) / GROUP;
+  const int gl = threadIdx.x % GROUP;
+  const bool active = gid < n_voxels;
+  double s[9];
+  uint32_t count;
+  voxel_moments_group<GROUP>(pts, sorted_idx, voxel_start, n_voxels, n_finite, gid, gl, active, s, count);
+  if (active && gl == 0) {
+    const int32_t key = voxel_key[gid];
+    finalize_one(gid, static_cast<int>(count), s, key, min_points, eig_ratio, records, icov64, n_valid, nullptr, nullptr, nullptr, nullptr);
+    if (dense_table != nullptr && records[gid].count >= min_points) dense_table[key] = static_cast<int32_t>(gid);
   }
 }
 
@@ -745,11 +788,6 @@ __device__ __forceinline__ void inv3_cofactor(const double a[3][3], double r[3][
   r[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id;
   r[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
 }
-
-__device__ __forceinline__ void finalize_one(uint32_t v, int count, const double (&m)[9], int32_t key, int min_points, double eig_ratio,
-                                             VoxelRecord* __restrict__ records, double* __restrict__ icov64,
-                                             unsigned int* __restrict__ n_valid, double* __restrict__ dbg_mean,
-                                             double* __restrict__ dbg_cov, double* __restrict__ dbg_icov, int* __restrict__ dbg_inflated);
 
 // dbg_cov / dbg_icov / dbg_inflated: optional full-precision dumps (parity API), NULL in production.
 __global__ void __launch_bounds__(kBuildThreads)

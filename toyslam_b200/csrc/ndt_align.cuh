@@ -1215,9 +1215,13 @@ __device__ __forceinline__ double eval_warp_f32(const float4* __restrict__ src, 
     const int i = (g << 5) + lane;
     if (i < n) {
       float px, py, pz;
+#ifdef NDTB200_NO_CACHED_POINTS
+      { const float4 pt = __ldg(src + i); px = pt.x; py = pt.y; pz = pt.z; }
+#else
       if (j == 0) { px = cached[0][0]; py = cached[0][1]; pz = cached[0][2]; }
       else if (j == 1) { px = cached[1][0]; py = cached[1][1]; pz = cached[1][2]; }
       else { const float4 pt = __ldg(src + i); px = pt.x; py = pt.y; pz = pt.z; }
+#endif
       point_f32<METHOD, HESS>(px, py, pz, ctx, m, d2f, d1f, acc);
     }
     if (++since == kFlushPoints) {  // bound the fp32 run length of a thread (large clouds only)

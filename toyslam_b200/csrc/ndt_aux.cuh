@@ -242,38 +242,62 @@ fitness_reduce_kernel(const float* __restrict__ best, int n_src, double max_rang
   }
 }
 
-// calculateScore (ndt_omp_impl.hpp:935-983): fp64, mean over neighbours of (-d1*e - d3), mean over points.
+// calculateScore (ndt_omp_impl.hpp:935-983) of ONE already transformed point: fp64, mean over its neighbours of
+// (-d1 * e - d3).  A point without a neighbourhood (also a non-finite one, see point_is_finite) scores 0.
+template <int METHOD>
+__device__ __forceinline__ double score_of_point(float px, float py, float pz, const MapView& map, double d1, double d2, double d3) {
+  if (!point_is_finite(px, py, pz)) return 0.0;
+  const int ix = lookup_cell(px, map.leaf[0], map.inv_leaf[0]);
+  const int iy = lookup_cell(py, map.leaf[1], map.inv_leaf[1]);
+  const int iz = lookup_cell(pz, map.leaf[2], map.inv_leaf[2]);
+  constexpr int K = num_offsets<METHOD>();
+  int recs[K];
+  int cnt = 0;
+  for (int k = 0; k < K; ++k) {
+    recs[k] = probe_neighbour<METHOD>(map, ix, iy, iz, k, px, py, pz);
+    cnt += recs[k] >= 0;
+  }
+  double score = 0;
+  for (int k = 0; k < K; ++k) {
+    if (recs[k] < 0) continue;
+    const VoxelRecord* R = map.records + recs[k];
+    const double* ic = map.icov64 + (size_t)recs[k] * 6;
+    const double r0 = static_cast<double>(px) - record_mean(*R, 0), r1 = static_cast<double>(py) - record_mean(*R, 1),
+                 r2 = static_cast<double>(pz) - record_mean(*R, 2);
+    const double u0 = ic[0] * r0 + ic[1] * r1 + ic[2] * r2, u1 = ic[1] * r0 + ic[3] * r1 + ic[4] * r2,
+                 u2 = ic[2] * r0 + ic[4] * r1 + ic[5] * r2;
+    const double e = exp(-d2 * (r0 * u0 + r1 * u1 + r2 * u2) / 2);
+    score += (-d1 * e - d3) / cnt;
+  }
+  return score;
+}
+
+// Scores of many clouds / many candidate poses in ONE launch (loop-closure screening): segment s covers the
+// points [seg_start[s], seg_start[s + 1]) of `cloud` (poses == nullptr: already transformed clouds, one segment each), or
+// the WHOLE cloud transformed by poses[s] (row-major 3x4 fp32, pcl::transformPointCloud arithmetic).  One CTA-partial per
+// (segment, chunk): part_sum[s * chunks + c]; the host adds a segment's partials in order.
 template <int METHOD>
 __global__ void __launch_bounds__(256)
-calculate_score_kernel(const float4* __restrict__ cloud, int n, const MapView map, double d1, double d2, double d3,
+calculate_score_kernel(const float4* __restrict__ cloud, const unsigned long long* __restrict__ seg_start, const float* __restrict__ poses,
+                       int n_points_per_pose, const MapView map, double d1, double d2, double d3, int chunks,
                        double* __restrict__ part_sum) {
   __shared__ double s_sum[8];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float T[12];
+  const int seg = blockIdx.y, chunk = blockIdx.x;
+  unsigned long long lo, hi;
+  if (poses) {
+    if (threadIdx.x < 12) T[threadIdx.x] = poses[(size_t)seg * 12 + threadIdx.x];
+    lo = 0; hi = static_cast<unsigned long long>(n_points_per_pose);
+  } else {
+    lo = seg_start[seg]; hi = seg_start[seg + 1];
+  }
+  __syncthreads();
   double score = 0;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < n) p = __ldg(cloud + i);
-  if (i < n && point_is_finite(p.x, p.y, p.z)) {  // a non-finite point has no neighbourhood (see point_is_finite)
-    const int ix = lookup_cell(p.x, map.leaf[0], map.inv_leaf[0]);
-    const int iy = lookup_cell(p.y, map.leaf[1], map.inv_leaf[1]);
-    const int iz = lookup_cell(p.z, map.leaf[2], map.inv_leaf[2]);
-    constexpr int K = num_offsets<METHOD>();
-    int recs[K];
-    int cnt = 0;
-    for (int k = 0; k < K; ++k) {
-      recs[k] = probe_neighbour<METHOD>(map, ix, iy, iz, k, p.x, p.y, p.z);
-      cnt += recs[k] >= 0;
-    }
-    for (int k = 0; k < K; ++k) {
-      if (recs[k] < 0) continue;
-      const VoxelRecord* R = map.records + recs[k];
-      const double* ic = map.icov64 + (size_t)recs[k] * 6;
-      const double r0 = static_cast<double>(p.x) - record_mean(*R, 0), r1 = static_cast<double>(p.y) - record_mean(*R, 1),
-                   r2 = static_cast<double>(p.z) - record_mean(*R, 2);
-      const double u0 = ic[0] * r0 + ic[1] * r1 + ic[2] * r2, u1 = ic[1] * r0 + ic[3] * r1 + ic[4] * r2,
-                   u2 = ic[2] * r0 + ic[4] * r1 + ic[5] * r2;
-      const double e = exp(-d2 * (r0 * u0 + r1 * u1 + r2 * u2) / 2);
-      score += (-d1 * e - d3) / cnt;
-    }
+  for (unsigned long long i = lo + (unsigned long long)chunk * 256 + threadIdx.x; i < hi; i += (unsigned long long)chunks * 256) {
+    const float4 p = __ldg(cloud + i);
+    float x = p.x, y = p.y, z = p.z;
+    if (poses) transform_point(T, p.x, p.y, p.z, x, y, z);
+    score += score_of_point<METHOD>(x, y, z, map, d1, d2, d3);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) score += __shfl_down_sync(0xffffffffu, score, o);
@@ -282,7 +306,7 @@ calculate_score_kernel(const float4* __restrict__ cloud, int n, const MapView ma
   if (threadIdx.x == 0) {
     double s = 0;
     for (int w = 0; w < 8; ++w) s += s_sum[w];
-    part_sum[blockIdx.x] = s;
+    part_sum[(size_t)seg * chunks + chunk] = s;
   }
 }
 

@@ -83,6 +83,7 @@ def load_library():
     L.ndtb200_set_source.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
     L.ndtb200_set_target_device.argtypes = [vp, vp, C.c_size_t, C.c_int]
     L.ndtb200_set_source_device.argtypes = [vp, vp, C.c_size_t]
+    L.ndtb200_set_target_device_view.argtypes = [vp, vp, C.c_size_t, C.c_int]
     L.ndtb200_align.argtypes = [vp, f32p, vp, C.c_size_t]
     L.ndtb200_align_async.argtypes = [vp, f32p]
     L.ndtb200_sync.argtypes = [vp]
@@ -103,12 +104,18 @@ def load_library():
     L.ndtb200_build_partials.argtypes = [vp, f32p, f32p, i64p]
     L.ndtb200_copy_partials.argtypes = [vp, vp, vp, vp]
     L.ndtb200_build_from_partials.argtypes = [vp, f32p, f32p, C.c_int64, vp, vp, vp, C.c_size_t]
+    L.ndtb200_partials_split.argtypes = [vp, i32p, C.c_int, i64p]
+    L.ndtb200_merge_partials.argtypes = [vp, f32p, f32p, C.c_int64, vp, vp, vp, C.c_size_t, i64p]
+    L.ndtb200_copy_records.argtypes = [vp, vp, vp]
+    L.ndtb200_set_map_from_records.argtypes = [vp, f32p, f32p, C.c_int64, vp, vp, C.c_size_t]
     L.ndtb200_align_batch.argtypes = [C.POINTER(vp), C.c_int, f32p, C.POINTER(vp), C.c_size_t, C.POINTER(Result)]
     L.ndtb200_align_batch_async.argtypes = [C.POINTER(vp), C.c_int, f32p, C.POINTER(vp), C.c_size_t]
     L.ndtb200_get_result.argtypes = [vp, C.POINTER(Result)]
     L.ndtb200_fitness_score.argtypes = [vp, C.c_double, f64p]
     L.ndtb200_fitness_sums.argtypes = [vp, C.c_double, f64p, i64p]
     L.ndtb200_calculate_score.argtypes = [vp, vp, C.c_size_t, C.c_size_t, f64p]
+    L.ndtb200_calculate_score_batch.argtypes = [vp, vp, C.POINTER(C.c_size_t), C.c_int, C.c_size_t, f64p]
+    L.ndtb200_score_poses.argtypes = [vp, f32p, C.c_int, f64p]
     L.ndtb200_get_map_info.argtypes = [vp, C.POINTER(MapInfo)]
     L.ndtb200_dump_point_keys.argtypes = [vp, i32p]
     L.ndtb200_dump_voxels.argtypes = [vp, i32p, i32p, f64p, f64p, f64p, i32p]
@@ -392,6 +399,13 @@ class NormalDistributionsTransform:
                                         allow=(ERR_NO_INPUT, ERR_GRID_OVERFLOW))
         return self.build_status
 
+    def set_target_device_view(self, dev_ptr, n, is_dense=True):
+        """setInputTarget without a copy: the caller's device buffer must outlive the map (ndtb200_set_target_device_view)."""
+        self._n_target = int(n)
+        self.build_status = self._check(self._L.ndtb200_set_target_device_view(self._h, dev_ptr, n, 1 if is_dense else 0),
+                                        allow=(ERR_NO_INPUT, ERR_GRID_OVERFLOW))
+        return self.build_status
+
     def set_source_device(self, dev_ptr, n):
         self._n_source = int(n)
         self._check(self._L.ndtb200_set_source_device(self._h, dev_ptr, n))
@@ -455,6 +469,31 @@ class NormalDistributionsTransform:
         gmin, gmax = np.ascontiguousarray(gmin, np.float32), np.ascontiguousarray(gmax, np.float32)
         return self._check(self._L.ndtb200_build_from_partials(self._h, _ptr(gmin, C.c_float), _ptr(gmax, C.c_float), int(n_finite_total),
                                                                keys_ptr, counts_ptr, moments_ptr, int(n_total)),
+                           allow=(ERR_NO_INPUT, ERR_GRID_OVERFLOW))
+
+    # ---- owner-partitioned sharded build (ndtb200_partials_split / merge_partials / copy_records / set_map_from_records) ----
+    def partials_split(self, upper_keys, world):
+        """Offsets (world + 1) of this handle's key-sorted partials at the owners' key boundaries."""
+        up = np.ascontiguousarray(upper_keys, dtype=np.int32)
+        offs = np.zeros(world + 1, dtype=np.int64)
+        self._check(self._L.ndtb200_partials_split(self._h, _ptr(up, C.c_int32) if world > 1 else None, int(world), _ptr(offs, C.c_int64)))
+        return offs
+
+    def merge_partials(self, gmin, gmax, n_finite_total, keys_ptr, counts_ptr, moments_ptr, n_total):
+        gmin, gmax = np.ascontiguousarray(gmin, np.float32), np.ascontiguousarray(gmax, np.float32)
+        n = C.c_int64(0)
+        st = self._check(self._L.ndtb200_merge_partials(self._h, _ptr(gmin, C.c_float), _ptr(gmax, C.c_float), int(n_finite_total),
+                                                        keys_ptr, counts_ptr, moments_ptr, int(n_total), C.byref(n)),
+                         allow=(ERR_NO_INPUT, ERR_GRID_OVERFLOW))
+        return st, int(n.value)
+
+    def copy_records(self, records_ptr, icov64_ptr):
+        self._check(self._L.ndtb200_copy_records(self._h, records_ptr, icov64_ptr))
+
+    def set_map_from_records(self, gmin, gmax, n_finite_total, records_ptr, icov64_ptr, n_total):
+        gmin, gmax = np.ascontiguousarray(gmin, np.float32), np.ascontiguousarray(gmax, np.float32)
+        return self._check(self._L.ndtb200_set_map_from_records(self._h, _ptr(gmin, C.c_float), _ptr(gmax, C.c_float), int(n_finite_total),
+                                                                records_ptr, icov64_ptr, int(n_total)),
                            allow=(ERR_NO_INPUT, ERR_GRID_OVERFLOW))
 
     def set_throughput_mode(self, on=True):
@@ -523,6 +562,28 @@ class NormalDistributionsTransform:
         v = C.c_double()
         self._check(self._L.ndtb200_calculate_score(self._h, p.ctypes.data, p.shape[0], 16, C.byref(v)))
         return v.value
+
+    def calculateScoreBatch(self, clouds):
+        """ndtb200_calculate_score_batch: calculateScore of every (already transformed) cloud of the list, one call."""
+        if len(clouds) == 0:
+            return np.zeros(0)
+        ps = [as_xyzw(c) for c in clouds]
+        offs = np.zeros(len(ps) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([p.shape[0] for p in ps])
+        allp = np.ascontiguousarray(np.concatenate(ps)) if offs[-1] else np.zeros((1, 4), np.float32)
+        out = np.zeros(len(ps), dtype=np.float64)
+        offs_c = (C.c_size_t * len(offs))(*[int(o) for o in offs])
+        self._check(self._L.ndtb200_calculate_score_batch(self._h, allp.ctypes.data, offs_c, len(ps), 16, _ptr(out, C.c_double)))
+        return out
+
+    def scorePoses(self, poses):
+        """ndtb200_score_poses: calculateScore of the current source under every candidate 4x4 pose."""
+        if len(poses) == 0:
+            return np.zeros(0)
+        g = np.concatenate([_colmajor(T) for T in poses]).astype(np.float32)
+        out = np.zeros(len(poses), dtype=np.float64)
+        self._check(self._L.ndtb200_score_poses(self._h, _ptr(g, C.c_float), len(poses), _ptr(out, C.c_double)))
+        return out
 
     # ---- stage dumps (parity API) ----
     def map_info(self):

@@ -54,22 +54,91 @@ class ShardedNdt:
             local[:, :3] = torch.as_tensor(np.ascontiguousarray(points[lo:hi, :3], dtype=np.float32)).to(dev)
         return self.setInputTargetShardedDevice(local, is_dense)
 
-    def setInputTargetShardedDevice(self, local, is_dense=True):
-        """Same, for a slice that already lives on this rank's GPU: `local` is an (n_r, 4) float32 CUDA tensor."""
+    def setInputTargetShardedDevice(self, local, is_dense=True, mode="owner"):
+        """Same, for a slice that already lives on this rank's GPU: `local` is an (n_r, 4) float32 CUDA tensor.
+
+        mode "owner" (default, SURVEY §8e row 3 as designed): the per-voxel partials travel to the rank that OWNS their key
+        range (all-to-all, 88 B per partial), the owner merges them in rank order and finalises its voxels, the finished
+        records (64 B + 48 B fp64 inverse covariance per voxel) are all-gathered — owners hold ascending key ranges, so
+        the concatenation in rank order is the key-sorted map — and every rank builds its voxel index.
+        mode "replicated": every rank gathers and merges ALL partials (the round-1 scheme; keeps the moments on every
+        rank for the parity dump)."""
+        import numpy as np
         import torch
         dist, ndt = self.dist, self.ndt
         dev = local.device
+        W = self.world
         mn, mx, nf = ndt.cloud_bounds(local.data_ptr(), local.shape[0], is_dense)
         t_mn = torch.tensor(mn, dtype=torch.float32, device=dev)
         t_mx = torch.tensor(mx, dtype=torch.float32, device=dev)
         t_nf = torch.tensor([nf], dtype=torch.int64, device=dev)
-        if self.world > 1:
+        if W > 1:
             dist.all_reduce(t_mn, op=dist.ReduceOp.MIN)
             dist.all_reduce(t_mx, op=dist.ReduceOp.MAX)
             dist.all_reduce(t_nf, op=dist.ReduceOp.SUM)
         gmin, gmax, nf_total = t_mn.cpu().numpy(), t_mx.cpu().numpy(), int(t_nf.item())
         st, nv = ndt.build_partials(gmin, gmax)
-        counts = torch.tensor([nv if st == 0 else 0], dtype=torch.int64, device=dev)
+        nv = nv if st == 0 else 0
+        keys = torch.zeros(max(1, nv), dtype=torch.int32, device=dev)
+        cnts = torch.zeros(max(1, nv), dtype=torch.int32, device=dev)
+        moms = torch.zeros((max(1, nv), 9), dtype=torch.float64, device=dev)
+        if nv > 0:
+            ndt.copy_partials(keys.data_ptr(), cnts.data_ptr(), moms.data_ptr())
+        if mode == "replicated" or W == 1:
+            return self._merge_replicated(local, keys, cnts, moms, nv, gmin, gmax, nf_total)
+        # ---- owners: ascending key ranges balanced by voxel count (splitters from a sample of every rank's sorted keys) ----
+        S = 256
+        sample = torch.full((S,), 2 ** 31 - 1, dtype=torch.int32, device=dev)
+        if nv > 0:
+            pos = torch.linspace(0, nv - 1, S, device=dev).long()
+            sample = keys[pos]
+        all_samples = torch.empty(W * S, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_samples, sample)
+        srt = torch.sort(all_samples).values
+        upper = [int(srt[(r + 1) * S].item()) for r in range(W - 1)]          # first key NOT owned by rank r
+        offs = ndt.partials_split(upper, W)
+        send = torch.tensor(np.diff(offs), dtype=torch.int64, device=dev)
+        recv = torch.empty(W, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv, send)
+        send_l, recv_l = [int(x) for x in send.tolist()], [int(x) for x in recv.tolist()]
+        n_in = int(sum(recv_l))
+        r_keys = torch.empty(max(1, n_in), dtype=torch.int32, device=dev)
+        r_cnts = torch.empty(max(1, n_in), dtype=torch.int32, device=dev)
+        r_moms = torch.empty((max(1, n_in), 9), dtype=torch.float64, device=dev)
+        dist.all_to_all_single(r_keys[:n_in], keys[:nv], recv_l, send_l)
+        dist.all_to_all_single(r_cnts[:n_in], cnts[:nv], recv_l, send_l)
+        dist.all_to_all_single(r_moms[:n_in], moms[:nv], recv_l, send_l)
+        torch.cuda.synchronize()
+        st2, n_own = ndt.merge_partials(gmin, gmax, nf_total, r_keys.data_ptr(), r_cnts.data_ptr(), r_moms.data_ptr(), n_in)
+        if st2 not in (0,):
+            n_own = 0
+        # ---- all-gather the finished records in rank (= key) order ----
+        own = torch.tensor([n_own], dtype=torch.int64, device=dev)
+        owns = torch.empty(W, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(owns, own)
+        owns_l = [int(x) for x in owns.tolist()]
+        cap = max(1, max(owns_l))
+        rec = torch.zeros((cap, 16), dtype=torch.int32, device=dev)            # 64-byte records
+        ic = torch.zeros((cap, 6), dtype=torch.float64, device=dev)
+        if n_own > 0:
+            ndt.copy_records(rec.data_ptr(), ic.data_ptr())
+        g_rec = torch.empty((W * cap, 16), dtype=torch.int32, device=dev)
+        g_ic = torch.empty((W * cap, 6), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(g_rec, rec)
+        dist.all_gather_into_tensor(g_ic, ic)
+        if any(o != cap for o in owns_l):
+            sel = torch.cat([torch.arange(r * cap, r * cap + owns_l[r], device=dev) for r in range(W)])
+            g_rec, g_ic = g_rec[sel].contiguous(), g_ic[sel].contiguous()
+        total = int(sum(owns_l))
+        torch.cuda.synchronize()
+        self._keep = (local, g_rec, g_ic)
+        return ndt.set_map_from_records(gmin, gmax, nf_total, g_rec.data_ptr(), g_ic.data_ptr(), total)
+
+    def _merge_replicated(self, local, keys, cnts, moms, nv, gmin, gmax, nf_total):
+        import torch
+        dist, ndt = self.dist, self.ndt
+        dev = local.device
+        counts = torch.tensor([nv], dtype=torch.int64, device=dev)
         all_counts = [torch.zeros_like(counts) for _ in range(self.world)]
         if self.world > 1:
             dist.all_gather(all_counts, counts)
@@ -77,11 +146,12 @@ class ShardedNdt:
             all_counts = [counts]
         sizes = [int(c.item()) for c in all_counts]
         cap = max(1, max(sizes))
-        keys = torch.zeros(cap, dtype=torch.int32, device=dev)
-        cnts = torch.zeros(cap, dtype=torch.int32, device=dev)
-        moms = torch.zeros((cap, 9), dtype=torch.float64, device=dev)
-        if sizes[self.rank] > 0:
-            ndt.copy_partials(keys.data_ptr(), cnts.data_ptr(), moms.data_ptr())
+        if keys.shape[0] < cap:
+            pad = cap - keys.shape[0]
+            keys = torch.cat([keys, torch.zeros(pad, dtype=keys.dtype, device=dev)])
+            cnts = torch.cat([cnts, torch.zeros(pad, dtype=cnts.dtype, device=dev)])
+            moms = torch.cat([moms, torch.zeros((pad, 9), dtype=moms.dtype, device=dev)])
+        keys, cnts, moms = keys[:cap].contiguous(), cnts[:cap].contiguous(), moms[:cap].contiguous()
         if self.world > 1:
             g_keys = torch.empty(self.world * cap, dtype=torch.int32, device=dev)
             g_cnts = torch.empty(self.world * cap, dtype=torch.int32, device=dev)
