@@ -109,6 +109,9 @@ def main():
                                             "p": [0.461994, 0.134161, -0.032969, 0.006620, -0.002877, -0.010950]},
         },
         "published_ms": {
+            "KDTREE_1thr": {"single": 207.697, "10times": 2059.19},
+            "KDTREE_8thr": {"single": 54.9903, "10times": 500.51},
+            "pcl_ndt": {"single": 282.222, "10times": 2921.92},
             "DIRECT7_1thr": {"single": 139.433, "10times": 1356.79},
             "DIRECT1_1thr": {"single": 34.6418, "10times": 317.03},
             "DIRECT7_8thr": {"single": 63.1442, "10times": 343.336},
