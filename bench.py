@@ -1053,7 +1053,7 @@ def run_c5(args):
                                   "n_gpus": world, "steps": reps, "ms_per_step": ms, "scaling": "strong", "dtype": "f64 moments / int32 keys",
                                   "data": "synthetic",
                                   "config": {"workload": "c5: VoxelGridCovariance build, %d points, resolution %.1f%s" %
-                                             (m * world, res, "" if world == 1 else " (sharded: %d points per GPU, partials all-gathered over NCCL and merged on every rank)" % m),
+                                             (m * world, res, "" if world == 1 else " (sharded: %d points per GPU; partials sent to the owner of their key range (all-to-all), owners merge + finalise, records all-gathered, NCCL)" % m),
                                              "voxels": info["n_voxels"], "valid": info["n_valid"],
                                              "timing": "host wall clock around the call, device synchronised on both sides, best of %d, max over ranks" % reps},
                                   "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",

@@ -76,3 +76,42 @@ def _emulated_on_one_gpu(world):
         assert dt < 1e-4 and dr < 1e-4
         assert abs(r["trans_probability"] - rr["trans_probability"]) <= 1e-5 * abs(rr["trans_probability"])
         assert abs(gpu.getFitnessScore() - ref.getFitnessScore()) <= 1e-6 * ref.getFitnessScore()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_cpp_sharded_host_over_nccl(world, tmp_path):
+    """pclomp_b200::ShardedNdt (include/pclomp_b200/sharded_ndt.hpp, NCCL plumbing, one process per GPU) through
+    apps/sharded_b200: source-sharded align on a replicated map (A) and on a map built by all ranks together
+    (owner-partitioned sharded build, B), against the oracle.  Needs `world` GPUs: on a smaller box the C++ host is
+    compile-checked only (the exchange kernels themselves run emulated in test_sharded_align_matches_oracle)."""
+    import numpy as np
+    from toyslam_b200 import _build
+    app = _build.build_sharded_app()
+    assert app is not None and os.path.exists(app)          # the C++ host compiles and links against NCCL
+    if _gpu_count() < world:
+        return
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import load_pair, transform_delta
+    tgt, src = load_pair()
+    tp, sp, idf = str(tmp_path / "t.bin"), str(tmp_path / "s.bin"), str(tmp_path / "nccl.id")
+    np.ascontiguousarray(tgt, dtype=np.float32).tofile(tp)
+    np.ascontiguousarray(src, dtype=np.float32).tofile(sp)
+    procs = [subprocess.Popen([app, str(r), str(world), idf, tp, sp], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(world)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [(p.returncode, o[1][-800:]) for p, o in zip(procs, outs)]
+    ref = oracle.NormalDistributionsTransform()
+    ref.setInputTarget(tgt); ref.setInputSource(src); ref.align()
+    rr = ref.result()
+    rows = {l.split()[1]: l.split() for l in outs[0][0].splitlines() if l.startswith("RESULT ")}
+    assert set(rows) == {"A", "B"}
+    for tag, f in rows.items():
+        g = {f[i]: f[i + 1] for i in range(2, 16, 2)}
+        assert int(g["converged"]) == 1 and int(g["iterations"]) == rr["iterations"] and int(g["evaluations"]) == rr["n_evaluations"]
+        T = np.array([float(x) for x in f[f.index("final") + 1:f.index("final") + 17]]).reshape(4, 4).T
+        dt, dr = transform_delta(T, rr["final"])
+        assert dt < 1e-4 and dr < 1e-4, (tag, dt, dr)
+        assert int(g["voxels"]) == ref.map_info()["n_voxels"] and int(g["valid"]) == ref.map_info()["n_valid"]
+        if tag == "A":
+            assert abs(float(g["fitness"]) - ref.getFitnessScore()) <= 1e-6 * ref.getFitnessScore()

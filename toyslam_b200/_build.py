@@ -63,10 +63,35 @@ def _build_app(src, out, force):
     return out
 
 
+SHARDED_SRC = os.path.join(_HERE, "..", "apps", "sharded_b200.cpp")
+SHARDED_BIN = os.path.join(_HERE, "..", "apps", "sharded_b200")
+
+
+def build_sharded_app(force=False):
+    """apps/sharded_b200: the multi-GPU paths through the C++ host (pclomp_b200::ShardedNdt over NCCL).  Needs nccl.h /
+    libnccl and the CUDA runtime headers; returns None where they are missing."""
+    cuda_inc = "/usr/local/cuda/include"
+    if not (os.path.exists("/usr/include/nccl.h") or os.path.exists(os.path.join(cuda_inc, "nccl.h"))):
+        return None
+    inc = os.path.join(_HERE, "..", "include")
+    deps = [SHARDED_SRC, LIB_PATH, os.path.join(inc, "pclomp_b200", "sharded_ndt.hpp"), os.path.join(inc, "ndt_b200.h")]
+    if not force and os.path.exists(SHARDED_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(SHARDED_BIN) for d in deps):
+        return SHARDED_BIN
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-I", inc, "-I", cuda_inc, SHARDED_SRC, "-o", SHARDED_BIN, "-L", LIB_DIR, "-lndt_b200",
+           "-L", "/usr/local/cuda/lib64", "-lcudart", "-lnccl", "-Wl,-rpath,$ORIGIN/../toyslam_b200/lib"]
+    try:
+        subprocess.check_call(cmd)
+    except subprocess.CalledProcessError:
+        return None
+    return SHARDED_BIN
+
+
 def build_apps(force=False):
     """The C++ programs over the header-only shim: apps/align_b200 (the reference's benchmark app: proves the
     reference-named API compiles and links) and apps/replay_b200 (PointCloud2 dump -> mapping loop).  Returns align_b200."""
     _build_app(REPLAY_SRC, REPLAY_BIN, force)
+    build_sharded_app(force)
     return _build_app(APP_SRC, APP_BIN, force)
 
 

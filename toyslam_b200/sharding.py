@@ -63,27 +63,41 @@ class ShardedNdt:
         the concatenation in rank order is the key-sorted map — and every rank builds its voxel index.
         mode "replicated": every rank gathers and merges ALL partials (the round-1 scheme; keeps the moments on every
         rank for the parity dump)."""
+        import os
+        import time
         import numpy as np
         import torch
         dist, ndt = self.dist, self.ndt
         dev = local.device
         W = self.world
+        timing = os.environ.get("NDTB200_SHARD_TIMING") is not None
+        marks = []
+
+        def mark(name):
+            if timing:
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+        mark("start")
         mn, mx, nf = ndt.cloud_bounds(local.data_ptr(), local.shape[0], is_dense)
-        t_mn = torch.tensor(mn, dtype=torch.float32, device=dev)
-        t_mx = torch.tensor(mx, dtype=torch.float32, device=dev)
+        mark("cloud_bounds")
+        # one MIN all-reduce for the box (max = -min(-x)), one SUM for the finite count
+        t_box = torch.tensor(np.concatenate([mn, -mx]), dtype=torch.float32, device=dev)
         t_nf = torch.tensor([nf], dtype=torch.int64, device=dev)
         if W > 1:
-            dist.all_reduce(t_mn, op=dist.ReduceOp.MIN)
-            dist.all_reduce(t_mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t_box, op=dist.ReduceOp.MIN)
             dist.all_reduce(t_nf, op=dist.ReduceOp.SUM)
-        gmin, gmax, nf_total = t_mn.cpu().numpy(), t_mx.cpu().numpy(), int(t_nf.item())
+        box = t_box.cpu().numpy()
+        gmin, gmax, nf_total = box[:3].copy(), (-box[3:]).copy(), int(t_nf.item())
+        mark("bbox_allreduce")
         st, nv = ndt.build_partials(gmin, gmax)
         nv = nv if st == 0 else 0
+        mark("build_partials")
         keys = torch.zeros(max(1, nv), dtype=torch.int32, device=dev)
         cnts = torch.zeros(max(1, nv), dtype=torch.int32, device=dev)
         moms = torch.zeros((max(1, nv), 9), dtype=torch.float64, device=dev)
         if nv > 0:
             ndt.copy_partials(keys.data_ptr(), cnts.data_ptr(), moms.data_ptr())
+        mark("copy_partials")
         if mode == "replicated" or W == 1:
             return self._merge_replicated(local, keys, cnts, moms, nv, gmin, gmax, nf_total)
         # ---- owners: ascending key ranges balanced by voxel count (splitters from a sample of every rank's sorted keys) ----
@@ -97,6 +111,7 @@ class ShardedNdt:
         srt = torch.sort(all_samples).values
         upper = [int(srt[(r + 1) * S].item()) for r in range(W - 1)]          # first key NOT owned by rank r
         offs = ndt.partials_split(upper, W)
+        mark("splitters")
         send = torch.tensor(np.diff(offs), dtype=torch.int64, device=dev)
         recv = torch.empty(W, dtype=torch.int64, device=dev)
         dist.all_to_all_single(recv, send)
@@ -109,30 +124,41 @@ class ShardedNdt:
         dist.all_to_all_single(r_cnts[:n_in], cnts[:nv], recv_l, send_l)
         dist.all_to_all_single(r_moms[:n_in], moms[:nv], recv_l, send_l)
         torch.cuda.synchronize()
+        mark("all_to_all")
         st2, n_own = ndt.merge_partials(gmin, gmax, nf_total, r_keys.data_ptr(), r_cnts.data_ptr(), r_moms.data_ptr(), n_in)
         if st2 not in (0,):
             n_own = 0
+        mark("merge_partials")
         # ---- all-gather the finished records in rank (= key) order ----
         own = torch.tensor([n_own], dtype=torch.int64, device=dev)
         owns = torch.empty(W, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(owns, own)
         owns_l = [int(x) for x in owns.tolist()]
-        cap = max(1, max(owns_l))
-        rec = torch.zeros((cap, 16), dtype=torch.int32, device=dev)            # 64-byte records
-        ic = torch.zeros((cap, 6), dtype=torch.float64, device=dev)
-        if n_own > 0:
-            ndt.copy_records(rec.data_ptr(), ic.data_ptr())
-        g_rec = torch.empty((W * cap, 16), dtype=torch.int32, device=dev)
-        g_ic = torch.empty((W * cap, 6), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(g_rec, rec)
-        dist.all_gather_into_tensor(g_ic, ic)
-        if any(o != cap for o in owns_l):
-            sel = torch.cat([torch.arange(r * cap, r * cap + owns_l[r], device=dev) for r in range(W)])
-            g_rec, g_ic = g_rec[sel].contiguous(), g_ic[sel].contiguous()
         total = int(sum(owns_l))
+        my_off = int(sum(owns_l[:self.rank]))
+        # uneven all-gather straight into the final arrays: every owner broadcasts its slice (owners hold ascending key
+        # ranges, so the rank-ordered concatenation IS the key-sorted map; no padding, no re-packing)
+        g_rec = torch.empty((max(1, total), 16), dtype=torch.int32, device=dev)       # 64-byte records
+        g_ic = torch.empty((max(1, total), 6), dtype=torch.float64, device=dev)
+        if n_own > 0:
+            ndt.copy_records(g_rec[my_off:my_off + n_own].data_ptr(), g_ic[my_off:my_off + n_own].data_ptr())
+        off = 0
+        works = []
+        for r in range(W):
+            if owns_l[r] > 0:
+                works.append(dist.broadcast(g_rec[off:off + owns_l[r]], src=r, async_op=True))
+                works.append(dist.broadcast(g_ic[off:off + owns_l[r]], src=r, async_op=True))
+            off += owns_l[r]
+        for wk in works:
+            wk.wait()
         torch.cuda.synchronize()
+        mark("allgather_records")
         self._keep = (local, g_rec, g_ic)
-        return ndt.set_map_from_records(gmin, gmax, nf_total, g_rec.data_ptr(), g_ic.data_ptr(), total)
+        st3 = ndt.set_map_from_records(gmin, gmax, nf_total, g_rec.data_ptr(), g_ic.data_ptr(), total)
+        mark("set_map_from_records")
+        if timing and self.rank == 0:
+            print("SHARD_TIMING " + " ".join("%s=%.3fms" % (b[0], (b[1] - a[1]) * 1e3) for a, b in zip(marks[:-1], marks[1:])), flush=True)
+        return st3
 
     def _merge_replicated(self, local, keys, cnts, moms, nv, gmin, gmax, nf_total):
         import torch
