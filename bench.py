@@ -24,6 +24,7 @@ sweep), mapper (the mapping-node loop as a device-resident pipeline).
 import argparse
 import os as _os
 _os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # no lazy kernel-load stalls inside timed regions
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per stream (up to 32): independent solves do not serialise
 import json
 import os
 import subprocess

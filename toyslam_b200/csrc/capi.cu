@@ -1161,6 +1161,11 @@ int ndtb200_default_params(ndtb200_params* p) {
 int ndtb200_create(ndtb200_handle** out, int device) {
   if (!out) return NDTB200_ERR_INVALID;
   *out = nullptr;
+  // Independent handles run on their own streams; streams are multiplexed onto CUDA_DEVICE_MAX_CONNECTIONS hardware
+  // queues, and kernels of streams that share a queue serialise.  Ask for the maximum (32) unless the caller chose a
+  // value; this only takes effect if it happens before the process creates its CUDA context (measured on c2, 64 solves
+  // in flight: 13.7 k -> 15.4 k aligns/s).
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
     return NDTB200_ERR_NO_DEVICE;  // no CPU fallback, by design
@@ -2413,6 +2418,13 @@ int ndtb200_set_throughput_mode(ndtb200_handle* h, int on) {
 // Independent scan pairs in flight together (SURVEY §8b "align_batch", §8e "batched scan pairs"): every handle owns
 // its map, source and stream; all solves are enqueued with the throughput CTA shape before the first wait, so up to
 // four persistent kernels share every SM and each one's barrier / Newton-step latency is covered by the others.
+// Independent scan pairs in flight together (SURVEY §8b "align_batch", §8e "batched scan pairs"): every handle owns
+// its map, source and stream; all solves are enqueued with the throughput CTA shape before the first wait, so up to
+// four persistent kernels share every SM and each one's barrier / Newton-step latency is covered by the others.
+// (Measured and rejected in round 2: dividing the SMs between the pairs instead — every solve a 1..8-CTA grid /
+// thread-block cluster of 1024-thread CTAs, all pairs side by side — reaches 7.6 k aligns/s on c2 against 15.4 k for
+// the shared full-width grids: with many points per thread the pass runs at about half the issue rate, and only as
+// many kernels run concurrently as the process has hardware queues — see CUDA_DEVICE_MAX_CONNECTIONS in bench.py.)
 int ndtb200_align_batch_async(ndtb200_handle* const* hs, int n, const float* guesses, void* const* out_points,
                               size_t out_stride_bytes) {
   if (!hs || n < 0) return NDTB200_ERR_INVALID;
