@@ -572,6 +572,27 @@ def run_b200(args):
            "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps, "ms_per_step": e2e_dt / e2e_steps * 1e3,
            "api": "ndtb200_set_source (pinned host cloud) + ndtb200_align_batch_async (host output clouds + result blocks), %d pairs per call, "
                   "batches pipelined, ndtb200_sync per handle at the end" % R}
+    # results only: the same pipeline without downloading the aligned cloud (out_points = NULL; the mapping node never reads
+    # `aligned`, ndt_rosbag_mapping_node.cpp:120-144): D2H = the 416-byte result block per align
+    def e2e_batch_pose_only():
+        for i in range(R):
+            handles[i].set_source_raw(src_hosts[i].data_ptr(), n_srcs[i], 16)
+        batch.align_async(None, None, 16)
+
+    e2e_batch_pose_only()
+    batch.sync()
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps // R):
+        e2e_batch_pose_only()
+    batch.sync()
+    torch.cuda.synchronize()
+    barrier(world)
+    e2e_po_dt = max_over_ranks(time.perf_counter() - t0, world, dev)
+    e2e["results_only"] = {"value": e2e_steps * world / e2e_po_dt, "unit": "aligns/s", "h2d_bytes_per_step": h2d // e2e_steps,
+                           "d2h_bytes_per_step": 416, "ms_per_step": e2e_po_dt / e2e_steps * 1e3,
+                           "api": "same pipeline with out_points = NULL: poses and counters come back, the aligned cloud stays on the device"}
     # the same through one blocking ndtb200_align at a time (what an unmodified caller of the reference's class does)
     n_single = max(8, min(64, e2e_steps))
     t0 = time.perf_counter()
@@ -798,7 +819,9 @@ def run_c3(args):
         hosts.append(hb)
     guesses = [np.eye(4)] + [workloads.relative_pose_matrix(poses[k - 1], poses[k]) for k in range(1, nd)]
     truths = [workloads.relative_pose_matrix(poses[k], poses[k + 1]) for k in range(nd)]
-    L = args.c3_lanes if args.c3_lanes > 0 else max(2, min(8, (os.cpu_count() or 16) // (2 * max(1, world))))
+    # lanes = handles + host threads per GPU; their waits yield the core (throughput-mode handles poll with sched_yield), so
+    # the count is not tied to the host core count: 16 lanes keep one GPU busy (measured 12.6 k pairs/s vs 10.7 k with 8)
+    L = args.c3_lanes if args.c3_lanes > 0 else 16
     lanes = []
     for _ in range(L):
         ndt = nb.NormalDistributionsTransform(device=local)
@@ -1095,8 +1118,7 @@ def main():
     ap.add_argument("--mapper-scans", type=int, default=200)
     ap.add_argument("--c3-distinct", type=int, default=128, help="distinct consecutive pairs generated per GPU (cycled)")
     ap.add_argument("--c3-lanes", type=int, default=0,
-                    help="handles (+ host threads) per GPU for the c3 pipeline; 0 = auto: min(8, host cores / (2 * GPUs)), at least 2 "
-                         "(every lane is a host thread that spins in stream synchronisation: do not oversubscribe the host)")
+                    help="handles (+ host threads) per GPU for the c3 pipeline; 0 = auto (16)")
     ap.add_argument("--c5-points", type=int, nargs="+", default=[10_000_000, 100_000_000])
     ap.add_argument("--c5-res", type=float, nargs="+", default=[0.5, 1.0, 2.0])
     ap.add_argument("--c4-scans", type=int, default=16)

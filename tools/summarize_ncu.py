@@ -78,8 +78,16 @@ def main():
     writes = [to_bytes(r[i_w], unit[i_w]) for r in vals]
     jpath = os.path.join(ROOT, "profiles", "align_kernel_ncu.json")
     js = json.load(open(jpath)) if os.path.exists(jpath) else {}
+    def avg(name):
+        if name not in hdr:
+            return None
+        i = hdr.index(name)
+        return sum(float(r[i]) for r in vals) / len(vals)
     js[method] = {"dram_bytes_per_launch": sum(reads) / len(reads) + sum(writes) / len(writes),
                   "dram_read_bytes_per_launch": sum(reads) / len(reads), "dram_write_bytes_per_launch": sum(writes) / len(writes),
+                  "issue_active_pct": avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                  "warps_active_pct": avg("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                  "duration_us_alone": avg("gpu__time_duration.sum"),
                   "source": "%s (ncu --set full, %d launches)" % (os.path.basename(rep), len(vals))}
     json.dump(js, open(jpath, "w"), indent=1)
     print("wrote profiles/%s_launches.md, profiles/%s_align_kernel.md, profiles/align_kernel_ncu.json" % (tag, tag))

@@ -45,6 +45,21 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+CHECKED_LIB_PATH = os.path.join(LIB_DIR, "libndt_b200_checked.so")
+
+
+def build_checked(force=False):
+    """The same library with -DNDTB200_CHECKED: device-side bounds / protocol assertions (NDT_CHECK) in the kernels.
+    Run the parity suite on it with NDTB200_LIB=toyslam_b200/lib/libndt_b200_checked.so (compute-sanitizer is closed on
+    this GPU pool)."""
+    if not force and os.path.exists(CHECKED_LIB_PATH) and os.path.getmtime(CHECKED_LIB_PATH) >= max(
+            os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)):
+        return CHECKED_LIB_PATH
+    cmd = [_nvcc()] + (["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []) + NVCC_FLAGS + ["-DNDTB200_CHECKED", "-o", CHECKED_LIB_PATH] + SOURCES
+    subprocess.check_call(cmd, cwd=CSRC)
+    return CHECKED_LIB_PATH
+
+
 APP_SRC = os.path.join(_HERE, "..", "apps", "align_b200.cpp")
 APP_BIN = os.path.join(_HERE, "..", "apps", "align_b200")
 REPLAY_SRC = os.path.join(_HERE, "..", "apps", "replay_b200.cpp")

@@ -1,5 +1,7 @@
 // capi.cu — host side of libndt_b200.so: handle, device memory, kernel orchestration, C ABI.
 // See include/ndt_b200.h for the contract of every entry point and the reference method it replaces.
+#include <sched.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -784,6 +786,10 @@ MapView make_view(const ndtb200_handle* h) {
     for (int a = 0; a < 3; ++a) { m.min_b[a] = 1; m.max_b[a] = 0; m.mul[a] = 0; }
   }
   m.min_points = h->prm.min_points_per_voxel;
+  m.n_cells = static_cast<unsigned long long>(h->grid.div_b[0]) * static_cast<unsigned long long>(h->grid.div_b[1]) *
+              static_cast<unsigned long long>(h->grid.div_b[2]);
+  m.n_records = static_cast<uint32_t>(h->n_voxels);
+  m.pad = 0;
   return m;
 }
 
@@ -1060,6 +1066,16 @@ int fetch_result(ndtb200_handle* h) {
   if (!h->result_copy_enqueued) {
     int st = enqueue_result_copy(h);
     if (st != NDTB200_OK) return st;
+  }
+  if (h->shape == 1) {
+    // throughput mode: many handles, each driven by its own host thread (the c3 pipeline): poll and YIELD instead of
+    // spinning inside cudaStreamSynchronize, so that more pipeline threads than host cores still make progress
+    while (true) {
+      const cudaError_t q = cudaStreamQuery(h->stream);
+      if (q == cudaSuccess) break;
+      if (q != cudaErrorNotReady) { h->err = std::string("cudaStreamQuery: ") + cudaGetErrorString(q); return NDTB200_ERR_CUDA; }
+      sched_yield();
+    }
   }
   CK(cudaStreamSynchronize(h->stream));
   h->result_copy_enqueued = false;
@@ -2281,7 +2297,28 @@ int ndtb200_mapper_create(ndtb200_mapper** out, int device, const ndtb200_params
               a->d_target.ensure(map_pts * 16) == cudaSuccess && a->d_out.ensure(map_pts * 16) == cudaSuccess &&
               a->d_keys_a.ensure(map_pts * 4) == cudaSuccess && a->d_keys_b.ensure(map_pts * 4) == cudaSuccess &&
               a->d_vals_a.ensure(map_pts * 4) == cudaSuccess && a->d_vals_b.ensure(map_pts * 4) == cudaSuccess &&
-              a->d_voxel_key.ensure(map_pts * 4) == cudaSuccess && a->d_voxel_start.ensure(map_pts * 4) == cudaSuccess;
+              a->d_voxel_key.ensure(map_pts * 4) == cudaSuccess && a->d_voxel_start.ensure(map_pts * 4) == cudaSuccess &&
+              a->d_status.ensure((size_t)kMaxSortPasses * (map_pts / kSortTile + 1) * 256 * sizeof(unsigned long long)) == cudaSuccess &&
+              a->d_sortmeta.ensure(kSortMetaBytes) == cudaSuccess && a->d_hist.ensure((map_pts / kScanTile + 64) * 4) == cudaSuccess &&
+              a->d_scan_tmp.ensure(scan_tmp_elems(map_pts / kScanTile + 64) * 4) == cudaSuccess;
+    // the two registration handles: everything a 64 k-point scan touches (build scratch, records, cell tables over a
+    // 32 MB = 8 M-cell grid, solver workspace), so that no scan of the drive is the first to allocate (a cudaFree +
+    // cudaMalloc pair in the loop was measured at 4 - 40 ms)
+    const size_t pts = kSmallMaxPoints, table_b = 32u << 20;
+    for (int i = 0; i < 2 && ok; ++i) {
+      ndtb200_handle* n = m->ndt[i];
+      ok = n->d_target.ensure(pts * 16) == cudaSuccess && n->d_source.ensure(pts * 16) == cudaSuccess && n->d_out.ensure(pts * 16) == cudaSuccess &&
+           n->d_keys_a.ensure(pts * 4) == cudaSuccess && n->d_keys_b.ensure(pts * 4) == cudaSuccess && n->d_vals_a.ensure(pts * 4) == cudaSuccess &&
+           n->d_vals_b.ensure(pts * 4) == cudaSuccess && n->d_voxel_key.ensure(pts * 4) == cudaSuccess && n->d_voxel_start.ensure(pts * 4) == cudaSuccess &&
+           n->d_moments.ensure(pts * 72) == cudaSuccess && n->d_records.ensure(pts * sizeof(VoxelRecord)) == cudaSuccess &&
+           n->d_icov64.ensure(pts * 48) == cudaSuccess && n->d_hist.ensure((size_t)256 * (pts / kSmallTile + 1) * 4) == cudaSuccess &&
+           n->d_scan_tmp.ensure((pts / kScanTile + 64 + 1024 + 64) * 4) == cudaSuccess && n->d_mm_partial.ensure((size_t)n->num_sms * 8 * 24) == cudaSuccess &&
+           n->d_mm_finite.ensure((size_t)n->num_sms * 8 * 4) == cudaSuccess && n->d_grid.ensure(sizeof(GridDesc)) == cudaSuccess &&
+           n->d_dense.ensure(table_b) == cudaSuccess && n->d_cell_all.ensure(table_b) == cudaSuccess &&
+           n->d_best.ensure(pts * 8 + 64) == cudaSuccess && n->d_tmp.ensure(pts * 16) == cudaSuccess &&
+           n->d_partials.ensure((size_t)2 * n->num_sms * kNVP * sizeof(double)) == cudaSuccess && n->d_result.ensure(sizeof(AlignResultDev)) == cudaSuccess &&
+           n->d_trace.ensure(ndtb200_handle::kTraceCap * sizeof(TraceRec)) == cudaSuccess;
+    }
     if (!ok) st = NDTB200_ERR_CUDA;
   }
   if (st != NDTB200_OK) { ndtb200_mapper_destroy(m); return st; }

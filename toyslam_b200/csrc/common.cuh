@@ -3,6 +3,22 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdio.h>
+
+// -DNDTB200_CHECKED: device-side bounds / protocol assertions in the hand-synchronised kernels (compute-sanitizer is
+// closed on this GPU pool: the checked build + the parity suite is the memory-safety evidence, profiles/r02_checked_build.md)
+#ifdef NDTB200_CHECKED
+#define NDT_CHECK(cond)                                                                                          \
+  do {                                                                                                           \
+    if (!(cond)) {                                                                                               \
+      printf("NDT_CHECK failed: %s at %s:%d (block %d thread %d)\n", #cond, __FILE__, __LINE__, blockIdx.x, threadIdx.x); \
+      __trap();                                                                                                  \
+    }                                                                                                            \
+  } while (0)
+#else
+#define NDT_CHECK(cond) do { } while (0)
+#endif
+
 namespace ndtb200 {
 
 // ---------------------------------------------------------------------------------------------
@@ -64,6 +80,9 @@ struct MapView {  // what the kernels need to probe the map
   float leaf[3];
   float inv_leaf[3];  // fl32(1 / leaf): fast path of lookup_cell only (the reference's lookup DIVIDES, Q8)
   int32_t min_points;
+  unsigned long long n_cells;  // dx*dy*dz (bounds of `dense` / `cell_all`)
+  uint32_t n_records;          // occupied voxels (bounds of `records` / `icov64` / `centroids`)
+  uint32_t pad;
 };
 
 // key -> record index of a VALID voxel, or -1.  Two interchangeable indexes over the same records:
@@ -71,6 +90,7 @@ struct MapView {  // what the kernels need to probe the map
 //     sector) — a single round trip, no compare, no collision chain; used whenever the table fits the memory budget;
 //   * hash: open addressing over the valid voxels, for huge sparse grids (up to the int32 key guard, Q9).
 __device__ __forceinline__ int map_find(const MapView& m, int32_t key) {
+  NDT_CHECK(key >= 0 && static_cast<unsigned long long>(key) < m.n_cells);
   if (m.dense != nullptr) return __ldg(m.dense + key);
   uint32_t h = hash_key(static_cast<uint32_t>(key), m.hash_shift);
   while (true) {

@@ -445,6 +445,7 @@ __device__ __forceinline__ void radix_scatter_tile(const uint32_t* __restrict__ 
   for (uint32_t j = threadIdx.x; j < count; j += kBuildThreads) {
     const uint32_t key = s_key[j];
     const uint32_t pos = s_gbase[(key >> shift) & 255u] + j;
+    NDT_CHECK(pos < n);
     keys_out[pos] = key;
     vals_out[pos] = s_val[j];
   }
@@ -500,6 +501,7 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
   for (int d = threadIdx.x; d < 256 * kSortWarps; d += kBuildThreads) (&warp_cnt[0][0])[d] = 0u;
   __syncthreads();
   const unsigned int tile = s_tile;
+  NDT_CHECK((size_t)tile * kTile < n);
   const size_t tbase = (size_t)tile * kTile;
   const size_t wbase = tbase + (size_t)warp * (32 * ROUNDS);
   uint32_t k[ROUNDS], v[ROUNDS];
@@ -549,6 +551,7 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
         if (flag == 0u) continue;
         excl += w & kMask;
         if (flag == 2u) break;
+        NDT_CHECK(t > 0);
         --t;
       }
       st_relaxed_u64(row + d, (2ull << 62) | (excl + off));
@@ -574,6 +577,7 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
   for (uint32_t j = threadIdx.x; j < count; j += kBuildThreads) {
     const uint32_t key = s_key[j];
     const unsigned long long pos = s_gbase[(key >> shift) & 255u] + j;
+    NDT_CHECK(pos < n && s_val[j] < n);
     keys_out[pos] = key;
     vals_out[pos] = s_val[j];
   }
@@ -667,7 +671,7 @@ __device__ __forceinline__ void voxel_moments_group(const float4* __restrict__ p
 #pragma unroll
       for (int u = 0; u < 4; ++u) idx[u] = (i0 + u * GROUP < e) ? __ldg(sorted_idx + i0 + u * GROUP) : 0xffffffffu;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) p[u] = (idx[u] != 0xffffffffu) ? ldg_gather16(pts + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 4; ++u) { NDT_CHECK(idx[u] == 0xffffffffu || i0 + u * GROUP < n_finite); p[u] = (idx[u] != 0xffffffffu) ? ldg_gather16(pts + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (idx[u] == 0xffffffffu) continue;
@@ -999,6 +1003,7 @@ dense_fill_kernel(const VoxelRecord* __restrict__ records, uint32_t n_voxels, in
   const uint32_t v = blockIdx.x * (uint32_t)blockDim.x + threadIdx.x;
   if (v >= n_voxels) return;
   if (records[v].count < min_points) return;  // sparse and rejected leaves are invisible to lookups (…_impl.hpp:395)
+  NDT_CHECK(records[v].key >= 0);
   table[records[v].key] = static_cast<int32_t>(v);
 }
 

@@ -262,7 +262,11 @@ __device__ __forceinline__ void probe_cells(const MapView& m, int ix, int iy, in
   }
   if (m.dense != nullptr) {  // uniform
 #pragma unroll
-    for (int k = 0; k < K; ++k) rec[k] = ok[k] ? __ldg(m.dense + key[k]) : -1;
+    for (int k = 0; k < K; ++k) {
+      NDT_CHECK(!ok[k] || (key[k] >= 0 && static_cast<unsigned long long>(key[k]) < m.n_cells));
+      rec[k] = ok[k] ? __ldg(m.dense + key[k]) : -1;
+      NDT_CHECK(rec[k] >= -1 && (rec[k] < 0 || static_cast<uint32_t>(rec[k]) < m.n_records));
+    }
   } else {
     HashSlot slot[K];
     uint32_t h[K];
@@ -471,6 +475,7 @@ __device__ __forceinline__ void grid_allreduce(const double* s_block, double* s_
                                                unsigned int launch_tag) {
   const unsigned int G = rc.G, bid = rc.bid;
   const int W = ws.world;
+  NDT_CHECK(bid < G && W >= 1 && W <= kMaxRanks && rc.rank >= 0 && rc.rank < W);
   if (G == 1 && W == 1) {
     if (threadIdx.x < kNV) s_tot[threadIdx.x] = s_block[threadIdx.x];
     __syncthreads();
@@ -1050,6 +1055,7 @@ struct RecordRegs { float4 a, b, c; };  // the 48 hot bytes of a voxel record
 
 __device__ __forceinline__ RecordRegs load_record(const VoxelRecord* R) {
   RecordRegs r;
+  NDT_CHECK((reinterpret_cast<unsigned long long>(R) & 15ull) == 0ull);
   r.a = __ldg(reinterpret_cast<const float4*>(R));
   r.b = __ldg(reinterpret_cast<const float4*>(R) + 1);
   r.c = __ldg(reinterpret_cast<const float4*>(R) + 2);
@@ -1124,6 +1130,7 @@ __device__ __forceinline__ void point_f32(float px, float py, float pz, const Ev
     for (int k = 0; k < K; ++k) {
       if (rec[k] < 0) continue;
       ++nh;
+      NDT_CHECK(static_cast<uint32_t>(rec[k]) < m.n_records);
       hit_f32<HESS>(load_record(m.records + rec[k]), tx, ty, tz, d2f, d1f, S, A, M);
     }
 #endif
@@ -1132,6 +1139,7 @@ __device__ __forceinline__ void point_f32(float px, float py, float pz, const Ev
     for (int k = 0; k < K; ++k) {
       const int rec = probe_neighbour<METHOD>(m, ix, iy, iz, k, tx, ty, tz);
       if (rec < 0) continue;
+      NDT_CHECK(static_cast<uint32_t>(rec) < m.n_records);
       ++nh;
       hit_f32<HESS>(load_record(m.records + rec), tx, ty, tz, d2f, d1f, S, A, M);
     }
@@ -1214,6 +1222,7 @@ __device__ __forceinline__ double eval_warp_f32(const float4* __restrict__ src, 
   for (int g = warp_global; g < n_groups; g += warps_total, ++j) {
     const int i = (g << 5) + lane;
     if (i < n) {
+      NDT_CHECK(i >= 0);
       float px, py, pz;
 #ifdef NDTB200_NO_CACHED_POINTS
       { const float4 pt = __ldg(src + i); px = pt.x; py = pt.y; pz = pt.z; }
