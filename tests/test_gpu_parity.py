@@ -256,6 +256,51 @@ def test_fused_and_staged_builds_identical(nb, monkeypatch):
     monkeypatch.delenv("NDTB200_BUILD_PATH")
 
 
+def test_payload_sort_build_identical(nb, monkeypatch):
+    """Clouds above 4 M points are sorted with the POINTS as the payload of the radix passes (map_build.cuh:
+    onesweep_payload_kernel) instead of (key, index) pairs + a gather: the same stable order and the same additions, so
+    the map, the solver's sums and the consumers of the lazily built index array (getFitnessScore, KDTREE) must agree
+    bit for bit with the (key, index) path.  NDTB200_PAYLOAD_SORT_MIN forces the path at test sizes."""
+    tgt, src = load_pair()
+    scene, _ = synthetic_scene(n_target=120000, seed=5, offset=(2000.0, -1500.0, 50.0))
+    nan_cloud = tgt.copy()
+    nan_cloud[::53, 2] = np.nan
+    nan_cloud[7::211, 0] = np.inf
+    one_pass = (tgt[:5000] * 0.1).astype(np.float32)                # < 256 cells at res 1.0: a single radix pass
+    cases = [(tgt, 1.0, True), (tgt, 0.5, True), (scene, 1.0, True), (scene, 0.3, True), (nan_cloud, 1.0, False), (one_pass, 1.0, True)]
+    monkeypatch.setenv("NDTB200_BUILD_PATH", "staged")
+    for cloud, res, dense in cases:
+        out = {}
+        for path, lo in (("pairs", str(1 << 40)), ("payload", "1")):
+            monkeypatch.setenv("NDTB200_PAYLOAD_SORT_MIN", lo)
+            g = nb.NormalDistributionsTransform()
+            g.setResolution(res)
+            st = g.setInputTarget(cloud, dense)
+            g.setInputSource(src)
+            e = g.eval_derivatives(np.array([0.3, 0.1, -0.02, 0.004, -0.002, -0.01]))
+            d = g.dump_voxels()                 # payload path: moments recomputed from the sorted cloud (sequential kernel)
+            g.align()
+            fit = g.getFitnessScore()           # payload path: builds the sorted index array on first use
+            d2 = g.dump_voxels()                # ... after which the moments come from the gather again
+            g.setNeighborhoodSearchMethod(oracle.KDTREE)
+            ek = g.eval_derivatives(np.array([0.1, 0.0, 0.02, 0.0, 0.001, 0.01]), compute_hessian=False)
+            out[path] = (st, g.map_info(), d, e, fit, d2, ek)
+        a, b = out["pairs"], out["payload"]
+        assert a[0] == b[0]
+        for k in ("min_b", "max_b", "div_b"):
+            assert np.array_equal(a[1][k], b[1][k])
+        assert a[1]["n_voxels"] == b[1]["n_voxels"] and a[1]["n_valid"] == b[1]["n_valid"]
+        for dd in (2, 5):
+            for k in ("keys", "counts", "mean", "cov", "icov", "inflated"):
+                assert np.array_equal(a[dd][k], b[dd][k], equal_nan=True), k
+        for ee in (3, 6):
+            assert a[ee]["score"] == b[ee]["score"] and np.array_equal(a[ee]["gradient"], b[ee]["gradient"])
+        assert np.array_equal(a[3]["hessian"], b[3]["hessian"])
+        assert a[4] == b[4]
+    monkeypatch.delenv("NDTB200_PAYLOAD_SORT_MIN")
+    monkeypatch.delenv("NDTB200_BUILD_PATH")
+
+
 def test_grid_overflow_guard(nb):
     tgt = np.array([[0, 0, 0], [3000, 3000, 3000], [1, 1, 1]], dtype=np.float32)
     ref = oracle.NormalDistributionsTransform()

@@ -81,6 +81,11 @@ struct ndtb200_handle {
   bool records_only_map = false;  // map installed from finished records (sharded build): no moments, no raw target
   bool moments_valid = false;  // d_moments holds the per-voxel moments of the current map (the staged build fuses them away)
   bool prefer_fused_build = false;  // set by the mapping pipeline: fused builds even with the small-CTA solve shape
+  // payload sort (clouds above kPayloadSortMin points): the sort moves the points themselves (key in .w); the sorted cloud
+  // ends in d_pay_a.  idx_lazy: the sorted point INDICES (d_vals_a: getFitnessScore, KDTREE centroids, parity dumps) were
+  // not produced by the build and are computed on first use (ensure_sorted_indices)
+  DevBuf d_pay_a, d_pay_b;
+  bool idx_lazy = false;
   DevBuf d_centroid;              // KDTREE mode: fp32 centroid of every voxel
   bool centroids_valid = false;
   DevBuf d_cell_all, d_best;      // getFitnessScore: cell table over all occupied voxels, per-query results
@@ -186,6 +191,7 @@ size_t scan_tmp_elems(size_t n) {
 
 void clear_map(ndtb200_handle* h) {
   h->records_only_map = false;
+  h->idx_lazy = false;
   h->cell_all_valid = false;
   h->centroids_valid = false;
   h->n_voxels = 0;
@@ -289,11 +295,18 @@ int sort_pairs(ndtb200_handle* h, size_t n, int passes, bool hist_ready) {
 
 // sort + the segment heads: -> d_voxel_key / d_voxel_start (n_vox entries), sorted indices in d_vals_a.  One
 // synchronisation (the voxel count, needed to size the voxel arrays).
+int segment_heads(ndtb200_handle* h, size_t n, uint32_t sentinel, uint32_t* n_vox_out);
+
 int sort_and_segment(ndtb200_handle* h, size_t n, uint32_t sentinel, int passes, uint32_t* n_vox_out, bool hist_ready = false) {
   {
     int st = sort_pairs(h, n, passes, hist_ready);
     if (st != NDTB200_OK) return st;
   }
+  return segment_heads(h, n, sentinel, n_vox_out);
+}
+
+// occupied voxels = segment heads of the sorted keys in d_keys_a -> d_voxel_key / d_voxel_start; one synchronisation
+int segment_heads(ndtb200_handle* h, size_t n, uint32_t sentinel, uint32_t* n_vox_out) {
   const int stiles = static_cast<int>((n + kScanTile - 1) / kScanTile);
   CK(h->d_hist.ensure((size_t)stiles * sizeof(uint32_t)));
   CK(h->d_scan_tmp.ensure(scan_tmp_elems(std::max<size_t>(stiles, 1)) * sizeof(uint32_t)));
@@ -315,6 +328,51 @@ int sort_and_segment(ndtb200_handle* h, size_t n, uint32_t sentinel, int passes,
                                                               h->d_voxel_start.as<uint32_t>());
   LAUNCHED(h);
   *n_vox_out = n_vox;
+  return NDTB200_OK;
+}
+
+// ---- payload sort (map_build.cuh: onesweep_payload_kernel) ------------------------------------------------------
+// Clouds of kPayloadSortMin points and more: the (key, index) sort is bound by the gather that follows it (64 B of DRAM
+// per point); here the passes carry the points.  Results are bit-identical to the (key, index) path (same stable order,
+// same additions): tests/test_gpu_full_size.py compares the two.  NDTB200_PAYLOAD_SORT_MIN overrides the threshold.
+constexpr size_t kPayloadSortMin = 4u << 20;
+bool use_payload_sort(const ndtb200_handle* h, size_t n) {
+  (void)h;
+  size_t lo = kPayloadSortMin;
+  if (const char* e = getenv("NDTB200_PAYLOAD_SORT_MIN")) lo = static_cast<size_t>(strtoull(e, nullptr, 10));
+  return n >= lo && n < (1ull << 30);
+}
+
+// stable LSD radix sort of the target cloud by voxel key, points as payload: sorted cloud (key in .w) -> d_pay_a, sorted
+// keys -> d_keys_a.  The digit histograms must already be in the sort meta block (voxel_key_kernel, keys == nullptr).
+int sort_payload(ndtb200_handle* h, const float4* pts, size_t n, int dense, uint32_t sentinel, int passes) {
+  const int ntiles = static_cast<int>((n + kPayTile - 1) / kPayTile);
+  unsigned long long* hist = sort_meta_hist(h);
+  unsigned long long* base = reinterpret_cast<unsigned long long*>(h->d_sortmeta.as<char>() + kSortMetaBaseOff);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(h->d_sortmeta.as<char>() + kSortMetaTicketOff);
+  CK(h->d_pay_a.ensure(n * sizeof(float4)));
+  if (passes > 1) CK(h->d_pay_b.ensure(n * sizeof(float4)));
+  CK(h->d_keys_a.ensure(n * sizeof(uint32_t)));
+  digit_base_kernel<<<1, 256, 0, h->stream>>>(hist, passes, base);
+  LAUNCHED(h);
+  const size_t status_bytes = (size_t)passes * ntiles * 256 * sizeof(uint32_t);
+  CK(h->d_status.ensure(status_bytes));
+  CK(cudaMemsetAsync(h->d_status.p, 0, status_bytes, h->stream));
+  // the last pass must land in d_pay_a: pass p writes a when (passes - 1 - p) is even
+  const float4* in = pts;
+  for (int pass = 0; pass < passes; ++pass) {
+    float4* out = ((passes - 1 - pass) % 2 == 0) ? h->d_pay_a.as<float4>() : h->d_pay_b.as<float4>();
+    uint32_t* st = h->d_status.as<uint32_t>() + (size_t)pass * ntiles * 256;
+    uint32_t* keys_out = (pass == passes - 1) ? h->d_keys_a.as<uint32_t>() : nullptr;
+    if (pass == 0)
+      onesweep_payload_kernel<true><<<ntiles, kBuildThreads, 0, h->stream>>>(in, static_cast<uint32_t>(n), dense, h->d_grid.as<GridDesc>(), sentinel,
+                                                                            0, base, st, tickets, out, keys_out);
+    else
+      onesweep_payload_kernel<false><<<ntiles, kBuildThreads, 0, h->stream>>>(in, static_cast<uint32_t>(n), dense, h->d_grid.as<GridDesc>(), sentinel,
+                                                                             pass * 8, base + pass * 256, st, tickets + pass, out, keys_out);
+    LAUNCHED(h);
+    in = out;
+  }
   return NDTB200_OK;
 }
 
@@ -492,19 +550,25 @@ int compute_moments(ndtb200_handle* h, uint32_t n_vox, uint32_t n_finite) {
   CK(h->d_moments.ensure((size_t)std::max<uint32_t>(n_vox, 1u) * 9 * sizeof(double)));
   h->moments_valid = true;
   if (n_vox == 0) return NDTB200_OK;
-  const float4* pts = target_pts(h);
-  const uint32_t* va = h->d_vals_a.as<uint32_t>();
+  // payload-sorted map: the sorted cloud is still in d_pay_a (sequential reads, no index array)
+  const bool seq = h->idx_lazy;
+  const float4* pts = seq ? h->d_pay_a.as<float4>() : target_pts(h);
+  const uint32_t* va = seq ? nullptr : h->d_vals_a.as<uint32_t>();
   const double avg = static_cast<double>(n_finite) / std::max<uint32_t>(1u, n_vox);
-  if (avg >= 48.0) {
-    const int blocks = static_cast<int>(((size_t)n_vox * 32 + kBuildThreads - 1) / kBuildThreads);
-    voxel_moments_kernel<32><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox, n_finite, h->d_moments.as<double>());
-  } else if (avg >= 10.0) {
-    const int blocks = static_cast<int>(((size_t)n_vox * 8 + kBuildThreads - 1) / kBuildThreads);
-    voxel_moments_kernel<8><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox, n_finite, h->d_moments.as<double>());
+  const int group = avg >= 48.0 ? 32 : (avg >= 10.0 ? 8 : 4);
+  const int blocks = static_cast<int>(((size_t)n_vox * group + kBuildThreads - 1) / kBuildThreads);
+#define NDTB200_MOMENTS(G, SEQ) \
+  voxel_moments_kernel<G, SEQ><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox, n_finite, h->d_moments.as<double>())
+  if (seq) {
+    if (group == 32) NDTB200_MOMENTS(32, true);
+    else if (group == 8) NDTB200_MOMENTS(8, true);
+    else NDTB200_MOMENTS(4, true);
   } else {
-    const int blocks = static_cast<int>(((size_t)n_vox * 4 + kBuildThreads - 1) / kBuildThreads);
-    voxel_moments_kernel<4><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_start.as<uint32_t>(), n_vox, n_finite, h->d_moments.as<double>());
+    if (group == 32) NDTB200_MOMENTS(32, false);
+    else if (group == 8) NDTB200_MOMENTS(8, false);
+    else NDTB200_MOMENTS(4, false);
   }
+#undef NDTB200_MOMENTS
   LAUNCHED(h);
   return NDTB200_OK;
 }
@@ -567,27 +631,38 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
   // 2. keys
   uint32_t sentinel = 0;
   const int passes = passes_for(h->grid, !dense, &sentinel);
-  CK(h->d_keys_a.ensure(n * sizeof(uint32_t)));
-  CK(h->d_keys_b.ensure(n * sizeof(uint32_t)));
-  CK(h->d_vals_a.ensure(n * sizeof(uint32_t)));
-  CK(h->d_vals_b.ensure(n * sizeof(uint32_t)));
+  const bool payload = use_payload_sort(h, n);
   {
     int st = sort_meta_reset(h);
     if (st != NDTB200_OK) return st;
   }
   const int key_blocks = grid_for(n, kBuildThreads * 4, h->num_sms * 8);
-  voxel_key_kernel<<<key_blocks, kBuildThreads, 0, h->stream>>>(pts, n, dense, h->d_grid.as<GridDesc>(), sentinel,
-                                                                 h->d_keys_a.as<uint32_t>(), nullptr, sort_meta_hist(h), passes);
-  LAUNCHED(h);
-
-  // 3. stable sort of (key, point index), one-sweep passes + 4. occupied voxels = segment heads
   uint32_t n_vox = 0;
-  {
+  if (payload) {
+    // large cloud: digit histograms only, then the passes carry the points (3. sort) + 4. segment heads
+    voxel_key_kernel<<<key_blocks, kBuildThreads, 0, h->stream>>>(pts, n, dense, h->d_grid.as<GridDesc>(), sentinel, nullptr, nullptr,
+                                                                   sort_meta_hist(h), passes);
+    LAUNCHED(h);
+    int st = sort_payload(h, pts, n, dense, sentinel, passes);
+    if (st != NDTB200_OK) return st;
+    st = segment_heads(h, n, sentinel, &n_vox);
+    if (st != NDTB200_OK) return st;
+    h->idx_lazy = true;
+  } else {
+    CK(h->d_keys_a.ensure(n * sizeof(uint32_t)));
+    CK(h->d_keys_b.ensure(n * sizeof(uint32_t)));
+    CK(h->d_vals_a.ensure(n * sizeof(uint32_t)));
+    CK(h->d_vals_b.ensure(n * sizeof(uint32_t)));
+    voxel_key_kernel<<<key_blocks, kBuildThreads, 0, h->stream>>>(pts, n, dense, h->d_grid.as<GridDesc>(), sentinel,
+                                                                   h->d_keys_a.as<uint32_t>(), nullptr, sort_meta_hist(h), passes);
+    LAUNCHED(h);
+    // 3. stable sort of (key, point index), one-sweep passes + 4. occupied voxels = segment heads
     int st = sort_and_segment(h, n, sentinel, passes, &n_vox, /*hist_ready=*/true);
     if (st != NDTB200_OK) return st;
   }
   h->n_voxels = n_vox;
-  const uint32_t* va = h->d_vals_a.as<uint32_t>();
+  const float4* mpts = payload ? h->d_pay_a.as<float4>() : pts;  // what the moments read: the sorted cloud, or a gather through the sorted indices
+  const uint32_t* va = payload ? nullptr : h->d_vals_a.as<uint32_t>();
   const uint32_t n_finite = static_cast<uint32_t>(h->grid.n_finite);
   const double avg = static_cast<double>(n_finite) / std::max<uint32_t>(1u, n_vox);
   const int group = avg >= 48.0 ? 32 : (avg >= 10.0 ? 8 : 4);  // lanes per voxel
@@ -618,12 +693,18 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
   h->moments_valid = false;
   if (n_vox > 0) {
     int32_t* table = h->use_dense ? h->d_dense.as<int32_t>() : nullptr;
-#define NDTB200_VOXEL_BUILD(G)                                                                                              \
-    voxel_build_kernel<G><<<blocks, kBuildThreads, 0, h->stream>>>(pts, va, h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), \
+#define NDTB200_VOXEL_BUILD(G, SEQ)                                                                                         \
+    voxel_build_kernel<G, SEQ><<<blocks, kBuildThreads, 0, h->stream>>>(mpts, va, h->d_voxel_key.as<int32_t>(), h->d_voxel_start.as<uint32_t>(), \
         n_vox, n_finite, h->prm.min_points_per_voxel, h->prm.eig_ratio, h->d_records.as<VoxelRecord>(), h->d_icov64.as<double>(), d_nvalid, table)
-    if (group == 32) NDTB200_VOXEL_BUILD(32);
-    else if (group == 8) NDTB200_VOXEL_BUILD(8);
-    else NDTB200_VOXEL_BUILD(4);
+    if (payload) {
+      if (group == 32) NDTB200_VOXEL_BUILD(32, true);
+      else if (group == 8) NDTB200_VOXEL_BUILD(8, true);
+      else NDTB200_VOXEL_BUILD(4, true);
+    } else {
+      if (group == 32) NDTB200_VOXEL_BUILD(32, false);
+      else if (group == 8) NDTB200_VOXEL_BUILD(8, false);
+      else NDTB200_VOXEL_BUILD(4, false);
+    }
 #undef NDTB200_VOXEL_BUILD
     LAUNCHED(h);
   }
@@ -728,6 +809,28 @@ int build_from_partials(ndtb200_handle* h, const float* gmin, const float* gmax,
   return NDTB200_OK;
 }
 
+// Sorted point indices of a payload-sorted map, on first use (getFitnessScore, KDTREE centroids): the (key, index) sort
+// of the same keys — stable, so the order equals the payload sort's and d_voxel_start stays valid.
+int ensure_sorted_indices(ndtb200_handle* h) {
+  if (!h->idx_lazy) return NDTB200_OK;
+  const size_t n = h->n_target;
+  uint32_t sentinel = 0;
+  const int passes = passes_for(h->grid, !h->target_dense, &sentinel);
+  CK(h->d_keys_a.ensure(n * sizeof(uint32_t)));
+  CK(h->d_keys_b.ensure(n * sizeof(uint32_t)));
+  CK(h->d_vals_a.ensure(n * sizeof(uint32_t)));
+  CK(h->d_vals_b.ensure(n * sizeof(uint32_t)));
+  int st = sort_meta_reset(h);
+  if (st != NDTB200_OK) return st;
+  voxel_key_kernel<<<grid_for(n, kBuildThreads * 4, h->num_sms * 8), kBuildThreads, 0, h->stream>>>(
+      target_pts(h), n, h->target_dense ? 1 : 0, h->d_grid.as<GridDesc>(), sentinel, h->d_keys_a.as<uint32_t>(), nullptr, sort_meta_hist(h), passes);
+  LAUNCHED(h);
+  st = sort_pairs(h, n, passes, /*hist_ready=*/true);
+  if (st != NDTB200_OK) return st;
+  h->idx_lazy = false;  // d_vals_a is valid from here on (compute_moments goes back to the gather, same sums)
+  return NDTB200_OK;
+}
+
 // cell table over ALL occupied voxels (shared by getFitnessScore and the KDTREE mode)
 int ensure_cell_table(ndtb200_handle* h) {
   if (h->cell_all_valid) return NDTB200_OK;
@@ -753,6 +856,8 @@ int ensure_kdtree_index(ndtb200_handle* h) {
   int st = ensure_cell_table(h);
   if (st != NDTB200_OK) return st;
   if (!h->centroids_valid) {
+    st = ensure_sorted_indices(h);
+    if (st != NDTB200_OK) return st;
     const uint32_t nv = static_cast<uint32_t>(h->n_voxels);
     CK(h->d_centroid.ensure((size_t)nv * sizeof(float4)));
     voxel_centroid_kernel<<<(nv + kBuildThreads - 1) / kBuildThreads, kBuildThreads, 0, h->stream>>>(
@@ -1219,7 +1324,7 @@ int ndtb200_destroy(ndtb200_handle* h) {
   ndtb200_comm_detach(h);
   if (h->aux) { ndtb200_destroy(h->aux); h->aux = nullptr; }
   DevBuf* bufs[] = {&h->d_target, &h->d_grid, &h->d_mm_partial, &h->d_mm_finite, &h->d_keys_a, &h->d_keys_b,
-                    &h->d_vals_a, &h->d_vals_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_sortmeta, &h->d_status, &h->d_voxel_key,
+                    &h->d_vals_a, &h->d_vals_b, &h->d_pay_a, &h->d_pay_b, &h->d_hist, &h->d_scan_tmp, &h->d_scalar, &h->d_sortmeta, &h->d_status, &h->d_voxel_key,
                     &h->d_voxel_start, &h->d_voxel_count, &h->d_moments, &h->d_records, &h->d_icov64, &h->d_hash, &h->d_dense, &h->d_source,
                     &h->d_cell_all, &h->d_best, &h->d_centroid, &h->d_partials, &h->d_totals, &h->d_sync, &h->d_result, &h->d_trace, &h->d_out, &h->d_tmp, &h->d_mail, &h->d_emu, &h->d_source_sorted};
   for (DevBuf* b : bufs) b->release();
@@ -1469,6 +1574,10 @@ static int fitness_sums(ndtb200_handle* h, double max_range, double* sum_out, un
   const bool use_grid = !force_brute && h->map_status == NDTB200_OK && h->n_voxels > 0 && ncell > 0 && ncell * sizeof(int32_t) <= (2ull << 30) &&
                         h->n_target <= 0x7fffffffull;
   if (use_grid) {
+    {
+      const int st = ensure_sorted_indices(h);  // payload-sorted map: the index array is built on first use
+      if (st != NDTB200_OK) return st;
+    }
     {
       const int st = ensure_cell_table(h);
       if (st != NDTB200_OK) return st;

@@ -186,7 +186,7 @@ voxel_key_kernel(const float4* __restrict__ pts, size_t n, int is_dense, const G
       float4 p = __ldg(pts + i);
       bool ok = is_dense || (isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
       if (ok) key = static_cast<uint32_t>(voxel_key_of(p, g));
-      keys[i] = key;
+      if (keys) keys[i] = key;  // nullptr: histograms only (the payload sort computes the keys again in its first pass)
       if (idx) idx[i] = static_cast<uint32_t>(i);
     }
     if (digit_hist) digit_hist_add(s_hist, key, in, passes);
@@ -583,6 +583,136 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// ONE-SWEEP pass that carries the POINT as the payload (clouds above kPayloadSortMin points).  Sorting (key, index)
+// pairs leaves the per-voxel moments with a random 16-byte gather that drags 64 B out of DRAM per point (2.0 ms of a
+// 5.8 ms build at 100 M points); here every pass moves the float4 itself with the key in .w (32 B of sequential traffic
+// per point and pass), so the moments read the sorted cloud front to back.  The ranking work per key is the same as in
+// onesweep_kernel (8 ballots, the issue-bound part), tiles are 2048 points (the payload lives in registers: 8 x float4).
+//   FROM_CLOUD: first pass — reads the caller's cloud and computes the key on the fly (the up-front digit histograms
+//   came from voxel_key_kernel with keys == nullptr); otherwise the key is the .w of the previous pass's output.
+//   keys_out != nullptr (last pass): the sorted keys also go to a plain uint32 array for the segment-head kernels.
+// status words are 32-bit (flag in bits 31..30, counts < 2^30): the host takes this path only for n < 2^30.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPayRounds = 8;
+constexpr int kPayTile = kBuildThreads * kPayRounds;
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool FROM_CLOUD>
+__global__ void __launch_bounds__(kBuildThreads, 4)
+onesweep_payload_kernel(const float4* __restrict__ in, uint32_t n, int is_dense, const GridDesc* __restrict__ gd, uint32_t sentinel,
+                        int shift, const unsigned long long* __restrict__ digit_base, uint32_t* __restrict__ status,
+                        unsigned int* __restrict__ ticket, float4* __restrict__ out, uint32_t* __restrict__ keys_out) {
+  constexpr int ROUNDS = kPayRounds;
+  constexpr int kTile = kPayTile;
+  __shared__ uint32_t warp_cnt[kSortWarps][256];
+  __shared__ uint32_t s_dstart[256];
+  __shared__ uint32_t s_gbase[256];
+  __shared__ uint32_t s_scan[kBuildThreads / 32 + 1];
+  __shared__ float4 s_pay[kTile];
+  __shared__ unsigned int s_tile;
+  __shared__ GridDesc g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  if (FROM_CLOUD && threadIdx.x == 32) g = *gd;
+  for (int d = threadIdx.x; d < 256 * kSortWarps; d += kBuildThreads) (&warp_cnt[0][0])[d] = 0u;
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  const uint32_t tbase = tile * (uint32_t)kTile;
+  NDT_CHECK(tbase < n);
+  const uint32_t wbase = tbase + (uint32_t)warp * (32 * ROUNDS);
+  float4 p[ROUNDS];
+  uint16_t rank[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t i = wbase + r * 32 + lane;
+    p[r] = (i < n) ? __ldcs(in + i) : make_float4(0.f, 0.f, 0.f, 0.f);  // streaming: every point is touched once per pass
+  }
+  if (FROM_CLOUD) {
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const bool ok = is_dense || (isfinite(p[r].x) && isfinite(p[r].y) && isfinite(p[r].z));
+      p[r].w = __uint_as_float(ok ? static_cast<uint32_t>(voxel_key_of(p[r], g)) : sentinel);
+    }
+  }
+  // stable rank of every point among the points of ITS WARP with the same digit
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t i = wbase + r * 32 + lane;
+    const bool valid = i < n;
+    const uint32_t d = (__float_as_uint(p[r].w) >> shift) & 255u;
+    const unsigned int m = digit_peers(d, valid);
+    uint32_t pos = 0;
+    if (valid) pos = warp_cnt[warp][d] + __popc(m & ((1u << lane) - 1u));
+    __syncwarp();
+    if (valid && lane == (__ffs(m) - 1)) warp_cnt[warp][d] += __popc(m);
+    __syncwarp();
+    rank[r] = static_cast<uint16_t>(pos);
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;  // one digit per thread (blockDim == 256)
+    uint32_t off = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = warp_cnt[w][d];
+      warp_cnt[w][d] = off;
+      off += c;
+    }
+    // publish this tile's count, then look back (decoupled look-back, see onesweep_kernel)
+    uint32_t* row = status + (size_t)tile * 256;
+    const uint32_t kMask = (1u << 30) - 1u;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      st_relaxed_u32(row + d, (2u << 30) | off);
+    } else {
+      st_relaxed_u32(row + d, (1u << 30) | off);
+      long long t = static_cast<long long>(tile) - 1;
+      while (true) {
+        const uint32_t w = ld_relaxed_u32(status + (size_t)t * 256 + d);
+        const uint32_t flag = w >> 30;
+        if (flag == 0u) continue;
+        excl += w & kMask;
+        if (flag == 2u) break;
+        NDT_CHECK(t > 0);
+        --t;
+      }
+      st_relaxed_u32(row + d, (2u << 30) | (excl + off));
+    }
+    uint32_t total;
+    const uint32_t dstart = block_exclusive_scan(off, s_scan, total);
+    s_dstart[d] = dstart;
+    s_gbase[d] = static_cast<uint32_t>(digit_base[d]) + excl - dstart;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t i = wbase + r * 32 + lane;
+    if (i < n) {
+      const uint32_t d = (__float_as_uint(p[r].w) >> shift) & 255u;
+      s_pay[s_dstart[d] + warp_cnt[warp][d] + rank[r]] = p[r];
+    }
+  }
+  __syncthreads();
+  const uint32_t count = (n - tbase < (uint32_t)kTile) ? n - tbase : (uint32_t)kTile;
+  for (uint32_t j = threadIdx.x; j < count; j += kBuildThreads) {
+    const float4 q = s_pay[j];
+    const uint32_t key = __float_as_uint(q.w);
+    const uint32_t pos = s_gbase[(key >> shift) & 255u] + j;
+    NDT_CHECK(pos < n);
+    out[pos] = q;
+    if (keys_out) keys_out[pos] = key;
+  }
+}
+
 // 8 consecutive sorted keys of this thread (two 16-byte loads) + the key before them; returns the head flags as bits
 __device__ __forceinline__ uint32_t load_heads(const uint32_t* __restrict__ skeys, size_t n, size_t base, uint32_t sentinel,
                                                uint32_t (&key)[kScanItems]) {
@@ -653,7 +783,9 @@ __device__ __forceinline__ float4 ldg_gather16(const float4* p) {
 
 // the GROUP lanes of voxel `gid` sum its points (4 gathers in flight per lane, index order) and fold by a fixed shuffle
 // tree: lane gl == 0 ends with the 9 sums.  Every lane of the warp must call this (shuffles).
-template <int GROUP>
+// SEQ: `pts` is the cloud already in sorted order (payload sort): the loads are sequential, sorted_idx is not read;
+// same lanes, same order of additions — bit-identical sums.
+template <int GROUP, bool SEQ = false>
 __device__ __forceinline__ void voxel_moments_group(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx,
                                                     const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
                                                     uint32_t gid, int gl, bool active, double (&s)[9], uint32_t& count) {
@@ -669,9 +801,12 @@ __device__ __forceinline__ void voxel_moments_group(const float4* __restrict__ p
       uint32_t idx[4];
       float4 p[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) idx[u] = (i0 + u * GROUP < e) ? __ldg(sorted_idx + i0 + u * GROUP) : 0xffffffffu;
+      for (int u = 0; u < 4; ++u) idx[u] = (i0 + u * GROUP < e) ? (SEQ ? i0 + u * GROUP : __ldg(sorted_idx + i0 + u * GROUP)) : 0xffffffffu;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { NDT_CHECK(idx[u] == 0xffffffffu || i0 + u * GROUP < n_finite); p[u] = (idx[u] != 0xffffffffu) ? ldg_gather16(pts + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f); }
+      for (int u = 0; u < 4; ++u) {
+        NDT_CHECK(idx[u] == 0xffffffffu || i0 + u * GROUP < n_finite);
+        p[u] = (idx[u] != 0xffffffffu) ? (SEQ ? __ldcs(pts + idx[u]) : ldg_gather16(pts + idx[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (idx[u] == 0xffffffffu) continue;
@@ -689,7 +824,7 @@ __device__ __forceinline__ void voxel_moments_group(const float4* __restrict__ p
   }
 }
 
-template <int GROUP>
+template <int GROUP, bool SEQ = false>
 __global__ void __launch_bounds__(kBuildThreads)
 voxel_moments_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx,
                      const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite,
@@ -699,7 +834,7 @@ voxel_moments_kernel(const float4* __restrict__ pts, const uint32_t* __restrict_
   const bool active = gid < n_voxels;
   double s[9];
   uint32_t count;
-  voxel_moments_group<GROUP>(pts, sorted_idx, voxel_start, n_voxels, n_finite, gid, gl, active, s, count);
+  voxel_moments_group<GROUP, SEQ>(pts, sorted_idx, voxel_start, n_voxels, n_finite, gid, gl, active, s, count);
   if (active && gl == 0) {
 #pragma unroll
     for (int k = 0; k < 9; ++k) moments[(size_t)gid * 9 + k] = s[k];
@@ -716,7 +851,7 @@ __device__ __forceinline__ void finalize_one(uint32_t v, int count, const double
 // finalize_one) straight from registers — the 72-byte moment row never goes to memory and back — and enters a valid
 // voxel into the direct-mapped cell table (nullptr: the hash index is filled afterwards).  Same arithmetic in the same
 // order as voxel_moments_kernel + finalize_voxels_kernel + dense_fill_kernel.
-template <int GROUP>
+template <int GROUP, bool SEQ = false>
 __global__ void __launch_bounds__(kBuildThreads, 5)  // <= 48 registers: the gather phase lives on resident warps; the finalize part may spill
 voxel_build_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx, const int32_t* __restrict__ voxel_key,
                    const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite, int min_points, double eig_ratio,
@@ -731,7 +866,7 @@ voxel_build_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ 
   {
     double s[9];
     uint32_t count;
-    voxel_moments_group<GROUP>(pts, sorted_idx, voxel_start, n_voxels, n_finite, gid, gl, active, s, count);
+    voxel_moments_group<GROUP, SEQ>(pts, sorted_idx, voxel_start, n_voxels, n_finite, gid, gl, active, s, count);
     if (gl == 0) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) s_m[threadIdx.x / GROUP][k] = s[k];
