@@ -130,3 +130,26 @@ def test_build_4m_points_properties(nb):
     ijk = (np.floor(host * np.float32(1.0)) - np.asarray(info["min_b"], dtype=np.float32)).astype(np.int64)
     exp = ijk[:, 0] + ijk[:, 1] * info["div_b"][0] + ijk[:, 2] * info["div_b"][0] * info["div_b"][1]
     assert np.array_equal(keys[sel], exp)
+
+
+def test_build_10m_points_against_oracle(nb):
+    """BASELINE configs[4] (C5) at 10 M points against the oracle: keys, counts, rejected-leaf and inflation flags exact,
+    means / covariances / inverse covariances within the parity bar.  10 M points is above the payload-sort threshold,
+    so this is also the at-size check of that path (onesweep_payload_kernel + the sequential moments)."""
+    import torch
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import build_bench
+    from test_gpu_parity import check_voxels
+    m = 10_000_000
+    pts = build_bench.surface_points(m, 20260104)
+    host = np.ascontiguousarray(pts[:, :3].cpu().numpy())
+    g = nb.NormalDistributionsTransform()
+    assert g.set_target_device(pts.data_ptr(), m) == 0
+    ref = oracle.NormalDistributionsTransform()
+    assert ref.setInputTarget(host) == 0
+    check_voxels(ref, g)
+    # the per-point keys of a 1 M-point slice, input order (the whole array would be 40 MB through the dump path twice)
+    sel = slice(3_000_000, 4_000_000)
+    assert np.array_equal(ref.point_keys()[sel], g.point_keys()[sel])

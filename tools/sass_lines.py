@@ -2,7 +2,7 @@
 """Per-source-line instruction and stall-sample shares of one profiled kernel: joins the SASS page of an ncu report
 (`ncu -i rep --page source --csv`) with the line table of the built library (`nvdisasm -g`).
 
-    python tools/sass_lines.py <report.ncu-rep> <kernel-mangled-substring> [top-N]
+    python tools/sass_lines.py <report.ncu-rep> <kernel-mangled-substring> [top-N] [demangled-name-substring]
 """
 import csv
 import os
@@ -42,10 +42,17 @@ def main():
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    # a report may hold several launches: one block per launch ("Kernel Name" row, header row, SASS rows); argv[4] = a
+    # substring of the demangled kernel name picks the block (default: the first)
+    want = sys.argv[4] if len(sys.argv) > 4 else None
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    hi = starts[0]
+    if want is not None:
+        hi = next(i for i in starts if i > 0 and rows[i - 1] and rows[i - 1][0] == "Kernel Name" and want in rows[i - 1][1])
     hdr = rows[hi]
     ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
-    data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    end = next((i for i in starts if i > hi), len(rows) + 1) - 1
+    data = [r for r in rows[hi + 1:end] if len(r) == len(hdr)]
     base = min(int(r[ia], 16) for r in data)
     tab = line_table(ksub)
     agg = {}

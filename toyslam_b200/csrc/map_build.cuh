@@ -594,6 +594,9 @@ onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict
 //   keys_out != nullptr (last pass): the sorted keys also go to a plain uint32 array for the segment-head kernels.
 // status words are 32-bit (flag in bits 31..30, counts < 2^30): the host takes this path only for n < 2^30.
 // ---------------------------------------------------------------------------------------------
+#ifndef NDTB200_LOOKBACK_SLEEP_NS
+#define NDTB200_LOOKBACK_SLEEP_NS 40
+#endif
 constexpr int kPayRounds = 8;
 constexpr int kPayTile = kBuildThreads * kPayRounds;
 
@@ -667,19 +670,31 @@ onesweep_payload_kernel(const float4* __restrict__ in, uint32_t n, int is_dense,
       warp_cnt[w][d] = off;
       off += c;
     }
-    // publish this tile's count, then look back (decoupled look-back, see onesweep_kernel)
+    // publish this tile's count right away; the look-back itself waits until the tile has been sorted into shared
+    // memory (the predecessors get that much more time to publish: 40 % of all stall samples sat in the spin below
+    // when the look-back came first, profiles/r02_build_kernels.md)
     uint32_t* row = status + (size_t)tile * 256;
+    st_relaxed_u32(row + d, ((tile == 0 ? 2u : 1u) << 30) | off);
+    uint32_t total;
+    const uint32_t dstart = block_exclusive_scan(off, s_scan, total);
+    s_dstart[d] = dstart;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const uint32_t i = wbase + r * 32 + lane;
+      if (i < n) {
+        const uint32_t dd = (__float_as_uint(p[r].w) >> shift) & 255u;
+        s_pay[s_dstart[dd] + warp_cnt[warp][dd] + rank[r]] = p[r];
+      }
+    }
     const uint32_t kMask = (1u << 30) - 1u;
     uint32_t excl = 0;
-    if (tile == 0) {
-      st_relaxed_u32(row + d, (2u << 30) | off);
-    } else {
-      st_relaxed_u32(row + d, (1u << 30) | off);
+    if (tile != 0) {
       long long t = static_cast<long long>(tile) - 1;
       while (true) {
         const uint32_t w = ld_relaxed_u32(status + (size_t)t * 256 + d);
         const uint32_t flag = w >> 30;
-        if (flag == 0u) continue;
+        if (flag == 0u) { __nanosleep(NDTB200_LOOKBACK_SLEEP_NS); continue; }  // not published yet: leave the issue slots to the co-resident tiles
         excl += w & kMask;
         if (flag == 2u) break;
         NDT_CHECK(t > 0);
@@ -687,19 +702,7 @@ onesweep_payload_kernel(const float4* __restrict__ in, uint32_t n, int is_dense,
       }
       st_relaxed_u32(row + d, (2u << 30) | (excl + off));
     }
-    uint32_t total;
-    const uint32_t dstart = block_exclusive_scan(off, s_scan, total);
-    s_dstart[d] = dstart;
     s_gbase[d] = static_cast<uint32_t>(digit_base[d]) + excl - dstart;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < ROUNDS; ++r) {
-    const uint32_t i = wbase + r * 32 + lane;
-    if (i < n) {
-      const uint32_t d = (__float_as_uint(p[r].w) >> shift) & 255u;
-      s_pay[s_dstart[d] + warp_cnt[warp][d] + rank[r]] = p[r];
-    }
   }
   __syncthreads();
   const uint32_t count = (n - tbase < (uint32_t)kTile) ? n - tbase : (uint32_t)kTile;
