@@ -156,6 +156,33 @@ class NormalDistributionsTransform : public pcl::Registration<PointSource, Point
     return v;
   }
 
+  // calculateScore of MANY already transformed clouds in one upload + one launch (loop-closure screening; not in the
+  // reference, which would loop over calculateScore)
+  std::vector<double> calculateScoreBatch(const std::vector<const PointCloudSource*>& clouds) {
+    std::vector<double> out(clouds.size(), 0.0);
+    if (!h_ || clouds.empty()) return out;
+    push();
+    std::vector<size_t> offs(clouds.size() + 1, 0);
+    for (size_t c = 0; c < clouds.size(); ++c) offs[c + 1] = offs[c] + clouds[c]->points.size();
+    std::vector<PointSource> all;
+    all.reserve(offs.back());
+    for (const PointCloudSource* c : clouds) all.insert(all.end(), c->points.begin(), c->points.end());
+    if (!all.empty())
+      ndtb200_calculate_score_batch(h_, all.data(), offs.data(), static_cast<int>(clouds.size()), sizeof(PointSource), out.data());
+    return out;
+  }
+  // calculateScore of the CURRENT source under many candidate poses (only the poses are uploaded)
+  template <class PoseContainer>  // any sequence of Eigen::Matrix4f (std::vector with or without Eigen's aligned allocator)
+  std::vector<double> scorePoses(const PoseContainer& poses) {
+    std::vector<double> out(poses.size(), 0.0);
+    if (!h_ || poses.empty()) return out;
+    push();
+    std::vector<float> flat(poses.size() * 16);
+    for (size_t k = 0; k < poses.size(); ++k) std::memcpy(&flat[k * 16], poses[k].data(), 16 * sizeof(float));
+    ndtb200_score_poses(h_, flat.data(), static_cast<int>(poses.size()), out.data());
+    return out;
+  }
+
   // [x, y, z, roll, pitch, yaw] -> Translation * AngleAxis(roll, X) * AngleAxis(pitch, Y) * AngleAxis(yaw, Z), fp32
   // (ndt_omp.h:216-233)
   static void convertTransform(const Eigen::Matrix<double, 6, 1>& x, Eigen::Affine3f& trans) {

@@ -53,6 +53,9 @@ int main() {
   Eigen::Matrix<double, 6, 1> x; for (int i = 0; i < 6; ++i) x(i) = 0.1 * i;
   Eigen::Affine3f A; Eigen::Matrix4f M;
   Ndt::convertTransform(x, A); Ndt::convertTransform(x, M);                 // ndt_omp.h:216-233
+  std::vector<const Cloud*> cands{&out, &out};
+  std::vector<Eigen::Matrix4f> poses(2, M);
+  (void)v.calculateScoreBatch(cands); (void)v.scorePoses(poses);            // batched calculateScore (loop-closure screening)
   pclomp_b200::VoxelGrid<pcl::PointXYZ> vg; vg.setLeafSize(0.1f, 0.2f, 0.3f); vg.setInputCloud(a); vg.filter(out);
   static_assert(pclomp_b200::KDTREE == 0 && pclomp_b200::DIRECT26 == 1 && pclomp_b200::DIRECT7 == 2 && pclomp_b200::DIRECT1 == 3, "ndt_omp.h:52-57");
   return M(3, 3) == 1.0f ? 0 : 1;
