@@ -56,6 +56,8 @@ struct ndtb200_handle {
   uint32_t launch_seq = 0;
   int last_blocks = 0;
   bool result_copy_enqueued = false;
+  bool want_fused_out = false;  // set by the entry points that know the caller wants align()'s output cloud
+  bool out_fused = false;       // the last solve wrote d_out itself
 
   // multi-GPU source sharding
   int comm_world = 1, comm_rank = 0;
@@ -1093,6 +1095,18 @@ int launch_align(ndtb200_handle* h, int mode, const double p0[6], const float T0
   ws.vranks = 1;
   ws.pad = 0;
   ws.vr = nullptr;
+  // the solve writes align()'s output cloud itself when the entry point knows the caller wants it (one launch less per
+  // align); not for sharded / emulated solves (a rank holds a slice) and not for the parity-evaluation modes
+  ws.out = nullptr;
+  ws.out_src = nullptr;
+  h->out_fused = false;
+  if (h->want_fused_out && mode == MODE_ALIGN && h->comm_world == 1 && emulate_world <= 1 && h->n_source > 0) {
+    CK(h->d_out.ensure(h->n_source * sizeof(float4)));
+    ws.out = h->d_out.as<float4>();
+    ws.out_src = h->d_source.as<float4>();
+    h->out_fused = true;
+  }
+  h->want_fused_out = false;
   if (emulate_world > 1) {
     // `emulate_world` ranks of a source-sharded solve inside ONE cooperative launch on this GPU (see VirtualRank): the
     // grid is divided evenly, every rank gets its own rows / barrier words / result block / mailbox and the contiguous
@@ -1458,10 +1472,12 @@ static int enqueue_output(ndtb200_handle* h, void* out_points, size_t out_stride
   if (out_stride_bytes < 16) { h->err = "out_stride_bytes must be >= 16"; return NDTB200_ERR_INVALID; }
   const int n = static_cast<int>(h->n_source);
   if (n == 0) return NDTB200_OK;
-  CK(h->d_out.ensure((size_t)n * sizeof(float4)));
-  transform_output_kernel<<<grid_for(n, 256, h->num_sms * 8), 256, 0, h->stream>>>(
-      h->d_source.as<float4>(), n, h->d_result.as<AlignResultDev>(), h->d_out.as<float4>());
-  LAUNCHED(h);
+  if (!h->out_fused) {  // the solve was launched without knowing an output would be asked for (ndtb200_align_async)
+    CK(h->d_out.ensure((size_t)n * sizeof(float4)));
+    transform_output_kernel<<<grid_for(n, 256, h->num_sms * 8), 256, 0, h->stream>>>(
+        h->d_source.as<float4>(), n, h->d_result.as<AlignResultDev>(), h->d_out.as<float4>());
+    LAUNCHED(h);
+  }
   if (out_stride_bytes == 16)
     CK(cudaMemcpyAsync(out_points, h->d_out.p, (size_t)n * 16, cudaMemcpyDeviceToHost, h->stream));
   else
@@ -1471,7 +1487,9 @@ static int enqueue_output(ndtb200_handle* h, void* out_points, size_t out_stride
 
 int ndtb200_align(ndtb200_handle* h, const float* guess, void* out_points, size_t out_stride_bytes) {
   if (!h) return NDTB200_ERR_INVALID;
+  h->want_fused_out = out_points != nullptr && out_stride_bytes >= 16;
   int st = ndtb200_align_async(h, guess);
+  h->want_fused_out = false;
   if (st != NDTB200_OK) return st;
   st = enqueue_output(h, out_points, out_stride_bytes);
   if (st != NDTB200_OK) return st;
@@ -2579,7 +2597,9 @@ int ndtb200_align_batch_async(ndtb200_handle* const* hs, int n, const float* gue
     if (!hs[i]) return NDTB200_ERR_INVALID;
     const int keep = hs[i]->shape;
     hs[i]->shape = 1;
+    hs[i]->want_fused_out = out_points != nullptr && out_points[i] != nullptr && out_stride_bytes >= 16;
     int st = ndtb200_align_async(hs[i], guesses ? guesses + 16 * (size_t)i : nullptr);
+    hs[i]->want_fused_out = false;
     hs[i]->shape = keep;
     if (st == NDTB200_OK && out_points) st = enqueue_output(hs[i], out_points[i], out_stride_bytes);
     if (st == NDTB200_OK) st = enqueue_result_copy(hs[i]);

@@ -122,6 +122,10 @@ struct AlignWorkspace {
   long long n_source_total;              // points of the whole (unsigned) source cloud
   int32_t vranks, pad;                   // > 1: `world` emulated ranks inside this one launch
   const VirtualRank* vr;                 // [vranks] (device memory)
+  // align()'s output cloud written by the solve itself (single-rank MODE_ALIGN launches whose caller asked for it):
+  // out[i] = final_transformation * out_src[i] in the CALLER's point order (out_src is the unsorted source)
+  float4* out;
+  const float4* out_src;
 };
 
 // What a CTA needs to know about the rank it works for (shared memory; filled once at kernel start).
@@ -1434,6 +1438,19 @@ ndt_align_kernel(const float4* __restrict__ src_in, const MapView map, const Ali
     __syncthreads();
   }
 
+  // pcl::Registration::align's output (transformPointCloud(source, final_transformation_)): every CTA holds the identical
+  // final_T in shared memory, so the cloud is written here instead of by a second kernel (same arithmetic as
+  // transform_output_kernel: bit-identical)
+  if (ws.out != nullptr) {  // uniform
+    const float4* __restrict__ osrc = ws.out_src;
+    for (int i = static_cast<int>(bid) * THREADS + threadIdx.x; i < n; i += static_cast<int>(G) * THREADS) {
+      const float4 p = __ldg(osrc + i);
+      float4 o;
+      transform_point(st.final_T, p.x, p.y, p.z, o.x, o.y, o.z);
+      o.w = 1.0f;
+      ws.out[i] = o;
+    }
+  }
   if (bid == 0 && threadIdx.x == 0) {
     AlignResultDev& r = *s_rc.result;
     for (int i = 0; i < 12; ++i) r.final_T[i] = st.final_T[i];
