@@ -826,9 +826,11 @@ def run_c3(args):
         hosts.append(hb)
     guesses = [np.eye(4)] + [workloads.relative_pose_matrix(poses[k - 1], poses[k]) for k in range(1, nd)]
     truths = [workloads.relative_pose_matrix(poses[k], poses[k + 1]) for k in range(nd)]
-    # lanes = handles + host threads per GPU; their waits yield the core (throughput-mode handles poll with sched_yield), so
-    # the count is not tied to the host core count: 16 lanes keep one GPU busy (measured 12.6 k pairs/s vs 10.7 k with 8)
-    L = args.c3_lanes if args.c3_lanes > 0 else 16
+    # lanes = handles + host threads per GPU (their waits yield the core: throughput-mode handles poll with sched_yield).
+    # Measured on three boxes, staged builds: 8 lanes 9.8 k / 10.8 k / 10.7 k pairs/s, 16 lanes 7.3 k / 9.5 k / 12.6 k — 8 is
+    # the steadier choice; C++ and Python lane threads measure the same (10.8 k vs 10.75 k): the lanes are bound by the
+    # ~12 launches + 2 synchronisations of a staged scan-sized build, not by the host language
+    L = args.c3_lanes if args.c3_lanes > 0 else 8
     lanes = []
     for _ in range(L):
         ndt = nb.NormalDistributionsTransform(device=local)
@@ -852,14 +854,35 @@ def run_c3(args):
             hd.sync()                                                            # the node reads every pose
             results[k] = hd.result()
 
-    def run(first, count):
+    def run_python(first, count):
         th = [threading.Thread(target=lane_loop, args=(li, first, count)) for li in range(L)]
         for t in th:
             t.start()
         for t in th:
             t.join()
 
+    # native lane driver (default): ndtb200_run_pairs drives every lane from its own C++ host thread — no Python
+    # threads, no GIL hand-offs between the ~5 calls of a pair
+    pipes = {}
+
+    def prepare_native(first, count):  # pointer / size / guess arrays of the pair list, built outside the timed region
+        if (first, count) not in pipes:
+            ks = [j % nd for j in range(first, first + count)]
+            pipes[(first, count)] = (ks, nb.PairPipeline(lanes, [(hosts[k].data_ptr(), len(scans[k])) for k in ks],
+                                                         [(hosts[k + 1].data_ptr(), len(scans[k + 1])) for k in ks], [guesses[k] for k in ks]))
+        return pipes[(first, count)]
+
+    def run_native(first, count):
+        ks, pipe = prepare_native(first, count)
+        pipe.run()
+        for k, r in zip(ks, pipe.results()):
+            results[k] = r
+
+    run = run_python if args.c3_driver == "python" else run_native
+
     run(0, max(args.warmup, L))  # warm-up: allocations, first launches
+    if run is run_native:
+        prepare_native(0, pairs_rank)
     torch.cuda.synchronize()
     for hd in lanes:
         hd.reset_launch_count()
@@ -900,8 +923,8 @@ def run_c3(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "c3: %d consecutive scan pairs of a simulated drive (%d distinct pairs per GPU cycled), scans downsampled "
                                    "0.3 m (%.0f pts mean), per pair: target-map build + align, node parameters (eps 0.01, max_iter 64, "
-                                   "step 0.1, res 1.0, %s), guess = true motion of the previous pair; %d lanes (handles + host threads) per GPU"
-                                   % (pairs_rank * world, nd, pts, args.method, L),
+                                   "step 0.1, res 1.0, %s), guess = true motion of the previous pair; %d lanes (handles + %s host threads) per GPU"
+                                   % (pairs_rank * world, nd, pts, args.method, L, "C++" if args.c3_driver == "native" else "Python"),
                        "parallelism": "pairs round-robin over GPUs and lanes; no collective"},
             "src_pt_iters_per_s": value * pts * evals, "evaluations_per_align": evals,
             "hessian_passes_per_align": float(np.mean([r["n_hessian_passes"] for r in done])),
@@ -1124,6 +1147,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "mapper"])
     ap.add_argument("--mapper-scans", type=int, default=200)
     ap.add_argument("--c3-distinct", type=int, default=128, help="distinct consecutive pairs generated per GPU (cycled)")
+    ap.add_argument("--c3-driver", choices=["native", "python"], default="native",
+                    help="c3: lanes driven by C++ host threads inside ndtb200_run_pairs (default) or by Python threads")
     ap.add_argument("--c3-lanes", type=int, default=0,
                     help="handles (+ host threads) per GPU for the c3 pipeline; 0 = auto (16)")
     ap.add_argument("--c5-points", type=int, nargs="+", default=[10_000_000, 100_000_000])

@@ -127,6 +127,15 @@ int ndtb200_set_throughput_mode(ndtb200_handle* h, int on);
  * first non-OK status is reported. */
 int ndtb200_align_batch(ndtb200_handle* const* hs, int n, const float* guesses, void* const* out_points,
                         size_t out_stride_bytes, ndtb200_result* results);
+/* Batched scan-to-scan odometry (BASELINE configs[2]; the per-scan body of ndt_rosbag_mapping_node.cpp:99-144 for
+ * many independent pairs): pair k = (targets[k], sources[k]), host clouds of n_targets[k] / n_sources[k] points with
+ * stride_bytes per record.  lanes[l] (one handle) is driven by its own HOST THREAD inside this call and takes the pairs
+ * l, l + n_lanes, ...: setInputTarget (upload + voxel-map build), setInputSource (upload), align(guess_k), result —
+ * so uploads, builds and solves of different pairs overlap on the device without any caller-side threading.
+ * guesses16: n_pairs column-major 4x4 or NULL (identity); results: n_pairs entries.  Returns the first non-OK status. */
+int ndtb200_run_pairs(ndtb200_handle* const* lanes, int n_lanes, const void* const* targets, const size_t* n_targets,
+                      const void* const* sources, const size_t* n_sources, size_t stride_bytes, const float* guesses16,
+                      int n_pairs, ndtb200_result* results);
 /* Enqueue-only half (every solve, output cloud and result copy goes onto its handle's stream; no host wait):
  * finish each handle with ndtb200_sync.  out_points: n host buffers (or NULL) as in ndtb200_align. */
 int ndtb200_align_batch_async(ndtb200_handle* const* hs, int n, const float* guesses, void* const* out_points,

@@ -17,6 +17,7 @@ from .ndt import (  # noqa: F401
     Mapper,
     NormalDistributionsTransform,
     align_batch,
+    PairPipeline,
     device_count,
     exported_symbols,
     guess_to_pose,
@@ -26,4 +27,4 @@ from .ndt import (  # noqa: F401
 )
 
 __all__ = ["NormalDistributionsTransform", "NdtError", "KDTREE", "DIRECT26", "DIRECT7", "DIRECT1",
-           "Batch", "Mapper", "align_batch", "device_count", "load_library", "library_path", "exported_symbols", "guess_to_pose", "pose_to_matrix"]
+           "Batch", "PairPipeline", "Mapper", "align_batch", "device_count", "load_library", "library_path", "exported_symbols", "guess_to_pose", "pose_to_matrix"]

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ndt_b200.h"
@@ -2618,6 +2619,38 @@ int ndtb200_align_batch(ndtb200_handle* const* hs, int n, const float* guesses, 
     if (st != NDTB200_OK && rc == NDTB200_OK) rc = st;
   }
   return rc;
+}
+
+int ndtb200_run_pairs(ndtb200_handle* const* lanes, int n_lanes, const void* const* targets, const size_t* n_targets,
+                      const void* const* sources, const size_t* n_sources, size_t stride_bytes, const float* guesses16,
+                      int n_pairs, ndtb200_result* results) {
+  if (!lanes || n_lanes < 1 || n_pairs < 0 || (n_pairs && (!targets || !n_targets || !sources || !n_sources || !results))) return NDTB200_ERR_INVALID;
+  for (int l = 0; l < n_lanes; ++l)
+    if (!lanes[l]) return NDTB200_ERR_INVALID;
+  std::vector<int> status(n_lanes, NDTB200_OK);
+  auto lane_loop = [&](int l) {
+    ndtb200_handle* h = lanes[l];
+    cudaSetDevice(h->device);
+    for (int k = l; k < n_pairs; k += n_lanes) {
+      int st = ndtb200_set_target(h, targets[k], n_targets[k], stride_bytes, 1);
+      if (st == NDTB200_OK) st = ndtb200_set_source(h, sources[k], n_sources[k], stride_bytes);
+      if (st == NDTB200_OK) st = ndtb200_align_async(h, guesses16 ? guesses16 + 16 * (size_t)k : nullptr);
+      if (st == NDTB200_OK) st = ndtb200_sync(h);  // the node reads every pose (yield-polling on throughput-mode handles)
+      if (st == NDTB200_OK) st = ndtb200_get_result(h, results + k);
+      if (st != NDTB200_OK) {
+        std::memset(results + k, 0, sizeof(ndtb200_result));
+        if (status[l] == NDTB200_OK) status[l] = st;
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  th.reserve(n_lanes);
+  for (int l = 1; l < n_lanes; ++l) th.emplace_back(lane_loop, l);
+  lane_loop(0);
+  for (std::thread& t : th) t.join();
+  for (int l = 0; l < n_lanes; ++l)
+    if (status[l] != NDTB200_OK) return status[l];
+  return NDTB200_OK;
 }
 
 void* ndtb200_stream(ndtb200_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }

@@ -110,6 +110,8 @@ def load_library():
     L.ndtb200_set_map_from_records.argtypes = [vp, f32p, f32p, C.c_int64, vp, vp, C.c_size_t]
     L.ndtb200_align_batch.argtypes = [C.POINTER(vp), C.c_int, f32p, C.POINTER(vp), C.c_size_t, C.POINTER(Result)]
     L.ndtb200_align_batch_async.argtypes = [C.POINTER(vp), C.c_int, f32p, C.POINTER(vp), C.c_size_t]
+    L.ndtb200_run_pairs.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t),
+                                    C.c_size_t, f32p, C.c_int, C.POINTER(Result)]
     L.ndtb200_get_result.argtypes = [vp, C.POINTER(Result)]
     L.ndtb200_fitness_score.argtypes = [vp, C.c_double, f64p]
     L.ndtb200_fitness_sums.argtypes = [vp, C.c_double, f64p, i64p]
@@ -139,6 +141,35 @@ def load_library():
     L.ndtb200_last_align_ms.argtypes = [vp, f32p]
     _lib = L
     return L
+
+
+class PairPipeline:
+    """Batched scan-to-scan odometry through ndtb200_run_pairs: `lanes` NDT objects, each driven by its own C++ host
+    thread inside the call (no Python threads, no GIL): pair k = setInputTarget(targets[k]) + setInputSource(sources[k])
+    + align(guesses[k]).  Clouds are given as (host pointer, point count) with 16-byte records (pinned memory for speed);
+    the ctypes arrays are built once per pair list."""
+
+    def __init__(self, lanes, targets, sources, guesses=None):
+        self._L = load_library()
+        self.lanes = list(lanes)
+        self.n_pairs = len(targets)
+        assert len(sources) == self.n_pairs
+        self._lanes = (C.c_void_p * len(self.lanes))(*[d._h for d in self.lanes])
+        self._tp = (C.c_void_p * max(1, self.n_pairs))(*[int(p) for p, _ in targets])
+        self._tn = (C.c_size_t * max(1, self.n_pairs))(*[int(n) for _, n in targets])
+        self._sp = (C.c_void_p * max(1, self.n_pairs))(*[int(p) for p, _ in sources])
+        self._sn = (C.c_size_t * max(1, self.n_pairs))(*[int(n) for _, n in sources])
+        self._g = None if guesses is None else np.concatenate([_colmajor(T) for T in guesses]).astype(np.float32)
+        self._res = (Result * max(1, self.n_pairs))()
+
+    def run(self):
+        st = self._L.ndtb200_run_pairs(self._lanes, len(self.lanes), self._tp, self._tn, self._sp, self._sn, 16,
+                                       _ptr(self._g, C.c_float) if self._g is not None else None, self.n_pairs, self._res)
+        if st != 0:
+            raise NdtError(st, "ndtb200_run_pairs failed: " + "; ".join(self._L.ndtb200_last_error(d._h).decode() for d in self.lanes[:4]))
+
+    def results(self):
+        return [NormalDistributionsTransform._result_dict(r) for r in self._res[:self.n_pairs]]
 
 
 class Batch:
