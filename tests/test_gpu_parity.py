@@ -226,8 +226,11 @@ def test_fused_and_staged_builds_identical(nb, monkeypatch):
     cases = [(tgt, 1.0, True), (tgt, 0.5, True), (tgt, 2.0, True), (scene, 1.0, True), (nan_cloud, 1.0, False), (tiny, 1.0, True)]
     for cloud, res, dense in cases:
         out = {}
-        for path in ("staged", "fused"):
-            monkeypatch.setenv("NDTB200_BUILD_PATH", path)
+        for path in ("staged", "fused", "cluster"):
+            # "cluster": the fused kernel launched as ONE thread-block cluster with hardware cluster barriers (the flavour
+            # handles in throughput mode use) instead of a cooperative launch with a global-memory barrier
+            monkeypatch.setenv("NDTB200_BUILD_PATH", "fused" if path == "cluster" else path)
+            monkeypatch.setenv("NDTB200_FUSED_LAUNCH", "cluster" if path == "cluster" else "coop")
             g = nb.NormalDistributionsTransform()
             g.setResolution(res)
             st = g.setInputTarget(cloud, dense)
@@ -236,16 +239,19 @@ def test_fused_and_staged_builds_identical(nb, monkeypatch):
             e = g.eval_derivatives(np.array([0.3, 0.1, -0.02, 0.004, -0.002, -0.01]))
             out[path] = (st, g.map_info(), g.point_keys(), d, e, g.voxelgrid_filter(cloud, 0.3), g.voxelgrid_filter(cloud, 1.7))
         monkeypatch.delenv("NDTB200_BUILD_PATH")
-        a, b = out["staged"], out["fused"]
-        assert a[0] == b[0]
-        for k in ("min_b", "max_b", "div_b"):
-            assert np.array_equal(a[1][k], b[1][k])
-        assert a[1]["n_voxels"] == b[1]["n_voxels"] and a[1]["n_valid"] == b[1]["n_valid"]
-        assert np.array_equal(a[2], b[2])
-        for k in ("keys", "counts", "mean", "cov", "icov", "inflated"):
-            assert np.array_equal(a[3][k], b[3][k], equal_nan=True), k
-        assert a[4]["score"] == b[4]["score"] and np.array_equal(a[4]["gradient"], b[4]["gradient"]) and np.array_equal(a[4]["hessian"], b[4]["hessian"])
-        assert np.array_equal(a[5], b[5], equal_nan=True) and np.array_equal(a[6], b[6], equal_nan=True)
+        monkeypatch.delenv("NDTB200_FUSED_LAUNCH")
+        a = out["staged"]
+        for other in ("fused", "cluster"):
+            b = out[other]
+            assert a[0] == b[0]
+            for k in ("min_b", "max_b", "div_b"):
+                assert np.array_equal(a[1][k], b[1][k])
+            assert a[1]["n_voxels"] == b[1]["n_voxels"] and a[1]["n_valid"] == b[1]["n_valid"]
+            assert np.array_equal(a[2], b[2])
+            for k in ("keys", "counts", "mean", "cov", "icov", "inflated"):
+                assert np.array_equal(a[3][k], b[3][k], equal_nan=True), (other, k)
+            assert a[4]["score"] == b[4]["score"] and np.array_equal(a[4]["gradient"], b[4]["gradient"]) and np.array_equal(a[4]["hessian"], b[4]["hessian"])
+            assert np.array_equal(a[5], b[5], equal_nan=True) and np.array_equal(a[6], b[6], equal_nan=True)
     # the guard and the empty cloud behave the same on both paths
     far = np.array([[0, 0, 0], [4000, 4000, 4000], [1, 1, 1], [2, 2, 2]], dtype=np.float32)
     for path in ("staged", "fused"):
@@ -1040,3 +1046,45 @@ def test_set_target_device_view_builds_without_copy(nb):
     del a
     c.align()
     assert np.array_equal(c.result()["final"], b.result()["final"]) and c.getFitnessScore() == b.getFitnessScore()
+
+
+def test_run_pairs_matches_single_calls(nb):
+    """ndtb200_run_pairs (batched scan-to-scan odometry: every lane = one handle + one C++ host thread inside the call) must
+    return, for every pair, exactly what setInputTarget / setInputSource / align return on a handle of its own."""
+    from util import as_xyzw_host
+    pairs = []
+    for seed in range(7):
+        tgt, src = synthetic_scene(n_target=20000 + 3000 * seed, n_source=5000 + 500 * seed, seed=20 + seed)
+        pairs.append((as_xyzw_host(tgt), as_xyzw_host(src)))
+    guesses = [np.eye(4, dtype=np.float32) for _ in pairs]
+    guesses[3][:3, 3] = (0.2, -0.1, 0.05)
+    lanes = [nb.NormalDistributionsTransform() for _ in range(3)]
+    for ln in lanes:
+        ln.setTransformationEpsilon(0.01)
+        ln.setMaximumIterations(40)
+    pipe = nb.PairPipeline(lanes, [(t.ctypes.data, len(t)) for t, _ in pairs], [(s.ctypes.data, len(s)) for _, s in pairs], guesses)
+    pipe.run()
+    got = pipe.results()
+    pipe.run()                                   # a second pass over the same pairs on the same lanes: identical bits
+    again = pipe.results()
+    for k, (t, s) in enumerate(pairs):
+        one = nb.NormalDistributionsTransform()
+        one.setTransformationEpsilon(0.01)
+        one.setMaximumIterations(40)
+        one.setInputTarget(t[:, :3])
+        one.setInputSource(s[:, :3])
+        one.align(guesses[k])
+        r = one.result()
+        for g in (got[k], again[k]):
+            assert g["iterations"] == r["iterations"] and g["n_evaluations"] == r["n_evaluations"] and g["converged"] == r["converged"]
+            assert np.array_equal(g["final"], r["final"])
+            assert g["trans_probability"] == r["trans_probability"]
+    # the oracle on one of the pairs (the pipeline is the same hot path, this is a plumbing check)
+    ref = oracle.NormalDistributionsTransform()
+    ref.setTransformationEpsilon(0.01)
+    ref.setMaximumIterations(40)
+    ref.setInputTarget(pairs[3][0][:, :3])
+    ref.setInputSource(pairs[3][1][:, :3])
+    ref.align(guesses[3])
+    dt, dr = transform_delta(got[3]["final"], ref.result()["final"])
+    assert dt < TRANS_TOL and dr < ROT_TOL

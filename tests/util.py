@@ -122,3 +122,10 @@ def oracle_mapping_loop(scans, voxel_leaf=0.3, map_voxel=0.5, eps=0.01, max_iter
         steps.append(rec)
         prev = filtered
     return steps, gmap
+
+
+def as_xyzw_host(points):
+    """(n,3) -> contiguous (n,4) float32 host array with w = 1 (the 16-byte PointXYZ record the C ABI takes by pointer)."""
+    p = np.ones((len(points), 4), dtype=np.float32)
+    p[:, :3] = np.asarray(points, dtype=np.float32)[:, :3]
+    return np.ascontiguousarray(p)

@@ -473,29 +473,57 @@ int finish_hash_index(ndtb200_handle* h, uint32_t n_vox) {
   return NDTB200_OK;
 }
 
-// ---- scan-sized clouds: the whole build (mode 0) or the VoxelGrid downsample (mode 1) in ONE cooperative launch ----
-// Rule: a scan-sized cloud on a handle in latency mode (one pipeline owns the GPU: a single caller, the mapping loop) is
-// built by the fused kernel.  Handles in throughput mode (many pairs in flight on their own streams) keep the staged
-// kernels by default: every cooperative launch must be fully co-resident, and although 16-CTA fused builds measured
-// 11.8-12.0 k pairs/s on c3 (staged: 9.7-9.8 k; 32-CTA builds 8.2 k, full-width 6.7 k) the same configuration also
-// produced 2.9 k and 6.4 k runs on other boxes — co-scheduling of many concurrent cooperative kernels is not
-// reproducible enough to be the default.  NDTB200_BUILD_PATH=fused selects it.
-constexpr int kFusedCtasThroughput = 16;
+// ---- scan-sized clouds: the whole build (mode 0) or the VoxelGrid downsample (mode 1) in ONE launch ----------------
+// Rule: a scan-sized cloud is built by the fused kernel (small_build.cuh).  Two launch flavours of the same code:
+//   * a handle in latency mode (one pipeline owns the GPU: a single caller, the mapping loop): COOPERATIVE launch over up
+//     to all SMs, phases separated by a counter barrier in global memory;
+//   * a handle in throughput mode (many pairs in flight on their own streams): the grid is ONE THREAD-BLOCK CLUSTER of up
+//     to 16 CTAs, an ordinary launch, phases separated by the hardware cluster barrier.  Round 1 ran these as 16-CTA
+//     cooperative launches: 11.8-12.0 k pairs/s on c3 on one box, 2.9 k and 6.4 k on others — many concurrent cooperative
+//     kernels are each admitted only when ALL their CTAs fit at once, and the admission order was not reproducible; a
+//     cluster is co-scheduled by the hardware on the SMs of one GPC, needs no such guarantee, and its barrier costs a
+//     fraction of the global-memory one.  Measured on c3 (8 lanes): staged builds 10.9 k pairs/s with 12 launches + 2
+//     synchronisations per pair, 8-CTA clusters 11.1 k with 3 launches + 1 synchronisation, 16-CTA clusters 9.6 k (one
+//     16-SM cluster per GPC at a time), 4-CTA 8.6 k.
+// NDTB200_BUILD_PATH=staged / fused forces one path, NDTB200_FUSED_LAUNCH=coop / cluster one flavour (tests: all agree
+// bit for bit).
+constexpr int kFusedCtasThroughput = 8;  // the portable cluster size
 bool use_fused_build(const ndtb200_handle* h, size_t n) {
+  (void)h;
   const char* e = getenv("NDTB200_BUILD_PATH");  // tests: "staged" / "fused" force one path (bit-identical results)
   if (e && std::strcmp(e, "staged") == 0) return false;
   if (e && std::strcmp(e, "fused") == 0) return n > 0 && n <= (size_t)0x7fffffff / 64;
-  return n > 0 && n <= kSmallMaxPoints && (h->shape == 0 || h->prefer_fused_build);
+  return n > 0 && n <= kSmallMaxPoints;
+}
+
+// cluster launch of the fused build: largest supported power-of-two cluster size <= want (16 needs the non-portable
+// opt-in; 8 is always available on sm_100)
+int fused_cluster_size(const void* fn, int want) {
+  static bool tried = false, nonportable_ok[2] = {false, false};
+  static const void* fns[2] = {nullptr, nullptr};
+  (void)tried;
+  int slot = -1;
+  for (int i = 0; i < 2; ++i) {
+    if (fns[i] == fn) { slot = i; break; }
+    if (fns[i] == nullptr) { fns[i] = fn; nonportable_ok[i] = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess; slot = i; break; }
+  }
+  const int cap = (slot >= 0 && nonportable_ok[slot]) ? 16 : 8;
+  int c = 1;
+  while (c * 2 <= want && c * 2 <= cap) c *= 2;
+  return c;
 }
 
 // Leaves: h->grid (host copy), *n_vox_out; mode 0: records / icov64 / moments / voxel lists / n_valid counter;
 // mode 1: centroids in h->d_out.  The sorted point indices end up in h->d_vals_a.  One host synchronisation.
 int run_fused_build(ndtb200_handle* h, const float4* pts, size_t n, int dense, int mode, uint32_t* n_vox_out) {
   int G = std::min(h->num_sms, grid_for(n, kBuildThreads, h->num_sms));
-  // throughput mode: many builds are in flight on different streams; a cooperative launch must be fully co-resident, so
-  // each one takes only a slice of the SMs and several of them run side by side
-  if (h->shape == 1 && !h->prefer_fused_build) G = std::min(G, kFusedCtasThroughput);
+  // throughput mode: many builds are in flight on different streams — each one is a single cluster of <= 16 CTAs
+  bool cluster = h->shape == 1 && !h->prefer_fused_build;
+  if (const char* e = getenv("NDTB200_FUSED_LAUNCH")) cluster = std::strcmp(e, "cluster") == 0 ? true : (std::strcmp(e, "coop") == 0 ? false : cluster);
   if (const char* e = getenv("NDTB200_FUSED_CTAS")) { const int c = atoi(e); if (c >= 1) G = std::min(G, c); }  // tuning
+  const void* fn = mode == 0 ? (cluster ? (const void*)small_build_kernel<0, true> : (const void*)small_build_kernel<0, false>)
+                             : (cluster ? (const void*)small_build_kernel<1, true> : (const void*)small_build_kernel<1, false>);
+  if (cluster) G = fused_cluster_size(fn, std::min(G, kFusedCtasThroughput));
   const int ntiles = static_cast<int>((n + kSmallTile - 1) / kSmallTile);
   const int stiles = static_cast<int>((n + kScanTile - 1) / kScanTile);
   CK(h->d_mm_partial.ensure((size_t)G * 6 * sizeof(float)));
@@ -534,8 +562,23 @@ int run_fused_build(ndtb200_handle* h, const float4* pts, size_t n, int dense, i
   a.centroids = h->d_out.as<float4>();
   a.sorted_idx_out = reinterpret_cast<uint32_t**>(sc + 160);
   void* args[] = {(void*)&a};
-  const void* fn = mode == 0 ? (const void*)small_build_kernel<0> : (const void*)small_build_kernel<1>;
-  CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kBuildThreads), args, 0, h->stream));
+  if (cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(kBuildThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = G;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelExC(&cfg, fn, args));
+  } else {
+    CK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(kBuildThreads), args, 0, h->stream));
+  }
   LAUNCHED(h);
   struct { uint32_t n_vox; uint32_t pad[39]; uint32_t* sorted; } back;
   static_assert(offsetof(decltype(back), sorted) == 160, "scalar block layout");

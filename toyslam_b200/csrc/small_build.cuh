@@ -53,7 +53,19 @@ struct SmallBuildArgs {
   uint32_t** sorted_idx_out;    // receives which of vals_a / vals_b holds the sorted point indices
 };
 
+// CLUSTER: the grid is ONE thread-block cluster (8 portable / 16 CTAs, launched with cudaLaunchAttributeClusterDimension
+// as an ordinary kernel): the phases are separated by the hardware cluster barrier (release / acquire at cluster scope)
+// instead of a counter in global memory.  The hardware co-schedules a cluster, so many such builds run side by side
+// (handles in throughput mode) without the co-residency requirement of a cooperative launch.
+template <bool CLUSTER>
 __device__ __forceinline__ void small_grid_sync(unsigned int* counter, unsigned int& phase) {
+  if (CLUSTER) {
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    ++phase;
+    return;
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -83,7 +95,7 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan_inplace(uint32_t* data, u
   return total;
 }
 
-template <int MODE>
+template <int MODE, bool CLUSTER = false>
 __global__ void __launch_bounds__(kBuildThreads)
 small_build_kernel(const SmallBuildArgs a) {
   __shared__ uint32_t warp_cnt[kSortWarps][256];
@@ -139,7 +151,7 @@ small_build_kernel(const SmallBuildArgs a) {
       a.mm_finite[blockIdx.x] = static_cast<unsigned int>(t);
     }
   }
-  small_grid_sync(a.barrier, phase);
+  small_grid_sync<CLUSTER>(a.barrier, phase);
 
   // ---- grid description: every CTA reduces the partials itself (identical result everywhere) ----
   {
@@ -196,7 +208,7 @@ small_build_kernel(const SmallBuildArgs a) {
     const bool ok = !check_finite || (isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
     a.keys_a[i] = ok ? static_cast<uint32_t>(voxel_key_of(p, g)) : sentinel;
   }
-  small_grid_sync(a.barrier, phase);
+  small_grid_sync<CLUSTER>(a.barrier, phase);
 
   // ---- stable LSD radix sort of (key, point index) ----
   const int ntiles = static_cast<int>((n + kSmallTile - 1) / kSmallTile);
@@ -205,11 +217,11 @@ small_build_kernel(const SmallBuildArgs a) {
     const int shift = pass * 8;
     uint32_t* totals = a.digit_totals + pass * 256;
     for (int t = blockIdx.x; t < ntiles; t += G) radix_count_tile<kSmallRounds>(ka, n, shift, a.hist, ntiles, t, warp_cnt, totals);
-    small_grid_sync(a.barrier, phase);
+    small_grid_sync<CLUSTER>(a.barrier, phase);
     for (int t = blockIdx.x; t < ntiles; t += G)
       radix_scatter_tile<kSmallRounds>(ka, pass == 0 ? nullptr : va, n, shift, a.hist, ntiles, t, kb, vb, warp_cnt, s_dstart, s_gbase,
                                        s_scan, s_key, s_val, totals);
-    small_grid_sync(a.barrier, phase);
+    small_grid_sync<CLUSTER>(a.barrier, phase);
     uint32_t* tk = ka; ka = kb; kb = tk;
     uint32_t* tv = va; va = vb; vb = tv;
   }
@@ -225,12 +237,12 @@ small_build_kernel(const SmallBuildArgs a) {
     block_exclusive_scan(c, s_scan, total);
     if (threadIdx.x == 0) a.tile_heads[t] = total;
   }
-  small_grid_sync(a.barrier, phase);
+  small_grid_sync<CLUSTER>(a.barrier, phase);
   if (blockIdx.x == 0) {
     const uint32_t total = cta_exclusive_scan_inplace(a.tile_heads, static_cast<uint32_t>(stiles), s_scan);
     if (threadIdx.x == 0) *a.n_vox = total;
   }
-  small_grid_sync(a.barrier, phase);
+  small_grid_sync<CLUSTER>(a.barrier, phase);
   const uint32_t n_vox = __ldcg(a.n_vox);
   for (int t = blockIdx.x; t < stiles; t += G) {
     const size_t base = (size_t)t * kScanTile + (size_t)threadIdx.x * kScanItems;
@@ -247,7 +259,7 @@ small_build_kernel(const SmallBuildArgs a) {
       }
     }
   }
-  small_grid_sync(a.barrier, phase);
+  small_grid_sync<CLUSTER>(a.barrier, phase);
 
   // ---- per voxel ----
   const uint32_t n_finite = static_cast<uint32_t>(g.n_finite);
