@@ -474,26 +474,25 @@ int finish_hash_index(ndtb200_handle* h, uint32_t n_vox) {
 }
 
 // ---- scan-sized clouds: the whole build (mode 0) or the VoxelGrid downsample (mode 1) in ONE launch ----------------
-// Rule: a scan-sized cloud is built by the fused kernel (small_build.cuh).  Two launch flavours of the same code:
-//   * a handle in latency mode (one pipeline owns the GPU: a single caller, the mapping loop): COOPERATIVE launch over up
-//     to all SMs, phases separated by a counter barrier in global memory;
-//   * a handle in throughput mode (many pairs in flight on their own streams): the grid is ONE THREAD-BLOCK CLUSTER of up
-//     to 16 CTAs, an ordinary launch, phases separated by the hardware cluster barrier.  Round 1 ran these as 16-CTA
-//     cooperative launches: 11.8-12.0 k pairs/s on c3 on one box, 2.9 k and 6.4 k on others — many concurrent cooperative
-//     kernels are each admitted only when ALL their CTAs fit at once, and the admission order was not reproducible; a
-//     cluster is co-scheduled by the hardware on the SMs of one GPC, needs no such guarantee, and its barrier costs a
-//     fraction of the global-memory one.  Measured on c3 (8 lanes): staged builds 10.9 k pairs/s with 12 launches + 2
-//     synchronisations per pair, 8-CTA clusters 11.1 k with 3 launches + 1 synchronisation, 16-CTA clusters 9.6 k (one
-//     16-SM cluster per GPC at a time), 4-CTA 8.6 k.
+// Rule: a scan-sized cloud on a handle in latency mode (one pipeline owns the GPU: a single caller, the mapping loop) is
+// built by the fused kernel (small_build.cuh), a COOPERATIVE launch over up to all SMs with a counter barrier in global
+// memory between the phases.  Handles in throughput mode (many pairs in flight on their own streams) keep the staged
+// kernels by default.  For them the fused kernel exists in a second launch flavour — the grid is ONE THREAD-BLOCK
+// CLUSTER of 8 CTAs, an ordinary launch, phases separated by the hardware cluster barrier (no co-residency admission
+// of a cooperative launch, which made round 1's 16-CTA cooperative builds bimodal: 11.8 k pairs/s on one box, 2.9 k
+// and 6.4 k on others) — selected by NDTB200_BUILD_PATH=fused.  Measured on c3, pairs/s at 1 / 2 / 4 GPUs of one
+// host: staged 10.9 k / 21.6 k / 38.0 k (12 launches + 2 synchronisations per pair), 8-CTA clusters 11.1 k / 22.2 k /
+// 33.0 k (3 launches + 1 synchronisation), 16-CTA clusters 9.6 k (one 16-SM cluster per GPC at a time), 4-CTA 8.6 k:
+// fewer launches do not buy throughput — the lanes are bound by the solves sharing the SMs, not by the launch rate —
+// so the staged path, which scales better, stays the default.
 // NDTB200_BUILD_PATH=staged / fused forces one path, NDTB200_FUSED_LAUNCH=coop / cluster one flavour (tests: all agree
 // bit for bit).
 constexpr int kFusedCtasThroughput = 8;  // the portable cluster size
 bool use_fused_build(const ndtb200_handle* h, size_t n) {
-  (void)h;
   const char* e = getenv("NDTB200_BUILD_PATH");  // tests: "staged" / "fused" force one path (bit-identical results)
   if (e && std::strcmp(e, "staged") == 0) return false;
   if (e && std::strcmp(e, "fused") == 0) return n > 0 && n <= (size_t)0x7fffffff / 64;
-  return n > 0 && n <= kSmallMaxPoints;
+  return n > 0 && n <= kSmallMaxPoints && (h->shape == 0 || h->prefer_fused_build);
 }
 
 // cluster launch of the fused build: largest supported power-of-two cluster size <= want (16 needs the non-portable
