@@ -93,7 +93,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def dist_setup(n_gpus):
+def dist_setup(n_gpus, bind=True):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -104,7 +104,62 @@ def dist_setup(n_gpus):
             torch.cuda.set_device(local)
         dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo",
                                 device_id=torch.device("cuda", local) if torch.cuda.is_available() else None)
+        if bind and torch.cuda.is_available() and os.environ.get("NDTB200_NO_BIND") is None:
+            bind_rank_to_gpu(local, world)  # before any pinned allocation
     return rank, world, local
+
+
+TOPOLOGY = {}
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_rank_to_gpu(local, world):
+    """Rank -> core binding for the multi-GPU runs (end-to-end efficiency at 8 GPUs).  One process per GPU:
+    the process (and with it the first-touch placement of its pinned staging buffers) is bound to the cores of the NUMA
+    node its GPU hangs off (sysfs numa_node of the GPU's PCI function); the cores of a node are divided evenly between
+    the ranks that share it.  Without NUMA information the allowed cores are simply divided between the local ranks.
+    Best effort: any failure leaves the affinity as it was.  The outcome is reported as `topology` in the JSON line."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        TOPOLOGY.update({"cores_allowed": len(allowed), "local_world": local_world, "numa_node": None, "bound_cores": len(allowed)})
+        if local_world <= 1:
+            return
+        nodes = {}
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            for g in range(local_world):
+                bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(g)).busId
+                bus = bus.decode() if isinstance(bus, bytes) else bus
+                path = "/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]
+                nodes[g] = int(open(path).read().strip()) if os.path.exists(path) else -1
+        except Exception:
+            nodes = {}
+        mine = nodes.get(local, -1)
+        pool, sharers = allowed, list(range(local_world))
+        if mine >= 0:
+            node_cpus = _parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % mine).read()) & set(allowed)
+            if node_cpus:
+                pool = sorted(node_cpus)
+                sharers = [g for g in range(local_world) if nodes.get(g, -1) == mine]
+                TOPOLOGY["numa_node"] = mine
+        k = sharers.index(local) if local in sharers else 0
+        per = max(1, len(pool) // max(1, len(sharers)))
+        cores = pool[k * per:(k + 1) * per] or pool
+        os.sched_setaffinity(0, cores)
+        TOPOLOGY.update({"bound_cores": len(cores), "gpu_numa_nodes": [nodes.get(g, -1) for g in range(local_world)] if nodes else None})
+    except Exception as e:  # pragma: no cover - best effort
+        TOPOLOGY["bind_error"] = str(e)[:120]
 
 
 def barrier(world):
@@ -349,7 +404,7 @@ def run_reference(args):
     host cores, same workload / metric / unit.  A step of the GPU arm is a batch of `--replicas` aligns; here a step is a
     bounded sample of that batch — ONE full align of one pair of the batch — so the run ends within minutes; the value is
     aligns/s either way."""
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_setup(args.gpus, bind=False)  # the CPU arm keeps all host cores
     if rank != 0:
         return 0
     import oracle
@@ -631,6 +686,7 @@ def run_b200(args):
                         "ms_max": float(np.max(lat_all)), "ms_mean": float(np.mean(lat_all)), "steps": len(lat_all),
                         "note": "one align in flight at a time, default CTA shape, inputs resident, CUDA events per launch (median)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_dram": roofline_dram,
+            "topology": dict(TOPOLOGY) or None,
             "wall_s_timed_region": wall}
     # ---- the path with a real exchange step: one large source sharded over the GPUs against a map larger than L2 (BASELINE
     # configs[3]), the fused derivative-pass + 29-value NVLink exchange kernel; strong scaling (N = 1: the same solve on one GPU)
@@ -830,7 +886,10 @@ def run_c3(args):
     # Measured on three boxes, staged builds: 8 lanes 9.8 k / 10.8 k / 10.7 k pairs/s, 16 lanes 7.3 k / 9.5 k / 12.6 k — 8 is
     # the steadier choice; C++ and Python lane threads measure the same (10.8 k vs 10.75 k): the lanes are bound by the
     # ~12 launches + 2 synchronisations of a staged scan-sized build, not by the host language
-    L = args.c3_lanes if args.c3_lanes > 0 else 8
+    # With several ranks on one host the lane threads must not oversubscribe the rank's cores (their waits poll): 8 lanes
+    # where a rank has >= 8 cores, fewer otherwise (8 GPUs on a 32-core host: 4) — measured 42.4 k pairs/s at 8 GPUs
+    # with 64 polling threads on 32 cores against 38.0 k at 4 GPUs
+    L = args.c3_lanes if args.c3_lanes > 0 else max(2, min(8, host_threads()))
     lanes = []
     for _ in range(L):
         ndt = nb.NormalDistributionsTransform(device=local)
@@ -930,7 +989,7 @@ def run_c3(args):
             "hessian_passes_per_align": float(np.mean([r["n_hessian_passes"] for r in done])),
             "iterations_per_align": float(np.mean([r["iterations"] for r in done])),
             "mean_translation_error_vs_truth_m": float(np.mean(err_t)), "max_translation_error_vs_truth_m": float(np.max(err_t)),
-            "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": wall,
+            "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": wall, "topology": dict(TOPOLOGY) or None,
             "e2e": {"value": pairs_rank * world / max_over_ranks(wall, world, dev), "unit": "aligns/s",
                     "h2d_bytes_per_step": int(2 * pts * 16), "d2h_bytes_per_step": 416,
                     "note": "the timed region IS end to end here: host scans (pinned) in, poses out, wall clock"}}
