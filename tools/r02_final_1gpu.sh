@@ -15,5 +15,6 @@ python bench.py --workload mapper > gpurun_out/r02_final_bench_mapper.json 2>> g
 python bench.py --workload c4 --c4-city-points 100000000 --steps 3 --warmup 3 > gpurun_out/r02_final_bench_c4.json 2>> gpurun_out/r02_final.err
 python bench.py --workload c5 --c5-points 10000000 100000000 500000000 > gpurun_out/r02_final_bench_c5.json 2>> gpurun_out/r02_final.err
 python tools/timeline.py > gpurun_out/r02_final_timeline.txt 2>> gpurun_out/r02_final.err
+python bench.py --workload c3 --c3-lanes 4 --no-cpu-baseline > gpurun_out/r02_final_bench_c3_lanes4.json 2>> gpurun_out/r02_final.err
 tail -c 600 gpurun_out/r02_final.err
 ls -la gpurun_out
