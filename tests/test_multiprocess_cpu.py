@@ -92,3 +92,29 @@ def test_c_abi_header_symbols_are_exported():
     for must in ("ndtb200_align", "ndtb200_align_batch", "ndtb200_set_target", "ndtb200_voxelgrid_filter", "ndtb200_mapper_push_scan",
                  "ndtb200_build_from_partials", "ndtb200_fitness_score"):
         assert must in names
+
+
+def test_rank_core_binding_helpers(monkeypatch):
+    """bench.py binds a rank to the cores of its GPU's NUMA node (or to an even share of the allowed cores): the cpulist
+    parser, the single-rank no-op and the even split between two local ranks (no GPU / no NVML here: the fallback)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert bench._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    try:
+        bench.TOPOLOGY.clear()
+        bench.bind_rank_to_gpu(0, 1)
+        assert os.sched_getaffinity(0) == before and bench.TOPOLOGY["bound_cores"] == len(before)
+        if len(before) >= 2:
+            monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+            shares = []
+            for local in (0, 1):
+                os.sched_setaffinity(0, before)
+                bench.TOPOLOGY.clear()
+                bench.bind_rank_to_gpu(local, 2)
+                shares.append(os.sched_getaffinity(0))
+            assert shares[0] and shares[1] and not (shares[0] & shares[1]) and (shares[0] | shares[1]) <= before
+            assert len(shares[0]) == len(before) // 2
+    finally:
+        os.sched_setaffinity(0, before)

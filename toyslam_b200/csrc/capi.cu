@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -498,9 +499,10 @@ bool use_fused_build(const ndtb200_handle* h, size_t n) {
 // cluster launch of the fused build: largest supported power-of-two cluster size <= want (16 needs the non-portable
 // opt-in; 8 is always available on sm_100)
 int fused_cluster_size(const void* fn, int want) {
-  static bool tried = false, nonportable_ok[2] = {false, false};
+  static std::mutex mu;  // lanes (host threads) build concurrently
+  std::lock_guard<std::mutex> lock(mu);
+  static bool nonportable_ok[2] = {false, false};
   static const void* fns[2] = {nullptr, nullptr};
-  (void)tried;
   int slot = -1;
   for (int i = 0; i < 2; ++i) {
     if (fns[i] == fn) { slot = i; break; }
