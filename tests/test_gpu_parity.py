@@ -273,7 +273,12 @@ def test_payload_sort_build_identical(nb, monkeypatch):
     nan_cloud[::53, 2] = np.nan
     nan_cloud[7::211, 0] = np.inf
     one_pass = (tgt[:5000] * 0.1).astype(np.float32)                # < 256 cells at res 1.0: a single radix pass
-    cases = [(tgt, 1.0, True), (tgt, 0.5, True), (scene, 1.0, True), (scene, 0.3, True), (nan_cloud, 1.0, False), (one_pass, 1.0, True)]
+    rng = np.random.default_rng(77)
+    centres = np.concatenate([rng.uniform([-150, -150, -100], [150, 150, 100], size=(40, 3)), [[-150.5, -150.5, -100.5], [150.5, 150.5, 100.5]]])
+    wide = (rng.uniform(-0.4, 0.4, size=(42, 9, 3)) + centres[:, None, :]).reshape(-1, 3).astype(np.float32)
+    assert np.prod(np.floor(wide.max(0)) - np.floor(wide.min(0)) + 1) > 2 ** 24   # 302 x 302 x 202 cells at res 1.0: four radix passes
+    cases = [(tgt, 1.0, True), (tgt, 0.5, True), (scene, 1.0, True), (scene, 0.3, True), (nan_cloud, 1.0, False), (one_pass, 1.0, True),
+             (wide, 1.0, True)]
     monkeypatch.setenv("NDTB200_BUILD_PATH", "staged")
     for cloud, res, dense in cases:
         out = {}
