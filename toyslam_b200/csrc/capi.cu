@@ -713,7 +713,7 @@ int build_map_ex(ndtb200_handle* h, const BuildOpts& o) {
   const uint32_t n_finite = static_cast<uint32_t>(h->grid.n_finite);
   const double avg = static_cast<double>(n_finite) / std::max<uint32_t>(1u, n_vox);
   const int group = avg >= 48.0 ? 32 : (avg >= 10.0 ? 8 : 4);  // lanes per voxel
-  const int blocks = static_cast<int>(((size_t)n_vox * group + kBuildThreads - 1) / kBuildThreads);
+  const int blocks = static_cast<int>(((size_t)n_vox + kBuildThreads - 1) / kBuildThreads);  // voxel_build_kernel: kBuildThreads voxels per CTA
 
   if (o.partial_only) {  // 5'. moments only: leave {voxel_key, count, moments} for the exchange
     int st = compute_moments(h, n_vox, n_finite);

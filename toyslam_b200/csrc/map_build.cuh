@@ -854,40 +854,48 @@ __device__ __forceinline__ void finalize_one(uint32_t v, int count, const double
 // finalize_one) straight from registers — the 72-byte moment row never goes to memory and back — and enters a valid
 // voxel into the direct-mapped cell table (nullptr: the hash index is filled afterwards).  Same arithmetic in the same
 // order as voxel_moments_kernel + finalize_voxels_kernel + dense_fill_kernel.
+#ifndef NDTB200_VB_MIN_BLOCKS
+#define NDTB200_VB_MIN_BLOCKS 4
+#endif
 template <int GROUP, bool SEQ = false>
-__global__ void __launch_bounds__(kBuildThreads, 5)  // <= 48 registers: the gather phase lives on resident warps; the finalize part may spill
+__global__ void __launch_bounds__(kBuildThreads, NDTB200_VB_MIN_BLOCKS)
 voxel_build_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ sorted_idx, const int32_t* __restrict__ voxel_key,
                    const uint32_t* __restrict__ voxel_start, uint32_t n_voxels, uint32_t n_finite, int min_points, double eig_ratio,
                    VoxelRecord* __restrict__ records, double* __restrict__ icov64, unsigned int* __restrict__ n_valid,
                    int32_t* __restrict__ dense_table) {
-  constexpr int kVoxPerCta = kBuildThreads / GROUP;
+  // A CTA owns kBuildThreads consecutive voxels: their moments are summed kBuildThreads / GROUP voxels at a time (GROUP
+  // rounds), then EVERY thread finalises one leaf.  The finalize is a ~3 us serial fp64 chain per thread: with one
+  // finalising warp per CTA (32 voxels per CTA, the first version) that latency was paid 8x as often per SM and bounded
+  // the kernel (655 us for 3 M voxels); the arithmetic per voxel is unchanged.
+  constexpr int kVoxPerRound = kBuildThreads / GROUP;
+  constexpr int kVoxPerCta = kBuildThreads;
   __shared__ double s_m[kVoxPerCta][9];
   __shared__ uint32_t s_cnt[kVoxPerCta];
-  const uint32_t gid = (blockIdx.x * (uint32_t)blockDim.x + threadIdx.x) / GROUP;
-  const int gl = threadIdx.x % GROUP;
-  const bool active = gid < n_voxels;
-  {
+  const int gl = threadIdx.x % GROUP, gi = threadIdx.x / GROUP;
+  const uint32_t v0 = blockIdx.x * (uint32_t)kVoxPerCta;
+#pragma unroll 1
+  for (int r = 0; r < GROUP; ++r) {
+    const uint32_t slot = r * kVoxPerRound + gi;
+    const uint32_t gid = v0 + slot;
+    const bool active = gid < n_voxels;
     double s[9];
     uint32_t count;
     voxel_moments_group<GROUP, SEQ>(pts, sorted_idx, voxel_start, n_voxels, n_finite, gid, gl, active, s, count);
     if (gl == 0) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) s_m[threadIdx.x / GROUP][k] = s[k];
-      s_cnt[threadIdx.x / GROUP] = count;
+      for (int k = 0; k < 9; ++k) s_m[slot][k] = s[k];
+      s_cnt[slot] = count;
     }
   }
   __syncthreads();
-  // the leaves of this CTA are finalised by its first threads, one voxel per lane (full warps instead of one lane per group)
-  if (threadIdx.x < kVoxPerCta) {
-    const uint32_t v = blockIdx.x * (uint32_t)kVoxPerCta + threadIdx.x;
-    if (v < n_voxels) {
-      double m[9];
+  const uint32_t v = v0 + threadIdx.x;
+  if (v < n_voxels) {
+    double m[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) m[k] = s_m[threadIdx.x][k];
-      const int32_t key = voxel_key[v];
-      finalize_one(v, static_cast<int>(s_cnt[threadIdx.x]), m, key, min_points, eig_ratio, records, icov64, n_valid, nullptr, nullptr, nullptr, nullptr);
-      if (dense_table != nullptr && records[v].count >= min_points) dense_table[key] = static_cast<int32_t>(v);
-    }
+    for (int k = 0; k < 9; ++k) m[k] = s_m[threadIdx.x][k];
+    const int32_t key = voxel_key[v];
+    finalize_one(v, static_cast<int>(s_cnt[threadIdx.x]), m, key, min_points, eig_ratio, records, icov64, n_valid, nullptr, nullptr, nullptr, nullptr);
+    if (dense_table != nullptr && records[v].count >= min_points) dense_table[key] = static_cast<int32_t>(v);
   }
 }
 
