@@ -3,14 +3,21 @@
 //
 //   minmax3d            -> bounding box (pcl::getMinMax3D, …_impl.hpp:72)
 //   grid_setup          -> min_b/max_b/div_b/divb_mul + int32 overflow guard (…_impl.hpp:75-103)
-//   voxel_key           -> per-point int32 key, bit-exact fp32 arithmetic (…_impl.hpp:218-223)
-//   radix sort          -> hand-written stable LSD radix sort of (key, point index), 8-bit digits
+//   voxel_key           -> per-point int32 key, bit-exact fp32 arithmetic (…_impl.hpp:218-223), and the 8-bit digit
+//                          histograms of all radix passes at once
+//   radix sort          -> hand-written stable LSD radix sort, 8-bit digits, ONE-SWEEP passes (decoupled look-back):
+//                          (key, point index) pairs (onesweep_kernel), or — clouds of 4 M points and more — the points
+//                          themselves with the key in .w (onesweep_payload_kernel), so that the moments read the sorted
+//                          cloud sequentially instead of gathering 64 B of DRAM per point
 //   segment heads       -> occupied-voxel list (= leaves_), per-voxel point ranges
-//   voxel_moments       -> per-voxel count, sum x, sum x x^T in fp64 (first pass, …_impl.hpp:233-262)
-//   finalize_voxels     -> mean, covariance, eigen-regularisation, inverse (second pass, …_impl.hpp:282-367)
-//   hash_insert         -> open-addressing HBM hash over the valid voxels
+//   voxel_build         -> per-voxel count, sum x, sum x x^T in fp64 (first pass, …_impl.hpp:233-262), then mean,
+//                          covariance, eigen-regularisation, inverse (second pass, …_impl.hpp:282-367) and the cell-table
+//                          entry, in one kernel (voxel_moments / finalize_voxels: the same two halves as separate
+//                          kernels, used by the sharded build and the parity dumps)
+//   hash_insert         -> open-addressing HBM hash over the valid voxels (grids whose cell table does not fit)
 //
-// All kernels are HBM-bound streaming / gather kernels: no tensor cores on this path.
+// All kernels are HBM / issue bound streaming kernels: no tensor cores on this path.  DESIGN.md §4.1 has the per-kernel
+// times and the reasoning for what bounds them.
 #pragma once
 #include "common.cuh"
 

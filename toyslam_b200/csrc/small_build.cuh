@@ -15,6 +15,10 @@
 //   MODE 1: per-voxel fp32 centroid in input order (pcl::VoxelGrid)                              -> float4 cloud
 //
 // Same arithmetic and same order as the staged kernels: results are bit-identical (tested path against path).
+//
+// Two launch flavours (template parameter CLUSTER): a cooperative launch over up to all SMs with a counter barrier in
+// global memory (latency-mode handles), or ONE thread-block cluster of <= 8 CTAs launched as an ordinary kernel with
+// the hardware cluster barrier (throughput-mode handles, NDTB200_BUILD_PATH=fused) — see run_fused_build in capi.cu.
 #pragma once
 #include "map_build.cuh"
 
